@@ -1,0 +1,156 @@
+/* vamp_b200.h - C ABI of libvamp_b200.so: the B200-native (sm_100a) likelihood / MCMC / BIC
+ * hot path of sarahappleby/VAMP.
+ *
+ * The reference (vamp_1.0, pure Python) has no FFI of its own: its hot path is the body of
+ * VPfit (vamp_1.0/vpfits.py) delegating to PyMC 2 / astropy / scipy.  Each entry point below
+ * names the reference interface it replaces (file:line under /root/reference).  The binding a
+ * reference maintainer would add (ctypes) is shown in INTEGRATION.md and shipped as
+ * vamp_b200/_lib.py.
+ *
+ * Conventions
+ *  - every function returns 0 on success, <0 on error; vamp_last_error() gives the message
+ *    (thread-local).  Nothing throws, nothing calls back into Python.
+ *  - *_host entry points take HOST buffers in the reference's physical units (Hz), copy them
+ *    to the device, run on the context's stream, copy results back and synchronise.
+ *  - *_dev entry points take caller-owned DEVICE pointers (e.g. torch tensors), are
+ *    asynchronous on the context's stream, and use SCALED units: for region r with ascending
+ *    frequency grid nu_0..nu_{P-1},  u = (nu - nu_0) / s_r,  s_r = (nu_{P-1} - nu_0)/(P-1),
+ *    so centroids live in [0, P-1] and widths are in mean-pixel units (vamp_regions_scale
+ *    returns nu_0 and s_r).  Amplitudes and sd are unit-free.
+ *  - parameter vectors: theta[item][4*cmax + 1] (double):
+ *        theta[4c+0..3] = amplitude, centroid, L_fwhm | sigma, G_fwhm | unused   (c < ncomp)
+ *        theta[4*cmax]  = sd (free noise parameter of VPfit(noise=None), vpfits.py:39)
+ *    mirroring estimated_variables[c]['amplitude'|'centroid'|'L_fwhm'|'G_fwhm'|'sigma']
+ *    (vpfits.py:232-262, 276-307).
+ */
+#ifndef VAMP_B200_H
+#define VAMP_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VAMP_ABI_VERSION 1
+
+enum { VAMP_F32 = 0, VAMP_F64 = 1 };          /* arithmetic of the pixel math */
+enum { VAMP_GAUSS = 0, VAMP_VOIGT = 1 };      /* VPfit(voigt=False|True) */
+
+typedef struct vamp_ctx vamp_ctx;
+typedef struct vamp_regions vamp_regions;
+
+const char* vamp_last_error(void);
+int vamp_abi_version(void);
+
+/* One context per process/GPU (holds device id, stream, scratch). */
+int vamp_ctx_create(int device, vamp_ctx** out);
+int vamp_ctx_destroy(vamp_ctx* ctx);
+int vamp_ctx_set_stream(vamp_ctx* ctx, void* cuda_stream);   /* cudaStream_t; NULL = default stream */
+int vamp_ctx_synchronize(vamp_ctx* ctx);
+
+/* Upload R absorption regions (what VPregion.__init__ holds: frequency_array, flux_array,
+ * noise_array - vamp_1.0/vpregion.py:10-19; built by vpspectrum.py:273-279).  HOST arrays,
+ * packed back to back, nu ascending inside each region.  lsf: odd number of taps or NULL
+ * (identity = the reference).  Precomputes, in float64 on the host, the scaled pixel
+ * coordinates relative to a per-256-pixel tile base for both precisions. */
+int vamp_regions_create(vamp_ctx* ctx, int R, const int* npix, const double* nu, const double* flux,
+                        const double* noise, const double* lsf, int lsf_taps, vamp_regions** out);
+int vamp_regions_destroy(vamp_regions* regions);
+int vamp_regions_info(const vamp_regions* regions, int* R, int* max_npix, long long* total_pix);
+int vamp_regions_scale(const vamp_regions* regions, double* nu0 /*[R]*/, double* scale /*[R]*/);
+
+/* K1 - fused model + likelihood.  Replaces, per item:
+ *   VPfit.VoigtFunction / GaussFunction (vpfits.py:44-76), total = Tau2flux(sum(profiles))
+ *   (vpfits.py:334-338, physics.py:98-105), the Normal("obs") log-density (vpfits.py:39,341;
+ *   per-pixel-noise form vamp_2.0/vamp_src/fit/fit.py:127-171) and VPfit.Chisquared
+ *   (vpfits.py:109-118).
+ * sd != NULL: lnL with the scalar noise parameter sd[item]; sd == NULL: lnL with the region's
+ * noise array.  out_chi2 always uses the noise array.  Any out_* may be NULL.
+ * out_flux[item*flux_stride + pixel] receives the model flux (the `total` deterministic). */
+int vamp_loglike_dev(vamp_ctx* ctx, const vamp_regions* regions, int dtype, int kind, int n_items,
+                     const int* item_region, const int* item_ncomp, int max_ncomp, const double* theta,
+                     int theta_stride, const double* sd, double* out_lnL, double* out_chi2,
+                     void* out_flux /* float* or double* per dtype */, long long flux_stride);
+/* Same, HOST buffers, theta in Hz (physical units); out_flux is double regardless of dtype. */
+int vamp_loglike_host(vamp_ctx* ctx, const vamp_regions* regions, int dtype, int kind, int n_items,
+                      const int* item_region, const int* item_ncomp, int max_ncomp, const double* theta,
+                      int theta_stride, const double* sd, double* out_lnL, double* out_chi2,
+                      double* out_flux, long long flux_stride);
+
+/* K2 - batched Metropolis chains, one warp per chain.  Replaces mcmc.sample(iter, burn, thin)
+ * (vpfits.py:393, 423, 425) i.e. PyMC 2's scalar Metropolis steppers + tune().  All pointers
+ * are DEVICE pointers owned by the caller; state persists across calls so a chain can be
+ * advanced in slices [it0, it1). */
+typedef struct vamp_mcmc_args {
+    int n_chains;
+    int cmax;                   /* component slots; theta_stride must be 4*cmax + 1 */
+    int max_ncomp;              /* max over item_ncomp (sizes shared memory) */
+    int sd_free;                /* 1 = VPfit(noise=None): sd ~ U(0,1) sampled; 0 = noise array */
+    int it0, it1;               /* iterations to run: [it0, it1) */
+    int burn, thin;             /* tally when i >= burn and i % thin == 0 (PyMC 2) */
+    int tune_interval;          /* PyMC 2 default 1000 */
+    int tune_throughout;        /* PyMC 2 default 1; 0 = adapt during burn-in only */
+    unsigned long long seed;    /* Philox key */
+    const int* item_region;     /* [n] */
+    const int* item_ncomp;      /* [n] */
+    const unsigned long long* chain_uid; /* [n] global chain ids (Philox counter) */
+    double* theta;              /* [n, 4*cmax+1] in/out, scaled units */
+    float* asf;                 /* [n, stride] adaptive scale factors */
+    float* psd;                 /* [n, stride] proposal sd (PyMC 2: |initial value|, 1 if 0) */
+    int* acc;                   /* [n, stride] accepted since last tune */
+    int* rej;                   /* [n, stride] */
+    int* acc_total;             /* [n, stride] accepted after burn-in */
+    double* logp;               /* [n] log posterior of current state (without uniform constants) */
+    double* lnL;                /* [n] */
+    double* best_theta;         /* [n, stride] highest-logp state seen at an iteration end */
+    double* best_logp;          /* [n] */
+    double* mean;               /* [n, stride] Welford mean of tallies   (mcmc.stats(), vpspectrum.py:400) */
+    double* m2;                 /* [n, stride] Welford M2 */
+    double* comom;              /* [n, cmax, 6] co-moments (A,c)(A,w1)(A,w2)(c,w1)(c,w2)(w1,w2) (chain_covariance, vpfits.py:432-456) */
+    int* ntally;                /* [n] */
+    double* sum_lnL;            /* [n] sum of lnL over tallies (DIC/BPIC) */
+    double* sum_lnL2;           /* [n] */
+    double* trace;              /* [n, trace_cap, stride] or NULL  (mcmc.trace(name)[:]) */
+    int trace_cap;
+} vamp_mcmc_args;
+
+/* from_prior != 0: draw PyMC 2-style initial values (xexp = 0.5, Uniforms from their priors,
+ * vpfits.py:239-252, 283-297) into theta; then (always) reset asf/psd/counters/statistics. */
+int vamp_mcmc_init_dev(vamp_ctx* ctx, const vamp_regions* regions, int kind, const vamp_mcmc_args* a, int from_prior);
+int vamp_mcmc_run_dev(vamp_ctx* ctx, const vamp_regions* regions, int dtype, int kind, const vamp_mcmc_args* a);
+
+/* K3 - batched Nelder-Mead MAP + BIC, one warp per start.  Replaces
+ * mc.MAP(model).fit(iterlim, tol) and map.BIC (vpfits.py:357-358, 419-427). */
+typedef struct vamp_map_args {
+    int n_starts;
+    int cmax, max_ncomp, sd_free;
+    int maxiter, maxfun;        /* scipy.optimize.fmin limits; maxfun <= 0: unlimited */
+    double xtol, ftol;          /* PyMC 2 MAP.fit: ftol = tol (1e-3), xtol = 1e-4 */
+    const int* item_region;     /* [n] */
+    const int* item_ncomp;      /* [n] */
+    double* theta;              /* [n, 4*cmax+1] in: start, out: optimum (scaled units) */
+    double* out_logp;           /* [n] */
+    double* out_lnL;            /* [n] */
+    double* out_chi2;           /* [n] noise-weighted chi^2 (VPfit.Chisquared) at the optimum */
+    double* out_bic;            /* [n] k ln P - 2 lnL, k = (3|4) ncomp + sd_free */
+    int* out_iters;             /* [n] */
+    int* out_nfev;              /* [n] */
+} vamp_map_args;
+int vamp_map_dev(vamp_ctx* ctx, const vamp_regions* regions, int dtype, int kind, const vamp_map_args* a);
+
+/* One component's optical depth tau(x) on an arbitrary HOST grid, evaluated in float64 on the
+ * device: VPfit.VoigtFunction(x, centroid, amplitude, L_fwhm, G_fwhm) (vpfits.py:58-76; kind =
+ * VAMP_VOIGT, w1 = L_fwhm, w2 = G_fwhm) or VPfit.GaussFunction(x, amplitude, centroid, sigma)
+ * (vpfits.py:44-54; kind = VAMP_GAUSS, w1 = sigma).  Physical units. */
+int vamp_profile_host(vamp_ctx* ctx, int kind, int n, const double* x, double centroid, double amplitude,
+                      double w1, double w2, double* out_tau);
+
+/* Device Faddeeva test hook: H(x, y) = sqrt(pi) y Re w(x + iy) for n HOST points (both
+ * precisions).  Used by the parity tests against scipy.special.wofz / mpmath. */
+int vamp_faddeeva_host(vamp_ctx* ctx, int dtype, int n, const double* x, const double* y, double* out_H);
+/* Philox4x32-10 known-answer hook (HOST buffers): out[4] for counter[4], key[2]. */
+int vamp_philox_host(vamp_ctx* ctx, const unsigned int* counter, const unsigned int* key, unsigned int* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VAMP_B200_H */

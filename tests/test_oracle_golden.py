@@ -1,0 +1,146 @@
+"""CPU: the oracle restatement against the golden vectors produced by the reference's own code
+(oracle/make_golden.py) and against independent evaluations (voigt_profile, mpmath)."""
+import os
+
+import numpy as np
+import pytest
+from scipy.special import wofz
+
+from oracle import density as D
+from oracle import region as OR
+from vamp_b200 import physics as P
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _cases(g):
+    return [str(n) for n in g["names"]]
+
+
+def test_profiles_match_reference_lines(golden_profiles):
+    g = golden_profiles
+    for name in _cases(g):
+        nu, comps, voigt = g[name + "/nu"], g[name + "/comps"], bool(g[name + "/voigt"])
+        taus = D.component_taus(nu, comps, voigt)
+        np.testing.assert_allclose(taus, g[name + "/taus"], rtol=1e-13, atol=1e-300, err_msg=name)
+        total = D.model_flux(nu, comps, voigt)
+        np.testing.assert_allclose(total, g[name + "/total"], rtol=1e-13, atol=1e-300, err_msg=name)
+        chi2 = D.chisquared(g[name + "/flux"], total, g[name + "/noise"])
+        assert chi2 == pytest.approx(float(g[name + "/chi2"]), rel=1e-12), name
+        red = D.reduced_chisquared(g[name + "/flux"], total, g[name + "/noise"], int(g[name + "/freedom"]))
+        assert red == pytest.approx(float(g[name + "/red_chi2"]), rel=1e-12), name
+        ll = D.noise_map_loglike(g[name + "/flux"], g[name + "/noise"], total)
+        assert ll == pytest.approx(float(g[name + "/lnL_noise_map"]), rel=1e-12), name
+        # PyMC 2 normal_like with tau = 1/noise^2 is the same formula (pins the restated 3P density)
+        assert D.normal_loglike(g[name + "/flux"], total, noise=g[name + "/noise"]) == pytest.approx(ll, rel=1e-12)
+
+
+def test_gaussian_width(golden_profiles):
+    g = golden_profiles
+    np.testing.assert_allclose(D.gaussian_width(g["gaussian_width_in"]), g["gaussian_width_out"], rtol=1e-15)
+
+
+def test_voigt_second_oracle(golden_profiles):
+    g = golden_profiles
+    for name in _cases(g):
+        if not bool(g[name + "/voigt"]):
+            continue
+        nu = g[name + "/nu"]
+        for a, c, L, G in g[name + "/comps"]:
+            if L / G < 1e-6 or G / L < 1e-5:
+                continue   # voigt_profile loses accuracy at the degenerate limits; wofz does not
+            t1 = D.voigt_tau(nu, c, a, L, G)
+            t2 = D.voigt_tau_via_voigt_profile(nu, c, a, L, G)
+            np.testing.assert_allclose(t1, t2, rtol=1e-9, atol=1e-14 * max(a, 1e-300), err_msg=name)
+
+
+def test_wofz_against_mpmath():
+    g = np.load(os.path.join(GOLDEN, "wofz_mp.npz"))
+    w = wofz(g["x"] + 1j * g["y"])
+    np.testing.assert_allclose(w.real, g["re"], rtol=2e-13, atol=1e-300)
+
+
+def test_normal_loglike_sd_form():
+    rng = np.random.default_rng(3)
+    f, m = rng.uniform(0, 1, 50), rng.uniform(0, 1, 50)
+    sd = 0.07
+    expect = np.sum(-0.5 * (f - m) ** 2 / sd ** 2) - 50 * np.log(sd) - 25 * np.log(2 * np.pi)
+    assert D.normal_loglike(f, m, sd=sd) == pytest.approx(expect, rel=1e-13)
+
+
+def test_bic_formula_pinned_by_notebook():
+    # vamp_1.0/vpfits_intro.ipynb cell 20: BIC -9693.75100483993, AIC -9788.96634665, 4 Voigt + sd, 2000 px
+    bic, aic = -9693.75100483993, -9788.96634665
+    k = D.n_free(4, voigt=True, sd_free=True)
+    assert k == 17
+    lnL = (2 * k - aic) / 2.0
+    assert D.bic(lnL, k, 2000) == pytest.approx(bic, abs=2e-6)
+    assert D.aic(lnL, k) == pytest.approx(aic, abs=1e-9)
+
+
+def test_log_prior_support():
+    x = np.linspace(10.0, 20.0, 11)
+    ok = np.array([[0.5, 15.0, 2.0, 3.0]])
+    lp = D.log_prior(ok, x, voigt=True, sd=0.3)
+    wmax = 5.0 * 2 * np.sqrt(2 * np.log(2))
+    assert lp == pytest.approx(np.log(0.5) - 0.5 - np.log(10.0) - 2 * np.log(wmax))
+    assert D.log_prior([[-0.1, 15, 2, 3]], x, True, sd=0.3) == -np.inf
+    assert D.log_prior([[0.5, 9.9, 2, 3]], x, True, sd=0.3) == -np.inf
+    assert D.log_prior([[0.5, 15, 2, wmax * 1.01]], x, True, sd=0.3) == -np.inf
+    assert D.log_prior([[0.5, 15, 2, 3]], x, True, sd=1.2) == -np.inf
+    assert D.log_prior([[0.5, 15, 5.1, 0]], x, False, sd=0.3) == -np.inf
+
+
+def test_lsf_identity_and_mass():
+    rng = np.random.default_rng(5)
+    f = rng.uniform(0.2, 1.0, 40)
+    np.testing.assert_allclose(D.lsf_convolve(f, [1.0]), f, rtol=0, atol=0)
+    lsf = np.array([0.1, 0.2, 0.4, 0.2, 0.1])
+    out = D.lsf_convolve(f, lsf)
+    np.testing.assert_allclose(out, 1 + np.convolve(f - 1, lsf, "same"), rtol=1e-14)
+    lsf2 = np.array([0.5, 0.3, 0.2])   # asymmetric: true convolution, not correlation
+    o2 = D.lsf_convolve(f, lsf2)
+    assert o2[5] == pytest.approx(1 + 0.5 * (f[6] - 1) + 0.3 * (f[5] - 1) + 0.2 * (f[4] - 1))
+
+
+def test_physics_matches_reference():
+    g = np.load(os.path.join(GOLDEN, "physics.npz"))
+    amp, sig, taus, edges = g["amp"], g["sig"], g["taus"], g["edges"]
+    assert P.constants["c"]["value"] == float(g["c"]) and P.constants["sigma0"]["value"] == float(g["sigma0"])
+    chk = lambda a, b: np.testing.assert_allclose(a, b, rtol=1e-14)
+    chk(P.ColumnDensity(amp, sig), g["ColumnDensity"])
+    chk(P.DopplerParameter(sig, 1215.67), g["DopplerParameter"])
+    chk(P.EquivalentWidthTau(taus, edges), g["EquivalentWidthTau"])
+    chk(P.EquivalentWidthFlux(np.exp(-taus), edges), g["EquivalentWidthFlux"])
+    chk(P.ErrorB(sig * 0.1, 1215.67), g["ErrorB"])
+    chk(P.ErrorN(amp, sig, amp * 0.05, sig * 0.1, np.zeros(3)), g["ErrorN"])
+    chk(P.Errorl(sig * 0.01), g["Errorl"])
+    chk(P.Tau2flux(taus), g["Tau2flux"])
+    np.testing.assert_allclose(P.Flux2tau(np.exp(-taus)), g["Flux2tau"], rtol=1e-14, atol=1e-16)
+    chk(P.Freq2wave(np.array([2.45e15, 2.46e15])), g["Freq2wave"])
+    chk(P.Wave2freq(edges), g["Wave2freq"])
+    chk(P.Wave2red(edges * 3.0, 1215.67), g["Wave2red"])
+
+
+def test_simba_region_goldens():
+    g = np.load(os.path.join(GOLDEN, "simba.npz"))
+    expect = {"simba_CII1036": [34, 42, 14, 20], "simba_H1215": [41, 48, 26]}   # simba_spec_demo.ipynb cells 15, 25
+    for key, dof in expect.items():
+        assert int(g[key + "/nregions"]) == len(dof)
+        for j, d in enumerate(dof):
+            flux = g["%s/r%d/flux" % (key, j)]
+            n0 = OR.estimate_n(flux)
+            assert n0 == int(g["%s/r%d/n0" % (key, j)]) == 1
+            assert OR.freedom(len(flux), n0) == int(g["%s/r%d/freedom" % (key, j)]) == d
+
+
+def test_region_ladder_rule():
+    # BIC decreases 1->2->3 then rises: keep n=3; first comparison uses bic_array[-1]
+    table = {1: ([-10, -12, -30], [5, 5, 5]), 2: ([-50, -52, -54], [3, 3, 3]), 3: ([-80, -80, -80], [2, 2, 2]),
+             4: ([-70, -75, -79], [1, 1, 1])}
+    kept, n_exit, hist = OR.region_fit_ladder(1, lambda n: table[n], chi_limit=1.5)
+    assert kept == 3 and n_exit == 3 and hist[0][1] == -30
+    # chi limit reached at n=2
+    table[2] = ([-50, -52, -54], [1, 1, 1])
+    kept, n_exit, _ = OR.region_fit_ladder(1, lambda n: table[n], chi_limit=1.5)
+    assert kept == 2 and n_exit == 2

@@ -1,0 +1,583 @@
+// vamp_cabi.cu - the C ABI of libvamp_b200.so (declared in include/vamp_b200.h).
+// Plain CUDA runtime; no torch, no Python.  See the header for the reference interfaces
+// (vamp_1.0/vpfits.py file:line) each entry point replaces.
+#include <cstdio>
+#include <cstdarg>
+#include <cstring>
+#include <cmath>
+#include <string>
+#include <vector>
+
+#include "../../include/vamp_b200.h"
+#include "vamp_kernels.h"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define VAMP_CUDA(expr)                                                                         \
+    do {                                                                                        \
+        cudaError_t e__ = (expr);                                                               \
+        if (e__ != cudaSuccess) return fail(-100, "%s: %s", #expr, cudaGetErrorString(e__));    \
+    } while (0)
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+}  // namespace
+
+struct vamp_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    DevBuf partial;     // k1_cta per-chunk partial sums
+    DevBuf scratch[8];  // staging for the *_host entry points
+};
+
+struct vamp_regions {
+    vamp_ctx* ctx = nullptr;
+    int R = 0;
+    int max_npix = 0;
+    long long total_pix = 0;   // unpadded
+    long long padded_pix = 0;
+    std::vector<int> npix, pix_off, tile_off;
+    std::vector<double> nu0, scale;
+    void* blob = nullptr;      // one device allocation for everything
+    RegionSetDev dev{};
+};
+
+namespace {
+
+template <typename T>
+__global__ void faddeeva_test_kernel(int n, const double* __restrict__ x, const double* __restrict__ y,
+                                     double* __restrict__ out) {
+    // evaluated through comp_shape so that the branch logic under test is the shipped one
+    const int i0 = (blockIdx.x * blockDim.x + threadIdx.x);
+    const int i = i0 < n ? i0 : n - 1;
+    // x = d * g with g = 1, y given directly; L2 chosen so that the very-far branch
+    // H = L^2/(L^2 + 4 d^2) equals y^2/(x^2+y^2) (x = 2 sqrt(ln2) d / G, y = sqrt(ln2) L / G).
+    CompC<T> cc;
+    cc.A = T(1);
+    cc.cb = T(0);
+    cc.g = T(1);
+    cc.y = T(y[i]);
+    cc.y2 = cc.y * cc.y;
+    cc.L2 = T(4.0 * y[i] * y[i]);
+    T du[1] = {T(x[i])};
+    T H[1];
+    comp_shape<T, VAMP_KIND_VOIGT, 1>(cc, du, H);
+    if (i0 < n) out[i] = (double)H[0];
+}
+
+template <int KIND>
+__global__ void profile_kernel(int n, const double* __restrict__ x, double c, double A, double w1, double w2,
+                               double* __restrict__ out) {
+    const int i0 = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = i0 < n ? i0 : n - 1;
+    const CompC<double> cc = make_comp<double, KIND>(A, 0.0, w1, w2, 0.0);
+    double du[1] = {x[i] - c};
+    double H[1];
+    comp_shape<double, KIND, 1>(cc, du, H);
+    if (i0 < n) out[i] = A * H[0];
+}
+
+__global__ void philox_test_kernel(const unsigned int* c, const unsigned int* k, unsigned int* out) {
+    const uint4 r = philox4x32_10(make_uint4(c[0], c[1], c[2], c[3]), make_uint2(k[0], k[1]));
+    out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
+}
+
+McmcDev to_dev(const vamp_regions* rg, const vamp_mcmc_args* a) {
+    McmcDev p{};
+    p.rs = rg->dev;
+    p.B = a->n_chains;
+    p.item_region = a->item_region;
+    p.item_ncomp = a->item_ncomp;
+    p.chain_uid = a->chain_uid;
+    p.cmax = a->cmax;
+    p.tstride = 4 * a->cmax + 1;
+    p.sd_free = a->sd_free;
+    p.it0 = a->it0;
+    p.it1 = a->it1;
+    p.burn = a->burn;
+    p.thin = a->thin > 0 ? a->thin : 1;
+    p.tune_interval = a->tune_interval > 0 ? a->tune_interval : 1000;
+    p.tune_throughout = a->tune_throughout;
+    p.seed = a->seed;
+    p.theta = a->theta;
+    p.asf = a->asf;
+    p.psd = a->psd;
+    p.acc = a->acc;
+    p.rej = a->rej;
+    p.acc_total = a->acc_total;
+    p.logp = a->logp;
+    p.lnL = a->lnL;
+    p.best_theta = a->best_theta;
+    p.best_logp = a->best_logp;
+    p.mean = a->mean;
+    p.m2 = a->m2;
+    p.comom = a->comom;
+    p.ntally = a->ntally;
+    p.sum_lnL = a->sum_lnL;
+    p.sum_lnL2 = a->sum_lnL2;
+    p.trace = a->trace;
+    p.trace_cap = a->trace_cap;
+    return p;
+}
+
+int check_mcmc(const vamp_regions* rg, const vamp_mcmc_args* a) {
+    if (!rg || !a) return fail(-1, "null argument");
+    if (a->n_chains < 0 || a->cmax < 1 || a->max_ncomp < 1 || a->max_ncomp > a->cmax)
+        return fail(-2, "bad sizes: n_chains=%d cmax=%d max_ncomp=%d", a->n_chains, a->cmax, a->max_ncomp);
+    if (rg->max_npix > VAMP_TILE_PIX)
+        return fail(-3, "MCMC/MAP kernels support regions of <= %d pixels (got %d); split the region", VAMP_TILE_PIX,
+                    rg->max_npix);
+    if (!a->item_region || !a->item_ncomp || !a->chain_uid || !a->theta || !a->asf || !a->psd || !a->acc || !a->rej ||
+        !a->acc_total || !a->logp || !a->lnL || !a->best_theta || !a->best_logp || !a->mean || !a->m2 || !a->comom ||
+        !a->ntally || !a->sum_lnL || !a->sum_lnL2)
+        return fail(-1, "null state pointer in vamp_mcmc_args");
+    return 0;
+}
+
+}  // namespace
+
+namespace {
+template <typename T>
+__global__ void widen_kernel(const T* in, double* out, long long n) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (double)in[i];
+}
+}  // namespace
+
+extern "C" {
+
+const char* vamp_last_error(void) { return g_err.c_str(); }
+int vamp_abi_version(void) { return VAMP_ABI_VERSION; }
+
+int vamp_ctx_create(int device, vamp_ctx** out) {
+    if (!out) return fail(-1, "null out");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(-10, "no CUDA device available (%s): vamp_b200 has no CPU fallback", cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(-2, "device %d out of range (%d devices)", device, ndev);
+    VAMP_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    VAMP_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(-11, "device %d is sm_%d%d; libvamp_b200 is built for sm_100a (B200) only", device, prop.major,
+                    prop.minor);
+    vamp_ctx* c = new vamp_ctx();
+    c->device = device;
+    *out = c;
+    return 0;
+}
+
+int vamp_ctx_destroy(vamp_ctx* ctx) {
+    if (!ctx) return 0;
+    cudaSetDevice(ctx->device);
+    ctx->partial.release();
+    for (auto& b : ctx->scratch) b.release();
+    delete ctx;
+    return 0;
+}
+
+int vamp_ctx_set_stream(vamp_ctx* ctx, void* s) {
+    if (!ctx) return fail(-1, "null ctx");
+    ctx->stream = reinterpret_cast<cudaStream_t>(s);
+    return 0;
+}
+
+int vamp_ctx_synchronize(vamp_ctx* ctx) {
+    if (!ctx) return fail(-1, "null ctx");
+    VAMP_CUDA(cudaSetDevice(ctx->device));
+    VAMP_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int vamp_regions_create(vamp_ctx* ctx, int R, const int* npix, const double* nu, const double* flux,
+                        const double* noise, const double* lsf, int lsf_taps, vamp_regions** out) {
+    if (!ctx || !out || !npix || !nu || !flux || !noise) return fail(-1, "null argument");
+    if (R <= 0) return fail(-2, "R must be positive");
+    if (lsf && (lsf_taps < 1 || (lsf_taps & 1) == 0 || lsf_taps > VAMP_MAX_LSF_TAPS))
+        return fail(-2, "lsf_taps must be odd and <= %d (got %d)", VAMP_MAX_LSF_TAPS, lsf_taps);
+    if (lsf && lsf_taps == 1 && lsf[0] != 1.0) return fail(-2, "a 1-tap LSF must be exactly 1.0 (identity)");
+    if (!lsf) lsf_taps = 0;
+    VAMP_CUDA(cudaSetDevice(ctx->device));
+    vamp_regions* rg = new vamp_regions();
+    rg->ctx = ctx;
+    rg->R = R;
+    rg->npix.assign(npix, npix + R);
+    rg->pix_off.resize(R);
+    rg->tile_off.resize(R);
+    rg->nu0.resize(R);
+    rg->scale.resize(R);
+    long long poff = 0, toff = 0, src = 0;
+    for (int r = 0; r < R; ++r) {
+        const int P = npix[r];
+        if (P < 1) { delete rg; return fail(-2, "region %d has %d pixels", r, P); }
+        rg->pix_off[r] = (int)poff;
+        rg->tile_off[r] = (int)toff;
+        poff += ((long long)P + 31) / 32 * 32;
+        toff += ((long long)P + VAMP_TILE_PIX - 1) / VAMP_TILE_PIX;
+        rg->max_npix = P > rg->max_npix ? P : rg->max_npix;
+        src += P;
+        if (poff > 2000000000LL) { delete rg; return fail(-2, "too many pixels in one region set"); }
+    }
+    rg->total_pix = src;
+    rg->padded_pix = poff;
+    const long long NP = poff, NT = toff;
+    std::vector<float> du32(NP, 0.f), f32(NP, 1.f), w32(NP, 0.f);
+    std::vector<double> du64(NP, 0.0), f64(NP, 1.0), w64(NP, 0.0), ubase(NT, 0.0), lognorm(R, 0.0);
+    src = 0;
+    for (int r = 0; r < R; ++r) {
+        const int P = npix[r];
+        const double* x = nu + src;
+        const double n0 = x[0];
+        double s = (P > 1) ? (x[P - 1] - x[0]) / (double)(P - 1) : 1.0;
+        if (!(s > 0.0) || !std::isfinite(s)) {
+            delete rg;
+            return fail(-4, "region %d: frequency grid must be ascending and finite", r);
+        }
+        rg->nu0[r] = n0;
+        rg->scale[r] = s;
+        const int ntile = (P + VAMP_TILE_PIX - 1) / VAMP_TILE_PIX;
+        double ln = 0.0;
+        for (int tl = 0; tl < ntile; ++tl) {
+            const int a = tl * VAMP_TILE_PIX;
+            const int b = (a + VAMP_TILE_PIX < P) ? a + VAMP_TILE_PIX : P;
+            const int mid = (a + b - 1) / 2;
+            const double ub = (x[mid] - n0) / s;
+            ubase[rg->tile_off[r] + tl] = ub;
+            for (int i = a; i < b; ++i) {
+                const long long o = rg->pix_off[r] + i;
+                const double u = (x[i] - n0) / s;
+                du64[o] = u - ub;
+                du32[o] = (float)(u - ub);
+                f64[o] = flux[src + i];
+                f32[o] = (float)flux[src + i];
+                const double w = 1.0 / noise[src + i];
+                w64[o] = w;
+                w32[o] = (float)w;
+                ln += std::log(std::fabs(w));
+            }
+        }
+        // padding inside the last 32-pixel granule: far away (tau = 0), flux 1, weight 0
+        for (long long o = rg->pix_off[r] + P; o < rg->pix_off[r] + ((long long)P + 31) / 32 * 32; ++o) {
+            du64[o] = 1.0e12;
+            du32[o] = 1.0e12f;
+        }
+        lognorm[r] = ln - 0.5 * (double)P * std::log(2.0 * M_PI);
+        src += P;
+    }
+    std::vector<float> l32(lsf_taps > 0 ? lsf_taps : 1, 1.f);
+    std::vector<double> l64(lsf_taps > 0 ? lsf_taps : 1, 1.0);
+    for (int i = 0; i < lsf_taps; ++i) { l64[i] = lsf[i]; l32[i] = (float)lsf[i]; }
+
+    // ---- one device blob
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    size_t o = 0;
+    const size_t o_npix = o; o += al(sizeof(int) * R);
+    const size_t o_poff = o; o += al(sizeof(int) * R);
+    const size_t o_toff = o; o += al(sizeof(int) * R);
+    const size_t o_du32 = o; o += al(sizeof(float) * NP);
+    const size_t o_f32 = o; o += al(sizeof(float) * NP);
+    const size_t o_w32 = o; o += al(sizeof(float) * NP);
+    const size_t o_du64 = o; o += al(sizeof(double) * NP);
+    const size_t o_f64 = o; o += al(sizeof(double) * NP);
+    const size_t o_w64 = o; o += al(sizeof(double) * NP);
+    const size_t o_ub = o; o += al(sizeof(double) * NT);
+    const size_t o_ln = o; o += al(sizeof(double) * R);
+    const size_t o_l32 = o; o += al(sizeof(float) * l32.size());
+    const size_t o_l64 = o; o += al(sizeof(double) * l64.size());
+    cudaError_t e = cudaMalloc(&rg->blob, o);
+    if (e != cudaSuccess) { delete rg; return fail(-100, "cudaMalloc(%zu): %s", o, cudaGetErrorString(e)); }
+    char* base = static_cast<char*>(rg->blob);
+    cudaStream_t st = ctx->stream;
+#define VAMP_UP(off, vec, bytes)                                                                         \
+    do {                                                                                                 \
+        e = cudaMemcpyAsync(base + (off), (vec), (bytes), cudaMemcpyHostToDevice, st);                   \
+        if (e != cudaSuccess) { cudaFree(rg->blob); delete rg; return fail(-100, "H2D: %s", cudaGetErrorString(e)); } \
+    } while (0)
+    VAMP_UP(o_npix, rg->npix.data(), sizeof(int) * R);
+    VAMP_UP(o_poff, rg->pix_off.data(), sizeof(int) * R);
+    VAMP_UP(o_toff, rg->tile_off.data(), sizeof(int) * R);
+    VAMP_UP(o_du32, du32.data(), sizeof(float) * NP);
+    VAMP_UP(o_f32, f32.data(), sizeof(float) * NP);
+    VAMP_UP(o_w32, w32.data(), sizeof(float) * NP);
+    VAMP_UP(o_du64, du64.data(), sizeof(double) * NP);
+    VAMP_UP(o_f64, f64.data(), sizeof(double) * NP);
+    VAMP_UP(o_w64, w64.data(), sizeof(double) * NP);
+    VAMP_UP(o_ub, ubase.data(), sizeof(double) * NT);
+    VAMP_UP(o_ln, lognorm.data(), sizeof(double) * R);
+    VAMP_UP(o_l32, l32.data(), sizeof(float) * l32.size());
+    VAMP_UP(o_l64, l64.data(), sizeof(double) * l64.size());
+#undef VAMP_UP
+    e = cudaStreamSynchronize(st);   // host vectors go out of scope
+    if (e != cudaSuccess) { cudaFree(rg->blob); delete rg; return fail(-100, "sync: %s", cudaGetErrorString(e)); }
+    RegionSetDev& d = rg->dev;
+    d.R = R;
+    d.npix = reinterpret_cast<int*>(base + o_npix);
+    d.pix_off = reinterpret_cast<int*>(base + o_poff);
+    d.tile_off = reinterpret_cast<int*>(base + o_toff);
+    d.du32 = reinterpret_cast<float*>(base + o_du32);
+    d.f32 = reinterpret_cast<float*>(base + o_f32);
+    d.w32 = reinterpret_cast<float*>(base + o_w32);
+    d.du64 = reinterpret_cast<double*>(base + o_du64);
+    d.f64 = reinterpret_cast<double*>(base + o_f64);
+    d.w64 = reinterpret_cast<double*>(base + o_w64);
+    d.ubase = reinterpret_cast<double*>(base + o_ub);
+    d.lognorm = reinterpret_cast<double*>(base + o_ln);
+    d.lsf32 = reinterpret_cast<float*>(base + o_l32);
+    d.lsf64 = reinterpret_cast<double*>(base + o_l64);
+    d.lsf_taps = lsf_taps;
+    *out = rg;
+    return 0;
+}
+
+int vamp_regions_destroy(vamp_regions* rg) {
+    if (!rg) return 0;
+    cudaSetDevice(rg->ctx->device);
+    if (rg->blob) cudaFree(rg->blob);
+    delete rg;
+    return 0;
+}
+
+int vamp_regions_info(const vamp_regions* rg, int* R, int* max_npix, long long* total_pix) {
+    if (!rg) return fail(-1, "null regions");
+    if (R) *R = rg->R;
+    if (max_npix) *max_npix = rg->max_npix;
+    if (total_pix) *total_pix = rg->total_pix;
+    return 0;
+}
+
+int vamp_regions_scale(const vamp_regions* rg, double* nu0, double* scale) {
+    if (!rg) return fail(-1, "null regions");
+    if (nu0) memcpy(nu0, rg->nu0.data(), sizeof(double) * rg->R);
+    if (scale) memcpy(scale, rg->scale.data(), sizeof(double) * rg->R);
+    return 0;
+}
+
+int vamp_loglike_dev(vamp_ctx* ctx, const vamp_regions* rg, int dtype, int kind, int B, const int* item_region,
+                     const int* item_ncomp, int max_ncomp, const double* theta, int theta_stride, const double* sd,
+                     double* out_lnL, double* out_chi2, void* out_flux, long long flux_stride) {
+    if (!ctx || !rg || !item_region || !item_ncomp || !theta) return fail(-1, "null argument");
+    if (dtype != VAMP_F32 && dtype != VAMP_F64) return fail(-2, "bad dtype %d", dtype);
+    if (kind != VAMP_GAUSS && kind != VAMP_VOIGT) return fail(-2, "bad kind %d", kind);
+    if (B < 0 || max_ncomp < 0 || theta_stride < 4 * max_ncomp) return fail(-2, "bad sizes");
+    if (out_flux && flux_stride < rg->max_npix) return fail(-2, "flux_stride %lld < max region size %d", flux_stride, rg->max_npix);
+    if (B == 0) return 0;
+    VAMP_CUDA(cudaSetDevice(ctx->device));
+    void* partial = nullptr;
+    if (rg->max_npix > VAMP_TILE_PIX) {
+        const int nchunk = (rg->max_npix + VAMP_K1_CHUNK - 1) / VAMP_K1_CHUNK;
+        VAMP_CUDA(ctx->partial.reserve(sizeof(double) * 2 * (size_t)B * nchunk));
+        partial = ctx->partial.p;
+    }
+    VAMP_CUDA(VAMP_DISPATCH4(vamp_launch_k1, dtype, kind, rg->dev, B, rg->max_npix, max_ncomp, item_region, item_ncomp, theta,
+                             theta_stride, sd, out_lnL, out_chi2, out_flux, flux_stride, partial, ctx->stream));
+    return 0;
+}
+
+
+int vamp_loglike_host(vamp_ctx* ctx, const vamp_regions* rg, int dtype, int kind, int B, const int* item_region,
+                      const int* item_ncomp, int max_ncomp, const double* theta, int theta_stride, const double* sd,
+                      double* out_lnL, double* out_chi2, double* out_flux, long long flux_stride) {
+    if (!ctx || !rg || !item_region || !item_ncomp || !theta) return fail(-1, "null argument");
+    if (B < 0 || max_ncomp < 0 || theta_stride < 4 * max_ncomp) return fail(-2, "bad sizes");
+    if (B == 0) return 0;
+    VAMP_CUDA(cudaSetDevice(ctx->device));
+    // physical (Hz) -> scaled units on the host
+    std::vector<double> ths((size_t)B * theta_stride);
+    for (int b = 0; b < B; ++b) {
+        const int r = item_region[b];
+        if (r < 0 || r >= rg->R) return fail(-2, "item %d: region %d out of range", b, r);
+        if (item_ncomp[b] < 0 || item_ncomp[b] > max_ncomp) return fail(-2, "item %d: ncomp %d > max_ncomp %d", b, item_ncomp[b], max_ncomp);
+        const double n0 = rg->nu0[r], s = rg->scale[r];
+        const double* src = theta + (size_t)b * theta_stride;
+        double* dst = ths.data() + (size_t)b * theta_stride;
+        for (int i = 0; i < theta_stride; ++i) dst[i] = src[i];
+        for (int c = 0; c < item_ncomp[b]; ++c) {
+            dst[4 * c + 1] = (src[4 * c + 1] - n0) / s;
+            dst[4 * c + 2] = src[4 * c + 2] / s;
+            dst[4 * c + 3] = src[4 * c + 3] / s;
+        }
+    }
+    cudaStream_t st = ctx->stream;
+    const size_t esz = dtype == VAMP_F32 ? sizeof(float) : sizeof(double);
+    VAMP_CUDA(ctx->scratch[0].reserve(sizeof(int) * B));
+    VAMP_CUDA(ctx->scratch[1].reserve(sizeof(int) * B));
+    VAMP_CUDA(ctx->scratch[2].reserve(sizeof(double) * ths.size()));
+    VAMP_CUDA(ctx->scratch[3].reserve(sizeof(double) * B));
+    VAMP_CUDA(ctx->scratch[4].reserve(sizeof(double) * 2 * B));
+    VAMP_CUDA(cudaMemcpyAsync(ctx->scratch[0].p, item_region, sizeof(int) * B, cudaMemcpyHostToDevice, st));
+    VAMP_CUDA(cudaMemcpyAsync(ctx->scratch[1].p, item_ncomp, sizeof(int) * B, cudaMemcpyHostToDevice, st));
+    VAMP_CUDA(cudaMemcpyAsync(ctx->scratch[2].p, ths.data(), sizeof(double) * ths.size(), cudaMemcpyHostToDevice, st));
+    if (sd) VAMP_CUDA(cudaMemcpyAsync(ctx->scratch[3].p, sd, sizeof(double) * B, cudaMemcpyHostToDevice, st));
+    double* d_lnL = static_cast<double*>(ctx->scratch[4].p);
+    double* d_chi = d_lnL + B;
+    void* d_flux = nullptr;
+    if (out_flux) {
+        VAMP_CUDA(ctx->scratch[5].reserve(esz * (size_t)B * flux_stride));
+        VAMP_CUDA(cudaMemsetAsync(ctx->scratch[5].p, 0, esz * (size_t)B * flux_stride, st));
+        d_flux = ctx->scratch[5].p;
+    }
+    int rc = vamp_loglike_dev(ctx, rg, dtype, kind, B, static_cast<int*>(ctx->scratch[0].p),
+                              static_cast<int*>(ctx->scratch[1].p), max_ncomp, static_cast<double*>(ctx->scratch[2].p),
+                              theta_stride, sd ? static_cast<double*>(ctx->scratch[3].p) : nullptr, d_lnL, d_chi, d_flux,
+                              flux_stride);
+    if (rc) return rc;
+    if (out_lnL) VAMP_CUDA(cudaMemcpyAsync(out_lnL, d_lnL, sizeof(double) * B, cudaMemcpyDeviceToHost, st));
+    if (out_chi2) VAMP_CUDA(cudaMemcpyAsync(out_chi2, d_chi, sizeof(double) * B, cudaMemcpyDeviceToHost, st));
+    if (out_flux) {
+        const long long n = (long long)B * flux_stride;
+        if (dtype == VAMP_F32) {
+            VAMP_CUDA(ctx->scratch[6].reserve(sizeof(double) * n));
+            widen_kernel<float><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(static_cast<float*>(d_flux),
+                                                                             static_cast<double*>(ctx->scratch[6].p), n);
+            VAMP_CUDA(cudaGetLastError());
+            VAMP_CUDA(cudaMemcpyAsync(out_flux, ctx->scratch[6].p, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+        } else {
+            VAMP_CUDA(cudaMemcpyAsync(out_flux, d_flux, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+        }
+    }
+    VAMP_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int vamp_mcmc_init_dev(vamp_ctx* ctx, const vamp_regions* rg, int kind, const vamp_mcmc_args* a, int from_prior) {
+    if (!ctx) return fail(-1, "null ctx");
+    if (int rc = check_mcmc(rg, a)) return rc;
+    VAMP_CUDA(cudaSetDevice(ctx->device));
+    const McmcDev p = to_dev(rg, a);
+    if (from_prior) VAMP_CUDA(kind == VAMP_VOIGT ? vamp_launch_init_prior_any_voigt(p, ctx->stream) : vamp_launch_init_prior_any_gauss(p, ctx->stream));
+    VAMP_CUDA(vamp_launch_init_state(p, ctx->stream));
+    return 0;
+}
+
+int vamp_mcmc_run_dev(vamp_ctx* ctx, const vamp_regions* rg, int dtype, int kind, const vamp_mcmc_args* a) {
+    if (!ctx) return fail(-1, "null ctx");
+    if (int rc = check_mcmc(rg, a)) return rc;
+    if (dtype != VAMP_F32 && dtype != VAMP_F64) return fail(-2, "bad dtype %d", dtype);
+    if (a->it1 < a->it0 || a->it0 < 0) return fail(-2, "bad iteration range [%d, %d)", a->it0, a->it1);
+    VAMP_CUDA(cudaSetDevice(ctx->device));
+    const McmcDev p = to_dev(rg, a);
+    VAMP_CUDA(VAMP_DISPATCH4(vamp_launch_k2, dtype, kind, p, rg->max_npix, a->max_ncomp, ctx->stream));
+    return 0;
+}
+
+int vamp_map_dev(vamp_ctx* ctx, const vamp_regions* rg, int dtype, int kind, const vamp_map_args* a) {
+    if (!ctx || !rg || !a) return fail(-1, "null argument");
+    if (a->n_starts < 0 || a->cmax < 1 || a->max_ncomp < 1 || a->max_ncomp > a->cmax) return fail(-2, "bad sizes");
+    if (rg->max_npix > VAMP_TILE_PIX)
+        return fail(-3, "MCMC/MAP kernels support regions of <= %d pixels (got %d); split the region", VAMP_TILE_PIX,
+                    rg->max_npix);
+    if (!a->item_region || !a->item_ncomp || !a->theta || !a->out_logp || !a->out_lnL || !a->out_chi2 || !a->out_bic ||
+        !a->out_iters || !a->out_nfev)
+        return fail(-1, "null pointer in vamp_map_args");
+    VAMP_CUDA(cudaSetDevice(ctx->device));
+    MapDev p{};
+    p.rs = rg->dev;
+    p.S = a->n_starts;
+    p.item_region = a->item_region;
+    p.item_ncomp = a->item_ncomp;
+    p.cmax = a->cmax;
+    p.tstride = 4 * a->cmax + 1;
+    p.sd_free = a->sd_free;
+    p.maxiter = a->maxiter;
+    p.maxfun = a->maxfun;
+    p.xtol = a->xtol;
+    p.ftol = a->ftol;
+    p.theta = a->theta;
+    p.out_logp = a->out_logp;
+    p.out_lnL = a->out_lnL;
+    p.out_chi2 = a->out_chi2;
+    p.out_bic = a->out_bic;
+    p.out_iters = a->out_iters;
+    p.out_nfev = a->out_nfev;
+    VAMP_CUDA(VAMP_DISPATCH4(vamp_launch_k3, dtype, kind, p, rg->max_npix, a->max_ncomp, ctx->stream));
+    return 0;
+}
+
+int vamp_faddeeva_host(vamp_ctx* ctx, int dtype, int n, const double* x, const double* y, double* out_H) {
+    if (!ctx || !x || !y || !out_H) return fail(-1, "null argument");
+    if (n <= 0) return 0;
+    VAMP_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    VAMP_CUDA(ctx->scratch[0].reserve(sizeof(double) * n));
+    VAMP_CUDA(ctx->scratch[1].reserve(sizeof(double) * n));
+    VAMP_CUDA(ctx->scratch[2].reserve(sizeof(double) * n));
+    VAMP_CUDA(cudaMemcpyAsync(ctx->scratch[0].p, x, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+    VAMP_CUDA(cudaMemcpyAsync(ctx->scratch[1].p, y, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+    const int grid = (n + 127) / 128;
+    if (dtype == VAMP_F32)
+        faddeeva_test_kernel<float><<<grid, 128, 0, st>>>(n, (double*)ctx->scratch[0].p, (double*)ctx->scratch[1].p, (double*)ctx->scratch[2].p);
+    else
+        faddeeva_test_kernel<double><<<grid, 128, 0, st>>>(n, (double*)ctx->scratch[0].p, (double*)ctx->scratch[1].p, (double*)ctx->scratch[2].p);
+    VAMP_CUDA(cudaGetLastError());
+    VAMP_CUDA(cudaMemcpyAsync(out_H, ctx->scratch[2].p, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+    VAMP_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int vamp_profile_host(vamp_ctx* ctx, int kind, int n, const double* x, double centroid, double amplitude, double w1,
+                      double w2, double* out_tau) {
+    if (!ctx || !x || !out_tau) return fail(-1, "null argument");
+    if (kind != VAMP_GAUSS && kind != VAMP_VOIGT) return fail(-2, "bad kind %d", kind);
+    if (n <= 0) return 0;
+    VAMP_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    VAMP_CUDA(ctx->scratch[0].reserve(sizeof(double) * n));
+    VAMP_CUDA(ctx->scratch[1].reserve(sizeof(double) * n));
+    VAMP_CUDA(cudaMemcpyAsync(ctx->scratch[0].p, x, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+    const int grid = (n + 127) / 128;
+    if (kind == VAMP_VOIGT)
+        profile_kernel<VAMP_KIND_VOIGT><<<grid, 128, 0, st>>>(n, (double*)ctx->scratch[0].p, centroid, amplitude, w1, w2, (double*)ctx->scratch[1].p);
+    else
+        profile_kernel<VAMP_KIND_GAUSS><<<grid, 128, 0, st>>>(n, (double*)ctx->scratch[0].p, centroid, amplitude, w1, w2, (double*)ctx->scratch[1].p);
+    VAMP_CUDA(cudaGetLastError());
+    VAMP_CUDA(cudaMemcpyAsync(out_tau, ctx->scratch[1].p, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+    VAMP_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int vamp_philox_host(vamp_ctx* ctx, const unsigned int* counter, const unsigned int* key, unsigned int* out) {
+    if (!ctx || !counter || !key || !out) return fail(-1, "null argument");
+    VAMP_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    VAMP_CUDA(ctx->scratch[0].reserve(64));
+    unsigned int* d = static_cast<unsigned int*>(ctx->scratch[0].p);
+    VAMP_CUDA(cudaMemcpyAsync(d, counter, 16, cudaMemcpyHostToDevice, st));
+    VAMP_CUDA(cudaMemcpyAsync(d + 4, key, 8, cudaMemcpyHostToDevice, st));
+    philox_test_kernel<<<1, 1, 0, st>>>(d, d + 4, d + 8);
+    VAMP_CUDA(cudaGetLastError());
+    VAMP_CUDA(cudaMemcpyAsync(out, d + 8, 16, cudaMemcpyDeviceToHost, st));
+    VAMP_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,367 @@
+// vamp_device.cuh - device-side building blocks shared by every kernel of the hot path.
+//
+// B200 (sm_100a) design notes
+//  * The path is FP32/FP64-FMA + MUFU bound: no tensor cores, almost no HBM
+//    traffic.  A *warp* owns one parameter vector ("item" / chain); the 32 lanes own pixels
+//    p = j*32 + lane, j < PPL, so spectrum loads are 128-byte coalesced and every per-pixel
+//    quantity (tau, flux, residual) lives in registers.  chi^2 / lnL are reduced with xor
+//    shuffles, which leaves the bit-identical sum in all lanes (warp-uniform accept decisions).
+//  * Pixel coordinates are stored relative to a per-256-pixel tile base (float64 on the host
+//    side of the subtraction) so the float32 path never sees the nu ~ 2.4e15 Hz cancellation
+//    (SURVEY.md section 7 "hard parts").
+//
+// Reference arithmetic restated here (vamp_1.0/): GaussFunction vpfits.py:44-54, VoigtFunction
+// vpfits.py:58-76 (astropy Voigt1D, wofz form), Tau2flux physics.py:98-105, total vpfits.py:334-338,
+// Normal likelihood vpfits.py:39,341, Chisquared vpfits.py:109-118.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+#define VAMP_FULL_MASK 0xffffffffu
+#define VAMP_TILE_PIX 256      // pixels per coordinate tile (= 32 lanes x 8 pixels)
+#define VAMP_MAX_PPL 8
+#define VAMP_MAX_LSF_TAPS 65
+
+enum VampKind { VAMP_KIND_GAUSS = 0, VAMP_KIND_VOIGT = 1 };
+
+// ------------------------------------------------------------------------------------------------
+// Region set (device view).  Built once per upload by vamp_regions_create (vamp_cabi.cu).
+struct RegionSetDev {
+    int R;
+    const int* npix;        // [R]   pixels per region
+    const int* pix_off;     // [R]   offset of the region in the pixel arrays (multiple of 32)
+    const int* tile_off;    // [R]   offset of the region's first tile in `ubase`
+    const float* du32;      // [Ppad] scaled pixel coordinate minus its tile base
+    const float* f32;       // [Ppad] flux
+    const float* w32;       // [Ppad] 1/noise (0 in padding)
+    const double* du64;
+    const double* f64;
+    const double* w64;
+    const double* ubase;    // [tiles] scaled coordinate of each tile's base
+    const double* lognorm;  // [R]   sum_i ln(1/noise_i) - P/2 ln(2 pi)
+    const float* lsf32;     // [taps] or nullptr
+    const double* lsf64;
+    int lsf_taps;           // odd, 0/1 = identity
+};
+
+template <typename T> struct RS;
+template <> struct RS<float> {
+    static __device__ __forceinline__ const float* du(const RegionSetDev& r) { return r.du32; }
+    static __device__ __forceinline__ const float* f(const RegionSetDev& r) { return r.f32; }
+    static __device__ __forceinline__ const float* w(const RegionSetDev& r) { return r.w32; }
+    static __device__ __forceinline__ const float* lsf(const RegionSetDev& r) { return r.lsf32; }
+};
+template <> struct RS<double> {
+    static __device__ __forceinline__ const double* du(const RegionSetDev& r) { return r.du64; }
+    static __device__ __forceinline__ const double* f(const RegionSetDev& r) { return r.f64; }
+    static __device__ __forceinline__ const double* w(const RegionSetDev& r) { return r.w64; }
+    static __device__ __forceinline__ const double* lsf(const RegionSetDev& r) { return r.lsf64; }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Scalar helpers per precision.
+template <typename T> struct Real;
+template <> struct Real<float> {
+    static __device__ __forceinline__ float rcp(float x) { return __fdividef(1.0f, x); }          // MUFU.RCP
+    static __device__ __forceinline__ float exp_neg(float t) { return exp2f(-1.4426950408889634f * t); }  // MUFU.EX2
+    static __device__ __forceinline__ float exp2_neg(float t) { return exp2f(-t); }
+    static __device__ __forceinline__ float fma_(float a, float b, float c) { return fmaf(a, b, c); }
+};
+template <> struct Real<double> {
+    static __device__ __forceinline__ double rcp(double x) { return 1.0 / x; }
+    static __device__ __forceinline__ double exp_neg(double t) { return exp(-t); }
+    static __device__ __forceinline__ double exp2_neg(double t) { return exp2(-t); }
+    static __device__ __forceinline__ double fma_(double a, double b, double c) { return fma(a, b, c); }
+};
+
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(VAMP_FULL_MASK, v, o);
+    return v;   // identical bits in every lane
+}
+
+// ------------------------------------------------------------------------------------------------
+// Faddeeva function.  H(x, y) = sqrt(pi) * y * Re w(x + i y)  (the unit-amplitude Voigt shape).
+//   core  : Weideman (1994) N-term rational, N = 12 (fp32) / 32 (fp64)
+//   far   : Laplace continued fraction, 4 (fp32) / 9 (fp64) levels, as a rational in 1/z^2
+//   vfar  : pure Lorentzian L^2/(L^2+4d^2) once |z|^2 >= FAR2 (also catches G -> 0 overflow)
+// Measured max |H - H_wofz| over the plane: 4.4e-7 (fp32), 7e-15 (fp64)  (tests/test_faddeeva*.py).
+// Hand-counted algorithmic flops per evaluation (FMA = 2), used by bench.py's roofline:
+//   fp32 core 113 + 1 MUFU, fp32 far 47 + 2 MUFU;  fp64 core 273, fp64 far 103.
+#include "faddeeva_tables.inc"
+
+template <typename T> struct Fad;
+template <> struct Fad<float> {
+    static constexpr int N = WEID_N_F32;
+    static constexpr int CFN = 3, CFD = 3;
+    static __device__ __forceinline__ float L() { return WEID_L_F32; }
+    static __device__ __forceinline__ float a(int i) { return WEID_A_F32[i]; }
+    static __device__ __forceinline__ float cfn(int i) { return CF_NUM_F32[i]; }
+    static __device__ __forceinline__ float cfd(int i) { return CF_DEN_F32[i]; }
+    static __device__ __forceinline__ float R2() { return 32.0f; }
+    static __device__ __forceinline__ float FAR2() { return 1.0e8f; }
+    static __device__ __forceinline__ float BIG() { return 1.0e18f; }
+};
+template <> struct Fad<double> {
+    static constexpr int N = WEID_N_F64;
+    static constexpr int CFN = 5, CFD = 6;
+    static __device__ __forceinline__ double L() { return WEID_L_F64; }
+    static __device__ __forceinline__ double a(int i) { return WEID_A_F64[i]; }
+    static __device__ __forceinline__ double cfn(int i) { return CF_NUM_F64[i]; }
+    static __device__ __forceinline__ double cfd(int i) { return CF_DEN_F64[i]; }
+    static __device__ __forceinline__ double R2() { return 64.0; }
+    static __device__ __forceinline__ double FAR2() { return 1.0e16; }
+    static __device__ __forceinline__ double BIG() { return 1.0e150; }
+};
+
+// H for |z|^2 < R2 : Weideman.  s = x^2 + y^2.
+template <typename T>
+__device__ __forceinline__ T fad_core(T x, T y, T s) {
+    const T L = Fad<T>::L();
+    const T r = Real<T>::rcp(s + (T(2) * L) * y + L * L);        // 1/|L - iz|^2
+    const T Zr = (L * L - s) * r;
+    const T Zi = (T(2) * L) * x * r;
+    T pr = Fad<T>::a(0), pi = T(0);
+#pragma unroll
+    for (int k = 1; k < Fad<T>::N; ++k) {
+        const T nr = Real<T>::fma_(pr, Zr, Real<T>::fma_(-pi, Zi, Fad<T>::a(k)));
+        pi = Real<T>::fma_(pr, Zi, pi * Zr);
+        pr = nr;
+    }
+    const T ir = (L + y) * r, ii = x * r;                          // 1/(L - iz)
+    const T i2r = ir * ir - ii * ii, i2i = T(2) * ir * ii;
+    const T rew = T(2) * (pr * i2r - pi * i2i) + T(0.56418958354775628695) * ir;
+    return T(1.77245385090551602730) * y * rew;
+}
+
+// H for R2 <= |z|^2 < FAR2 : continued fraction in t = 1/z, v = t^2.
+template <typename T>
+__device__ __forceinline__ T fad_far(T x, T y, T s) {
+    const T rs = Real<T>::rcp(s);
+    const T tr = x * rs, ti = -y * rs;
+    const T vr = tr * tr - ti * ti, vi = T(2) * tr * ti;
+    T nr = Fad<T>::cfn(Fad<T>::CFN - 1), ni = T(0);
+#pragma unroll
+    for (int k = Fad<T>::CFN - 2; k >= 0; --k) {
+        const T a = Real<T>::fma_(nr, vr, Real<T>::fma_(-ni, vi, Fad<T>::cfn(k)));
+        ni = Real<T>::fma_(nr, vi, ni * vr);
+        nr = a;
+    }
+    T dr = Fad<T>::cfd(Fad<T>::CFD - 1), di = T(0);
+#pragma unroll
+    for (int k = Fad<T>::CFD - 2; k >= 0; --k) {
+        const T a = Real<T>::fma_(dr, vr, Real<T>::fma_(-di, vi, Fad<T>::cfd(k)));
+        di = Real<T>::fma_(dr, vi, di * vr);
+        dr = a;
+    }
+    const T er = nr * dr + ni * di, ei = ni * dr - nr * di;      // N conj(D)
+    const T imq = tr * ei + ti * er;                              // Im(t N conj(D))
+    return -y * imq * Real<T>::rcp(dr * dr + di * di);
+}
+
+// ------------------------------------------------------------------------------------------------
+// One absorption component in device units (scaled pixel coordinates of its region).
+template <typename T>
+struct CompC {
+    T A;     // amplitude (tau at line centre for Gauss; amplitude_L for Voigt)
+    T cb;    // centroid minus the coordinate-tile base
+    T g;     // Gauss: sqrt(log2(e)/2)/sigma ; Voigt: 2 sqrt(ln2)/G
+    T y;     // Voigt: sqrt(ln2) L / G
+    T y2;    // y*y
+    T L2;    // L*L
+};
+
+template <typename T, int KIND>
+__device__ __forceinline__ CompC<T> make_comp(double A, double c, double w1, double w2, double ubase) {
+    CompC<T> cc;
+    cc.A = T(A);
+    cc.cb = T(c - ubase);
+    if (KIND == VAMP_KIND_GAUSS) {
+        cc.g = T(0.84932180028801904272 / w1);        // sqrt(0.5*log2(e)) / sigma
+        cc.y = cc.y2 = cc.L2 = T(0);
+    } else {
+        const double big = (double)Fad<T>::BIG();
+        cc.g = T(fmin(1.66510922231539551270 / w2, big));       // 2 sqrt(ln 2) / G
+        cc.y = T(fmin(0.83255461115769775635 * w1 / w2, big));  // sqrt(ln 2) L / G
+        cc.y2 = cc.y * cc.y;
+        cc.L2 = T(w1 * w1);
+    }
+    return cc;
+}
+
+// Unit-amplitude shape of one component at PPL pixels of this lane.  All branches are
+// warp-uniform (ballots), so no divergence: a j-row of 32 consecutive pixels is almost
+// always entirely core or entirely far.
+template <typename T, int KIND, int PPL>
+__device__ __forceinline__ void comp_shape(const CompC<T>& cc, const T (&du)[PPL], T (&H)[PPL]) {
+    if (KIND == VAMP_KIND_GAUSS) {
+#pragma unroll
+        for (int j = 0; j < PPL; ++j) {
+            const T q = (du[j] - cc.cb) * cc.g;
+            H[j] = Real<T>::exp2_neg(q * q);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < PPL; ++j) {
+            const T d = du[j] - cc.cb;
+            const T x = d * cc.g;
+            const T s = Real<T>::fma_(x, x, cc.y2);
+            const bool far = !(s < Fad<T>::R2());               // also true for inf / NaN
+            const unsigned m = __ballot_sync(VAMP_FULL_MASK, far);
+            T h;
+            if (m == 0u) {
+                h = fad_core<T>(x, cc.y, s);
+            } else {
+                const bool vfar = !(s < Fad<T>::FAR2());
+                T hf = fad_far<T>(x, cc.y, s);
+                if (__any_sync(VAMP_FULL_MASK, vfar)) {
+                    const T d2 = T(2) * d;
+                    const T lor = cc.L2 * Real<T>::rcp(Real<T>::fma_(d2, d2, cc.L2));
+                    hf = vfar ? lor : hf;
+                }
+                if (m == VAMP_FULL_MASK) {
+                    h = hf;
+                } else {
+                    const T hc = fad_core<T>(x, cc.y, far ? T(0) : s);
+                    h = far ? hf : hc;
+                }
+            }
+            H[j] = h;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Per-lane view of one region tile (<= 32*PPL pixels).
+template <typename T, int PPL>
+struct LaneTile {
+    T du[PPL];
+    T f[PPL];
+    T w[PPL];          // 1/noise; 0 for p >= P
+    unsigned valid;    // bit j set when pixel j*32+lane < P
+};
+
+template <typename T, int PPL>
+__device__ __forceinline__ void load_tile(LaneTile<T, PPL>& t, const RegionSetDev& rs, int off, int P, int lane) {
+    t.valid = 0u;
+#pragma unroll
+    for (int j = 0; j < PPL; ++j) {
+        const int p = j * 32 + lane;
+        const bool ok = p < P;
+        // padding inside the 32-pixel granule is initialised (du far away, f = 1, w = 0) but rows
+        // beyond the granule are not: guard the load.
+        t.du[j] = ok ? RS<T>::du(rs)[off + p] : T(0);
+        t.f[j] = ok ? RS<T>::f(rs)[off + p] : T(1);
+        t.w[j] = ok ? RS<T>::w(rs)[off + p] : T(0);
+        t.valid |= ok ? (1u << j) : 0u;
+    }
+}
+
+// LSF: out[p] = 1 + sum_t lsf[t] * (m[p + h - t] - 1), zero outside [0, P).  `buf` is a
+// warp-private shared buffer of 32*PPL + 2h elements, `lsf_s` the taps in shared memory.
+template <typename T, int PPL>
+__device__ __forceinline__ void lsf_apply(T (&m)[PPL], unsigned valid, T* buf, const T* lsf_s, int taps, int lane) {
+    const int h = taps >> 1;
+    __syncwarp();
+    for (int i = lane; i < 2 * h; i += 32) {           // zero both halos
+        const int idx = (i < h) ? i : (32 * PPL + i);
+        buf[idx] = T(0);
+    }
+#pragma unroll
+    for (int j = 0; j < PPL; ++j) buf[h + j * 32 + lane] = ((valid >> j) & 1u) ? (m[j] - T(1)) : T(0);
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < PPL; ++j) {
+        T acc = T(1);
+        const T* b = buf + j * 32 + lane + 2 * h;
+        for (int t = 0; t < taps; ++t) acc = Real<T>::fma_(lsf_s[t], b[-t], acc);
+        m[j] = acc;
+    }
+}
+
+// Sum of squared residuals of this lane: S = sum (f-m)^2 over valid pixels, X = sum ((f-m) w)^2.
+template <typename T, int PPL>
+__device__ __forceinline__ void lane_residuals(const LaneTile<T, PPL>& t, const T (&m)[PPL], T& S, T& X) {
+    S = T(0);
+    X = T(0);
+#pragma unroll
+    for (int j = 0; j < PPL; ++j) {
+        const T r = ((t.valid >> j) & 1u) ? (t.f[j] - m[j]) : T(0);
+        S = Real<T>::fma_(r, r, S);
+        const T rw = r * t.w[j];
+        X = Real<T>::fma_(rw, rw, X);
+    }
+}
+
+// Per-translation-unit instantiation: every kernel file is compiled once per (precision, profile
+// kind) with -DVAMP_INST_F64=0|1 -DVAMP_INST_VOIGT=0|1 so the 12 objects build in parallel.
+#if defined(VAMP_INST_F64) && defined(VAMP_INST_VOIGT)
+#if VAMP_INST_F64
+typedef double InstT;
+#define VAMP_TN f64
+#else
+typedef float InstT;
+#define VAMP_TN f32
+#endif
+#if VAMP_INST_VOIGT
+#define VAMP_KN voigt
+#else
+#define VAMP_KN gauss
+#endif
+constexpr int InstKind = VAMP_INST_VOIGT ? VAMP_KIND_VOIGT : VAMP_KIND_GAUSS;
+#define VAMP_CAT3_(a, b, c) a##_##b##_##c
+#define VAMP_CAT3(a, b, c) VAMP_CAT3_(a, b, c)
+#define VAMP_INST_NAME(name) VAMP_CAT3(name, VAMP_TN, VAMP_KN)
+#endif
+
+// Parameter vector layout shared by host and device (scaled units):
+//   theta[4*c + 0..3] = (amplitude, centroid, L_fwhm | sigma, G_fwhm | unused),  c < ncomp
+//   theta[4*cmax]     = sd   (only when the noise parameter is free)
+#define VAMP_TH(c, i) (4 * (c) + (i))
+
+// Full model evaluation for a warp-owned item: tau summed over components in registers,
+// m = exp(-tau), optional LSF.  Leaves the model flux in m[].
+template <typename T, int KIND, int PPL>
+__device__ __forceinline__ void eval_model(const LaneTile<T, PPL>& t, const double* __restrict__ theta, int ncomp,
+                                           double ubase, T (&m)[PPL], T* lsf_buf, const T* lsf_s, int taps, int lane) {
+    T tau[PPL];
+#pragma unroll
+    for (int j = 0; j < PPL; ++j) tau[j] = T(0);
+    for (int c = 0; c < ncomp; ++c) {
+        const CompC<T> cc = make_comp<T, KIND>(theta[VAMP_TH(c, 0)], theta[VAMP_TH(c, 1)], theta[VAMP_TH(c, 2)],
+                                               theta[VAMP_TH(c, 3)], ubase);
+        T H[PPL];
+        comp_shape<T, KIND, PPL>(cc, t.du, H);
+#pragma unroll
+        for (int j = 0; j < PPL; ++j) tau[j] = Real<T>::fma_(cc.A, H[j], tau[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < PPL; ++j) m[j] = Real<T>::exp_neg(tau[j]);
+    if (taps > 1) lsf_apply<T, PPL>(m, t.valid, lsf_buf, lsf_s, taps, lane);
+}
+
+// Gaussian log-likelihood from the reduced sums (double, warp-uniform).
+//   sd free (vpfits.py:39,341):      lnL = -S/(2 sd^2) - P ln sd - P/2 ln 2pi
+//   per-pixel noise (fit.py:127-171): lnL = -X/2 + sum ln(1/noise) - P/2 ln 2pi
+__device__ __forceinline__ double lnL_sd(double S, double sd, int P) {
+    return -0.5 * S / (sd * sd) - P * (log(sd) + 0.91893853320467274178);
+}
+__device__ __forceinline__ double lnL_noise(double X, double lognorm) { return -0.5 * X + lognorm; }
+
+// ------------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al. 2011), counter-based: chains are keyed by a global chain id so
+// results do not depend on how regions are sharded over GPUs.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += 0x9E3779B9u;
+        k.y += 0xBB67AE85u;
+    }
+    return c;
+}
+__device__ __forceinline__ double u01(uint32_t x) { return ((double)x + 0.5) * 2.3283064365386962890625e-10; }  // (0,1)

@@ -1,0 +1,499 @@
+// vamp_k2.cu - K2: batched Metropolis sampler, one warp per chain, whole chains on device.
+//
+// Replaces the reference's hot loop  mcmc.sample(iter, burn, thin)  (vamp_1.0/vpfits.py:393,
+// 423-425): PyMC 2's auto-assigned scalar Metropolis steppers with adaptive-scale tuning
+// (restated in oracle/sampler.py).  Thousands of independent chains - every candidate
+// component count of the BIC sweep and every restart - advance inside ONE launch; there is no
+// host round trip, no kernel-per-iteration, and no HBM traffic beyond the initial spectrum
+// load and the optional tallies.
+//
+// Per chain (= warp):
+//   * pixels p = j*32 + lane live in registers (flux, coordinate, running tau);
+//   * the unit-amplitude shape H_c of every component is cached in warp-private shared
+//     memory, so a single-parameter step re-evaluates ONE component (P Voigt evaluations) -
+//     the same economy PyMC 2's LazyFunction cache gives the reference - and an amplitude or
+//     noise-parameter step re-evaluates none;
+//   * sum (f-m)^2 is reduced with xor shuffles: every lane holds the identical value and takes
+//     the identical accept decision (no divergence, no broadcast);
+//   * Philox4x32-10 keyed by (seed, global chain id): lane l draws the Box-Muller pair and the
+//     two log-uniforms of steps 2l, 2l+1 of a 64-step block, handed out with shuffles;
+//   * tallies (i >= burn and i % thin == 0) feed Welford means / co-moments (the reference's
+//     mcmc.stats() and chain_covariance, vpfits.py:432-456) and an optional trace.
+#include "vamp_device.cuh"
+#include "vamp_kernels.h"
+
+namespace {
+
+constexpr int K2_WARPS = 4;
+constexpr double FWHM_PER_SIGMA = 2.35482004503094938202;
+
+struct WarpRng {
+    double z0, z1, lu0, lu1;
+    uint32_t uid_lo, uid_hi, k0, k1;
+    __device__ __forceinline__ void refill(unsigned long long blk, int lane) {
+        const uint4 x = philox4x32_10(make_uint4(uid_lo, uid_hi, (uint32_t)blk, ((uint32_t)(blk >> 32) << 8) | (uint32_t)lane),
+                                      make_uint2(k0, k1));
+        const double rad = sqrt(-2.0 * log(u01(x.x)));
+        double sn, cs;
+        sincospi(2.0 * u01(x.y), &sn, &cs);
+        z0 = rad * cs;
+        z1 = rad * sn;
+        lu0 = log(u01(x.z));
+        lu1 = log(u01(x.w));
+    }
+    // normal deviate and log-uniform of step q (warp-uniform result)
+    __device__ __forceinline__ void get(unsigned long long q, int lane, double& z, double& lu) {
+        if ((q & 63ull) == 0ull) refill(q >> 6, lane);
+        const int slot = (int)(q & 63ull);
+        const double zs = (slot & 1) ? z1 : z0;
+        const double ls = (slot & 1) ? lu1 : lu0;
+        z = __shfl_sync(VAMP_FULL_MASK, zs, slot >> 1);
+        lu = __shfl_sync(VAMP_FULL_MASK, ls, slot >> 1);
+    }
+};
+
+// PyMC 2.3 Metropolis.tune switch (oracle/sampler.py:pymc2_tune)
+__device__ __forceinline__ float tune_factor(float rate) {
+    if (rate < 0.001f) return 0.1f;
+    if (rate < 0.05f) return 0.5f;
+    if (rate < 0.2f) return 0.9f;
+    if (rate > 0.95f) return 10.0f;
+    if (rate > 0.75f) return 2.0f;
+    if (rate > 0.5f) return 1.1f;
+    return 1.0f;
+}
+
+struct WarpSmem {          // pointers into this warp's shared-memory slice
+    double* th;
+    double* best;
+    double* mean;
+    double* m2;
+    double* comom;
+    float* asf;
+    float* psd;
+    int* acc;
+    int* rej;
+    int* acct;
+};
+
+// sum of squared residuals (WT: noise-weighted) of the model  exp(-(base + A*H))  [* LSF]
+template <typename T, int PPL, bool WT>
+__device__ __forceinline__ T chain_S(const T (&f)[PPL], const T (&w)[PPL], unsigned valid, const T (&base)[PPL], T A,
+                                     const T (&H)[PPL], T* lsf_buf, const T* lsf_s, int taps, int lane) {
+    T m[PPL];
+#pragma unroll
+    for (int j = 0; j < PPL; ++j) m[j] = Real<T>::exp_neg(Real<T>::fma_(A, H[j], base[j]));
+    if (taps > 1) lsf_apply<T, PPL>(m, valid, lsf_buf, lsf_s, taps, lane);
+    T S = T(0);
+#pragma unroll
+    for (int j = 0; j < PPL; ++j) {
+        T r = ((valid >> j) & 1u) ? (f[j] - m[j]) : T(0);
+        if (WT) r *= w[j];
+        S = Real<T>::fma_(r, r, S);
+    }
+    return warp_sum(S);
+}
+
+template <typename T, int KIND, int PPL, bool WT>
+__device__ void mcmc_chain(const McmcDev& p, int chain, int lane, const WarpSmem& ws, T* Hc, T* lsf_buf,
+                           const T* lsf_s) {
+    constexpr int NP = (KIND == VAMP_KIND_VOIGT) ? 4 : 3;
+    constexpr int HS = 32 * PPL;                      // shape-cache stride per component
+    const RegionSetDev& rs = p.rs;
+    const int r = p.item_region[chain];
+    const int P = rs.npix[r];
+    const int n = p.item_ncomp[chain];
+    const int ts = p.tstride;
+    const int sdi = 4 * p.cmax;
+    const int k = NP * n + (WT ? 0 : 1);
+    const int taps = rs.lsf_taps;
+    const double ubase = rs.ubase[rs.tile_off[r]];
+    const double lognorm = rs.lognorm[r];
+    const double c_hi = (double)(P - 1);
+    const double w_hi = 0.5 * (double)(P - 1) * (KIND == VAMP_KIND_VOIGT ? FWHM_PER_SIGMA : 1.0);
+
+    // ---- state -> shared
+    const size_t gb = (size_t)chain * ts;
+    for (int i = lane; i < ts; i += 32) {
+        ws.th[i] = p.theta[gb + i];
+        ws.best[i] = p.best_theta[gb + i];
+        ws.mean[i] = p.mean[gb + i];
+        ws.m2[i] = p.m2[gb + i];
+        ws.asf[i] = p.asf[gb + i];
+        ws.psd[i] = p.psd[gb + i];
+        ws.acc[i] = p.acc[gb + i];
+        ws.rej[i] = p.rej[gb + i];
+        ws.acct[i] = p.acc_total[gb + i];
+    }
+    for (int i = lane; i < 6 * p.cmax; i += 32) ws.comom[i] = p.comom[(size_t)chain * 6 * p.cmax + i];
+    double best_logp = p.best_logp[chain];
+    int ntally = p.ntally[chain];
+    double sum_lnL = p.sum_lnL[chain], sum_lnL2 = p.sum_lnL2[chain];
+    __syncwarp();
+
+    // ---- this lane's pixels (registers for the whole chain)
+    T du[PPL], f[PPL], w[PPL];
+    unsigned valid = 0u;
+    {
+        const int off = rs.pix_off[r];
+#pragma unroll
+        for (int j = 0; j < PPL; ++j) {
+            const int px = j * 32 + lane;
+            const bool ok = px < P;
+            du[j] = ok ? RS<T>::du(rs)[off + px] : T(0);
+            f[j] = ok ? RS<T>::f(rs)[off + px] : T(1);
+            w[j] = (WT && ok) ? RS<T>::w(rs)[off + px] : T(0);
+            valid |= ok ? (1u << j) : 0u;
+        }
+    }
+
+    // ---- build the shape cache and the current sum of squares.  Each lane only ever touches
+    // its own cache slots (j*32 + lane), so the cache needs no warp synchronisation.
+    T base[PPL], H[PPL];
+#pragma unroll
+    for (int j = 0; j < PPL; ++j) base[j] = T(0);
+    for (int c = 0; c < n; ++c) {
+        const CompC<T> cc = make_comp<T, KIND>(ws.th[VAMP_TH(c, 0)], ws.th[VAMP_TH(c, 1)], ws.th[VAMP_TH(c, 2)],
+                                               ws.th[VAMP_TH(c, 3)], ubase);
+        comp_shape<T, KIND, PPL>(cc, du, H);
+#pragma unroll
+        for (int j = 0; j < PPL; ++j) {
+            Hc[c * HS + j * 32 + lane] = H[j];
+            base[j] = Real<T>::fma_(cc.A, H[j], base[j]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < PPL; ++j) H[j] = T(0);
+    double Scur = (double)chain_S<T, PPL, WT>(f, w, valid, base, T(0), H, lsf_buf, lsf_s, taps, lane);
+    double sd = WT ? 1.0 : ws.th[sdi];
+
+    WarpRng rng;
+    {
+        const unsigned long long uid = p.chain_uid[chain];
+        rng.uid_lo = (uint32_t)uid;
+        rng.uid_hi = (uint32_t)(uid >> 32);
+        rng.k0 = (uint32_t)p.seed;
+        rng.k1 = (uint32_t)(p.seed >> 32);
+    }
+    unsigned long long q = (unsigned long long)p.it0 * (unsigned long long)k;
+    if (q & 63ull) rng.refill(q >> 6, lane);
+
+    for (int it = p.it0; it < p.it1; ++it) {
+        // ---- tuning (PyMC 2: every tune_interval iterations; optionally only during burn-in)
+        if (it > 0 && (it % p.tune_interval) == 0 && (p.tune_throughout || it <= p.burn)) {
+            for (int i = lane; i < ts; i += 32) {
+                const int a = ws.acc[i], b = ws.rej[i];
+                if (a + b > 0) {
+                    const float nf = ws.asf[i] * tune_factor((float)a / (float)(a + b));
+                    if (nf > 0.0f) ws.asf[i] = nf;
+                }
+                ws.acc[i] = 0;
+                ws.rej[i] = 0;
+            }
+            __syncwarp();
+        }
+        const bool post_burn = it >= p.burn;
+
+        for (int c = 0; c < n; ++c) {
+            // base = tau of the other components (from the cache; no drift accumulates)
+#pragma unroll
+            for (int j = 0; j < PPL; ++j) base[j] = T(0);
+            for (int c2 = 0; c2 < n; ++c2) {
+                if (c2 == c) continue;
+                const T A2 = T(ws.th[VAMP_TH(c2, 0)]);
+#pragma unroll
+                for (int j = 0; j < PPL; ++j) base[j] = Real<T>::fma_(A2, Hc[c2 * HS + j * 32 + lane], base[j]);
+            }
+            double pA = ws.th[VAMP_TH(c, 0)], pc = ws.th[VAMP_TH(c, 1)], pw1 = ws.th[VAMP_TH(c, 2)],
+                   pw2 = ws.th[VAMP_TH(c, 3)];
+
+#pragma unroll 1
+            for (int i = 0; i < NP; ++i) {
+                const int idx = VAMP_TH(c, i);
+                double z, lu;
+                rng.get(q, lane, z, lu);
+                ++q;
+                const double cur = (i == 0) ? pA : (i == 1) ? pc : (i == 2) ? pw1 : pw2;
+                const double prop = cur + z * (double)(ws.asf[idx] * ws.psd[idx]);
+                bool ok;
+                if (i == 0) ok = prop > 0.0;
+                else if (i == 1) ok = (prop >= 0.0) && (prop <= c_hi);
+                else if (KIND == VAMP_KIND_VOIGT && i == 2) ok = (prop >= 0.0) && (prop <= w_hi);
+                else ok = (prop > 0.0) && (prop <= w_hi);
+                bool accept = false;
+                if (ok) {
+                    double dprior = 0.0;
+                    T Anew;
+                    if (i == 0) {
+#pragma unroll
+                        for (int j = 0; j < PPL; ++j) H[j] = Hc[c * HS + j * 32 + lane];
+                        Anew = T(prop);
+                        dprior = (log(prop) - prop) - (log(pA) - pA);
+                    } else {
+                        const CompC<T> cc = make_comp<T, KIND>(pA, (i == 1) ? prop : pc, (i == 2) ? prop : pw1,
+                                                               (i == 3) ? prop : pw2, ubase);
+                        comp_shape<T, KIND, PPL>(cc, du, H);
+                        Anew = cc.A;
+                    }
+                    const double Snew = (double)chain_S<T, PPL, WT>(f, w, valid, base, Anew, H, lsf_buf, lsf_s, taps, lane);
+                    const double dl = WT ? -0.5 * (Snew - Scur) : -0.5 * (Snew - Scur) / (sd * sd);
+                    accept = lu < dl + dprior;      // false for NaN
+                    if (accept) {
+                        Scur = Snew;
+                        if (i == 0) pA = prop;
+                        else {
+                            if (i == 1) pc = prop;
+                            else if (i == 2) pw1 = prop;
+                            else pw2 = prop;
+#pragma unroll
+                            for (int j = 0; j < PPL; ++j) Hc[c * HS + j * 32 + lane] = H[j];
+                        }
+                    }
+                }
+                if (lane == 0) {
+                    if (accept) { ws.acc[idx] += 1; if (post_burn) ws.acct[idx] += 1; ws.th[idx] = prop; }
+                    else ws.rej[idx] += 1;
+                }
+            }
+            __syncwarp();
+        }
+
+        if (!WT) {
+            double z, lu;
+            rng.get(q, lane, z, lu);
+            ++q;
+            const double prop = sd + z * (double)(ws.asf[sdi] * ws.psd[sdi]);
+            bool accept = false;
+            if (prop > 0.0 && prop <= 1.0) {
+                const double d = -0.5 * Scur * (1.0 / (prop * prop) - 1.0 / (sd * sd)) - P * (log(prop) - log(sd));
+                accept = lu < d;
+            }
+            if (accept) sd = prop;
+            if (lane == 0) {
+                if (accept) { ws.acc[sdi] += 1; if (post_burn) ws.acct[sdi] += 1; ws.th[sdi] = prop; }
+                else ws.rej[sdi] += 1;
+            }
+            __syncwarp();
+        }
+
+        // ---- end of iteration: exact log-posterior of the current state (no incremental drift)
+        const double lnL = WT ? lnL_noise(Scur, lognorm) : lnL_sd(Scur, sd, P);
+        double lp = 0.0;
+        for (int c = 0; c < n; ++c) {
+            const double a = ws.th[VAMP_TH(c, 0)];
+            lp += log(a) - a;
+        }
+        const double logp = lnL + lp;
+        if (logp > best_logp) {
+            best_logp = logp;
+            for (int i = lane; i < ts; i += 32) ws.best[i] = ws.th[i];
+        }
+        if (post_burn && (it % p.thin) == 0) {
+            ++ntally;
+            sum_lnL += lnL;
+            sum_lnL2 += lnL * lnL;
+            const double inv = 1.0 / (double)ntally;
+            const double wgt = (double)(ntally - 1) * inv;
+            for (int i = lane; i < 6 * n; i += 32) {          // co-moments first (need the old means)
+                const int c = i / 6, pr = i - 6 * c;
+                const int a = (pr < 3) ? 0 : (pr < 5 ? 1 : 2);
+                const int b = (pr < 3) ? pr + 1 : (pr < 5 ? pr - 1 : 3);
+                const double da = ws.th[VAMP_TH(c, a)] - ws.mean[VAMP_TH(c, a)];
+                const double db = ws.th[VAMP_TH(c, b)] - ws.mean[VAMP_TH(c, b)];
+                ws.comom[i] += wgt * da * db;
+            }
+            __syncwarp();
+            for (int i = lane; i < ts; i += 32) {
+                const double x = ws.th[i];
+                const double d = x - ws.mean[i];
+                const double mn = ws.mean[i] + d * inv;
+                ws.mean[i] = mn;
+                ws.m2[i] += d * (x - mn);
+            }
+            if (p.trace) {
+                const int slot = ntally - 1;
+                if (slot < p.trace_cap)
+                    for (int i = lane; i < ts; i += 32)
+                        p.trace[((size_t)chain * p.trace_cap + slot) * ts + i] = ws.th[i];
+            }
+        }
+        __syncwarp();
+    }
+
+    // ---- state -> global
+    for (int i = lane; i < ts; i += 32) {
+        p.theta[gb + i] = ws.th[i];
+        p.best_theta[gb + i] = ws.best[i];
+        p.mean[gb + i] = ws.mean[i];
+        p.m2[gb + i] = ws.m2[i];
+        p.asf[gb + i] = ws.asf[i];
+        p.acc[gb + i] = ws.acc[i];
+        p.rej[gb + i] = ws.rej[i];
+        p.acc_total[gb + i] = ws.acct[i];
+    }
+    for (int i = lane; i < 6 * p.cmax; i += 32) p.comom[(size_t)chain * 6 * p.cmax + i] = ws.comom[i];
+    if (lane == 0) {
+        const double lnL = WT ? lnL_noise(Scur, lognorm) : lnL_sd(Scur, sd, P);
+        double lp = 0.0;
+        for (int c = 0; c < n; ++c) {
+            const double a = ws.th[VAMP_TH(c, 0)];
+            lp += log(a) - a;
+        }
+        p.lnL[chain] = lnL;
+        p.logp[chain] = lnL + lp;
+        p.best_logp[chain] = best_logp;
+        p.ntally[chain] = ntally;
+        p.sum_lnL[chain] = sum_lnL;
+        p.sum_lnL2[chain] = sum_lnL2;
+    }
+}
+
+__host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
+
+template <typename T>
+__host__ __device__ inline size_t k2_warp_bytes(int ppl_max, int ncomp_max, int cmax, bool lsf) {
+    const int ts = 4 * cmax + 1;
+    size_t b = 0;
+    b += align16(sizeof(double) * (4 * ts + 6 * cmax));       // th, best, mean, m2, comom
+    b += align16(sizeof(float) * 2 * ts);                      // asf, psd
+    b += align16(sizeof(int) * 3 * ts);                        // acc, rej, acct
+    b += align16(sizeof(T) * (size_t)ncomp_max * 32 * ppl_max); // shape cache
+    if (lsf) b += align16(sizeof(T) * (32 * ppl_max + VAMP_MAX_LSF_TAPS));
+    return b;
+}
+
+template <typename T, int KIND, bool WT>
+__global__ void __launch_bounds__(K2_WARPS * 32, (sizeof(T) == 4) ? 4 : 2)
+k2_mcmc_kernel(McmcDev p, int ppl_max, int ncomp_max) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool LSF = p.rs.lsf_taps > 1;
+    T* lsf_s = reinterpret_cast<T*>(smem_raw);
+    const size_t head = align16(sizeof(T) * VAMP_MAX_LSF_TAPS);
+    if (LSF) {
+        for (int i = threadIdx.x; i < p.rs.lsf_taps; i += blockDim.x) lsf_s[i] = RS<T>::lsf(p.rs)[i];
+        __syncthreads();
+    }
+    const int chain = blockIdx.x * K2_WARPS + warp;
+    if (chain >= p.B) return;
+    const int ts = p.tstride;
+    unsigned char* base = smem_raw + head + (size_t)warp * k2_warp_bytes<T>(ppl_max, ncomp_max, p.cmax, LSF);
+    WarpSmem ws;
+    ws.th = reinterpret_cast<double*>(base);
+    ws.best = ws.th + ts;
+    ws.mean = ws.best + ts;
+    ws.m2 = ws.mean + ts;
+    ws.comom = ws.m2 + ts;
+    base += align16(sizeof(double) * (4 * ts + 6 * p.cmax));
+    ws.asf = reinterpret_cast<float*>(base);
+    ws.psd = ws.asf + ts;
+    base += align16(sizeof(float) * 2 * ts);
+    ws.acc = reinterpret_cast<int*>(base);
+    ws.rej = ws.acc + ts;
+    ws.acct = ws.rej + ts;
+    base += align16(sizeof(int) * 3 * ts);
+    T* Hc = reinterpret_cast<T*>(base);
+    base += align16(sizeof(T) * (size_t)ncomp_max * 32 * ppl_max);
+    T* lsf_buf = reinterpret_cast<T*>(base);
+
+    const int P = p.rs.npix[p.item_region[chain]];
+    const int ppl = (P + 31) >> 5;
+    // NOTE: the shape-cache stride is 32*PPL of the *instantiated* PPL, always <= 32*ppl_max.
+    if (ppl <= 1) mcmc_chain<T, KIND, 1, WT>(p, chain, lane, ws, Hc, lsf_buf, lsf_s);
+    else if (ppl <= 2) mcmc_chain<T, KIND, 2, WT>(p, chain, lane, ws, Hc, lsf_buf, lsf_s);
+    else if (ppl <= 4) mcmc_chain<T, KIND, 4, WT>(p, chain, lane, ws, Hc, lsf_buf, lsf_s);
+    else mcmc_chain<T, KIND, 8, WT>(p, chain, lane, ws, Hc, lsf_buf, lsf_s);
+}
+
+// ---- initial states -------------------------------------------------------------------------
+// PyMC 2 semantics (oracle/sampler.py:Model.initial): xexp value = 0.5 (vpfits.py:240,284); a
+// mc.Uniform without value= starts at a draw from its prior; sd ~ U(0,1) likewise.
+template <int KIND>
+__global__ void init_prior_kernel(McmcDev p) {
+    const int chain = blockIdx.x * blockDim.x + threadIdx.x;
+    if (chain >= p.B) return;
+    constexpr int NP = (KIND == VAMP_KIND_VOIGT) ? 4 : 3;
+    const int P = p.rs.npix[p.item_region[chain]];
+    const int n = p.item_ncomp[chain];
+    const double c_hi = (double)(P - 1);
+    const double w_hi = 0.5 * (double)(P - 1) * (KIND == VAMP_KIND_VOIGT ? FWHM_PER_SIGMA : 1.0);
+    const unsigned long long uid = p.chain_uid[chain];
+    const uint2 key = make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32) ^ 0x494E4954u);   // "INIT" stream
+    double* th = p.theta + (size_t)chain * p.tstride;
+    for (int i = 0; i < p.tstride; ++i) th[i] = 0.0;
+    for (int c = 0; c < n; ++c) {
+        const uint4 x = philox4x32_10(make_uint4((uint32_t)uid, (uint32_t)(uid >> 32), (uint32_t)c, 0u), key);
+        th[VAMP_TH(c, 0)] = 0.5;
+        th[VAMP_TH(c, 1)] = u01(x.x) * c_hi;
+        th[VAMP_TH(c, 2)] = u01(x.y) * w_hi;
+        if (NP == 4) th[VAMP_TH(c, 3)] = u01(x.z) * w_hi;
+    }
+    if (p.sd_free) {
+        const uint4 x = philox4x32_10(make_uint4((uint32_t)uid, (uint32_t)(uid >> 32), 0xFFFFFFFFu, 0u), key);
+        th[4 * p.cmax] = u01(x.x);
+    }
+}
+
+// Reset sampler state around a given theta: proposal_sd = |value| (1 if 0), asf = 1, counters 0.
+__global__ void init_state_kernel(McmcDev p) {
+    const int chain = blockIdx.x * blockDim.x + threadIdx.x;
+    if (chain >= p.B) return;
+    const size_t gb = (size_t)chain * p.tstride;
+    for (int i = 0; i < p.tstride; ++i) {
+        const double v = p.theta[gb + i];
+        p.psd[gb + i] = (v != 0.0) ? (float)fabs(v) : 1.0f;
+        p.asf[gb + i] = 1.0f;
+        p.acc[gb + i] = 0;
+        p.rej[gb + i] = 0;
+        p.acc_total[gb + i] = 0;
+        p.best_theta[gb + i] = v;
+        p.mean[gb + i] = 0.0;
+        p.m2[gb + i] = 0.0;
+    }
+    for (int i = 0; i < 6 * p.cmax; ++i) p.comom[(size_t)chain * 6 * p.cmax + i] = 0.0;
+    p.best_logp[chain] = -INFINITY;
+    p.logp[chain] = -INFINITY;
+    p.lnL[chain] = -INFINITY;
+    p.ntally[chain] = 0;
+    p.sum_lnL[chain] = 0.0;
+    p.sum_lnL2[chain] = 0.0;
+}
+
+template <typename T, int KIND, bool WT>
+cudaError_t launch_k2_t(const McmcDev& p, int max_npix, int max_ncomp, cudaStream_t st) {
+    const bool LSF = p.rs.lsf_taps > 1;
+    const int ppl_max = max_npix <= 32 ? 1 : (max_npix <= 64 ? 2 : (max_npix <= 128 ? 4 : 8));
+    const size_t smem = align16(sizeof(T) * VAMP_MAX_LSF_TAPS) + K2_WARPS * k2_warp_bytes<T>(ppl_max, max_ncomp, p.cmax, LSF);
+    auto kern = k2_mcmc_kernel<T, KIND, WT>;
+    if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const int grid = (p.B + K2_WARPS - 1) / K2_WARPS;
+    kern<<<grid, K2_WARPS * 32, smem, st>>>(p, ppl_max, max_ncomp);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+#if VAMP_INST_F64 == 0
+// precision-independent helpers live in the f32 objects only
+cudaError_t VAMP_CAT3(vamp_launch_init_prior, any, VAMP_KN)(const McmcDev& p, cudaStream_t st) {
+    if (p.B <= 0) return cudaSuccess;
+    init_prior_kernel<InstKind><<<(p.B + 127) / 128, 128, 0, st>>>(p);
+    return cudaGetLastError();
+}
+#if VAMP_INST_VOIGT == 0
+cudaError_t vamp_launch_init_state(const McmcDev& p, cudaStream_t st) {
+    if (p.B <= 0) return cudaSuccess;
+    init_state_kernel<<<(p.B + 127) / 128, 128, 0, st>>>(p);
+    return cudaGetLastError();
+}
+#endif
+#endif
+
+cudaError_t VAMP_INST_NAME(vamp_launch_k2)(const McmcDev& p, int max_npix, int max_ncomp, cudaStream_t st) {
+    if (p.B <= 0 || p.it1 <= p.it0) return cudaSuccess;
+    if (max_npix > VAMP_TILE_PIX) return cudaErrorInvalidValue;
+    return p.sd_free ? launch_k2_t<InstT, InstKind, false>(p, max_npix, max_ncomp, st)
+                     : launch_k2_t<InstT, InstKind, true>(p, max_npix, max_ncomp, st);
+}

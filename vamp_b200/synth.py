@@ -1,0 +1,128 @@
+"""Synthetic absorption regions for the BASELINE.json configs.
+
+Pure numpy, float64, counter-based ``numpy.random.Philox`` keyed by the *global
+region id* so that every rank (and the CPU oracle) generates identical inputs.
+The flux recipe follows ``vamp_1.0/vpfits_intro.ipynb`` cell 7:
+``flux = Tau2flux(sum tau) + N(0, sigma)``, negatives clipped to 0, constant
+noise vector.  Profiles are evaluated with ``scipy.special.wofz`` - this is
+workload generation, not the product path.
+"""
+import numpy as np
+from scipy.special import wofz
+
+SEED_BASE = 0x56414D50  # "VAMP"
+C_REF = 2.98e8          # vamp_1.0/physics.py:3 (the reference's own value)
+DNU = 4.0213e10         # Hz: 5 km/s at 1215.67 A with C_REF (matches simba_H1215.h5)
+NU_LYA = C_REF / (1215.67e-10)
+FWHM_PER_SIGMA = 2.0 * np.sqrt(2.0 * np.log(2.0))
+
+
+def rng_for(region_id, stream=0):
+    return np.random.Generator(np.random.Philox(key=[(SEED_BASE ^ int(region_id)) & 0xFFFFFFFFFFFFFFFF, int(stream)]))
+
+
+def voigt_tau(x, amplitude, centroid, L_fwhm, G_fwhm):
+    z = (2.0 * (x - centroid) + 1j * L_fwhm) * np.sqrt(np.log(2.0)) / G_fwhm
+    return wofz(z).real * np.sqrt(np.pi * np.log(2.0)) / G_fwhm * L_fwhm * amplitude
+
+
+def gauss_tau(x, amplitude, centroid, sigma):
+    return amplitude * np.exp(-0.5 * ((x - centroid) / sigma) ** 2)
+
+
+def frequency_grid(P):
+    """Ascending frequency grid centred on Ly-alpha, DNU per pixel."""
+    return NU_LYA + (np.arange(P, dtype=np.float64) - (P - 1) / 2.0) * DNU
+
+
+def make_region(P, n_true, snr, region_id, voigt=True, lsf=None):
+    """One synthetic region.  Returns a dict with ``nu`` (Hz, ascending), ``flux``,
+    ``noise`` (constant ``1/snr`` vector), ``truth`` ``[n_true, 4]`` =
+    ``(amplitude, centroid, L_fwhm | sigma, G_fwhm | 0)`` in Hz and ``clean``."""
+    rng = rng_for(region_id)
+    nu = frequency_grid(P)
+    sig_px = rng.uniform(3.0, 10.0, n_true)
+    if P < 64:
+        sig_px = rng.uniform(1.0, max(1.5, P / 12.0), n_true)
+    amp = rng.uniform(0.2, 3.0, n_true)
+    lo, hi = 0.1 * (P - 1), 0.9 * (P - 1)
+    cen_px = np.empty(n_true)
+    for k in range(n_true):
+        for _ in range(200):
+            c = rng.uniform(lo, hi)
+            if all(abs(c - cen_px[j]) >= 1.5 * max(sig_px[k], sig_px[j]) for j in range(k)):
+                break
+        cen_px[k] = c
+    ratio = 10.0 ** rng.uniform(-2.0, np.log10(0.3), n_true)
+    truth = np.zeros((n_true, 4))
+    truth[:, 0] = amp
+    truth[:, 1] = nu[0] + cen_px * DNU
+    tau = np.zeros(P)
+    for k in range(n_true):
+        if voigt:
+            G = FWHM_PER_SIGMA * sig_px[k] * DNU
+            truth[k, 2], truth[k, 3] = ratio[k] * G, G
+            tau += voigt_tau(nu, amp[k], truth[k, 1], truth[k, 2], truth[k, 3])
+        else:
+            truth[k, 2] = sig_px[k] * DNU
+            tau += gauss_tau(nu, amp[k], truth[k, 1], truth[k, 2])
+    clean = np.exp(-tau)
+    if lsf is not None:
+        lsf = np.asarray(lsf, dtype=np.float64)
+        h = lsf.size // 2
+        clean = 1.0 + np.convolve(np.concatenate([np.zeros(h), clean - 1.0, np.zeros(h)]), lsf, "valid")
+    sigma = 1.0 / float(snr)
+    flux = clean + rng.normal(0.0, sigma, P)
+    flux[flux < 0.0] = 0.0
+    return {"nu": nu, "flux": flux, "noise": np.full(P, sigma), "truth": truth, "clean": clean,
+            "voigt": bool(voigt), "region_id": int(region_id), "snr": float(snr)}
+
+
+def gaussian_lsf(fwhm_px=2.0, taps=7):
+    """Normalised Gaussian LSF (config C3: FWHM 2 px, 7 taps)."""
+    s = fwhm_px / FWHM_PER_SIGMA
+    t = np.arange(taps) - taps // 2
+    w = np.exp(-0.5 * (t / s) ** 2)
+    return w / w.sum()
+
+
+def config_c1():
+    """C1: one HI Ly-alpha region, 1 Voigt component, 200 px, SNR 50, seed 1."""
+    return make_region(200, 1, 50.0, region_id=1, voigt=True)
+
+
+def config_c2(region_id=2, n_true=3):
+    """C2: blended 256-px region (BIC sweep over n = 1..6 with 4096 chains each)."""
+    return make_region(256, n_true, 50.0, region_id=region_id, voigt=True)
+
+
+def config_c4_region(region_id):
+    """C4: one of the 10^5 mixed regions: P ~ U{32..256}, n ~ U{1..8}, SNR in {10,30,100}."""
+    r = rng_for(region_id, stream=1)
+    P = int(r.integers(32, 257))
+    n_true = int(r.integers(1, 9))
+    n_true = max(1, min(n_true, P // 24))
+    snr = float(r.choice([10.0, 30.0, 100.0]))
+    return make_region(P, n_true, snr, region_id=region_id, voigt=True)
+
+
+def prior_draw_theta(nu, n, voigt, rng, posterior_like=None):
+    """Parameter vectors for throughput runs: prior draws
+    (A ~ Gamma(2,1), c ~ U, widths ~ U(0, w_max)) or, with ``posterior_like`` =
+    a truth array, truth +- 5 %.  Returns ``[n, 4]`` in Hz."""
+    span = nu[-1] - nu[0]
+    sigma_max = span / 2.0
+    w_max = sigma_max * FWHM_PER_SIGMA if voigt else sigma_max
+    th = np.zeros((n, 4))
+    if posterior_like is not None:
+        t = np.asarray(posterior_like)
+        idx = rng.integers(0, t.shape[0], n)
+        th[:] = t[idx] * (1.0 + rng.uniform(-0.05, 0.05, (n, 4)))
+        th[:, 1] = t[idx, 1] + rng.uniform(-0.05, 0.05, n) * t[idx, 3 if voigt else 2]
+        return th
+    th[:, 0] = rng.gamma(2.0, 1.0, n)
+    th[:, 1] = rng.uniform(nu[0], nu[-1], n)
+    th[:, 2] = rng.uniform(0.0, w_max, n)
+    if voigt:
+        th[:, 3] = rng.uniform(0.0, w_max, n)
+    return th
