@@ -1,0 +1,167 @@
+"""GPU: K2 (batched Metropolis) and K3 (Nelder-Mead MAP + BIC) against the oracle.
+
+* step-for-step: fp64 chains reproduce the CPU replay of the device algorithm driven by the
+  oracle density (oracle/chain_replay.py) - control flow, Philox use, cached-tau bookkeeping;
+* statistical: posterior means / widths agree with the restated PyMC 2 sampler
+  (oracle/sampler.py) and with the known truth within Monte-Carlo error;
+* K3 against scipy.optimize.fmin on the oracle density from the same start.
+"""
+import numpy as np
+import pytest
+from scipy.optimize import fmin
+
+from oracle import chain_replay as CR
+from oracle import density as D
+from oracle import sampler as OS
+from vamp_b200 import engine, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _scaled_grid(regs, r=0):
+    nu = np.asarray(regs.host_regions[r][0])
+    return (nu - regs.nu0[r]) / regs.scale[r]
+
+
+@pytest.mark.parametrize("voigt,sd_free,P,n,lsf", [
+    (True, True, 200, 1, None), (True, True, 256, 3, None), (False, True, 120, 2, None),
+    (True, False, 50, 2, None), (False, False, 17, 1, None), (True, True, 96, 2, "lsf"),
+])
+def test_chain_replay_fp64(ctx, voigt, sd_free, P, n, lsf):
+    lsf = synth.gaussian_lsf(2.0, 7) if lsf else None
+    reg = synth.make_region(P, n, 40.0, 900 + P, voigt=voigt, lsf=lsf)
+    regs = engine.Regions(ctx, [(reg["nu"], reg["flux"], reg["noise"])], lsf=lsf)
+    B, iters, burn, thin, tune = 4, 120, 40, 5, 25
+    uid = np.array([7, 8, 2 ** 33 + 5, 123456789], dtype=np.uint64)
+    seed = 0xDEADBEEFCAFE
+    s = engine.Sampler(regs, np.zeros(B, np.int32), np.full(B, n, np.int32), uid, voigt=voigt, sd_free=sd_free,
+                       dtype="f64", seed=seed, burn=burn, thin=thin, tune_interval=tune, tune_throughout=True,
+                       trace_cap=(iters - burn) // thin + 2, cmax=n + 1)
+    s.init()
+    th0 = s.get("theta").copy()
+    for b in range(B):   # the device's prior draw is the replay's prior draw
+        np.testing.assert_allclose(th0[b], CR.initial_state(int(uid[b]), seed, P, n, voigt, sd_free, n + 1), rtol=1e-15)
+    s.run(60)
+    s.run(iters - 60)    # resume mid-way: state and RNG position persist across launches
+    u = _scaled_grid(regs)
+    th, tr, ntal = s.get("theta"), s.get("trace"), s.get("ntally")
+    mean, m2, best, blp, lnL = s.get("mean"), s.get("m2"), s.get("best_theta"), s.get("best_logp"), s.get("lnL")
+    for b in range(B):
+        ref = CR.replay_chain(u, reg["flux"], reg["noise"], th0[b], n, voigt, sd_free, int(uid[b]), seed, iters, burn,
+                              thin, tune, True, n + 1, lsf=lsf)
+        assert ntal[b] == ref["ntally"] == len(ref["trace"])
+        np.testing.assert_allclose(tr[b, : ntal[b]], ref["trace"], rtol=1e-8, atol=1e-10, err_msg="chain %d" % b)
+        np.testing.assert_allclose(th[b], ref["theta"], rtol=1e-8, atol=1e-10)
+        np.testing.assert_allclose(mean[b], ref["mean"], rtol=1e-8, atol=1e-10)
+        np.testing.assert_allclose(m2[b], ref["m2"], rtol=1e-6, atol=1e-10)
+        np.testing.assert_allclose(best[b], ref["best_theta"], rtol=1e-8, atol=1e-10)
+        assert blp[b] == pytest.approx(ref["best_logp"], rel=1e-9, abs=1e-7)
+        assert lnL[b] == pytest.approx(ref["lnL"], rel=1e-9, abs=1e-7)
+
+
+def test_chain_fp32_tracks_fp64_initially(ctx):
+    """fp32 and fp64 chains share the RNG stream: identical accept/reject history at first."""
+    reg = synth.config_c2()
+    regs = engine.Regions(ctx, [(reg["nu"], reg["flux"], reg["noise"])])
+    out = {}
+    for dt in ("f32", "f64"):
+        s = engine.Sampler(regs, np.zeros(8, np.int32), np.full(8, 2, np.int32), np.arange(8, dtype=np.uint64) + 50,
+                           voigt=True, dtype=dt, seed=5, burn=0, thin=1, tune_interval=10, tune_throughout=True)
+        s.init()
+        s.run(12)
+        out[dt] = s.get("theta")
+    np.testing.assert_allclose(out["f32"], out["f64"], rtol=5e-3, atol=5e-3)
+
+
+def _posterior_case():
+    reg = synth.make_region(128, 1, 30.0, 4242, voigt=False)
+    return reg
+
+
+def test_posterior_matches_pymc2_restatement_and_truth(ctx):
+    """Gaussian 1-component region: pooled device chains vs the restated PyMC 2 chain vs truth."""
+    reg = _posterior_case()
+    regs = engine.Regions(ctx, [(reg["nu"], reg["flux"], reg["noise"])])
+    B = 256
+    s = engine.Sampler(regs, np.zeros(B, np.int32), np.ones(B, np.int32), np.arange(B, dtype=np.uint64), voigt=False,
+                       dtype="f32", seed=99, burn=3000, thin=10, tune_interval=100, tune_throughout=False,
+                       trace_cap=0)
+    s.init()
+    s.run(8000)
+    blp = s.get("best_logp")
+    good = blp > blp.max() - 30.0           # chains that found the line (others sit in a noise mode)
+    assert good.mean() > 0.5
+    mean = s.get("mean")[good]
+    var = (s.get("m2")[good] / s.get("ntally")[good][:, None])
+    scale, nu0 = regs.scale[0], regs.nu0[0]
+    gm = mean.mean(axis=0)
+    gs = np.sqrt(var.mean(axis=0) + mean.var(axis=0))
+    amp, cen, sig, sd = gm[0], gm[1] * scale + nu0, gm[2] * scale, gm[4]
+    t = reg["truth"][0]
+    assert abs(amp - t[0]) < 5 * gs[0] and abs(cen - t[1]) < 5 * gs[1] * scale and abs(sig - t[2]) < 5 * gs[2] * scale
+    assert sd == pytest.approx(1 / 30.0, rel=0.25)
+    # the restated PyMC 2 sampler on the same density (CPU, one chain from a good start)
+    model = OS.Model(reg["nu"], reg["flux"], 1, False)
+    start = np.array([t[0], t[1], t[2], 1 / 30.0])
+    rng = np.random.default_rng(1)
+    trace, _, _ = OS.metropolis_sample(model, start, 6000, 1000, 5, rng, tune_interval=200,
+                                       proposal_sd=np.array([0.1, 0.3 * scale, 0.3 * scale, 0.003]))
+    pm, ps = trace.mean(axis=0), trace.std(axis=0)
+    neff = 40.0                              # conservative effective sample size of the CPU chain
+    assert abs(amp - pm[0]) < 5 * ps[0] / np.sqrt(neff) + 3 * gs[0] / np.sqrt(good.sum())
+    assert abs(cen - pm[1]) < 5 * ps[1] / np.sqrt(neff) + 3 * gs[1] * scale / np.sqrt(good.sum())
+    assert abs(sig - pm[2]) < 5 * ps[2] / np.sqrt(neff) + 3 * gs[2] * scale / np.sqrt(good.sum())
+    # posterior widths agree within 35 %
+    np.testing.assert_allclose([gs[0], gs[1] * scale, gs[2] * scale], ps[:3], rtol=0.35)
+
+
+@pytest.mark.parametrize("voigt,sd_free", [(False, True), (True, True), (True, False)])
+def test_map_polish_against_scipy_fmin(ctx, voigt, sd_free):
+    reg = synth.make_region(160, 2, 50.0, 777, voigt=voigt)
+    regs = engine.Regions(ctx, [(reg["nu"], reg["flux"], reg["noise"])])
+    u = _scaled_grid(regs)
+    n, cmax = 2, 2
+    rng = np.random.default_rng(4)
+    truth_s = regs.to_scaled(reg["truth"][None], [0])[0]
+    S = 6
+    starts = np.zeros((S, 4 * cmax + 1))
+    for i in range(S):
+        pert = truth_s * (1 + rng.uniform(-0.25, 0.25, truth_s.shape))
+        if not voigt:
+            pert[:, 3] = 0.0
+        starts[i, : 4 * n] = pert.reshape(-1)
+        starts[i, 4 * cmax] = 0.05 if sd_free else 0.0
+    s = engine.Sampler(regs, np.zeros(S, np.int32), np.full(S, n, np.int32), np.arange(S, dtype=np.uint64), voigt=voigt,
+                       sd_free=sd_free, dtype="f64", cmax=cmax)
+    res = s.map_polish(starts, np.zeros(S, np.int32), np.full(S, n, np.int32), maxiter=4000, xtol=1e-4, ftol=1e-3)
+    NP = 4 if voigt else 3
+    free = [4 * c + i for c in range(n) for i in range(NP)] + ([4 * cmax] if sd_free else [])
+
+    def neg_logp(p, full):
+        full = full.copy()
+        full[free] = p
+        comps = full[: 4 * n].reshape(n, 4)
+        lp = D.log_posterior(comps, u, reg["flux"], voigt, sd=full[4 * cmax] if sd_free else None,
+                             noise=None if sd_free else reg["noise"])
+        # the device omits the constant uniform-prior terms; add them back for comparison
+        if np.isfinite(lp):
+            c_lo, c_hi, w_max = D.prior_bounds(u, voigt)
+            lp += n * np.log(c_hi - c_lo) + n * (NP - 2) * np.log(w_max)
+        return -lp if np.isfinite(lp) else np.inf
+
+    th = res["theta"].cpu().numpy()
+    for i in range(S):
+        x0 = starts[i][free]
+        xopt, fopt, it, fc, _ = fmin(neg_logp, x0, args=(starts[i],), xtol=1e-4, ftol=1e-3, maxiter=4000, maxfun=10 ** 9,
+                                     full_output=True, disp=0)
+        f_dev = -float(res["logp"][i])
+        assert neg_logp(th[i][free], starts[i]) == pytest.approx(f_dev, rel=1e-9, abs=1e-7)   # reported logp is exact
+        # same algorithm, same start: the optimum value agrees to the stopping tolerance
+        assert f_dev == pytest.approx(fopt, abs=5e-3), (i, f_dev, fopt, int(res["iters"][i]), it)
+        k = len(free)
+        comps = th[i][: 4 * n].reshape(n, 4)
+        lnL = D.normal_loglike(reg["flux"], D.model_flux(u, comps, voigt), sd=th[i][4 * cmax] if sd_free else None,
+                               noise=None if sd_free else reg["noise"])
+        assert float(res["lnL"][i]) == pytest.approx(lnL, rel=1e-9)
+        assert float(res["bic"][i]) == pytest.approx(D.bic(lnL, k, 160), rel=1e-9)
+        assert float(res["chi2"][i]) == pytest.approx(D.chisquared(reg["flux"], D.model_flux(u, comps, voigt), reg["noise"]), rel=1e-8)

@@ -1,0 +1,155 @@
+"""Batched model fitting: every (region, candidate component count, restart, chain) at once.
+
+This is the GPU-shaped core under ``VPfit.find_bic``, ``VPregion.region_fit`` and
+``fit_regions``: where the reference runs ``3 restarts x (MCMC, MAP)`` sequentially for one
+candidate ``n`` at a time (vamp_1.0/vpfits.py:417-428, vpregion.py:58-60), all candidates of all
+regions advance inside one K2 launch, their best chains are polished in one K3 launch, and
+only the small BIC / chi^2 / MAP tables travel back to the host, where the reference's
+acceptance rule is replayed (``ladder_replay``).
+
+Chains are keyed by ``(region uid, n, restart, chain)`` for the Philox stream, so results do
+not depend on batching or on how regions are sharded over GPUs.
+"""
+import numpy as np
+
+from . import engine
+
+
+def chain_uids(region_uid, n, restarts, chains_per_restart):
+    """64-bit Philox chain ids: region uid (40 bits) | n (8 bits) | chain-in-model (16 bits)."""
+    c = np.arange(restarts * chains_per_restart, dtype=np.uint64)
+    return (np.uint64(int(region_uid) & 0xFFFFFFFFFF) << np.uint64(24)) | (np.uint64(int(n) & 0xFF) << np.uint64(16)) | c
+
+
+class ModelBatch:
+    """Result tables of one batched fit (numpy, host).  Shapes: M models, G restarts."""
+
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+    def red_chi(self, freedom):
+        """``ReducedChisquared`` per restart (vpfits.py:428) given per-model d.o.f."""
+        return self.chi2 / np.asarray(freedom, dtype=np.float64)[:, None]
+
+
+def fit_models(regions, models, voigt=False, sd_free=True, iterations=3000, burn=300, thin=15, restarts=3,
+               chains_per_restart=32, polish_top=4, dtype="f32", seed=0, region_uids=None, tune_interval=50,
+               tune_throughout=True, keep_sampler=False, trace=False, maxiter=None, xtol=1e-4, ftol=1e-3,
+               polish_dtype="f64"):
+    """Fit ``models = [(region_index, n), ...]`` on the device-resident ``regions``.
+
+    Per model and restart group: prior-drawn starts -> ``iterations`` of K2 Metropolis ->
+    Nelder-Mead polish (K3) of the group's ``polish_top`` best chains -> the group's MAP,
+    ``BIC = k ln P - 2 lnL`` and noise-weighted chi^2 (the quantities ``find_bic`` appends,
+    vpfits.py:427-428).  Returns a :class:`ModelBatch`."""
+    torch = engine._torch()
+    models = [(int(r), int(n)) for r, n in models]
+    M, G, Cn = len(models), int(restarts), int(chains_per_restart)
+    if M == 0:
+        raise ValueError("no models to fit")
+    region_uids = np.arange(regions.R, dtype=np.int64) if region_uids is None else np.asarray(region_uids)
+    cmax = max(n for _, n in models)
+    per = G * Cn
+    item_region = np.repeat(np.array([r for r, _ in models], dtype=np.int32), per)
+    item_ncomp = np.repeat(np.array([n for _, n in models], dtype=np.int32), per)
+    uid = np.concatenate([chain_uids(region_uids[r], n, G, Cn) for r, n in models])
+    # launch order: homogeneous CTAs (same pixel class and component count) finish together
+    ppl = (regions.npix[item_region] + 31) // 32
+    order = np.lexsort((np.arange(M * per), item_ncomp, ppl))
+    inv = np.empty_like(order)
+    inv[order] = np.arange(order.size)
+    cap = max(0, (int(iterations) - int(burn) + int(thin) - 1) // max(int(thin), 1) + 1) if trace else 0
+    s = engine.Sampler(regions, item_region[order], item_ncomp[order], uid[order], voigt=voigt, sd_free=sd_free,
+                       dtype=dtype, seed=seed, burn=burn, thin=thin, tune_interval=tune_interval,
+                       tune_throughout=tune_throughout, trace_cap=cap, cmax=cmax)
+    s.init()
+    s.run(iterations)
+    dev = s.ctx.torch_device
+    d_inv = torch.from_numpy(inv).to(dev)
+    # ---- top-K chains of every (model, restart) by best log-posterior, on the device
+    K = max(1, min(int(polish_top), Cn))
+    best_logp = s.t["best_logp"][d_inv].view(M * G, Cn)
+    best_logp = torch.nan_to_num(best_logp, nan=-float("inf"))
+    top = best_logp.topk(K, dim=1).indices                                   # [M*G, K] chain-in-group
+    flat = (torch.arange(M * G, device=dev)[:, None] * Cn + top).reshape(-1)  # logical chain ids
+    phys = d_inv[flat]                                                        # sampler rows
+    starts = s.t["best_theta"][phys].contiguous()
+    res = s._map(starts, s.t["item_region"][phys].contiguous(), s.t["item_ncomp"][phys].contiguous(), cmax,
+                 int(maxiter or iterations), 0, xtol, ftol, polish_dtype)
+    logp = torch.nan_to_num(res["logp"].view(M * G, K), nan=-float("inf"))
+    win = logp.argmax(dim=1)                                                  # [M*G]
+    pick = torch.arange(M * G, device=dev) * K + win
+    out = {k: res[k][pick].view(M, G).cpu().numpy() for k in ("logp", "lnL", "chi2", "bic")}
+    out["iters"] = res["iters"][pick].view(M, G).cpu().numpy()
+    theta_map = res["theta"][pick].cpu().numpy()                              # [M*G, ts] scaled
+    primary_rows = phys.view(M * G, K)[torch.arange(M * G, device=dev), win]  # sampler row of the winning chain
+    prow = primary_rows.cpu().numpy()
+    ts = s.ts
+    comps_s = theta_map[:, : 4 * cmax].reshape(M * G, cmax, 4)
+    reg_of = np.repeat(np.array([r for r, _ in models]), G)
+    comps = regions.to_physical(comps_s, reg_of).reshape(M, G, cmax, 4)
+    sd = theta_map[:, 4 * cmax].reshape(M, G) if sd_free else None
+    # posterior summaries of the winning chains (Welford accumulators of K2)
+    ntal = s.t["ntally"][primary_rows].cpu().numpy().reshape(M, G)
+    mean_s = s.t["mean"][primary_rows].cpu().numpy()
+    m2_s = s.t["m2"][primary_rows].cpu().numpy()
+    com = s.t["comom"][primary_rows].cpu().numpy().reshape(M, G, cmax, 6)
+    sc = regions.scale[reg_of][:, None]
+    mean_c = regions.to_physical(mean_s[:, : 4 * cmax].reshape(M * G, cmax, 4), reg_of).reshape(M, G, cmax, 4)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        var_s = m2_s / np.maximum(ntal.reshape(-1, 1), 1)
+    std_c = np.sqrt(var_s[:, : 4 * cmax]).reshape(M * G, cmax, 4)
+    std_c[:, :, 1:] *= sc[:, :, None]
+    std_c = std_c.reshape(M, G, cmax, 4)
+    acc = s.t["acc_total"].sum().item()
+    mb = ModelBatch(models=models, M=M, G=G, cmax=cmax, voigt=bool(voigt), sd_free=bool(sd_free),
+                    bic=out["bic"], chi2=out["chi2"], lnL=out["lnL"], logp=out["logp"], nm_iters=out["iters"],
+                    theta=comps, sd=sd, mean=mean_c, std=std_c, comom=com, ntally=ntal,
+                    sd_mean=mean_s[:, 4 * cmax].reshape(M, G) if sd_free else None,
+                    sd_std=np.sqrt(var_s[:, 4 * cmax]).reshape(M, G) if sd_free else None,
+                    primary_rows=prow.reshape(M, G), accepted_post_burn=int(acc),
+                    voigt_evals=s.voigt_evals(iterations), n_chains=M * per,
+                    scale=regions.scale[[r for r, _ in models]], iterations=int(iterations),
+                    host_regions=getattr(regions, "host_regions", None))
+    if keep_sampler:
+        mb.sampler = s
+        mb.inv = inv
+    return mb
+
+
+def ladder_replay(n0, tables, chi_limit=1.5, verbose=False, log=print):
+    """Replay of ``VPregion.region_fit``'s acceptance rule (vamp_1.0/vpregion.py:54-91) on
+    precomputed tables ``tables[n] = (bic_array, red_chi_array)``.
+
+    Returns ``(kept_n, exit_n, decided)``; ``decided`` is False when the rule needs a
+    candidate that is not in ``tables`` yet (the caller fits more and replays).  Reference
+    quirks kept: the first candidate is compared through ``bic_array[-1]`` (not the mean);
+    when BIC stops decreasing the previous candidate's fit is kept."""
+    n = int(n0)
+    if n not in tables:
+        return None, n, False
+    bic_old = tables[n][0][-1]
+    kept = n
+    n += 1
+    while True:
+        if n not in tables:
+            return kept, n, False
+        bic_array, red = tables[n]
+        cur = float(np.average(bic_array))
+        if bic_old > cur:
+            if verbose:
+                log("Old BIC value of {:.2f} is greater than the current {:.2f}.".format(bic_old, cur))
+            bic_old, kept = cur, n
+            if np.average(red) < chi_limit:
+                if verbose:
+                    log("Reduced Chi squared is less than {}".format(chi_limit))
+                    log("Final n={}".format(n))
+                return kept, n, True
+            n += 1
+            if verbose:
+                log("Increasing the number of lines to: {}".format(n))
+        else:
+            if verbose:
+                log("BIC increased with increasing the line number, stopping.")
+                log("Final n={}.".format(n - 1))
+            return kept, n - 1, True

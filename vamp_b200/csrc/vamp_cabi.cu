@@ -85,9 +85,10 @@ __global__ void faddeeva_test_kernel(int n, const double* __restrict__ x, const 
     cc.A = T(1);
     cc.cb = T(0);
     cc.g = T(1);
-    cc.y = T(y[i]);
+    const double yc = fmin(y[i], (double)Fad<T>::BIG());      // make_comp clamps the same way
+    cc.y = T(yc);
     cc.y2 = cc.y * cc.y;
-    cc.L2 = T(4.0 * y[i] * y[i]);
+    cc.L2 = T(4.0 * yc * yc);
     T du[1] = {T(x[i])};
     T H[1];
     comp_shape<T, VAMP_KIND_VOIGT, 1>(cc, du, H);

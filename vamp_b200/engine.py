@@ -94,6 +94,7 @@ class Regions:
         self.ctx = ctx
         self.lib = ctx.lib
         regions = list(regions)
+        self.host_regions = regions          # kept for read-backs (VPfit._x / _flux)
         self.R = len(regions)
         self.npix = np.array([len(r[0]) for r in regions], dtype=np.int32)
         nu = np.ascontiguousarray(np.concatenate([np.asarray(r[0], dtype=np.float64) for r in regions]))
