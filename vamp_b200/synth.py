@@ -35,10 +35,20 @@ def frequency_grid(P):
     return NU_LYA + (np.arange(P, dtype=np.float64) - (P - 1) / 2.0) * DNU
 
 
-def make_region(P, n_true, snr, region_id, voigt=True, lsf=None):
+def voigt_peak_shape(L_fwhm, G_fwhm):
+    """H(0, y) = sqrt(pi) y erfcx(y): tau at line centre per unit ``amplitude_L``."""
+    y = np.sqrt(np.log(2.0)) * L_fwhm / G_fwhm
+    return np.sqrt(np.pi) * y * wofz(1j * y).real
+
+
+def make_region(P, n_true, snr, region_id, voigt=True, lsf=None, ratio_range=(0.01, 0.3)):
     """One synthetic region.  Returns a dict with ``nu`` (Hz, ascending), ``flux``,
     ``noise`` (constant ``1/snr`` vector), ``truth`` ``[n_true, 4]`` =
-    ``(amplitude, centroid, L_fwhm | sigma, G_fwhm | 0)`` in Hz and ``clean``."""
+    ``(amplitude, centroid, L_fwhm | sigma, G_fwhm | 0)`` in Hz and ``clean``.
+
+    The central optical depth tau_0 ~ U(0.2, 3); for Voigt components the
+    model's ``amplitude_L`` is tau_0 / H(0, y) (``tau0`` holds the drawn central depths).
+    ``ratio_range``: log-uniform range of L_fwhm / G_fwhm."""
     rng = rng_for(region_id)
     nu = frequency_grid(P)
     sig_px = rng.uniform(3.0, 10.0, n_true)
@@ -53,7 +63,7 @@ def make_region(P, n_true, snr, region_id, voigt=True, lsf=None):
             if all(abs(c - cen_px[j]) >= 1.5 * max(sig_px[k], sig_px[j]) for j in range(k)):
                 break
         cen_px[k] = c
-    ratio = 10.0 ** rng.uniform(-2.0, np.log10(0.3), n_true)
+    ratio = 10.0 ** rng.uniform(np.log10(ratio_range[0]), np.log10(ratio_range[1]), n_true)
     truth = np.zeros((n_true, 4))
     truth[:, 0] = amp
     truth[:, 1] = nu[0] + cen_px * DNU
@@ -62,7 +72,8 @@ def make_region(P, n_true, snr, region_id, voigt=True, lsf=None):
         if voigt:
             G = FWHM_PER_SIGMA * sig_px[k] * DNU
             truth[k, 2], truth[k, 3] = ratio[k] * G, G
-            tau += voigt_tau(nu, amp[k], truth[k, 1], truth[k, 2], truth[k, 3])
+            truth[k, 0] = amp[k] / voigt_peak_shape(truth[k, 2], truth[k, 3])
+            tau += voigt_tau(nu, truth[k, 0], truth[k, 1], truth[k, 2], truth[k, 3])
         else:
             truth[k, 2] = sig_px[k] * DNU
             tau += gauss_tau(nu, amp[k], truth[k, 1], truth[k, 2])
@@ -75,7 +86,7 @@ def make_region(P, n_true, snr, region_id, voigt=True, lsf=None):
     flux = clean + rng.normal(0.0, sigma, P)
     flux[flux < 0.0] = 0.0
     return {"nu": nu, "flux": flux, "noise": np.full(P, sigma), "truth": truth, "clean": clean,
-            "voigt": bool(voigt), "region_id": int(region_id), "snr": float(snr)}
+            "voigt": bool(voigt), "region_id": int(region_id), "snr": float(snr), "tau0": amp}
 
 
 def gaussian_lsf(fwhm_px=2.0, taps=7):
