@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""bench.py - the driver's measurement contract for the VAMP hot path on B200.
+
+Metric (BASELINE.json): Voigt logL pixel-component evaluations per second, measured over whole
+fits of the configuration the metric is quoted on (configs[1], "C2"):
+
+    one synthetic blended 256-pixel region per GPU, BIC model-selection sweep over n = 1..6
+    Voigt components, 4096 chains per candidate (4 restart groups x 1024), 3000 iterations
+    (burn 300, thin 15) of the scalar Metropolis sampler, Nelder-Mead MAP polish, BIC table,
+    component-count selection.
+
+A *step* = one such fit.  ``value`` counts the Voigt pixel-component evaluations the sampler
+actually computed (device counters: one component re-evaluated over the region per in-bounds
+centroid/width step; amplitude, noise and out-of-bounds steps compute none) divided by the
+device time of the step, inputs resident in HBM.  ``e2e`` times the public API call
+(``vamp_b200.fit_regions``) with host numpy buffers: spectrum upload, fit, read-back of the
+per-region result records.  N > 1: one rank per GPU, each fits its own region (weak scaling,
+Philox keyed by global region id), one NCCL all-gather of the result records per step.
+
+``--impl reference``: the reference's arithmetic on the host cores - the oracle's restatement
+of the PyMC 2 scalar Metropolis sampler over the reference density (numpy + scipy.special.wofz,
+exactly what vamp_1.0/vpfits.py computes through astropy/PyMC), one process per core, on a
+bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "voigt_logl_pixel_component_evals_per_sec"
+UNIT = "evals/s"
+N_CAND = 6
+RESTARTS = 4
+CHAINS_PER_RESTART = 1024
+ITERS, BURN, THIN = 3000, 300, 15
+WORKLOAD = ("C2: 256-px synthetic blended Voigt region (3 true components, S/N 50) per GPU; BIC sweep n=1..6, "
+            "4096 chains per candidate (4 restarts x 1024), 3000 iterations burn 300 thin 15, NM polish, BIC selection")
+
+
+def config_dict(n_gpus):
+    return {"workload": WORKLOAD, "pixels": 256, "candidates": "1..6", "chains_per_candidate": RESTARTS * CHAINS_PER_RESTART,
+            "iterations": ITERS, "burn": BURN, "thin": THIN, "regions_per_gpu": 1, "parallelism": "regions sharded, %d rank(s)" % n_gpus,
+            "l2": "flushed between steps (512 MiB write); working set is compute-bound and far below L2"}
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx = float(r[2])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        busy = [v for v in sm if v > 500] or sm
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def _ref_worker(args):
+    """One host core: restated PyMC 2 scalar Metropolis on the reference density."""
+    region_id, n, iters, seed = args
+    from oracle import sampler as OS
+    from vamp_b200 import synth
+    reg = synth.config_c2(region_id=region_id)
+    model = OS.Model(reg["nu"], reg["flux"], n, True)
+    rng = np.random.default_rng(seed)
+    t0 = time.perf_counter()
+    OS.metropolis_sample(model, model.initial(rng), iters, iters // 10, THIN, rng)
+    dt = time.perf_counter() - t0
+    # the restated sampler recomputes every component at every scalar step (no LazyFunction cache)
+    evals = iters * model.k * n * len(reg["nu"])
+    return evals, dt
+
+
+def reference_sample(cores, iters, seed=0):
+    """Bounded sample of the C2 workload on ``cores`` host cores: chains for n = 1..6 round-robin."""
+    import multiprocessing as mp
+    jobs = [(2, 1 + (i % N_CAND), iters, seed + i) for i in range(max(cores, 1))]
+    t0 = time.perf_counter()
+    if cores > 1:
+        with mp.get_context("fork").Pool(cores) as pool:
+            res = pool.map(_ref_worker, jobs)
+    else:
+        res = [_ref_worker(jobs[0])]
+    wall = time.perf_counter() - t0
+    evals = sum(r[0] for r in res)
+    return evals / wall, evals, wall
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    iters = 40
+    for _ in range(args.warmup if args.warmup < 2 else 1):
+        reference_sample(cores, 5)
+    t_steps, ev = [], 0
+    for k in range(args.steps):
+        v, e, w = reference_sample(cores, iters, seed=100 + k)
+        t_steps.append(w)
+        ev += e
+    total = sum(t_steps)
+    value = ev / total
+    sample = ("restated PyMC2 scalar Metropolis over the reference density (numpy + scipy.special.wofz), C2 region, "
+              "%d chains (n=1..6 round-robin) x %d iterations per step, one process per core" % (cores, iters))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * total / max(args.steps, 1), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_dict(args.gpus),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from vamp_b200 import batch, engine, flops, synth
+    from vamp_b200.fit_regions import fit_regions
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the GPU arm has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ctx = engine.default_context(local_rank)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    region_id = 2 + rank                    # weak scaling: one C2 region per GPU, keyed by global id
+    reg = synth.config_c2(region_id=region_id)
+    host_regions = [(reg["nu"], reg["flux"], reg["noise"])]
+    models = [(0, n) for n in range(1, N_CAND + 1)]
+    flush = torch.empty(512 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+    regs = engine.Regions(ctx, host_regions)
+
+    # -------- device-resident step: prior draw -> K2 -> top-K -> K3 -> BIC table (no host copies)
+    work_per_step = {}
+
+    def device_step(seed):
+        mb = batch.fit_models(regs, models, voigt=True, sd_free=True, iterations=ITERS, burn=BURN, thin=THIN,
+                              restarts=RESTARTS, chains_per_restart=CHAINS_PER_RESTART, polish_top=4, dtype="f32",
+                              seed=seed, region_uids=[region_id], keep_sampler=True)
+        return mb
+
+    # warm-up (also measures the algorithmic work and the K2 / K3 kernel times with events on the stream)
+    k2_ms, k3_ms = [], []
+    mb = None
+    for w in range(max(args.warmup, 1)):
+        flush.fill_(float(w))
+        mb = device_step(seed=1000 + w)
+        torch.cuda.synchronize()
+    work = mb.sampler.work()
+    chains = mb.n_chains
+    n_free_evals = work["shape_pix"]
+    # kernel-level timing of the dominant kernel (K2) on the launching stream
+    s = mb.sampler
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    s.init()
+    s.t["work"].zero_()
+    torch.cuda.synchronize()
+    ev[0].record()
+    s.run(ITERS)
+    ev[1].record()
+    torch.cuda.synchronize()
+    k2_time = ev[0].elapsed_time(ev[1]) * 1e-3
+    work_k2 = s.work()
+    flops_k2 = flops.k2_flops(work_k2, "f32", voigt=True)
+
+    clocks = ClockSampler(local_rank)
+    barrier()
+    clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_host0 = time.perf_counter()
+    e0.record()
+    evals = 0.0
+    last = None
+    for k in range(args.steps):
+        flush.fill_(float(k))
+        last = device_step(seed=2000 + k)
+        evals += last.work["shape_pix"]
+        if world > 1:                      # gather the BIC tables (the only data-path exchange)
+            t = torch.from_numpy(np.ascontiguousarray(last.bic)).to(dev)
+            out = torch.empty((world,) + tuple(t.shape), dtype=t.dtype, device=dev)
+            dist.all_gather_into_tensor(out, t)
+    e1.record()
+    barrier()
+    dev_s = e0.elapsed_time(e1) * 1e-3
+    wall_s = time.perf_counter() - t_host0
+    clk = clocks.stop()
+    tt = torch.tensor([dev_s, evals], dtype=torch.float64, device=dev)
+    if world > 1:
+        tmax = tt.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = tt.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        dev_s, evals = float(tmax[0]), float(tsum[1])
+    value = evals / dev_s
+
+    # -------- end to end through the public API with host buffers
+    barrier()
+    stats = {}
+    t0 = time.perf_counter()
+    ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ee0.record()
+    e2e_evals = 0.0
+    d2h = 0
+    for k in range(args.steps):
+        flush.fill_(float(k))
+        st = {}
+        res = fit_regions(host_regions, uids=[region_id], distributed=False, voigt=True, iterations=ITERS, burn=BURN,
+                          thin=THIN, restarts=RESTARTS, chains_per_restart=CHAINS_PER_RESTART, window=N_CAND, n0=[1],
+                          nmax=N_CAND, seed=3000 + k, stats=st)
+        e2e_evals += st["voigt_evals_actual"] if "voigt_evals_actual" in st else st["voigt_evals"]
+        stats = st
+        if world > 1:
+            t = torch.tensor([float(res[0].n)], dtype=torch.float64, device=dev)
+            out = torch.empty(world, dtype=torch.float64, device=dev)
+            dist.all_gather_into_tensor(out, t)
+    ee1.record()
+    barrier()
+    e2e_s = max(ee0.elapsed_time(ee1) * 1e-3, time.perf_counter() - t0 if world == 1 else 0.0)
+    e2e_t = torch.tensor([e2e_s, e2e_evals], dtype=torch.float64, device=dev)
+    if world > 1:
+        a = e2e_t.clone()
+        dist.all_reduce(a, op=dist.ReduceOp.MAX)
+        b = e2e_t.clone()
+        dist.all_reduce(b, op=dist.ReduceOp.SUM)
+        e2e_s, e2e_evals = float(a[0]), float(b[1])
+    h2d = int(sum(a.nbytes for a in host_regions[0]) + 4)
+    rec_bytes = int(8 * (6 + 2 * N_CAND * RESTARTS + 1 + 3 * (1 + N_CAND) * 4 + 3))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    sm_max = float(peaks.get("sm_max_mhz", 1965.0))
+    nsm = torch.cuda.get_device_properties(dev).multi_processor_count
+    peak_tf = flops.fp32_peak_tflops(nsm, sm_max)
+    achieved_tf = flops_k2 / k2_time / 1e12
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    # algorithmic HBM bytes of one K2 launch: spectrum tile per chain + chain state in/out
+    P = 256
+    ts = 4 * N_CAND + 1
+    alg_bytes = chains * (P * 8 + 2 * (ts * (8 * 4 + 4 * 2 + 4 * 3) + 6 * N_CAND * 8 + 64))
+    roofline = {"bound": "fp32", "kernel": "k2_mcmc_kernel<float, VOIGT>", "achieved": achieved_tf, "peak": peak_tf,
+                "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
+                "peak_source": "SMs x 128 x 2 x sm_max_mhz (MEASURED_PEAKS.json %s MHz, %d SMs)" % (sm_max, nsm),
+                "kernel_ms": k2_time * 1e3, "algorithmic_flops_per_launch": flops_k2,
+                "evals_per_launch": work_k2["shape_pix"], "far_path_fraction": work_k2["far_pix"] / max(work_k2["shape_pix"], 1),
+                "kernel_evals_per_sec": work_k2["shape_pix"] / k2_time,
+                "traffic": None,
+                "hbm": {"achieved_gbs": alg_bytes / k2_time / 1e9, "peak_gbs": hbm_peak,
+                        "algorithmic_bytes_per_launch": alg_bytes}}
+    if clk.get("sm_mhz"):
+        roofline["frac_at_observed_clock"] = achieved_tf / flops.fp32_peak_tflops(nsm, clk["sm_mhz"])
+
+    cpu_v, cpu_e, cpu_w = reference_sample(1, 60, seed=7)
+    cpu_baseline = {"value": cpu_v, "unit": UNIT, "cores": 1, "kind": "port",
+                    "sample": "restated PyMC2 scalar Metropolis over the reference density (numpy + scipy wofz), C2 region, "
+                              "n=1, 60 iterations on one core (%.1f s)" % cpu_w}
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * dev_s / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_dict(world),
+            "clocks": clk,
+            "e2e": {"value": e2e_evals / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": rec_bytes,
+                    "ms_per_step": 1e3 * e2e_s / max(args.steps, 1)},
+            "gpu_launches": 4 * args.steps,
+            "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "regions_per_sec": world * args.steps / dev_s,
+            "chains_per_step": chains * world,
+            "selected_n": int(batch.ladder_replay(1, {n: (last.bic[n - 1], last.chi2[n - 1] / 253.0) for n in range(1, N_CAND + 1)})[0]),
+            "host_wall_s": wall_s}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="vamp_b200", choices=["vamp_b200", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

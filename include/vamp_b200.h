@@ -111,6 +111,9 @@ typedef struct vamp_mcmc_args {
     double* sum_lnL2;           /* [n] */
     double* trace;              /* [n, trace_cap, stride] or NULL  (mcmc.trace(name)[:]) */
     int trace_cap;
+    unsigned long long* work;   /* [n, 3] or NULL, accumulated: component evaluations (each over the region's
+                                   pixels), far-path pixels among them, likelihood passes - the
+                                   algorithmic work bench.py's roofline is computed from */
 } vamp_mcmc_args;
 
 /* from_prior != 0: draw PyMC 2-style initial values (xexp = 0.5, Uniforms from their priors,

@@ -29,7 +29,7 @@ class McmcArgs(C.Structure):
         ("rej", C.c_void_p), ("acc_total", C.c_void_p), ("logp", C.c_void_p), ("lnL", C.c_void_p),
         ("best_theta", C.c_void_p), ("best_logp", C.c_void_p), ("mean", C.c_void_p), ("m2", C.c_void_p),
         ("comom", C.c_void_p), ("ntally", C.c_void_p), ("sum_lnL", C.c_void_p), ("sum_lnL2", C.c_void_p),
-        ("trace", C.c_void_p), ("trace_cap", C.c_int),
+        ("trace", C.c_void_p), ("trace_cap", C.c_int), ("work", C.c_void_p),
     ]
 
 

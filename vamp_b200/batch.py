@@ -108,7 +108,7 @@ def fit_models(regions, models, voigt=False, sd_free=True, iterations=3000, burn
                     sd_mean=mean_s[:, 4 * cmax].reshape(M, G) if sd_free else None,
                     sd_std=np.sqrt(var_s[:, 4 * cmax]).reshape(M, G) if sd_free else None,
                     primary_rows=prow.reshape(M, G), accepted_post_burn=int(acc),
-                    voigt_evals=s.voigt_evals(iterations), n_chains=M * per,
+                    voigt_evals=s.voigt_evals(iterations), work=s.work(), n_chains=M * per,
                     scale=regions.scale[[r for r, _ in models]], iterations=int(iterations),
                     host_regions=getattr(regions, "host_regions", None))
     if keep_sampler:

@@ -147,6 +147,7 @@ McmcDev to_dev(const vamp_regions* rg, const vamp_mcmc_args* a) {
     p.sum_lnL2 = a->sum_lnL2;
     p.trace = a->trace;
     p.trace_cap = a->trace_cap;
+    p.work = a->work;
     return p;
 }
 

@@ -194,8 +194,12 @@ __device__ __forceinline__ CompC<T> make_comp(double A, double c, double w1, dou
 // Unit-amplitude shape of one component at PPL pixels of this lane.  All branches are
 // warp-uniform (ballots), so no divergence: a j-row of 32 consecutive pixels is almost
 // always entirely core or entirely far.
-template <typename T, int KIND, int PPL>
-__device__ __forceinline__ void comp_shape(const CompC<T>& cc, const T (&du)[PPL], T (&H)[PPL]) {
+// far-path pixel counter (algorithmic-flop accounting for the roofline; see bench.py): `vm[j]`
+// is the ballot of valid pixels of row j, `nfar` accumulates valid pixels that took the
+// continued-fraction / Lorentzian path.  COUNT = false compiles it away.
+template <typename T, int KIND, int PPL, bool COUNT>
+__device__ __forceinline__ void comp_shape_c(const CompC<T>& cc, const T (&du)[PPL], T (&H)[PPL],
+                                             const unsigned (&vm)[PPL], unsigned& nfar) {
     if (KIND == VAMP_KIND_GAUSS) {
 #pragma unroll
         for (int j = 0; j < PPL; ++j) {
@@ -210,6 +214,7 @@ __device__ __forceinline__ void comp_shape(const CompC<T>& cc, const T (&du)[PPL
             const T s = Real<T>::fma_(x, x, cc.y2);
             const bool far = !(s < Fad<T>::R2());               // also true for inf / NaN
             const unsigned m = __ballot_sync(VAMP_FULL_MASK, far);
+            if (COUNT) nfar += __popc(m & vm[j]);
             T h;
             if (m == 0u) {
                 h = fad_core<T>(x, cc.y, s);
@@ -231,6 +236,15 @@ __device__ __forceinline__ void comp_shape(const CompC<T>& cc, const T (&du)[PPL
             H[j] = h;
         }
     }
+}
+
+template <typename T, int KIND, int PPL>
+__device__ __forceinline__ void comp_shape(const CompC<T>& cc, const T (&du)[PPL], T (&H)[PPL]) {
+    unsigned vm[PPL];
+#pragma unroll
+    for (int j = 0; j < PPL; ++j) vm[j] = 0u;
+    unsigned nfar = 0u;
+    comp_shape_c<T, KIND, PPL, false>(cc, du, H, vm, nfar);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -147,6 +147,13 @@ __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, const WarpSmem
         }
     }
 
+    // ---- work counters (algorithmic-flop accounting): valid pixels per row, far-path pixels,
+    // shape evaluations (in-bounds centroid/width steps) and likelihood evaluations
+    unsigned vm[PPL];
+#pragma unroll
+    for (int j = 0; j < PPL; ++j) vm[j] = __ballot_sync(VAMP_FULL_MASK, (valid >> j) & 1u);
+    unsigned long long n_far = 0ull, n_shape = 0ull, n_like = 0ull;
+
     // ---- build the shape cache and the current sum of squares.  Each lane only ever touches
     // its own cache slots (j*32 + lane), so the cache needs no warp synchronisation.
     T base[PPL], H[PPL];
@@ -232,10 +239,14 @@ __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, const WarpSmem
                     } else {
                         const CompC<T> cc = make_comp<T, KIND>(pA, (i == 1) ? prop : pc, (i == 2) ? prop : pw1,
                                                                (i == 3) ? prop : pw2, ubase);
-                        comp_shape<T, KIND, PPL>(cc, du, H);
+                        unsigned nf = 0u;
+                        comp_shape_c<T, KIND, PPL, true>(cc, du, H, vm, nf);
+                        n_far += nf;
+                        ++n_shape;
                         Anew = cc.A;
                     }
                     const double Snew = (double)chain_S<T, PPL, WT>(f, w, valid, base, Anew, H, lsf_buf, lsf_s, taps, lane);
+                    ++n_like;
                     const double dl = WT ? -0.5 * (Snew - Scur) : -0.5 * (Snew - Scur) / (sd * sd);
                     accept = lu < dl + dprior;      // false for NaN
                     if (accept) {
@@ -345,6 +356,11 @@ __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, const WarpSmem
         p.ntally[chain] = ntally;
         p.sum_lnL[chain] = sum_lnL;
         p.sum_lnL2[chain] = sum_lnL2;
+        if (p.work) {
+            p.work[3 * (size_t)chain + 0] += n_shape;    // component evaluations (x P pixels each)
+            p.work[3 * (size_t)chain + 1] += n_far;      // of their pixels: far-path ones
+            p.work[3 * (size_t)chain + 2] += n_like;     // exp(-tau) + residual passes (x P pixels)
+        }
     }
 }
 

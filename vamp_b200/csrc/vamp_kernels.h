@@ -52,6 +52,7 @@ struct McmcDev {
     double* sum_lnL2;                    // [B]
     double* trace;                       // [B, trace_cap, tstride] or nullptr
     int trace_cap;
+    unsigned long long* work;            // [B, 3] or nullptr: shape evals, far-path pixels, likelihood passes
 };
 cudaError_t vamp_launch_init_prior_any_gauss(const McmcDev& p, cudaStream_t st);
 cudaError_t vamp_launch_init_prior_any_voigt(const McmcDev& p, cudaStream_t st);

@@ -294,6 +294,7 @@ class Sampler:
             "sum_lnL": torch.zeros(B, dtype=f64, device=dev),
             "sum_lnL2": torch.zeros(B, dtype=f64, device=dev),
             "trace": torch.zeros((B, self.trace_cap, ts), dtype=f64, device=dev) if self.trace_cap > 0 else None,
+            "work": torch.zeros((B, 3), dtype=torch.int64, device=dev),
         }
 
     def _args(self, it0=0, it1=0):
@@ -306,6 +307,7 @@ class Sampler:
             setattr(a, name, self.t[name].data_ptr())
         a.trace = self.t["trace"].data_ptr() if self.t["trace"] is not None else None
         a.trace_cap = self.trace_cap
+        a.work = self.t["work"].data_ptr()
         return a
 
     def init(self, theta0_scaled=None):
@@ -335,6 +337,15 @@ class Sampler:
         amplitude and sd steps re-evaluate none."""
         P = self.regions.npix[self.item_region_h].astype(np.int64)
         return int(np.sum(P * self.item_ncomp_h.astype(np.int64) * (self.np_per - 1)) * int(iters))
+
+    def work(self):
+        """Work actually done so far (device counters): dict of pixel-level totals
+        ``shape_pix`` (profile pixel-component evaluations), ``far_pix`` (those on the
+        continued-fraction path), ``like_pix`` (exp(-tau)+residual pixel passes)."""
+        w = self.t["work"].cpu().numpy().astype(np.float64)
+        P = self.regions.npix[self.item_region_h].astype(np.float64)
+        return {"shape_pix": float(np.sum(w[:, 0] * P)), "far_pix": float(np.sum(w[:, 1])),
+                "like_pix": float(np.sum(w[:, 2] * P))}
 
     def loglike_evals(self, iters):
         """Pixel evaluations of exp(-tau) + residual (one per scalar step per pixel)."""

@@ -1,0 +1,215 @@
+"""``fit_regions`` - fit many independent absorption regions, sharded over the GPUs of a node.
+
+The reference fits the regions of a spectrum one after the other in a Python loop
+(vamp_1.0/vpspectrum.py:273-430) and parallelises only by process-per-spectrum-file
+(vamp_1.0/do_vamp.py:85-96).  Regions share nothing, so here they are the shard axis
+(SURVEY.md section 8e): one process per GPU, every rank fits its own regions with the batched
+kernels (all candidate component counts x restarts x chains of all its regions in one K2 and
+one K3 launch per round), and a single fixed-size-record all-gather (NCCL over NVLink when the
+process group is NCCL) assembles the per-region BIC tables and posterior summaries on every
+rank.  There is no per-iteration communication.  Philox streams are keyed by the *global*
+region uid, so a region's result is independent of world size and placement.
+"""
+import numpy as np
+
+from . import batch, engine
+
+
+def estimate_n(flux_array):
+    """Initial component count, as ``VPregion.estimate_n`` (vamp_1.0/vpregion.py:21-35)."""
+    from scipy.ndimage import gaussian_filter
+    from scipy.signal import argrelextrema
+    k = argrelextrema(gaussian_filter(np.asarray(flux_array, dtype=np.float64), 3), np.less)[0].shape[0]
+    return int(k) if k >= 4 else 1
+
+
+def region_cost(npix, n0, window, voigt):
+    """Relative cost of fitting a region: pixels x sum over candidates of free parameters."""
+    per = 4 if voigt else 3
+    return float(npix) * sum(per * n + 1 for n in range(n0, n0 + window))
+
+
+def lpt_partition(costs, world_size):
+    """Longest-processing-time-first static partition.  Returns a list of index lists
+    (deterministic: ties broken by index)."""
+    order = sorted(range(len(costs)), key=lambda i: (-costs[i], i))
+    loads = [0.0] * world_size
+    parts = [[] for _ in range(world_size)]
+    for i in order:
+        r = min(range(world_size), key=lambda k: (loads[k], k))
+        parts[r].append(i)
+        loads[r] += costs[i]
+    return [sorted(p) for p in parts]
+
+
+class RegionResult:
+    """Per-region outcome: chosen ``n``, the BIC / reduced-chi^2 ladder, the MAP parameters of
+    the kept fit (physical units) and posterior mean / std of its winning chain."""
+
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+
+def _record_len(nmax, G, cmax):
+    return 6 + 2 * nmax * G + 1 + 3 * cmax * 4 + 3
+
+
+def pack_record(uid, status, n0, kept, exit_n, tables, nmax, G, cmax, theta, sd, mean, std, sd_mean, sd_std, lnL):
+    rec = np.full(_record_len(nmax, G, cmax), np.nan)
+    rec[0:6] = [uid, status, n0, kept, exit_n, len(tables)]
+    bic = np.full((nmax, G), np.nan)
+    red = np.full((nmax, G), np.nan)
+    for n, (b, r) in tables.items():
+        if n - n0 < nmax:
+            bic[n - n0], red[n - n0] = b, r
+    o = 6
+    rec[o: o + nmax * G] = bic.reshape(-1); o += nmax * G
+    rec[o: o + nmax * G] = red.reshape(-1); o += nmax * G
+    rec[o] = lnL; o += 1
+    for arr in (theta, mean, std):
+        a = np.full((cmax, 4), np.nan)
+        a[: arr.shape[0]] = arr[:cmax]
+        rec[o: o + cmax * 4] = a.reshape(-1); o += cmax * 4
+    rec[o: o + 3] = [np.nan if sd is None else sd, np.nan if sd_mean is None else sd_mean,
+                     np.nan if sd_std is None else sd_std]
+    return rec
+
+
+def unpack_record(rec, nmax, G, cmax):
+    uid, status, n0, kept, exit_n, ncand = (int(v) for v in rec[0:6])
+    o = 6
+    bic = rec[o: o + nmax * G].reshape(nmax, G); o += nmax * G
+    red = rec[o: o + nmax * G].reshape(nmax, G); o += nmax * G
+    lnL = rec[o]; o += 1
+    arrs = []
+    for _ in range(3):
+        arrs.append(rec[o: o + cmax * 4].reshape(cmax, 4)[:kept].copy()); o += cmax * 4
+    sd, sd_mean, sd_std = rec[o: o + 3]
+    return RegionResult(uid=uid, status=status, n0=n0, n=kept, exit_n=exit_n,
+                        bic={n0 + i: bic[i].copy() for i in range(min(ncand, nmax))},
+                        red_chi={n0 + i: red[i].copy() for i in range(min(ncand, nmax))},
+                        lnL=lnL, theta=arrs[0], mean=arrs[1], std=arrs[2], sd=sd, sd_mean=sd_mean, sd_std=sd_std)
+
+
+def fit_local(regions_host, uids, voigt=False, sd_free=True, iterations=3000, burn=300, thin=15, restarts=3,
+              chains_per_restart=32, window=3, max_rounds=4, chi_limit=1.5, dtype="f32", seed=0, lsf=None,
+              n0=None, nmax=12, ctx=None, polish_top=4, tune_interval=50, stats=None, cmax_rec=None):
+    """Fit the given regions on this process's GPU.  Returns ``[R, record_len]`` float64."""
+    ctx = ctx or engine.default_context()
+    R = len(regions_host)
+    G = int(restarts)
+    n0 = [estimate_n(r[1]) for r in regions_host] if n0 is None else [int(v) for v in n0]
+    cap = [max(1, (len(r[1]) - 1) // 2) for r in regions_host]
+    freedom = [len(regions_host[i][1]) - 3 * n0[i] for i in range(R)]        # vpregion.py:37-39, frozen at n0
+    cmax_rec = int(cmax_rec or (max(n0) + nmax if R else 1 + nmax))
+    if R == 0:
+        return np.zeros((0, _record_len(nmax, G, cmax_rec)))
+    regs = engine.Regions(ctx, regions_host, lsf=lsf)
+    if stats is not None:
+        stats["h2d_bytes"] = stats.get("h2d_bytes", 0) + regs.h2d_bytes
+    tables = [dict() for _ in range(R)]
+    fits = [dict() for _ in range(R)]
+    nxt = list(n0)
+    active = list(range(R))
+    outcome = [None] * R
+    for _ in range(max_rounds):
+        if not active:
+            break
+        models, owner = [], []
+        for i in active:
+            for n in range(nxt[i], min(nxt[i] + window, n0[i] + nmax)):
+                if n <= cap[i] or n == nxt[i]:
+                    models.append((i, n))
+                    owner.append(i)
+        mb = batch.fit_models(regs, models, voigt=voigt, sd_free=sd_free, iterations=iterations, burn=burn, thin=thin,
+                              restarts=G, chains_per_restart=chains_per_restart, polish_top=polish_top, dtype=dtype,
+                              seed=seed, region_uids=uids, tune_interval=tune_interval)
+        if stats is not None:
+            stats["voigt_evals"] = stats.get("voigt_evals", 0) + mb.voigt_evals
+            stats["voigt_evals_actual"] = stats.get("voigt_evals_actual", 0) + mb.work["shape_pix"]
+            stats["launches"] = stats.get("launches", 0) + 4
+            stats["chains"] = stats.get("chains", 0) + mb.n_chains
+        for m, (i, n) in enumerate(models):
+            tables[i][n] = (mb.bic[m].copy(), mb.chi2[m] / freedom[i])
+            fits[i][n] = (mb, m)
+        still = []
+        for i in active:
+            kept, exit_n, decided = batch.ladder_replay(n0[i], tables[i], chi_limit)
+            last = max(tables[i])
+            if decided or last >= min(cap[i], n0[i] + nmax - 1):
+                outcome[i] = (kept, exit_n if decided else kept, 0 if decided else 1)
+            else:
+                nxt[i] = last + 1
+                still.append(i)
+        active = still
+    for i in active:      # rounds exhausted: keep the best so far
+        kept, exit_n, _ = batch.ladder_replay(n0[i], tables[i], chi_limit)
+        outcome[i] = (kept, kept, 2)
+    out = np.empty((R, _record_len(nmax, G, cmax_rec)))
+    for i in range(R):
+        kept, exit_n, status = outcome[i]
+        mb, m = fits[i][kept]
+        g = int(np.nanargmin(mb.bic[m])) if np.any(np.isfinite(mb.bic[m])) else 0
+        out[i] = pack_record(uids[i], status, n0[i], kept, exit_n, tables[i], nmax, G, cmax_rec,
+                             mb.theta[m, g, :kept], None if mb.sd is None else mb.sd[m, g], mb.mean[m, g, :kept],
+                             mb.std[m, g, :kept], None if mb.sd_mean is None else mb.sd_mean[m, g],
+                             None if mb.sd_std is None else mb.sd_std[m, g], mb.lnL[m, g])
+    return out
+
+
+def gather_records(local, world_size, rec_len, device=None):
+    """All-gather of the ranks' ``[R_r, rec_len]`` record blocks (padded to the longest) with
+    ``torch.distributed`` - NCCL over NVLink on GPUs, gloo in the CPU tests."""
+    import torch
+    import torch.distributed as dist
+    dev = device or "cpu"
+    counts = torch.zeros(world_size, dtype=torch.int64, device=dev)
+    mine = torch.tensor([local.shape[0]], dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(counts, mine)
+    rmax = int(counts.max().item())
+    buf = torch.full((rmax, rec_len), float("nan"), dtype=torch.float64, device=dev)
+    if local.shape[0]:
+        buf[: local.shape[0]] = torch.from_numpy(np.ascontiguousarray(local)).to(dev)
+    allbuf = torch.empty((world_size * rmax, rec_len), dtype=torch.float64, device=dev)
+    dist.all_gather_into_tensor(allbuf, buf)
+    allbuf = allbuf.cpu().numpy().reshape(world_size, rmax, rec_len)
+    cnt = counts.cpu().numpy()
+    return np.concatenate([allbuf[r, : cnt[r]] for r in range(world_size)], axis=0)
+
+
+def fit_regions(regions_host, uids=None, distributed=None, fit_fn=None, **kw):
+    """Fit ``regions_host = [(nu, flux, noise), ...]`` (host float64 arrays, nu ascending).
+
+    With an initialised ``torch.distributed`` process group (or ``distributed=True``) the
+    regions are LPT-partitioned over the ranks, each rank fits its share on its own GPU and
+    the records are all-gathered; every rank returns the full, uid-ordered result list.
+    ``fit_fn`` (tests only) replaces the GPU fit of a shard."""
+    import torch.distributed as dist
+    R = len(regions_host)
+    uids = list(range(R)) if uids is None else [int(u) for u in uids]
+    voigt = kw.get("voigt", False)
+    window = kw.get("window", 3)
+    nmax = kw.get("nmax", 12)
+    G = kw.get("restarts", 3)
+    n0 = kw.pop("n0", None)
+    n0 = [estimate_n(r[1]) for r in regions_host] if n0 is None else [int(v) for v in n0]
+    cmax_rec = (max(n0) if n0 else 1) + nmax
+    rec_len = _record_len(nmax, G, cmax_rec)
+    use_dist = dist.is_available() and dist.is_initialized() if distributed is None else bool(distributed)
+    fit_fn = fit_fn or fit_local
+    if not use_dist:
+        recs = fit_fn(regions_host, uids, n0=n0, cmax_rec=cmax_rec, **kw)
+    else:
+        world, rank = dist.get_world_size(), dist.get_rank()
+        costs = [region_cost(len(regions_host[i][1]), n0[i], window, voigt) for i in range(R)]
+        mine = lpt_partition(costs, world)[rank]
+        local = fit_fn([regions_host[i] for i in mine], [uids[i] for i in mine], n0=[n0[i] for i in mine],
+                       cmax_rec=cmax_rec, **kw)        # same record geometry on every rank
+        assert local.shape[1] == rec_len
+        device = None
+        if dist.get_backend() == "nccl":
+            import torch
+            device = torch.device("cuda", torch.cuda.current_device())
+        recs = gather_records(local, world, rec_len, device)
+    order = np.argsort([int(r[0]) for r in recs], kind="stable")
+    return [unpack_record(recs[i], nmax, G, cmax_rec) for i in order]

@@ -1,0 +1,54 @@
+"""Hand-counted algorithmic work of the shipped kernels (FMA = 2 flops, MUFU = 1).
+
+Used by ``bench.py`` for ``roofline.achieved`` and stated in DESIGN.md section 5; cross-check with
+ncu ``smsp__sass_thread_inst_executed_op_{fadd,fmul,ffma}_pred_on`` (profiles/).
+Counts follow ``vamp_b200/csrc/vamp_device.cuh`` line by line.
+
+fp32 ``fad_core`` (Weideman N = 12), per pixel:
+    r = rcp(s + 2L*y + L*L)            FMA + ADD + MUFU           = 4
+    Zr = (L*L - s) * r                 ADD + MUL                  = 2
+    Zi = 2L * x * r                    2 MUL                      = 2
+    11 Horner steps (2 FMA, MUL, FMA)  11 * 7                     = 77
+    ir, ii                             ADD + 2 MUL                = 3
+    i2r, i2i                           MUL + FMA, 2 MUL           = 5
+    rew, H                             MUL, FMA, MUL, FMA, 2 MUL  = 9
+                                                                   ---- 102
+fp32 ``fad_far`` (4-level continued fraction):
+    rs, tr, ti                         MUFU + 2 MUL               = 3
+    vr, vi                             MUL + FMA, 2 MUL           = 5
+    N(v), D(v): 2 Horner steps each    4 * 7                      = 28
+    er, ei, imq                        3 * (MUL + FMA)            = 9
+    |D|^2, rcp, -y*imq*rcp             MUL + FMA + MUFU + 2 MUL   = 6
+                                                                   ---- 51
+common per shape pixel: d = du - cb, x = d*g, s = fma(x,x,y2)     = 4
+per likelihood pixel:  tau = fma(A,H,base), exp2(-c*tau) (MUL+MUFU), r = f - m, S = fma(r,r,S)  = 7
+    (+ 1 for the noise weight, + 2 per LSF tap)
+fp64: same structure with N = 32 (31 Horner steps) and 9 CF levels (4 + 5 Horner steps); the
+    reciprocal and exp are multi-instruction sequences, counted as 10 and 30 flops.
+"""
+
+F32 = {"core": 102.0, "far": 51.0, "shape_common": 4.0, "like": 7.0}
+F64 = {"core": 4 + 2 + 2 + 31 * 7 + 3 + 5 + 9 + 9, "far": 3 + 5 + 9 * 7 + 9 + 6 + 18, "shape_common": 4.0,
+       "like": 36.0}
+GAUSS = {"shape": 5.0}      # d, q = d*g, q*q, exp2 (MUFU): SUB + MUL + MUL + MUFU + neg
+
+
+def k2_flops(work, dtype="f32", voigt=True, weighted=False, lsf_taps=0):
+    """Algorithmic flops of the K2 work counters ``{shape_pix, far_pix, like_pix}``."""
+    t = F32 if dtype in ("f32", 0) else F64
+    like = t["like"] + (1.0 if weighted else 0.0) + (2.0 * lsf_taps if lsf_taps > 1 else 0.0)
+    if voigt:
+        core_pix = work["shape_pix"] - work["far_pix"]
+        shape = core_pix * t["core"] + work["far_pix"] * t["far"] + work["shape_pix"] * t["shape_common"]
+    else:
+        shape = work["shape_pix"] * GAUSS["shape"]
+    return shape + work["like_pix"] * like
+
+
+def fp32_peak_tflops(sms=148, mhz=1965.0):
+    """SMs x 128 lanes x 2 (FMA) x clock."""
+    return sms * 128 * 2 * mhz * 1e6 / 1e12
+
+
+def fp64_peak_tflops(sms=148, mhz=1965.0):
+    return sms * 64 * 2 * mhz * 1e6 / 1e12
