@@ -30,7 +30,7 @@ constexpr double FWHM_PER_SIGMA = 2.35482004503094938202;
 struct WarpRng {
     double z0, z1, lu0, lu1;
     uint32_t uid_lo, uid_hi, k0, k1;
-    __device__ __forceinline__ void refill(unsigned long long blk, int lane) {
+    __device__ __noinline__ void refill(unsigned long long blk, int lane) {
         const uint4 x = philox4x32_10(make_uint4(uid_lo, uid_hi, (uint32_t)blk, ((uint32_t)(blk >> 32) << 8) | (uint32_t)lane),
                                       make_uint2(k0, k1));
         const double rad = sqrt(-2.0 * log(u01(x.x)));
@@ -76,29 +76,77 @@ struct WarpSmem {          // pointers into this warp's shared-memory slice
     int* acct;
 };
 
-// sum of squared residuals (WT: noise-weighted) of the model  exp(-(base + A*H))  [* LSF]
-template <typename T, int PPL, bool WT>
-__device__ __forceinline__ T chain_S(const T (&f)[PPL], const T (&w)[PPL], unsigned valid, const T (&base)[PPL], T A,
-                                     const T (&H)[PPL], T* lsf_buf, const T* lsf_s, int taps, int lane) {
-    T m[PPL];
-#pragma unroll
-    for (int j = 0; j < PPL; ++j) m[j] = Real<T>::exp_neg(Real<T>::fma_(A, H[j], base[j]));
-    if (taps > 1) lsf_apply<T, PPL>(m, valid, lsf_buf, lsf_s, taps, lane);
-    T S = T(0);
-#pragma unroll
-    for (int j = 0; j < PPL; ++j) {
-        T r = ((valid >> j) & 1u) ? (f[j] - m[j]) : T(0);
-        if (WT) r *= w[j];
-        S = Real<T>::fma_(r, r, S);
+// ------------------------------------------------------------------------------------------------
+// Row-streaming chain kernel.
+//
+// First version of this kernel kept the lane's pixels in registers and fully unrolled the
+// per-row Voigt evaluation for PPL = 1/2/4/8: 34 k SASS instructions (544 KB) per kernel, and ncu
+// showed the warps stalled on instruction fetch (stall_no_instruction 7.4 warps per issue,
+// issue-active 32 %, profiles/r1_k2_a_unrolled_baseline.txt).  This version streams the rows
+// (32 pixels each, two rows in flight for ILP) through ONE copy of the core / far code:
+//   * du, flux (and 1/noise) of a row come from global memory - 3 KB per region, always L1 hits;
+//   * the per-component shape cache, the tau of the other components ("base") and the
+//     proposed shape live in warp-private shared memory, lane-private slots (no syncs);
+//   * accepting a centroid/width step flips a slot index instead of copying the shape.
+// The hot loop is now a few hundred instructions and the register footprint is halved.
+
+template <typename T>
+__device__ __forceinline__ T real_log(double x);
+template <> __device__ __forceinline__ float real_log<float>(double x) { return __logf((float)x); }
+template <> __device__ __forceinline__ double real_log<double>(double x) { return log(x); }
+
+// component constants with the divisions done in T (double divisions cost ~20 instructions each
+// and are executed redundantly by every lane once per scalar step)
+template <typename T, int KIND>
+__device__ __forceinline__ CompC<T> make_comp_fast(double A, double c, double w1, double w2, double ubase) {
+    CompC<T> cc;
+    cc.A = T(A);
+    cc.cb = T(c - ubase);
+    if (KIND == VAMP_KIND_GAUSS) {
+        cc.g = T(0.84932180028801904272) / T(w1);
+        cc.y = cc.y2 = cc.L2 = T(0);
+    } else {
+        const T ig = T(1) / T(w2);
+        cc.g = fmin(T(1.66510922231539551270) * ig, Fad<T>::BIG());
+        cc.y = fmin(T(0.83255461115769775635) * T(w1) * ig, Fad<T>::BIG());
+        cc.y2 = cc.y * cc.y;
+        cc.L2 = T(w1) * T(w1);
     }
-    return warp_sum(S);
+    return cc;
 }
 
-template <typename T, int KIND, int PPL, bool WT>
-__device__ void mcmc_chain(const McmcDev& p, int chain, int lane, const WarpSmem& ws, T* Hc, T* lsf_buf,
-                           const T* lsf_s) {
+// shape of one row (32 pixels); every branch is warp-uniform and each body exists once
+template <typename T, int KIND>
+__device__ __forceinline__ T row_shape(const CompC<T>& cc, T du, unsigned vmask, unsigned& nfar) {
+    if (KIND == VAMP_KIND_GAUSS) {
+        const T q = (du - cc.cb) * cc.g;
+        return Real<T>::exp2_neg(q * q);
+    }
+    const T d = du - cc.cb;
+    const T x = d * cc.g;
+    const T s = Real<T>::fma_(x, x, cc.y2);
+    const bool far = !(s < Fad<T>::R2());
+    const unsigned m = __ballot_sync(VAMP_FULL_MASK, far);
+    nfar += __popc(m & vmask);
+    T h = T(0);
+    if (m != VAMP_FULL_MASK) h = fad_core<T>(x, cc.y, far ? T(0) : s);
+    if (m != 0u) {
+        T hf = fad_far<T>(x, cc.y, s);
+        const bool vfar = !(s < Fad<T>::FAR2());
+        if (__any_sync(VAMP_FULL_MASK, vfar)) {
+            const T d2 = T(2) * d;
+            const T lor = cc.L2 * Real<T>::rcp(Real<T>::fma_(d2, d2, cc.L2));
+            hf = vfar ? lor : hf;
+        }
+        h = far ? hf : h;
+    }
+    return h;
+}
+
+template <typename T, int KIND, bool WT>
+__device__ void mcmc_chain(const McmcDev& p, int chain, int lane, const WarpSmem& ws, T* Hbuf, T* basebuf, T* lsf_buf,
+                           const T* lsf_s, int HS) {
     constexpr int NP = (KIND == VAMP_KIND_VOIGT) ? 4 : 3;
-    constexpr int HS = 32 * PPL;                      // shape-cache stride per component
     const RegionSetDev& rs = p.rs;
     const int r = p.item_region[chain];
     const int P = rs.npix[r];
@@ -107,10 +155,14 @@ __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, const WarpSmem
     const int sdi = 4 * p.cmax;
     const int k = NP * n + (WT ? 0 : 1);
     const int taps = rs.lsf_taps;
+    const int nrows = (P + 31) >> 5;
     const double ubase = rs.ubase[rs.tile_off[r]];
     const double lognorm = rs.lognorm[r];
     const double c_hi = (double)(P - 1);
     const double w_hi = 0.5 * (double)(P - 1) * (KIND == VAMP_KIND_VOIGT ? FWHM_PER_SIGMA : 1.0);
+    const T* __restrict__ gdu = RS<T>::du(rs) + rs.pix_off[r];
+    const T* __restrict__ gf = RS<T>::f(rs) + rs.pix_off[r];
+    const T* __restrict__ gw = RS<T>::w(rs) + rs.pix_off[r];
 
     // ---- state -> shared
     const size_t gb = (size_t)chain * ts;
@@ -131,48 +183,93 @@ __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, const WarpSmem
     double sum_lnL = p.sum_lnL[chain], sum_lnL2 = p.sum_lnL2[chain];
     __syncwarp();
 
-    // ---- this lane's pixels (registers for the whole chain)
-    T du[PPL], f[PPL], w[PPL];
-    unsigned valid = 0u;
-    {
-        const int off = rs.pix_off[r];
-#pragma unroll
-        for (int j = 0; j < PPL; ++j) {
-            const int px = j * 32 + lane;
-            const bool ok = px < P;
-            du[j] = ok ? RS<T>::du(rs)[off + px] : T(0);
-            f[j] = ok ? RS<T>::f(rs)[off + px] : T(1);
-            w[j] = (WT && ok) ? RS<T>::w(rs)[off + px] : T(0);
-            valid |= ok ? (1u << j) : 0u;
-        }
-    }
-
-    // ---- work counters (algorithmic-flop accounting): valid pixels per row, far-path pixels,
-    // shape evaluations (in-bounds centroid/width steps) and likelihood evaluations
-    unsigned vm[PPL];
-#pragma unroll
-    for (int j = 0; j < PPL; ++j) vm[j] = __ballot_sync(VAMP_FULL_MASK, (valid >> j) & 1u);
     unsigned long long n_far = 0ull, n_shape = 0ull, n_like = 0ull;
+    // slot table: component c's shape lives in Hbuf[slot(c)*HS ...]; slot n is the spare one
+    unsigned long long slots = 0ull;
+    for (int c = 0; c <= n; ++c) slots |= (unsigned long long)c << (4 * c);
+    auto slot_of = [&](int c) -> int { return (int)((slots >> (4 * c)) & 15ull); };
 
-    // ---- build the shape cache and the current sum of squares.  Each lane only ever touches
-    // its own cache slots (j*32 + lane), so the cache needs no warp synchronisation.
-    T base[PPL], H[PPL];
-#pragma unroll
-    for (int j = 0; j < PPL; ++j) base[j] = T(0);
-    for (int c = 0; c < n; ++c) {
-        const CompC<T> cc = make_comp<T, KIND>(ws.th[VAMP_TH(c, 0)], ws.th[VAMP_TH(c, 1)], ws.th[VAMP_TH(c, 2)],
-                                               ws.th[VAMP_TH(c, 3)], ubase);
-        comp_shape<T, KIND, PPL>(cc, du, H);
-#pragma unroll
-        for (int j = 0; j < PPL; ++j) {
-            Hc[c * HS + j * 32 + lane] = H[j];
-            base[j] = Real<T>::fma_(cc.A, H[j], base[j]);
+    // sum of squared (weighted) residuals of  exp(-(base + A*H))  with H either freshly evaluated
+    // for component constants `cc` (and written to `Hdst`) or read from `Hsrc`
+    auto pass = [&](bool fresh, const CompC<T>& cc, T A, const T* Hsrc, T* Hdst) -> double {
+        T S = T(0);
+        unsigned nf = 0u;
+#pragma unroll 2
+        for (int j = 0; j < nrows; ++j) {
+            const int px = j * 32 + lane;
+            const int left = P - j * 32;
+            const unsigned vmask = left >= 32 ? VAMP_FULL_MASK : ((1u << left) - 1u);
+            const bool ok = px < P;
+            T H;
+            if (fresh) {
+                const T du = ok ? __ldg(gdu + px) : T(0);
+                H = row_shape<T, KIND>(cc, du, vmask, nf);
+                Hdst[px] = H;
+            } else {
+                H = Hsrc[px];
+            }
+            const T m = Real<T>::exp_neg(Real<T>::fma_(A, H, basebuf[px]));
+            if (taps > 1) {
+                lsf_buf[(taps >> 1) + px] = ok ? (m - T(1)) : T(0);
+            } else {
+                T rr = ok ? (__ldg(gf + px) - m) : T(0);
+                if (WT) rr *= ok ? __ldg(gw + px) : T(0);
+                S = Real<T>::fma_(rr, rr, S);
+            }
+        }
+        if (taps > 1) {
+            const int h = taps >> 1;
+            for (int i = lane; i < 2 * h; i += 32) lsf_buf[(i < h) ? i : (32 * nrows + i)] = T(0);
+            __syncwarp();
+            for (int j = 0; j < nrows; ++j) {
+                const int px = j * 32 + lane;
+                const bool ok = px < P;
+                T acc = T(1);
+                const T* bq = lsf_buf + px + 2 * h;
+                for (int t = 0; t < taps; ++t) acc = Real<T>::fma_(lsf_s[t], bq[-t], acc);
+                T rr = ok ? (__ldg(gf + px) - acc) : T(0);
+                if (WT) rr *= ok ? __ldg(gw + px) : T(0);
+                S = Real<T>::fma_(rr, rr, S);
+            }
+            __syncwarp();
+        }
+        n_far += nf;
+        ++n_like;
+        return (double)warp_sum(S);
+    };
+
+    // ---- build the shape cache and the current sum of squares
+    for (int j = 0; j < nrows; ++j) basebuf[j * 32 + lane] = T(0);
+    {
+        unsigned dummy = 0u;
+        for (int c = 0; c < n; ++c) {
+            const CompC<T> cc = make_comp<T, KIND>(ws.th[VAMP_TH(c, 0)], ws.th[VAMP_TH(c, 1)], ws.th[VAMP_TH(c, 2)],
+                                                   ws.th[VAMP_TH(c, 3)], ubase);
+            T* Hd = Hbuf + slot_of(c) * HS;
+            for (int j = 0; j < nrows; ++j) {
+                const int px = j * 32 + lane;
+                const T du = px < P ? __ldg(gdu + px) : T(0);
+                const T H = row_shape<T, KIND>(cc, du, 0u, dummy);
+                Hd[px] = H;
+                basebuf[px] = Real<T>::fma_(cc.A, H, basebuf[px]);
+            }
         }
     }
-#pragma unroll
-    for (int j = 0; j < PPL; ++j) H[j] = T(0);
-    double Scur = (double)chain_S<T, PPL, WT>(f, w, valid, base, T(0), H, lsf_buf, lsf_s, taps, lane);
+    CompC<T> cz;
+    cz.A = cz.cb = cz.g = cz.y = cz.y2 = cz.L2 = T(0);
+    T* Hspare = Hbuf + slot_of(n) * HS;
+    for (int j = 0; j < nrows; ++j) Hspare[j * 32 + lane] = T(0);
+    double Scur = pass(false, cz, T(0), Hspare, nullptr);     // base holds the full tau here
+    n_far = 0ull;
+    n_like = 0ull;
     double sd = WT ? 1.0 : ws.th[sdi];
+    double logsd = WT ? 0.0 : log(sd);
+    double half_inv_var = WT ? 0.5 : 0.5 / (sd * sd);
+    double lp = 0.0;                                          // sum_c (ln A_c - A_c), kept incrementally
+    for (int c = 0; c < n; ++c) {
+        const double a = ws.th[VAMP_TH(c, 0)];
+        lp += log(a) - a;
+    }
 
     WarpRng rng;
     {
@@ -202,14 +299,16 @@ __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, const WarpSmem
         const bool post_burn = it >= p.burn;
 
         for (int c = 0; c < n; ++c) {
-            // base = tau of the other components (from the cache; no drift accumulates)
-#pragma unroll
-            for (int j = 0; j < PPL; ++j) base[j] = T(0);
+            // base = tau of the other components, rebuilt from the cache (no drift accumulates)
+            for (int j = 0; j < nrows; ++j) basebuf[j * 32 + lane] = T(0);
             for (int c2 = 0; c2 < n; ++c2) {
                 if (c2 == c) continue;
                 const T A2 = T(ws.th[VAMP_TH(c2, 0)]);
-#pragma unroll
-                for (int j = 0; j < PPL; ++j) base[j] = Real<T>::fma_(A2, Hc[c2 * HS + j * 32 + lane], base[j]);
+                const T* Hs = Hbuf + slot_of(c2) * HS;
+                for (int j = 0; j < nrows; ++j) {
+                    const int px = j * 32 + lane;
+                    basebuf[px] = Real<T>::fma_(A2, Hs[px], basebuf[px]);
+                }
             }
             double pA = ws.th[VAMP_TH(c, 0)], pc = ws.th[VAMP_TH(c, 1)], pw1 = ws.th[VAMP_TH(c, 2)],
                    pw2 = ws.th[VAMP_TH(c, 3)];
@@ -229,35 +328,30 @@ __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, const WarpSmem
                 else ok = (prop > 0.0) && (prop <= w_hi);
                 bool accept = false;
                 if (ok) {
-                    double dprior = 0.0;
-                    T Anew;
+                    double dprior = 0.0, Snew;
+                    const int sc = slot_of(c), sp = slot_of(n);
                     if (i == 0) {
-#pragma unroll
-                        for (int j = 0; j < PPL; ++j) H[j] = Hc[c * HS + j * 32 + lane];
-                        Anew = T(prop);
-                        dprior = (log(prop) - prop) - (log(pA) - pA);
+                        Snew = pass(false, cz, T(prop), Hbuf + sc * HS, nullptr);
+                        dprior = (double)real_log<T>(prop / pA) - (prop - pA);
                     } else {
-                        const CompC<T> cc = make_comp<T, KIND>(pA, (i == 1) ? prop : pc, (i == 2) ? prop : pw1,
-                                                               (i == 3) ? prop : pw2, ubase);
-                        unsigned nf = 0u;
-                        comp_shape_c<T, KIND, PPL, true>(cc, du, H, vm, nf);
-                        n_far += nf;
+                        const CompC<T> cc = make_comp_fast<T, KIND>(pA, (i == 1) ? prop : pc, (i == 2) ? prop : pw1,
+                                                                    (i == 3) ? prop : pw2, ubase);
                         ++n_shape;
-                        Anew = cc.A;
+                        Snew = pass(true, cc, cc.A, nullptr, Hbuf + sp * HS);
                     }
-                    const double Snew = (double)chain_S<T, PPL, WT>(f, w, valid, base, Anew, H, lsf_buf, lsf_s, taps, lane);
-                    ++n_like;
-                    const double dl = WT ? -0.5 * (Snew - Scur) : -0.5 * (Snew - Scur) / (sd * sd);
-                    accept = lu < dl + dprior;      // false for NaN
+                    accept = lu < (Scur - Snew) * half_inv_var + dprior;      // false for NaN
                     if (accept) {
                         Scur = Snew;
-                        if (i == 0) pA = prop;
-                        else {
+                        if (i == 0) {
+                            pA = prop;
+                            lp += dprior;
+                        } else {
                             if (i == 1) pc = prop;
                             else if (i == 2) pw1 = prop;
                             else pw2 = prop;
-#pragma unroll
-                            for (int j = 0; j < PPL; ++j) Hc[c * HS + j * 32 + lane] = H[j];
+                            // the proposed shape becomes the component's shape: swap slot indices
+                            slots &= ~((15ull << (4 * c)) | (15ull << (4 * n)));
+                            slots |= ((unsigned long long)sp << (4 * c)) | ((unsigned long long)sc << (4 * n));
                         }
                     }
                 }
@@ -275,11 +369,17 @@ __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, const WarpSmem
             ++q;
             const double prop = sd + z * (double)(ws.asf[sdi] * ws.psd[sdi]);
             bool accept = false;
+            double lprop = 0.0;
             if (prop > 0.0 && prop <= 1.0) {
-                const double d = -0.5 * Scur * (1.0 / (prop * prop) - 1.0 / (sd * sd)) - P * (log(prop) - log(sd));
+                lprop = log(prop);
+                const double d = -Scur * (0.5 / (prop * prop) - half_inv_var) - P * (lprop - logsd);
                 accept = lu < d;
             }
-            if (accept) sd = prop;
+            if (accept) {
+                sd = prop;
+                logsd = lprop;
+                half_inv_var = 0.5 / (prop * prop);
+            }
             if (lane == 0) {
                 if (accept) { ws.acc[sdi] += 1; if (post_burn) ws.acct[sdi] += 1; ws.th[sdi] = prop; }
                 else ws.rej[sdi] += 1;
@@ -287,13 +387,8 @@ __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, const WarpSmem
             __syncwarp();
         }
 
-        // ---- end of iteration: exact log-posterior of the current state (no incremental drift)
-        const double lnL = WT ? lnL_noise(Scur, lognorm) : lnL_sd(Scur, sd, P);
-        double lp = 0.0;
-        for (int c = 0; c < n; ++c) {
-            const double a = ws.th[VAMP_TH(c, 0)];
-            lp += log(a) - a;
-        }
+        // ---- end of iteration: log-posterior of the current state
+        const double lnL = WT ? (-0.5 * Scur + lognorm) : (-Scur * half_inv_var - P * (logsd + 0.91893853320467274178));
         const double logp = lnL + lp;
         if (logp > best_logp) {
             best_logp = logp;
@@ -345,13 +440,13 @@ __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, const WarpSmem
     for (int i = lane; i < 6 * p.cmax; i += 32) p.comom[(size_t)chain * 6 * p.cmax + i] = ws.comom[i];
     if (lane == 0) {
         const double lnL = WT ? lnL_noise(Scur, lognorm) : lnL_sd(Scur, sd, P);
-        double lp = 0.0;
+        double lpx = 0.0;
         for (int c = 0; c < n; ++c) {
             const double a = ws.th[VAMP_TH(c, 0)];
-            lp += log(a) - a;
+            lpx += log(a) - a;
         }
         p.lnL[chain] = lnL;
-        p.logp[chain] = lnL + lp;
+        p.logp[chain] = lnL + lpx;
         p.best_logp[chain] = best_logp;
         p.ntally[chain] = ntally;
         p.sum_lnL[chain] = sum_lnL;
@@ -373,13 +468,13 @@ __host__ __device__ inline size_t k2_warp_bytes(int ppl_max, int ncomp_max, int 
     b += align16(sizeof(double) * (4 * ts + 6 * cmax));       // th, best, mean, m2, comom
     b += align16(sizeof(float) * 2 * ts);                      // asf, psd
     b += align16(sizeof(int) * 3 * ts);                        // acc, rej, acct
-    b += align16(sizeof(T) * (size_t)ncomp_max * 32 * ppl_max); // shape cache
+    b += align16(sizeof(T) * (size_t)(ncomp_max + 2) * 32 * ppl_max); // shape cache (+ spare slot) + base
     if (lsf) b += align16(sizeof(T) * (32 * ppl_max + VAMP_MAX_LSF_TAPS));
     return b;
 }
 
 template <typename T, int KIND, bool WT>
-__global__ void __launch_bounds__(K2_WARPS * 32, (sizeof(T) == 4) ? 4 : 2)
+__global__ void __launch_bounds__(K2_WARPS * 32, (sizeof(T) == 4) ? 7 : 3)
 k2_mcmc_kernel(McmcDev p, int ppl_max, int ncomp_max) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -408,17 +503,12 @@ k2_mcmc_kernel(McmcDev p, int ppl_max, int ncomp_max) {
     ws.rej = ws.acc + ts;
     ws.acct = ws.rej + ts;
     base += align16(sizeof(int) * 3 * ts);
-    T* Hc = reinterpret_cast<T*>(base);
-    base += align16(sizeof(T) * (size_t)ncomp_max * 32 * ppl_max);
+    const int HS = 32 * ppl_max;
+    T* Hbuf = reinterpret_cast<T*>(base);                       // [(ncomp_max + 1)][HS]
+    T* basebuf = Hbuf + (size_t)(ncomp_max + 1) * HS;           // [HS]
+    base += align16(sizeof(T) * (size_t)(ncomp_max + 2) * HS);
     T* lsf_buf = reinterpret_cast<T*>(base);
-
-    const int P = p.rs.npix[p.item_region[chain]];
-    const int ppl = (P + 31) >> 5;
-    // NOTE: the shape-cache stride is 32*PPL of the *instantiated* PPL, always <= 32*ppl_max.
-    if (ppl <= 1) mcmc_chain<T, KIND, 1, WT>(p, chain, lane, ws, Hc, lsf_buf, lsf_s);
-    else if (ppl <= 2) mcmc_chain<T, KIND, 2, WT>(p, chain, lane, ws, Hc, lsf_buf, lsf_s);
-    else if (ppl <= 4) mcmc_chain<T, KIND, 4, WT>(p, chain, lane, ws, Hc, lsf_buf, lsf_s);
-    else mcmc_chain<T, KIND, 8, WT>(p, chain, lane, ws, Hc, lsf_buf, lsf_s);
+    mcmc_chain<T, KIND, WT>(p, chain, lane, ws, Hbuf, basebuf, lsf_buf, lsf_s, HS);
 }
 
 // ---- initial states -------------------------------------------------------------------------
