@@ -244,7 +244,7 @@ int vamp_regions_create(vamp_ctx* ctx, int R, const int* npix, const double* nu,
         if (P < 1) { delete rg; return fail(-2, "region %d has %d pixels", r, P); }
         rg->pix_off[r] = (int)poff;
         rg->tile_off[r] = (int)toff;
-        poff += ((long long)P + 31) / 32 * 32;
+        poff += ((long long)P + 63) / 64 * 64;     // row pairs of the chain kernel never need masking
         toff += ((long long)P + VAMP_TILE_PIX - 1) / VAMP_TILE_PIX;
         rg->max_npix = P > rg->max_npix ? P : rg->max_npix;
         src += P;
@@ -288,8 +288,9 @@ int vamp_regions_create(vamp_ctx* ctx, int R, const int* npix, const double* nu,
                 ln += std::log(std::fabs(w));
             }
         }
-        // padding inside the last 32-pixel granule: far away (tau = 0), flux 1, weight 0
-        for (long long o = rg->pix_off[r] + P; o < rg->pix_off[r] + ((long long)P + 31) / 32 * 32; ++o) {
+        // padding up to the 64-pixel granule: far away (tau = 0 exactly), flux 1, weight 0, so padded
+        // pixels contribute nothing to any sum and kernels may read them unmasked
+        for (long long o = rg->pix_off[r] + P; o < rg->pix_off[r] + ((long long)P + 63) / 64 * 64; ++o) {
             du64[o] = 1.0e12;
             du32[o] = 1.0e12f;
         }

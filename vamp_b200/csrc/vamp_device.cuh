@@ -30,7 +30,8 @@ enum VampKind { VAMP_KIND_GAUSS = 0, VAMP_KIND_VOIGT = 1 };
 struct RegionSetDev {
     int R;
     const int* npix;        // [R]   pixels per region
-    const int* pix_off;     // [R]   offset of the region in the pixel arrays (multiple of 32)
+    const int* pix_off;     // [R]   offset of the region in the pixel arrays (multiple of 64; padding
+                            //       pixels hold du = 1e12, flux = 1, 1/noise = 0 and may be read unmasked)
     const int* tile_off;    // [R]   offset of the region's first tile in `ubase`
     const float* du32;      // [Ppad] scaled pixel coordinate minus its tile base
     const float* f32;       // [Ppad] flux
@@ -63,9 +64,19 @@ template <> struct RS<double> {
 // Scalar helpers per precision.
 template <typename T> struct Real;
 template <> struct Real<float> {
-    static __device__ __forceinline__ float rcp(float x) { return __fdividef(1.0f, x); }          // MUFU.RCP
-    static __device__ __forceinline__ float exp_neg(float t) { return exp2f(-1.4426950408889634f * t); }  // MUFU.EX2
-    static __device__ __forceinline__ float exp2_neg(float t) { return exp2f(-t); }
+    // raw MUFU ops (no range fix-up code): 1-2 ulp, denormals flushed - see the accuracy tests
+    static __device__ __forceinline__ float rcp(float x) {
+        float r;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+        return r;
+    }
+    static __device__ __forceinline__ float ex2(float x) {
+        float r;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+        return r;
+    }
+    static __device__ __forceinline__ float exp_neg(float t) { return ex2(-1.4426950408889634f * t); }
+    static __device__ __forceinline__ float exp2_neg(float t) { return ex2(-t); }
     static __device__ __forceinline__ float fma_(float a, float b, float c) { return fmaf(a, b, c); }
 };
 template <> struct Real<double> {

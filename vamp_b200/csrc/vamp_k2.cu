@@ -30,7 +30,7 @@ constexpr double FWHM_PER_SIGMA = 2.35482004503094938202;
 struct WarpRng {
     double z0, z1, lu0, lu1;
     uint32_t uid_lo, uid_hi, k0, k1;
-    __device__ __noinline__ void refill(unsigned long long blk, int lane) {
+    __device__ __forceinline__ void refill(unsigned long long blk, int lane) {
         const uint4 x = philox4x32_10(make_uint4(uid_lo, uid_hi, (uint32_t)blk, ((uint32_t)(blk >> 32) << 8) | (uint32_t)lane),
                                       make_uint2(k0, k1));
         const double rad = sqrt(-2.0 * log(u01(x.x)));
@@ -115,9 +115,10 @@ __device__ __forceinline__ CompC<T> make_comp_fast(double A, double c, double w1
     return cc;
 }
 
-// shape of one row (32 pixels); every branch is warp-uniform and each body exists once
+// shape of one row (32 pixels); every branch is warp-uniform and each body exists once.
+// Padding pixels (du = 1e12) take the Lorentzian limit and evaluate to exactly 0.
 template <typename T, int KIND>
-__device__ __forceinline__ T row_shape(const CompC<T>& cc, T du, unsigned vmask, unsigned& nfar) {
+__device__ __forceinline__ T row_shape(const CompC<T>& cc, T du, unsigned& nfar) {
     if (KIND == VAMP_KIND_GAUSS) {
         const T q = (du - cc.cb) * cc.g;
         return Real<T>::exp2_neg(q * q);
@@ -127,7 +128,7 @@ __device__ __forceinline__ T row_shape(const CompC<T>& cc, T du, unsigned vmask,
     const T s = Real<T>::fma_(x, x, cc.y2);
     const bool far = !(s < Fad<T>::R2());
     const unsigned m = __ballot_sync(VAMP_FULL_MASK, far);
-    nfar += __popc(m & vmask);
+    nfar += __popc(m);
     T h = T(0);
     if (m != VAMP_FULL_MASK) h = fad_core<T>(x, cc.y, far ? T(0) : s);
     if (m != 0u) {
@@ -143,7 +144,82 @@ __device__ __forceinline__ T row_shape(const CompC<T>& cc, T du, unsigned vmask,
     return h;
 }
 
-template <typename T, int KIND, bool WT>
+// One likelihood pass over the region, two rows (64 pixels) per trip, nothing masked: the
+// region arrays and the shared-memory rows are padded to 64 pixels with neutral values.
+// FRESH: evaluate the component `cc` and store its shape to Hdst; else read the shape from Hsrc.
+// Returns sum (f - m)^2 (WT: noise-weighted) of m = exp(-(base + A*H)) [convolved with the LSF].
+template <typename T, int KIND, bool WT, bool LSF, bool FRESH>
+__device__ __forceinline__ double chain_pass(const CompC<T>& cc, T A, const T* __restrict__ Hsrc, T* __restrict__ Hdst,
+                                             const T* __restrict__ basebuf, const T* __restrict__ gdu,
+                                             const T* __restrict__ gf, const T* __restrict__ gw, int npairs, int P, int lane,
+                                             T* lsf_buf, const T* lsf_s, int taps, unsigned& nfar) {
+    T S0 = T(0), S1 = T(0);
+    const T* pb = basebuf + lane;
+    const T* ps = Hsrc + lane;
+    T* pd = Hdst + lane;
+    const T* pu = gdu + lane;
+    const T* pf = gf + lane;
+    const T* pw = gw + lane;
+    T* pl = lsf_buf + (taps >> 1) + lane;
+#pragma unroll 1
+    for (int jj = 0; jj < npairs; ++jj) {
+        T H0, H1;
+        if (FRESH) {
+            const T du0 = __ldg(pu), du1 = __ldg(pu + 32);
+            H0 = row_shape<T, KIND>(cc, du0, nfar);
+            H1 = row_shape<T, KIND>(cc, du1, nfar);
+            pd[0] = H0;
+            pd[32] = H1;
+            pu += 64;
+            pd += 64;
+        } else {
+            H0 = ps[0];
+            H1 = ps[32];
+            ps += 64;
+        }
+        const T m0 = Real<T>::exp_neg(Real<T>::fma_(A, H0, pb[0]));
+        const T m1 = Real<T>::exp_neg(Real<T>::fma_(A, H1, pb[32]));
+        pb += 64;
+        if (LSF) {
+            pl[0] = m0 - T(1);
+            pl[32] = m1 - T(1);
+            pl += 64;
+        } else {
+            T r0 = __ldg(pf) - m0, r1 = __ldg(pf + 32) - m1;
+            pf += 64;
+            if (WT) {
+                r0 *= __ldg(pw);
+                r1 *= __ldg(pw + 32);
+                pw += 64;
+            }
+            S0 = Real<T>::fma_(r0, r0, S0);
+            S1 = Real<T>::fma_(r1, r1, S1);
+        }
+    }
+    if (LSF) {
+        const int h = taps >> 1;
+        for (int i = lane; i < 2 * h; i += 32) lsf_buf[(i < h) ? i : (64 * npairs + i)] = T(0);
+        __syncwarp();
+        pf = gf + lane;
+        pw = gw + lane;
+        const T* bq = lsf_buf + lane + 2 * h;
+        for (int j = 0; j < 2 * npairs; ++j) {
+            T acc = T(1);
+            for (int t = 0; t < taps; ++t) acc = Real<T>::fma_(lsf_s[t], bq[-t], acc);
+            // the convolution leaks into the padding pixels next to the region edge: mask them
+            T rr = (j * 32 + lane < P) ? (__ldg(pf) - acc) : T(0);
+            if (WT) rr *= __ldg(pw);
+            S0 = Real<T>::fma_(rr, rr, S0);
+            bq += 32;
+            pf += 32;
+            pw += 32;
+        }
+        __syncwarp();
+    }
+    return (double)warp_sum(S0 + S1);
+}
+
+template <typename T, int KIND, bool WT, bool LSF>
 __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, const WarpSmem& ws, T* Hbuf, T* basebuf, T* lsf_buf,
                            const T* lsf_s, int HS) {
     constexpr int NP = (KIND == VAMP_KIND_VOIGT) ? 4 : 3;
@@ -153,9 +229,11 @@ __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, const WarpSmem
     const int n = p.item_ncomp[chain];
     const int ts = p.tstride;
     const int sdi = 4 * p.cmax;
-    const int k = NP * n + (WT ? 0 : 1);
+    const int ncs = NP * n;                        // component steps per iteration
+    const int k = ncs + (WT ? 0 : 1);
     const int taps = rs.lsf_taps;
-    const int nrows = (P + 31) >> 5;
+    const int npairs = (P + 63) >> 6;
+    const int tune_interval = p.tune_interval, thin = p.thin, burn = p.burn, tune_throughout = p.tune_throughout;
     const double ubase = rs.ubase[rs.tile_off[r]];
     const double lognorm = rs.lognorm[r];
     const double c_hi = (double)(P - 1);
@@ -189,79 +267,30 @@ __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, const WarpSmem
     for (int c = 0; c <= n; ++c) slots |= (unsigned long long)c << (4 * c);
     auto slot_of = [&](int c) -> int { return (int)((slots >> (4 * c)) & 15ull); };
 
-    // sum of squared (weighted) residuals of  exp(-(base + A*H))  with H either freshly evaluated
-    // for component constants `cc` (and written to `Hdst`) or read from `Hsrc`
-    auto pass = [&](bool fresh, const CompC<T>& cc, T A, const T* Hsrc, T* Hdst) -> double {
-        T S = T(0);
-        unsigned nf = 0u;
-#pragma unroll 2
-        for (int j = 0; j < nrows; ++j) {
-            const int px = j * 32 + lane;
-            const int left = P - j * 32;
-            const unsigned vmask = left >= 32 ? VAMP_FULL_MASK : ((1u << left) - 1u);
-            const bool ok = px < P;
-            T H;
-            if (fresh) {
-                const T du = ok ? __ldg(gdu + px) : T(0);
-                H = row_shape<T, KIND>(cc, du, vmask, nf);
-                Hdst[px] = H;
-            } else {
-                H = Hsrc[px];
-            }
-            const T m = Real<T>::exp_neg(Real<T>::fma_(A, H, basebuf[px]));
-            if (taps > 1) {
-                lsf_buf[(taps >> 1) + px] = ok ? (m - T(1)) : T(0);
-            } else {
-                T rr = ok ? (__ldg(gf + px) - m) : T(0);
-                if (WT) rr *= ok ? __ldg(gw + px) : T(0);
-                S = Real<T>::fma_(rr, rr, S);
-            }
-        }
-        if (taps > 1) {
-            const int h = taps >> 1;
-            for (int i = lane; i < 2 * h; i += 32) lsf_buf[(i < h) ? i : (32 * nrows + i)] = T(0);
-            __syncwarp();
-            for (int j = 0; j < nrows; ++j) {
-                const int px = j * 32 + lane;
-                const bool ok = px < P;
-                T acc = T(1);
-                const T* bq = lsf_buf + px + 2 * h;
-                for (int t = 0; t < taps; ++t) acc = Real<T>::fma_(lsf_s[t], bq[-t], acc);
-                T rr = ok ? (__ldg(gf + px) - acc) : T(0);
-                if (WT) rr *= ok ? __ldg(gw + px) : T(0);
-                S = Real<T>::fma_(rr, rr, S);
-            }
-            __syncwarp();
-        }
-        n_far += nf;
-        ++n_like;
-        return (double)warp_sum(S);
-    };
-
     // ---- build the shape cache and the current sum of squares
-    for (int j = 0; j < nrows; ++j) basebuf[j * 32 + lane] = T(0);
+    CompC<T> cz;
+    cz.A = cz.cb = cz.g = cz.y = cz.y2 = cz.L2 = T(0);
+    for (int j = 0; j < 2 * npairs; ++j) basebuf[j * 32 + lane] = T(0);
     {
         unsigned dummy = 0u;
         for (int c = 0; c < n; ++c) {
             const CompC<T> cc = make_comp<T, KIND>(ws.th[VAMP_TH(c, 0)], ws.th[VAMP_TH(c, 1)], ws.th[VAMP_TH(c, 2)],
                                                    ws.th[VAMP_TH(c, 3)], ubase);
             T* Hd = Hbuf + slot_of(c) * HS;
-            for (int j = 0; j < nrows; ++j) {
+            for (int j = 0; j < 2 * npairs; ++j) {
                 const int px = j * 32 + lane;
-                const T du = px < P ? __ldg(gdu + px) : T(0);
-                const T H = row_shape<T, KIND>(cc, du, 0u, dummy);
+                const T H = row_shape<T, KIND>(cc, __ldg(gdu + px), dummy);
                 Hd[px] = H;
                 basebuf[px] = Real<T>::fma_(cc.A, H, basebuf[px]);
             }
         }
+        T* Hspare = Hbuf + slot_of(n) * HS;
+        for (int j = 0; j < 2 * npairs; ++j) Hspare[j * 32 + lane] = T(0);
+        // base holds the full tau here: one cached pass with A = 0 gives the current S
     }
-    CompC<T> cz;
-    cz.A = cz.cb = cz.g = cz.y = cz.y2 = cz.L2 = T(0);
-    T* Hspare = Hbuf + slot_of(n) * HS;
-    for (int j = 0; j < nrows; ++j) Hspare[j * 32 + lane] = T(0);
-    double Scur = pass(false, cz, T(0), Hspare, nullptr);     // base holds the full tau here
-    n_far = 0ull;
-    n_like = 0ull;
+    unsigned nf32 = 0u;
+    double Scur = chain_pass<T, KIND, WT, LSF, false>(cz, T(0), Hbuf + slot_of(n) * HS, nullptr, basebuf, gdu, gf, gw,
+                                                      npairs, P, lane, lsf_buf, lsf_s, taps, nf32);
     double sd = WT ? 1.0 : ws.th[sdi];
     double logsd = WT ? 0.0 : log(sd);
     double half_inv_var = WT ? 0.5 : 0.5 / (sd * sd);
@@ -280,11 +309,11 @@ __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, const WarpSmem
         rng.k1 = (uint32_t)(p.seed >> 32);
     }
     unsigned long long q = (unsigned long long)p.it0 * (unsigned long long)k;
-    if (q & 63ull) rng.refill(q >> 6, lane);
+    bool need_fill = true;                 // (re)fill at the first step and whenever a 64-step block starts
 
     for (int it = p.it0; it < p.it1; ++it) {
         // ---- tuning (PyMC 2: every tune_interval iterations; optionally only during burn-in)
-        if (it > 0 && (it % p.tune_interval) == 0 && (p.tune_throughout || it <= p.burn)) {
+        if (it > 0 && (it % tune_interval) == 0 && (tune_throughout || it <= burn)) {
             for (int i = lane; i < ts; i += 32) {
                 const int a = ws.acc[i], b = ws.rej[i];
                 if (a + b > 0) {
@@ -296,49 +325,71 @@ __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, const WarpSmem
             }
             __syncwarp();
         }
-        const bool post_burn = it >= p.burn;
+        const bool post_burn = it >= burn;
 
-        for (int c = 0; c < n; ++c) {
-            // base = tau of the other components, rebuilt from the cache (no drift accumulates)
-            for (int j = 0; j < nrows; ++j) basebuf[j * 32 + lane] = T(0);
-            for (int c2 = 0; c2 < n; ++c2) {
-                if (c2 == c) continue;
-                const T A2 = T(ws.th[VAMP_TH(c2, 0)]);
-                const T* Hs = Hbuf + slot_of(c2) * HS;
-                for (int j = 0; j < nrows; ++j) {
-                    const int px = j * 32 + lane;
-                    basebuf[px] = Real<T>::fma_(A2, Hs[px], basebuf[px]);
-                }
-            }
-            double pA = ws.th[VAMP_TH(c, 0)], pc = ws.th[VAMP_TH(c, 1)], pw1 = ws.th[VAMP_TH(c, 2)],
-                   pw2 = ws.th[VAMP_TH(c, 3)];
-
+        int c = 0, i = 0;
+        double pA = 0.0, pc = 0.0, pw1 = 0.0, pw2 = 0.0;
 #pragma unroll 1
-            for (int i = 0; i < NP; ++i) {
-                const int idx = VAMP_TH(c, i);
-                double z, lu;
-                rng.get(q, lane, z, lu);
-                ++q;
+        for (int st = 0; st < k; ++st) {
+            // ---- one (normal, log-uniform) pair; the only RNG call site of the kernel
+            if (need_fill || (q & 63ull) == 0ull) {
+                rng.refill(q >> 6, lane);
+                need_fill = false;
+            }
+            double z, lu;
+            {
+                const int slot = (int)(q & 63ull);
+                const double zs = (slot & 1) ? rng.z1 : rng.z0;
+                const double ls = (slot & 1) ? rng.lu1 : rng.lu0;
+                z = __shfl_sync(VAMP_FULL_MASK, zs, slot >> 1);
+                lu = __shfl_sync(VAMP_FULL_MASK, ls, slot >> 1);
+            }
+            ++q;
+            bool accept = false;
+            int idx;
+            double prop;
+            if (st < ncs) {
+                idx = VAMP_TH(c, i);
+                if (i == 0) {
+                    // new component: base = tau of the others, rebuilt from the cache (no drift)
+                    __syncwarp();
+                    for (int j = 0; j < 2 * npairs; ++j) basebuf[j * 32 + lane] = T(0);
+                    for (int c2 = 0; c2 < n; ++c2) {
+                        if (c2 == c) continue;
+                        const T A2 = T(ws.th[VAMP_TH(c2, 0)]);
+                        const T* Hs = Hbuf + slot_of(c2) * HS + lane;
+                        T* bb = basebuf + lane;
+                        for (int j = 0; j < 2 * npairs; ++j) bb[j * 32] = Real<T>::fma_(A2, Hs[j * 32], bb[j * 32]);
+                    }
+                    pA = ws.th[idx];
+                    pc = ws.th[idx + 1];
+                    pw1 = ws.th[idx + 2];
+                    pw2 = ws.th[idx + 3];
+                }
                 const double cur = (i == 0) ? pA : (i == 1) ? pc : (i == 2) ? pw1 : pw2;
-                const double prop = cur + z * (double)(ws.asf[idx] * ws.psd[idx]);
+                prop = cur + z * (double)(ws.asf[idx] * ws.psd[idx]);
                 bool ok;
                 if (i == 0) ok = prop > 0.0;
                 else if (i == 1) ok = (prop >= 0.0) && (prop <= c_hi);
                 else if (KIND == VAMP_KIND_VOIGT && i == 2) ok = (prop >= 0.0) && (prop <= w_hi);
                 else ok = (prop > 0.0) && (prop <= w_hi);
-                bool accept = false;
                 if (ok) {
                     double dprior = 0.0, Snew;
                     const int sc = slot_of(c), sp = slot_of(n);
                     if (i == 0) {
-                        Snew = pass(false, cz, T(prop), Hbuf + sc * HS, nullptr);
+                        Snew = chain_pass<T, KIND, WT, LSF, false>(cz, T(prop), Hbuf + sc * HS, nullptr, basebuf, gdu, gf,
+                                                                   gw, npairs, P, lane, lsf_buf, lsf_s, taps, nf32);
                         dprior = (double)real_log<T>(prop / pA) - (prop - pA);
                     } else {
                         const CompC<T> cc = make_comp_fast<T, KIND>(pA, (i == 1) ? prop : pc, (i == 2) ? prop : pw1,
                                                                     (i == 3) ? prop : pw2, ubase);
                         ++n_shape;
-                        Snew = pass(true, cc, cc.A, nullptr, Hbuf + sp * HS);
+                        nf32 = 0u;
+                        Snew = chain_pass<T, KIND, WT, LSF, true>(cc, cc.A, nullptr, Hbuf + sp * HS, basebuf, gdu, gf, gw,
+                                                                  npairs, P, lane, lsf_buf, lsf_s, taps, nf32);
+                        n_far += nf32;
                     }
+                    ++n_like;
                     accept = lu < (Scur - Snew) * half_inv_var + dprior;      // false for NaN
                     if (accept) {
                         Scur = Snew;
@@ -355,72 +406,65 @@ __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, const WarpSmem
                         }
                     }
                 }
-                if (lane == 0) {
-                    if (accept) { ws.acc[idx] += 1; if (post_burn) ws.acct[idx] += 1; ws.th[idx] = prop; }
-                    else ws.rej[idx] += 1;
+                if (++i == NP) {
+                    i = 0;
+                    ++c;
+                }
+            } else {
+                idx = sdi;
+                prop = sd + z * (double)(ws.asf[sdi] * ws.psd[sdi]);
+                if (prop > 0.0 && prop <= 1.0) {
+                    const double lprop = log(prop);
+                    const double hv = 0.5 / (prop * prop);
+                    accept = lu < -Scur * (hv - half_inv_var) - P * (lprop - logsd);
+                    if (accept) {
+                        sd = prop;
+                        logsd = lprop;
+                        half_inv_var = hv;
+                    }
                 }
             }
-            __syncwarp();
-        }
-
-        if (!WT) {
-            double z, lu;
-            rng.get(q, lane, z, lu);
-            ++q;
-            const double prop = sd + z * (double)(ws.asf[sdi] * ws.psd[sdi]);
-            bool accept = false;
-            double lprop = 0.0;
-            if (prop > 0.0 && prop <= 1.0) {
-                lprop = log(prop);
-                const double d = -Scur * (0.5 / (prop * prop) - half_inv_var) - P * (lprop - logsd);
-                accept = lu < d;
-            }
-            if (accept) {
-                sd = prop;
-                logsd = lprop;
-                half_inv_var = 0.5 / (prop * prop);
-            }
             if (lane == 0) {
-                if (accept) { ws.acc[sdi] += 1; if (post_burn) ws.acct[sdi] += 1; ws.th[sdi] = prop; }
-                else ws.rej[sdi] += 1;
+                if (accept) { ws.acc[idx] += 1; if (post_burn) ws.acct[idx] += 1; ws.th[idx] = prop; }
+                else ws.rej[idx] += 1;
             }
-            __syncwarp();
         }
+        __syncwarp();
 
         // ---- end of iteration: log-posterior of the current state
         const double lnL = WT ? (-0.5 * Scur + lognorm) : (-Scur * half_inv_var - P * (logsd + 0.91893853320467274178));
         const double logp = lnL + lp;
         if (logp > best_logp) {
             best_logp = logp;
-            for (int i = lane; i < ts; i += 32) ws.best[i] = ws.th[i];
+            for (int i2 = lane; i2 < ts; i2 += 32) ws.best[i2] = ws.th[i2];
         }
-        if (post_burn && (it % p.thin) == 0) {
+        if (post_burn && (it % thin) == 0) {
             ++ntally;
             sum_lnL += lnL;
             sum_lnL2 += lnL * lnL;
             const double inv = 1.0 / (double)ntally;
             const double wgt = (double)(ntally - 1) * inv;
-            for (int i = lane; i < 6 * n; i += 32) {          // co-moments first (need the old means)
-                const int c = i / 6, pr = i - 6 * c;
+            for (int i2 = lane; i2 < 6 * n; i2 += 32) {          // co-moments first (need the old means)
+                const int cc2 = i2 / 6, pr = i2 - 6 * cc2;
                 const int a = (pr < 3) ? 0 : (pr < 5 ? 1 : 2);
                 const int b = (pr < 3) ? pr + 1 : (pr < 5 ? pr - 1 : 3);
-                const double da = ws.th[VAMP_TH(c, a)] - ws.mean[VAMP_TH(c, a)];
-                const double db = ws.th[VAMP_TH(c, b)] - ws.mean[VAMP_TH(c, b)];
-                ws.comom[i] += wgt * da * db;
+                const double da = ws.th[VAMP_TH(cc2, a)] - ws.mean[VAMP_TH(cc2, a)];
+                const double db = ws.th[VAMP_TH(cc2, b)] - ws.mean[VAMP_TH(cc2, b)];
+                ws.comom[i2] += wgt * da * db;
             }
             __syncwarp();
-            for (int i = lane; i < ts; i += 32) {
-                const double x = ws.th[i];
-                const double d = x - ws.mean[i];
-                const double mn = ws.mean[i] + d * inv;
-                ws.mean[i] = mn;
-                ws.m2[i] += d * (x - mn);
+            for (int i2 = lane; i2 < ts; i2 += 32) {
+                const double x = ws.th[i2];
+                const double d = x - ws.mean[i2];
+                const double mn = ws.mean[i2] + d * inv;
+                ws.mean[i2] = mn;
+                ws.m2[i2] += d * (x - mn);
             }
             if (p.trace) {
                 const int slot = ntally - 1;
                 if (slot < p.trace_cap)
-                    for (int i = lane; i < ts; i += 32)
-                        p.trace[((size_t)chain * p.trace_cap + slot) * ts + i] = ws.th[i];
+                    for (int i2 = lane; i2 < ts; i2 += 32)
+                        p.trace[((size_t)chain * p.trace_cap + slot) * ts + i2] = ws.th[i2];
             }
         }
         __syncwarp();
@@ -452,9 +496,10 @@ __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, const WarpSmem
         p.sum_lnL[chain] = sum_lnL;
         p.sum_lnL2[chain] = sum_lnL2;
         if (p.work) {
-            p.work[3 * (size_t)chain + 0] += n_shape;    // component evaluations (x P pixels each)
-            p.work[3 * (size_t)chain + 1] += n_far;      // of their pixels: far-path ones
-            p.work[3 * (size_t)chain + 2] += n_like;     // exp(-tau) + residual passes (x P pixels)
+            const unsigned long long pads = (unsigned long long)(64 * npairs - P);   // padding pixels are always "far"
+            p.work[3 * (size_t)chain + 0] += n_shape;               // component evaluations (x P pixels each)
+            p.work[3 * (size_t)chain + 1] += n_far - n_shape * pads; // of their pixels: far-path ones
+            p.work[3 * (size_t)chain + 2] += n_like;                // exp(-tau) + residual passes (x P pixels)
         }
     }
 }
@@ -473,12 +518,11 @@ __host__ __device__ inline size_t k2_warp_bytes(int ppl_max, int ncomp_max, int 
     return b;
 }
 
-template <typename T, int KIND, bool WT>
-__global__ void __launch_bounds__(K2_WARPS * 32, (sizeof(T) == 4) ? 7 : 3)
+template <typename T, int KIND, bool WT, bool LSF>
+__global__ void __launch_bounds__(K2_WARPS * 32, (sizeof(T) == 4) ? 5 : 3)
 k2_mcmc_kernel(McmcDev p, int ppl_max, int ncomp_max) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const bool LSF = p.rs.lsf_taps > 1;
     T* lsf_s = reinterpret_cast<T*>(smem_raw);
     const size_t head = align16(sizeof(T) * VAMP_MAX_LSF_TAPS);
     if (LSF) {
@@ -508,7 +552,7 @@ k2_mcmc_kernel(McmcDev p, int ppl_max, int ncomp_max) {
     T* basebuf = Hbuf + (size_t)(ncomp_max + 1) * HS;           // [HS]
     base += align16(sizeof(T) * (size_t)(ncomp_max + 2) * HS);
     T* lsf_buf = reinterpret_cast<T*>(base);
-    mcmc_chain<T, KIND, WT>(p, chain, lane, ws, Hbuf, basebuf, lsf_buf, lsf_s, HS);
+    mcmc_chain<T, KIND, WT, LSF>(p, chain, lane, ws, Hbuf, basebuf, lsf_buf, lsf_s, HS);
 }
 
 // ---- initial states -------------------------------------------------------------------------
@@ -565,12 +609,11 @@ __global__ void init_state_kernel(McmcDev p) {
     p.sum_lnL2[chain] = 0.0;
 }
 
-template <typename T, int KIND, bool WT>
+template <typename T, int KIND, bool WT, bool LSF>
 cudaError_t launch_k2_t(const McmcDev& p, int max_npix, int max_ncomp, cudaStream_t st) {
-    const bool LSF = p.rs.lsf_taps > 1;
-    const int ppl_max = max_npix <= 32 ? 1 : (max_npix <= 64 ? 2 : (max_npix <= 128 ? 4 : 8));
+    const int ppl_max = 2 * ((max_npix + 63) / 64);          // rows, in pairs of 32-pixel rows
     const size_t smem = align16(sizeof(T) * VAMP_MAX_LSF_TAPS) + K2_WARPS * k2_warp_bytes<T>(ppl_max, max_ncomp, p.cmax, LSF);
-    auto kern = k2_mcmc_kernel<T, KIND, WT>;
+    auto kern = k2_mcmc_kernel<T, KIND, WT, LSF>;
     if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -600,6 +643,10 @@ cudaError_t vamp_launch_init_state(const McmcDev& p, cudaStream_t st) {
 cudaError_t VAMP_INST_NAME(vamp_launch_k2)(const McmcDev& p, int max_npix, int max_ncomp, cudaStream_t st) {
     if (p.B <= 0 || p.it1 <= p.it0) return cudaSuccess;
     if (max_npix > VAMP_TILE_PIX) return cudaErrorInvalidValue;
-    return p.sd_free ? launch_k2_t<InstT, InstKind, false>(p, max_npix, max_ncomp, st)
-                     : launch_k2_t<InstT, InstKind, true>(p, max_npix, max_ncomp, st);
+    const bool lsf = p.rs.lsf_taps > 1;
+    if (p.sd_free)
+        return lsf ? launch_k2_t<InstT, InstKind, false, true>(p, max_npix, max_ncomp, st)
+                   : launch_k2_t<InstT, InstKind, false, false>(p, max_npix, max_ncomp, st);
+    return lsf ? launch_k2_t<InstT, InstKind, true, true>(p, max_npix, max_ncomp, st)
+               : launch_k2_t<InstT, InstKind, true, false>(p, max_npix, max_ncomp, st);
 }
