@@ -103,10 +103,10 @@ __device__ __forceinline__ CompC<T> make_comp_fast(double A, double c, double w1
     cc.A = T(A);
     cc.cb = T(c - ubase);
     if (KIND == VAMP_KIND_GAUSS) {
-        cc.g = T(0.84932180028801904272) / T(w1);
+        cc.g = T(0.84932180028801904272) * Real<T>::rcp(T(w1));
         cc.y = cc.y2 = cc.L2 = T(0);
     } else {
-        const T ig = T(1) / T(w2);
+        const T ig = Real<T>::rcp(T(w2));
         cc.g = fmin(T(1.66510922231539551270) * ig, Fad<T>::BIG());
         cc.y = fmin(T(0.83255461115769775635) * T(w1) * ig, Fad<T>::BIG());
         cc.y2 = cc.y * cc.y;
@@ -144,6 +144,35 @@ __device__ __forceinline__ T row_shape(const CompC<T>& cc, T du, unsigned& nfar)
     return h;
 }
 
+// Two rows at once.  When both rows take the same path (the common case) their two dependent
+// Horner / continued-fraction chains sit in one basic block and interleave (ILP 2).
+template <typename T, int KIND>
+__device__ __forceinline__ void row_shape2(const CompC<T>& cc, T du0, T du1, T& H0, T& H1, unsigned& nfar) {
+    if (KIND == VAMP_KIND_GAUSS) {
+        const T q0 = (du0 - cc.cb) * cc.g, q1 = (du1 - cc.cb) * cc.g;
+        H0 = Real<T>::exp2_neg(q0 * q0);
+        H1 = Real<T>::exp2_neg(q1 * q1);
+        return;
+    }
+    const T d0 = du0 - cc.cb, d1 = du1 - cc.cb;
+    const T x0 = d0 * cc.g, x1 = d1 * cc.g;
+    const T s0 = Real<T>::fma_(x0, x0, cc.y2), s1 = Real<T>::fma_(x1, x1, cc.y2);
+    const bool far0 = !(s0 < Fad<T>::R2()), far1 = !(s1 < Fad<T>::R2());
+    const unsigned m0 = __ballot_sync(VAMP_FULL_MASK, far0), m1 = __ballot_sync(VAMP_FULL_MASK, far1);
+    nfar += __popc(m0) + __popc(m1);
+    if ((m0 | m1) == 0u) {
+        H0 = fad_core<T>(x0, cc.y, s0);
+        H1 = fad_core<T>(x1, cc.y, s1);
+    } else if ((m0 & m1) == VAMP_FULL_MASK && !__any_sync(VAMP_FULL_MASK, !(fmax(s0, s1) < Fad<T>::FAR2()))) {
+        H0 = fad_far<T>(x0, cc.y, s0);
+        H1 = fad_far<T>(x1, cc.y, s1);
+    } else {
+        unsigned dummy = 0u;
+        H0 = row_shape<T, KIND>(cc, du0, dummy);
+        H1 = row_shape<T, KIND>(cc, du1, dummy);
+    }
+}
+
 // One likelihood pass over the region, two rows (64 pixels) per trip, nothing masked: the
 // region arrays and the shared-memory rows are padded to 64 pixels with neutral values.
 // FRESH: evaluate the component `cc` and store its shape to Hdst; else read the shape from Hsrc.
@@ -166,8 +195,7 @@ __device__ __forceinline__ double chain_pass(const CompC<T>& cc, T A, const T* _
         T H0, H1;
         if (FRESH) {
             const T du0 = __ldg(pu), du1 = __ldg(pu + 32);
-            H0 = row_shape<T, KIND>(cc, du0, nfar);
-            H1 = row_shape<T, KIND>(cc, du1, nfar);
+            row_shape2<T, KIND>(cc, du0, du1, H0, H1, nfar);
             pd[0] = H0;
             pd[32] = H1;
             pu += 64;
@@ -353,13 +381,22 @@ __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, const WarpSmem
                 if (i == 0) {
                     // new component: base = tau of the others, rebuilt from the cache (no drift)
                     __syncwarp();
-                    for (int j = 0; j < 2 * npairs; ++j) basebuf[j * 32 + lane] = T(0);
-                    for (int c2 = 0; c2 < n; ++c2) {
-                        if (c2 == c) continue;
-                        const T A2 = T(ws.th[VAMP_TH(c2, 0)]);
-                        const T* Hs = Hbuf + slot_of(c2) * HS + lane;
-                        T* bb = basebuf + lane;
-                        for (int j = 0; j < 2 * npairs; ++j) bb[j * 32] = Real<T>::fma_(A2, Hs[j * 32], bb[j * 32]);
+                    T* bb = basebuf + lane;
+                    if (c == 0) {
+                        // once per iteration: rebuild from the cache, so rounding never accumulates
+                        for (int j = 0; j < 2 * npairs; ++j) bb[j * 32] = T(0);
+                        for (int c2 = 1; c2 < n; ++c2) {
+                            const T A2 = T(ws.th[VAMP_TH(c2, 0)]);
+                            const T* Hs = Hbuf + slot_of(c2) * HS + lane;
+                            for (int j = 0; j < 2 * npairs; ++j) bb[j * 32] = Real<T>::fma_(A2, Hs[j * 32], bb[j * 32]);
+                        }
+                    } else {
+                        // next component: base += tau_{c-1} - tau_c  (two FMAs per pixel instead of n - 1)
+                        const T Ap = T(ws.th[VAMP_TH(c - 1, 0)]), Ac = T(ws.th[idx]);
+                        const T* Hp = Hbuf + slot_of(c - 1) * HS + lane;
+                        const T* Hn = Hbuf + slot_of(c) * HS + lane;
+                        for (int j = 0; j < 2 * npairs; ++j)
+                            bb[j * 32] = Real<T>::fma_(-Ac, Hn[j * 32], Real<T>::fma_(Ap, Hp[j * 32], bb[j * 32]));
                     }
                     pA = ws.th[idx];
                     pc = ws.th[idx + 1];
@@ -379,7 +416,7 @@ __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, const WarpSmem
                     if (i == 0) {
                         Snew = chain_pass<T, KIND, WT, LSF, false>(cz, T(prop), Hbuf + sc * HS, nullptr, basebuf, gdu, gf,
                                                                    gw, npairs, P, lane, lsf_buf, lsf_s, taps, nf32);
-                        dprior = (double)real_log<T>(prop / pA) - (prop - pA);
+                        dprior = (double)real_log<T>((double)(T(prop) * Real<T>::rcp(T(pA)))) - (prop - pA);
                     } else {
                         const CompC<T> cc = make_comp_fast<T, KIND>(pA, (i == 1) ? prop : pc, (i == 2) ? prop : pw1,
                                                                     (i == 3) ? prop : pw2, ubase);
@@ -424,9 +461,17 @@ __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, const WarpSmem
                     }
                 }
             }
-            if (lane == 0) {
-                if (accept) { ws.acc[idx] += 1; if (post_burn) ws.acct[idx] += 1; ws.th[idx] = prop; }
-                else ws.rej[idx] += 1;
+            {   // counters and state: every lane computes, lane 0 stores (no divergent branch)
+                const int na = ws.acc[idx] + (accept ? 1 : 0);
+                const int nr = ws.rej[idx] + (accept ? 0 : 1);
+                const int nt = ws.acct[idx] + ((accept && post_burn) ? 1 : 0);
+                const double nv = accept ? prop : ws.th[idx];
+                if (lane == 0) {
+                    ws.acc[idx] = na;
+                    ws.rej[idx] = nr;
+                    ws.acct[idx] = nt;
+                    ws.th[idx] = nv;
+                }
             }
         }
         __syncwarp();
