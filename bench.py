@@ -132,7 +132,7 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    iters = 40
+    iters = 150
     for _ in range(args.warmup if args.warmup < 2 else 1):
         reference_sample(cores, 5)
     t_steps, ev = [], 0

@@ -255,6 +255,8 @@ int vamp_regions_create(vamp_ctx* ctx, int R, const int* npix, const double* nu,
     const long long NP = poff, NT = toff;
     std::vector<float> du32(NP, 0.f), f32(NP, 1.f), w32(NP, 0.f);
     std::vector<double> du64(NP, 0.0), f64(NP, 1.0), w64(NP, 0.0), ubase(NT, 0.0), lognorm(R, 0.0);
+    std::vector<float> duf32(2 * NP);
+    std::vector<double> duf64(2 * NP);
     src = 0;
     for (int r = 0; r < R; ++r) {
         const int P = npix[r];
@@ -297,6 +299,10 @@ int vamp_regions_create(vamp_ctx* ctx, int R, const int* npix, const double* nu,
         lognorm[r] = ln - 0.5 * (double)P * std::log(2.0 * M_PI);
         src += P;
     }
+    for (long long i = 0; i < NP; ++i) {
+        duf32[2 * i] = du32[i]; duf32[2 * i + 1] = f32[i];
+        duf64[2 * i] = du64[i]; duf64[2 * i + 1] = f64[i];
+    }
     std::vector<float> l32(lsf_taps > 0 ? lsf_taps : 1, 1.f);
     std::vector<double> l64(lsf_taps > 0 ? lsf_taps : 1, 1.0);
     for (int i = 0; i < lsf_taps; ++i) { l64[i] = lsf[i]; l32[i] = (float)lsf[i]; }
@@ -313,6 +319,8 @@ int vamp_regions_create(vamp_ctx* ctx, int R, const int* npix, const double* nu,
     const size_t o_du64 = o; o += al(sizeof(double) * NP);
     const size_t o_f64 = o; o += al(sizeof(double) * NP);
     const size_t o_w64 = o; o += al(sizeof(double) * NP);
+    const size_t o_duf32 = o; o += al(sizeof(float) * 2 * NP);
+    const size_t o_duf64 = o; o += al(sizeof(double) * 2 * NP);
     const size_t o_ub = o; o += al(sizeof(double) * NT);
     const size_t o_ln = o; o += al(sizeof(double) * R);
     const size_t o_l32 = o; o += al(sizeof(float) * l32.size());
@@ -335,6 +343,8 @@ int vamp_regions_create(vamp_ctx* ctx, int R, const int* npix, const double* nu,
     VAMP_UP(o_du64, du64.data(), sizeof(double) * NP);
     VAMP_UP(o_f64, f64.data(), sizeof(double) * NP);
     VAMP_UP(o_w64, w64.data(), sizeof(double) * NP);
+    VAMP_UP(o_duf32, duf32.data(), sizeof(float) * 2 * NP);
+    VAMP_UP(o_duf64, duf64.data(), sizeof(double) * 2 * NP);
     VAMP_UP(o_ub, ubase.data(), sizeof(double) * NT);
     VAMP_UP(o_ln, lognorm.data(), sizeof(double) * R);
     VAMP_UP(o_l32, l32.data(), sizeof(float) * l32.size());
@@ -353,6 +363,8 @@ int vamp_regions_create(vamp_ctx* ctx, int R, const int* npix, const double* nu,
     d.du64 = reinterpret_cast<double*>(base + o_du64);
     d.f64 = reinterpret_cast<double*>(base + o_f64);
     d.w64 = reinterpret_cast<double*>(base + o_w64);
+    d.duf32 = reinterpret_cast<float2*>(base + o_duf32);
+    d.duf64 = reinterpret_cast<double2*>(base + o_duf64);
     d.ubase = reinterpret_cast<double*>(base + o_ub);
     d.lognorm = reinterpret_cast<double*>(base + o_ln);
     d.lsf32 = reinterpret_cast<float*>(base + o_l32);

@@ -39,6 +39,8 @@ struct RegionSetDev {
     const double* du64;
     const double* f64;
     const double* w64;
+    const float2* duf32;    // [Ppad] (du, flux) interleaved: one 8-byte load per pixel in the chain kernel
+    const double2* duf64;
     const double* ubase;    // [tiles] scaled coordinate of each tile's base
     const double* lognorm;  // [R]   sum_i ln(1/noise_i) - P/2 ln(2 pi)
     const float* lsf32;     // [taps] or nullptr
@@ -52,12 +54,16 @@ template <> struct RS<float> {
     static __device__ __forceinline__ const float* f(const RegionSetDev& r) { return r.f32; }
     static __device__ __forceinline__ const float* w(const RegionSetDev& r) { return r.w32; }
     static __device__ __forceinline__ const float* lsf(const RegionSetDev& r) { return r.lsf32; }
+    typedef float2 Pair;
+    static __device__ __forceinline__ const float2* duf(const RegionSetDev& r) { return r.duf32; }
 };
 template <> struct RS<double> {
     static __device__ __forceinline__ const double* du(const RegionSetDev& r) { return r.du64; }
     static __device__ __forceinline__ const double* f(const RegionSetDev& r) { return r.f64; }
     static __device__ __forceinline__ const double* w(const RegionSetDev& r) { return r.w64; }
     static __device__ __forceinline__ const double* lsf(const RegionSetDev& r) { return r.lsf64; }
+    typedef double2 Pair;
+    static __device__ __forceinline__ const double2* duf(const RegionSetDev& r) { return r.duf64; }
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -75,12 +81,17 @@ template <> struct Real<float> {
         asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
         return r;
     }
+    // exp(-tau) as exp_scaled(NEGK * tau): the chain kernel keeps tau pre-multiplied by NEGK
+    static __device__ __forceinline__ float NEGK() { return -1.4426950408889634f; }
+    static __device__ __forceinline__ float exp_scaled(float v) { return ex2(v); }
     static __device__ __forceinline__ float exp_neg(float t) { return ex2(-1.4426950408889634f * t); }
     static __device__ __forceinline__ float exp2_neg(float t) { return ex2(-t); }
     static __device__ __forceinline__ float fma_(float a, float b, float c) { return fmaf(a, b, c); }
 };
 template <> struct Real<double> {
     static __device__ __forceinline__ double rcp(double x) { return 1.0 / x; }
+    static __device__ __forceinline__ double NEGK() { return -1.0; }
+    static __device__ __forceinline__ double exp_scaled(double v) { return exp(v); }
     static __device__ __forceinline__ double exp_neg(double t) { return exp(-t); }
     static __device__ __forceinline__ double exp2_neg(double t) { return exp2(-t); }
     static __device__ __forceinline__ double fma_(double a, double b, double c) { return fma(a, b, c); }
@@ -100,7 +111,7 @@ __device__ __forceinline__ T warp_sum(T v) {
 //   vfar  : pure Lorentzian L^2/(L^2+4d^2) once |z|^2 >= FAR2 (also catches G -> 0 overflow)
 // Measured max |H - H_wofz| over the plane: 4.4e-7 (fp32), 7e-15 (fp64)  (tests/test_faddeeva*.py).
 // Hand-counted algorithmic flops per evaluation (FMA = 2), used by bench.py's roofline:
-//   fp32 core 113 + 1 MUFU, fp32 far 47 + 2 MUFU;  fp64 core 273, fp64 far 103.
+//   see vamp_b200/flops.py (fp32: core 71, far 51; fp64: core 151, far 110).
 #include "faddeeva_tables.inc"
 
 template <typename T> struct Fad;
@@ -127,24 +138,32 @@ template <> struct Fad<double> {
     static __device__ __forceinline__ double BIG() { return 1.0e150; }
 };
 
-// H for |z|^2 < R2 : Weideman.  s = x^2 + y^2.
+// H for |z|^2 < R2 (valid over the whole upper half plane): Weideman.  s = x^2 + y^2.
+// p(Z) has REAL coefficients, so it is evaluated with the real second-order recurrence
+//   b_k = c_k + t b_{k+1} - n b_{k+2},  t = 2 Re Z, n = |Z|^2,   p(Z) = b_1 Z + c_0 - n b_2
+// (division of p by (W - Z)(W - conj Z)): 2 FMAs per coefficient instead of the 4 of a complex
+// Horner step, and a dependent chain of one FMA per step.  Same accuracy (tests/test_k1_gpu.py).
 template <typename T>
 __device__ __forceinline__ T fad_core(T x, T y, T s) {
     const T L = Fad<T>::L();
     const T r = Real<T>::rcp(s + (T(2) * L) * y + L * L);        // 1/|L - iz|^2
     const T Zr = (L * L - s) * r;
     const T Zi = (T(2) * L) * x * r;
-    T pr = Fad<T>::a(0), pi = T(0);
+    const T t = Zr + Zr;
+    const T n = Real<T>::fma_(Zr, Zr, Zi * Zi);
+    T b1 = Fad<T>::a(0), b2 = T(0);                                // a(j) = c_{N-1-j}
 #pragma unroll
-    for (int k = 1; k < Fad<T>::N; ++k) {
-        const T nr = Real<T>::fma_(pr, Zr, Real<T>::fma_(-pi, Zi, Fad<T>::a(k)));
-        pi = Real<T>::fma_(pr, Zi, pi * Zr);
-        pr = nr;
+    for (int j = 1; j < Fad<T>::N - 1; ++j) {
+        const T nb = Real<T>::fma_(t, b1, Real<T>::fma_(-n, b2, Fad<T>::a(j)));
+        b2 = b1;
+        b1 = nb;
     }
+    const T pr = Real<T>::fma_(b1, Zr, Real<T>::fma_(-n, b2, Fad<T>::a(Fad<T>::N - 1)));
+    const T pi = b1 * Zi;
     const T ir = (L + y) * r, ii = x * r;                          // 1/(L - iz)
     const T i2r = ir * ir - ii * ii, i2i = T(2) * ir * ii;
-    const T rew = T(2) * (pr * i2r - pi * i2i) + T(0.56418958354775628695) * ir;
-    return T(1.77245385090551602730) * y * rew;
+    const T q = pr * i2r - pi * i2i;                               // Re(p / (L - iz)^2)
+    return y * Real<T>::fma_(T(3.54490770181103205460), q, ir);    // sqrt(pi) y (2 q + ir / sqrt(pi))
 }
 
 // H for R2 <= |z|^2 < FAR2 : continued fraction in t = 1/z, v = t^2.
@@ -256,6 +275,98 @@ __device__ __forceinline__ void comp_shape(const CompC<T>& cc, const T (&du)[PPL
     for (int j = 0; j < PPL; ++j) vm[j] = 0u;
     unsigned nfar = 0u;
     comp_shape_c<T, KIND, PPL, false>(cc, du, H, vm, nfar);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Row-streaming evaluation (K2 / K3): one 32-pixel row per call, path chosen per ROW.
+// component constants with the divisions done in T (double divisions cost ~20 instructions each
+// and are executed redundantly by every lane once per scalar step)
+template <typename T, int KIND>
+__device__ __forceinline__ CompC<T> make_comp_fast(double A, double c, double w1, double w2, double ubase) {
+    CompC<T> cc;
+    cc.A = T(A);
+    cc.cb = T(c - ubase);
+    if (KIND == VAMP_KIND_GAUSS) {
+        cc.g = T(0.84932180028801904272) * Real<T>::rcp(T(w1));
+        cc.y = cc.y2 = cc.L2 = T(0);
+    } else {
+        const T ig = Real<T>::rcp(T(w2));
+        cc.g = fmin(T(1.66510922231539551270) * ig, Fad<T>::BIG());
+        cc.y = fmin(T(0.83255461115769775635) * T(w1) * ig, Fad<T>::BIG());
+        cc.y2 = cc.y * cc.y;
+        cc.L2 = T(w1) * T(w1);
+    }
+    return cc;
+}
+
+// shape of one row (32 pixels); every branch is warp-uniform and each body exists once.
+// Padding pixels (du = 1e12) take the Lorentzian limit and evaluate to exactly 0.
+template <typename T, int KIND>
+__device__ __forceinline__ T row_shape(const CompC<T>& cc, T du, unsigned& nfar) {
+    if (KIND == VAMP_KIND_GAUSS) {
+        const T q = (du - cc.cb) * cc.g;
+        return Real<T>::exp2_neg(q * q);
+    }
+    const T d = du - cc.cb;
+    const T x = d * cc.g;
+    const T s = Real<T>::fma_(x, x, cc.y2);
+    const bool far = !(s < Fad<T>::R2());
+    const unsigned m = __ballot_sync(VAMP_FULL_MASK, far);
+    const bool vfar = !(s < Fad<T>::FAR2());
+    if (__any_sync(VAMP_FULL_MASK, vfar)) {
+        // overflow guard (padding pixels, G -> 0): per-lane select of all three forms
+        nfar += __popc(m);
+        const T d2 = T(2) * d;
+        const T lor = cc.L2 * Real<T>::rcp(Real<T>::fma_(d2, d2, cc.L2));
+        const T hf = fad_far<T>(x, cc.y, vfar ? Fad<T>::R2() : s);
+        const T hc = fad_core<T>(far ? T(0) : x, cc.y, far ? T(0) : s);
+        return vfar ? lor : (far ? hf : hc);
+    }
+    if (m == VAMP_FULL_MASK) {
+        nfar += 32u;
+        return fad_far<T>(x, cc.y, s);
+    }
+    // mixed rows: the Weideman form is valid over the whole plane, so the row takes it as a whole
+    return fad_core<T>(x, cc.y, s);
+}
+
+// Two rows at once.  When both rows take the same path (the common case) their two dependent
+// Horner / continued-fraction chains sit in one basic block and interleave (ILP 2).
+template <typename T, int KIND>
+__device__ __forceinline__ void row_shape2(const CompC<T>& cc, T du0, T du1, T& H0, T& H1, unsigned& nfar) {
+    if (KIND == VAMP_KIND_GAUSS) {
+        const T q0 = (du0 - cc.cb) * cc.g, q1 = (du1 - cc.cb) * cc.g;
+        H0 = Real<T>::exp2_neg(q0 * q0);
+        H1 = Real<T>::exp2_neg(q1 * q1);
+        return;
+    }
+    const T d0 = du0 - cc.cb, d1 = du1 - cc.cb;
+    const T x0 = d0 * cc.g, x1 = d1 * cc.g;
+    const T s0 = Real<T>::fma_(x0, x0, cc.y2), s1 = Real<T>::fma_(x1, x1, cc.y2);
+    // row policy: all 32 pixels far -> continued fraction, otherwise Weideman for the whole row
+    const bool far0 = __all_sync(VAMP_FULL_MASK, !(s0 < Fad<T>::R2()));
+    const bool far1 = __all_sync(VAMP_FULL_MASK, !(s1 < Fad<T>::R2()));
+    const bool big = __any_sync(VAMP_FULL_MASK, !(fmax(s0, s1) < Fad<T>::FAR2()));
+    if (big) {
+        H0 = row_shape<T, KIND>(cc, du0, nfar);
+        H1 = row_shape<T, KIND>(cc, du1, nfar);
+    } else if (far0 && far1) {
+        nfar += 64u;
+        H0 = fad_far<T>(x0, cc.y, s0);
+        H1 = fad_far<T>(x1, cc.y, s1);
+    } else if (!far0 && !far1) {
+        H0 = fad_core<T>(x0, cc.y, s0);
+        H1 = fad_core<T>(x1, cc.y, s1);
+    } else {
+        nfar += 32u;
+        if (far0) {
+            H0 = fad_far<T>(x0, cc.y, s0);
+            H1 = fad_core<T>(x1, cc.y, s1);
+        } else {
+            H0 = fad_core<T>(x0, cc.y, s0);
+            H1 = fad_far<T>(x1, cc.y, s1);
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -95,130 +95,48 @@ __device__ __forceinline__ T real_log(double x);
 template <> __device__ __forceinline__ float real_log<float>(double x) { return __logf((float)x); }
 template <> __device__ __forceinline__ double real_log<double>(double x) { return log(x); }
 
-// component constants with the divisions done in T (double divisions cost ~20 instructions each
-// and are executed redundantly by every lane once per scalar step)
-template <typename T, int KIND>
-__device__ __forceinline__ CompC<T> make_comp_fast(double A, double c, double w1, double w2, double ubase) {
-    CompC<T> cc;
-    cc.A = T(A);
-    cc.cb = T(c - ubase);
-    if (KIND == VAMP_KIND_GAUSS) {
-        cc.g = T(0.84932180028801904272) * Real<T>::rcp(T(w1));
-        cc.y = cc.y2 = cc.L2 = T(0);
-    } else {
-        const T ig = Real<T>::rcp(T(w2));
-        cc.g = fmin(T(1.66510922231539551270) * ig, Fad<T>::BIG());
-        cc.y = fmin(T(0.83255461115769775635) * T(w1) * ig, Fad<T>::BIG());
-        cc.y2 = cc.y * cc.y;
-        cc.L2 = T(w1) * T(w1);
-    }
-    return cc;
-}
-
-// shape of one row (32 pixels); every branch is warp-uniform and each body exists once.
-// Padding pixels (du = 1e12) take the Lorentzian limit and evaluate to exactly 0.
-template <typename T, int KIND>
-__device__ __forceinline__ T row_shape(const CompC<T>& cc, T du, unsigned& nfar) {
-    if (KIND == VAMP_KIND_GAUSS) {
-        const T q = (du - cc.cb) * cc.g;
-        return Real<T>::exp2_neg(q * q);
-    }
-    const T d = du - cc.cb;
-    const T x = d * cc.g;
-    const T s = Real<T>::fma_(x, x, cc.y2);
-    const bool far = !(s < Fad<T>::R2());
-    const unsigned m = __ballot_sync(VAMP_FULL_MASK, far);
-    nfar += __popc(m);
-    T h = T(0);
-    if (m != VAMP_FULL_MASK) h = fad_core<T>(x, cc.y, far ? T(0) : s);
-    if (m != 0u) {
-        T hf = fad_far<T>(x, cc.y, s);
-        const bool vfar = !(s < Fad<T>::FAR2());
-        if (__any_sync(VAMP_FULL_MASK, vfar)) {
-            const T d2 = T(2) * d;
-            const T lor = cc.L2 * Real<T>::rcp(Real<T>::fma_(d2, d2, cc.L2));
-            hf = vfar ? lor : hf;
-        }
-        h = far ? hf : h;
-    }
-    return h;
-}
-
-// Two rows at once.  When both rows take the same path (the common case) their two dependent
-// Horner / continued-fraction chains sit in one basic block and interleave (ILP 2).
-template <typename T, int KIND>
-__device__ __forceinline__ void row_shape2(const CompC<T>& cc, T du0, T du1, T& H0, T& H1, unsigned& nfar) {
-    if (KIND == VAMP_KIND_GAUSS) {
-        const T q0 = (du0 - cc.cb) * cc.g, q1 = (du1 - cc.cb) * cc.g;
-        H0 = Real<T>::exp2_neg(q0 * q0);
-        H1 = Real<T>::exp2_neg(q1 * q1);
-        return;
-    }
-    const T d0 = du0 - cc.cb, d1 = du1 - cc.cb;
-    const T x0 = d0 * cc.g, x1 = d1 * cc.g;
-    const T s0 = Real<T>::fma_(x0, x0, cc.y2), s1 = Real<T>::fma_(x1, x1, cc.y2);
-    const bool far0 = !(s0 < Fad<T>::R2()), far1 = !(s1 < Fad<T>::R2());
-    const unsigned m0 = __ballot_sync(VAMP_FULL_MASK, far0), m1 = __ballot_sync(VAMP_FULL_MASK, far1);
-    nfar += __popc(m0) + __popc(m1);
-    if ((m0 | m1) == 0u) {
-        H0 = fad_core<T>(x0, cc.y, s0);
-        H1 = fad_core<T>(x1, cc.y, s1);
-    } else if ((m0 & m1) == VAMP_FULL_MASK && !__any_sync(VAMP_FULL_MASK, !(fmax(s0, s1) < Fad<T>::FAR2()))) {
-        H0 = fad_far<T>(x0, cc.y, s0);
-        H1 = fad_far<T>(x1, cc.y, s1);
-    } else {
-        unsigned dummy = 0u;
-        H0 = row_shape<T, KIND>(cc, du0, dummy);
-        H1 = row_shape<T, KIND>(cc, du1, dummy);
-    }
-}
-
 // One likelihood pass over the region, two rows (64 pixels) per trip, nothing masked: the
 // region arrays and the shared-memory rows are padded to 64 pixels with neutral values.
 // FRESH: evaluate the component `cc` and store its shape to Hdst; else read the shape from Hsrc.
-// Returns sum (f - m)^2 (WT: noise-weighted) of m = exp(-(base + A*H)) [convolved with the LSF].
+// `An` and `basebuf` are pre-multiplied by NEGK (-log2(e) in fp32) so m = ex2(fma(An, H, base)).
+// Returns sum (f - m)^2 (WT: noise-weighted) of m = exp(-(tau_others + A*H)) [convolved with the LSF].
 template <typename T, int KIND, bool WT, bool LSF, bool FRESH>
-__device__ __forceinline__ double chain_pass(const CompC<T>& cc, T A, const T* __restrict__ Hsrc, T* __restrict__ Hdst,
-                                             const T* __restrict__ basebuf, const T* __restrict__ gdu,
-                                             const T* __restrict__ gf, const T* __restrict__ gw, int npairs, int P, int lane,
+__device__ __forceinline__ double chain_pass(const CompC<T>& cc, T An, const T* __restrict__ Hsrc, T* __restrict__ Hdst,
+                                             const T* __restrict__ basebuf, const typename RS<T>::Pair* __restrict__ gduf,
+                                             const T* __restrict__ gw, int npairs, int P, int lane,
                                              T* lsf_buf, const T* lsf_s, int taps, unsigned& nfar) {
+    typedef typename RS<T>::Pair Pair;
     T S0 = T(0), S1 = T(0);
-    const T* pb = basebuf + lane;
-    const T* ps = Hsrc + lane;
-    T* pd = Hdst + lane;
-    const T* pu = gdu + lane;
-    const T* pf = gf + lane;
-    const T* pw = gw + lane;
-    T* pl = lsf_buf + (taps >> 1) + lane;
+    int o = lane;                                   // element offset of row 0 of the current pair
+    T* pl = lsf_buf + (taps >> 1);
 #pragma unroll 1
-    for (int jj = 0; jj < npairs; ++jj) {
-        T H0, H1;
+    for (int jj = 0; jj < npairs; ++jj, o += 64) {
+        T H0, H1, f0, f1;
         if (FRESH) {
-            const T du0 = __ldg(pu), du1 = __ldg(pu + 32);
-            row_shape2<T, KIND>(cc, du0, du1, H0, H1, nfar);
-            pd[0] = H0;
-            pd[32] = H1;
-            pu += 64;
-            pd += 64;
+            const Pair v0 = __ldg(gduf + o), v1 = __ldg(gduf + o + 32);
+            f0 = v0.y;
+            f1 = v1.y;
+            row_shape2<T, KIND>(cc, v0.x, v1.x, H0, H1, nfar);
+            Hdst[o] = H0;
+            Hdst[o + 32] = H1;
         } else {
-            H0 = ps[0];
-            H1 = ps[32];
-            ps += 64;
+            H0 = Hsrc[o];
+            H1 = Hsrc[o + 32];
+            if (!LSF) {
+                f0 = __ldg(&gduf[o].y);
+                f1 = __ldg(&gduf[o + 32].y);
+            }
         }
-        const T m0 = Real<T>::exp_neg(Real<T>::fma_(A, H0, pb[0]));
-        const T m1 = Real<T>::exp_neg(Real<T>::fma_(A, H1, pb[32]));
-        pb += 64;
+        const T m0 = Real<T>::exp_scaled(Real<T>::fma_(An, H0, basebuf[o]));
+        const T m1 = Real<T>::exp_scaled(Real<T>::fma_(An, H1, basebuf[o + 32]));
         if (LSF) {
-            pl[0] = m0 - T(1);
-            pl[32] = m1 - T(1);
-            pl += 64;
+            pl[o] = m0 - T(1);
+            pl[o + 32] = m1 - T(1);
         } else {
-            T r0 = __ldg(pf) - m0, r1 = __ldg(pf + 32) - m1;
-            pf += 64;
+            T r0 = f0 - m0, r1 = f1 - m1;
             if (WT) {
-                r0 *= __ldg(pw);
-                r1 *= __ldg(pw + 32);
-                pw += 64;
+                r0 *= __ldg(gw + o);
+                r1 *= __ldg(gw + o + 32);
             }
             S0 = Real<T>::fma_(r0, r0, S0);
             S1 = Real<T>::fma_(r1, r1, S1);
@@ -228,19 +146,16 @@ __device__ __forceinline__ double chain_pass(const CompC<T>& cc, T A, const T* _
         const int h = taps >> 1;
         for (int i = lane; i < 2 * h; i += 32) lsf_buf[(i < h) ? i : (64 * npairs + i)] = T(0);
         __syncwarp();
-        pf = gf + lane;
-        pw = gw + lane;
         const T* bq = lsf_buf + lane + 2 * h;
         for (int j = 0; j < 2 * npairs; ++j) {
             T acc = T(1);
             for (int t = 0; t < taps; ++t) acc = Real<T>::fma_(lsf_s[t], bq[-t], acc);
             // the convolution leaks into the padding pixels next to the region edge: mask them
-            T rr = (j * 32 + lane < P) ? (__ldg(pf) - acc) : T(0);
-            if (WT) rr *= __ldg(pw);
+            const int px = j * 32 + lane;
+            T rr = (px < P) ? (__ldg(&gduf[px].y) - acc) : T(0);
+            if (WT) rr *= __ldg(gw + px);
             S0 = Real<T>::fma_(rr, rr, S0);
             bq += 32;
-            pf += 32;
-            pw += 32;
         }
         __syncwarp();
     }
@@ -267,8 +182,9 @@ __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, const WarpSmem
     const double c_hi = (double)(P - 1);
     const double w_hi = 0.5 * (double)(P - 1) * (KIND == VAMP_KIND_VOIGT ? FWHM_PER_SIGMA : 1.0);
     const T* __restrict__ gdu = RS<T>::du(rs) + rs.pix_off[r];
-    const T* __restrict__ gf = RS<T>::f(rs) + rs.pix_off[r];
+    const typename RS<T>::Pair* __restrict__ gduf = RS<T>::duf(rs) + rs.pix_off[r];
     const T* __restrict__ gw = RS<T>::w(rs) + rs.pix_off[r];
+    const T NK = Real<T>::NEGK();
 
     // ---- state -> shared
     const size_t gb = (size_t)chain * ts;
@@ -309,7 +225,7 @@ __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, const WarpSmem
                 const int px = j * 32 + lane;
                 const T H = row_shape<T, KIND>(cc, __ldg(gdu + px), dummy);
                 Hd[px] = H;
-                basebuf[px] = Real<T>::fma_(cc.A, H, basebuf[px]);
+                basebuf[px] = Real<T>::fma_(NK * cc.A, H, basebuf[px]);
             }
         }
         T* Hspare = Hbuf + slot_of(n) * HS;
@@ -317,7 +233,7 @@ __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, const WarpSmem
         // base holds the full tau here: one cached pass with A = 0 gives the current S
     }
     unsigned nf32 = 0u;
-    double Scur = chain_pass<T, KIND, WT, LSF, false>(cz, T(0), Hbuf + slot_of(n) * HS, nullptr, basebuf, gdu, gf, gw,
+    double Scur = chain_pass<T, KIND, WT, LSF, false>(cz, T(0), Hbuf + slot_of(n) * HS, nullptr, basebuf, gduf, gw,
                                                       npairs, P, lane, lsf_buf, lsf_s, taps, nf32);
     double sd = WT ? 1.0 : ws.th[sdi];
     double logsd = WT ? 0.0 : log(sd);
@@ -336,7 +252,9 @@ __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, const WarpSmem
         rng.k0 = (uint32_t)p.seed;
         rng.k1 = (uint32_t)(p.seed >> 32);
     }
-    unsigned long long q = (unsigned long long)p.it0 * (unsigned long long)k;
+    // step counter q = 64 * qblk + qslot; a (normal, log-uniform) pair per step
+    unsigned long long qblk = ((unsigned long long)p.it0 * (unsigned long long)k) >> 6;
+    int qslot = (int)(((unsigned long long)p.it0 * (unsigned long long)k) & 63ull);
     bool need_fill = true;                 // (re)fill at the first step and whenever a 64-step block starts
 
     for (int it = p.it0; it < p.it1; ++it) {
@@ -360,19 +278,22 @@ __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, const WarpSmem
 #pragma unroll 1
         for (int st = 0; st < k; ++st) {
             // ---- one (normal, log-uniform) pair; the only RNG call site of the kernel
-            if (need_fill || (q & 63ull) == 0ull) {
-                rng.refill(q >> 6, lane);
+            if (need_fill) {
+                rng.refill(qblk, lane);
                 need_fill = false;
             }
             double z, lu;
             {
-                const int slot = (int)(q & 63ull);
-                const double zs = (slot & 1) ? rng.z1 : rng.z0;
-                const double ls = (slot & 1) ? rng.lu1 : rng.lu0;
-                z = __shfl_sync(VAMP_FULL_MASK, zs, slot >> 1);
-                lu = __shfl_sync(VAMP_FULL_MASK, ls, slot >> 1);
+                const double zs = (qslot & 1) ? rng.z1 : rng.z0;
+                const double ls = (qslot & 1) ? rng.lu1 : rng.lu0;
+                z = __shfl_sync(VAMP_FULL_MASK, zs, qslot >> 1);
+                lu = __shfl_sync(VAMP_FULL_MASK, ls, qslot >> 1);
             }
-            ++q;
+            if (++qslot == 64) {
+                qslot = 0;
+                ++qblk;
+                need_fill = true;
+            }
             bool accept = false;
             int idx;
             double prop;
@@ -386,13 +307,13 @@ __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, const WarpSmem
                         // once per iteration: rebuild from the cache, so rounding never accumulates
                         for (int j = 0; j < 2 * npairs; ++j) bb[j * 32] = T(0);
                         for (int c2 = 1; c2 < n; ++c2) {
-                            const T A2 = T(ws.th[VAMP_TH(c2, 0)]);
+                            const T A2 = NK * T(ws.th[VAMP_TH(c2, 0)]);
                             const T* Hs = Hbuf + slot_of(c2) * HS + lane;
                             for (int j = 0; j < 2 * npairs; ++j) bb[j * 32] = Real<T>::fma_(A2, Hs[j * 32], bb[j * 32]);
                         }
                     } else {
                         // next component: base += tau_{c-1} - tau_c  (two FMAs per pixel instead of n - 1)
-                        const T Ap = T(ws.th[VAMP_TH(c - 1, 0)]), Ac = T(ws.th[idx]);
+                        const T Ap = NK * T(ws.th[VAMP_TH(c - 1, 0)]), Ac = NK * T(ws.th[idx]);
                         const T* Hp = Hbuf + slot_of(c - 1) * HS + lane;
                         const T* Hn = Hbuf + slot_of(c) * HS + lane;
                         for (int j = 0; j < 2 * npairs; ++j)
@@ -414,7 +335,7 @@ __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, const WarpSmem
                     double dprior = 0.0, Snew;
                     const int sc = slot_of(c), sp = slot_of(n);
                     if (i == 0) {
-                        Snew = chain_pass<T, KIND, WT, LSF, false>(cz, T(prop), Hbuf + sc * HS, nullptr, basebuf, gdu, gf,
+                        Snew = chain_pass<T, KIND, WT, LSF, false>(cz, NK * T(prop), Hbuf + sc * HS, nullptr, basebuf, gduf,
                                                                    gw, npairs, P, lane, lsf_buf, lsf_s, taps, nf32);
                         dprior = (double)real_log<T>((double)(T(prop) * Real<T>::rcp(T(pA)))) - (prop - pA);
                     } else {
@@ -422,7 +343,7 @@ __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, const WarpSmem
                                                                     (i == 3) ? prop : pw2, ubase);
                         ++n_shape;
                         nf32 = 0u;
-                        Snew = chain_pass<T, KIND, WT, LSF, true>(cc, cc.A, nullptr, Hbuf + sp * HS, basebuf, gdu, gf, gw,
+                        Snew = chain_pass<T, KIND, WT, LSF, true>(cc, NK * cc.A, nullptr, Hbuf + sp * HS, basebuf, gduf, gw,
                                                                   npairs, P, lane, lsf_buf, lsf_s, taps, nf32);
                         n_far += nf32;
                     }

@@ -4,15 +4,17 @@ Used by ``bench.py`` for ``roofline.achieved`` and stated in DESIGN.md section 5
 ncu ``smsp__sass_thread_inst_executed_op_{fadd,fmul,ffma}_pred_on`` (profiles/).
 Counts follow ``vamp_b200/csrc/vamp_device.cuh`` line by line.
 
-fp32 ``fad_core`` (Weideman N = 12), per pixel:
+fp32 ``fad_core`` (Weideman N = 12, real second-order recurrence), per pixel:
     r = rcp(s + 2L*y + L*L)            FMA + ADD + MUFU           = 4
     Zr = (L*L - s) * r                 ADD + MUL                  = 2
     Zi = 2L * x * r                    2 MUL                      = 2
-    11 Horner steps (2 FMA, MUL, FMA)  11 * 7                     = 77
+    t = 2 Zr, n = |Z|^2                ADD, MUL + FMA             = 4
+    10 recurrence steps (2 FMA)        10 * 4                     = 40
+    pr (2 FMA), pi (MUL)                                          = 5
     ir, ii                             ADD + 2 MUL                = 3
     i2r, i2i                           MUL + FMA, 2 MUL           = 5
-    rew, H                             MUL, FMA, MUL, FMA, 2 MUL  = 9
-                                                                   ---- 102
+    q, H                               MUL + FMA, FMA + MUL       = 6
+                                                                   ---- 71
 fp32 ``fad_far`` (4-level continued fraction):
     rs, tr, ti                         MUFU + 2 MUL               = 3
     vr, vi                             MUL + FMA, 2 MUL           = 5
@@ -21,14 +23,14 @@ fp32 ``fad_far`` (4-level continued fraction):
     |D|^2, rcp, -y*imq*rcp             MUL + FMA + MUFU + 2 MUL   = 6
                                                                    ---- 51
 common per shape pixel: d = du - cb, x = d*g, s = fma(x,x,y2)     = 4
-per likelihood pixel:  tau = fma(A,H,base), exp2(-c*tau) (MUL+MUFU), r = f - m, S = fma(r,r,S)  = 7
+per likelihood pixel:  v = fma(An,H,base) (tau pre-scaled by -log2 e), ex2 (MUFU), r = f - m, S = fma(r,r,S)  = 6
     (+ 1 for the noise weight, + 2 per LSF tap)
-fp64: same structure with N = 32 (31 Horner steps) and 9 CF levels (4 + 5 Horner steps); the
+fp64: same structure with N = 32 (30 recurrence steps) and 9 CF levels (4 + 5 Horner steps); the
     reciprocal and exp are multi-instruction sequences, counted as 10 and 30 flops.
 """
 
-F32 = {"core": 102.0, "far": 51.0, "shape_common": 4.0, "like": 7.0}
-F64 = {"core": 4 + 2 + 2 + 31 * 7 + 3 + 5 + 9 + 9, "far": 3 + 5 + 9 * 7 + 9 + 6 + 18, "shape_common": 4.0,
+F32 = {"core": 71.0, "far": 51.0, "shape_common": 4.0, "like": 6.0}
+F64 = {"core": 13 + 2 + 2 + 4 + 30 * 4 + 5 + 3 + 5 + 6, "far": 3 + 5 + 9 * 7 + 9 + 6 + 18, "shape_common": 4.0,
        "like": 36.0}
 GAUSS = {"shape": 5.0}      # d, q = d*g, q*q, exp2 (MUFU): SUB + MUL + MUL + MUFU + neg
 
