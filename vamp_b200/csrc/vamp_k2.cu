@@ -25,10 +25,14 @@
 namespace {
 
 constexpr int K2_WARPS = 4;
+#ifndef VAMP_K2_MINBLOCKS
+#define VAMP_K2_MINBLOCKS 6
+#endif
 constexpr double FWHM_PER_SIGMA = 2.35482004503094938202;
 
+template <typename T>
 struct WarpRng {
-    double z0, z1, lu0, lu1;
+    T z0, z1, lu0, lu1;      // kept in the kernel's precision: half the registers in the fp32 kernel
     uint32_t uid_lo, uid_hi, k0, k1;
     __device__ __forceinline__ void refill(unsigned long long blk, int lane) {
         const uint4 x = philox4x32_10(make_uint4(uid_lo, uid_hi, (uint32_t)blk, ((uint32_t)(blk >> 32) << 8) | (uint32_t)lane),
@@ -36,19 +40,10 @@ struct WarpRng {
         const double rad = sqrt(-2.0 * log(u01(x.x)));
         double sn, cs;
         sincospi(2.0 * u01(x.y), &sn, &cs);
-        z0 = rad * cs;
-        z1 = rad * sn;
-        lu0 = log(u01(x.z));
-        lu1 = log(u01(x.w));
-    }
-    // normal deviate and log-uniform of step q (warp-uniform result)
-    __device__ __forceinline__ void get(unsigned long long q, int lane, double& z, double& lu) {
-        if ((q & 63ull) == 0ull) refill(q >> 6, lane);
-        const int slot = (int)(q & 63ull);
-        const double zs = (slot & 1) ? z1 : z0;
-        const double ls = (slot & 1) ? lu1 : lu0;
-        z = __shfl_sync(VAMP_FULL_MASK, zs, slot >> 1);
-        lu = __shfl_sync(VAMP_FULL_MASK, ls, slot >> 1);
+        z0 = T(rad * cs);
+        z1 = T(rad * sn);
+        lu0 = T(log(u01(x.z)));
+        lu1 = T(log(u01(x.w)));
     }
 };
 
@@ -74,6 +69,8 @@ struct WarpSmem {          // pointers into this warp's shared-memory slice
     int* acc;
     int* rej;
     int* acct;
+    double* sc;                  // [0] best_logp, [1] sum_lnL, [2] sum_lnL2
+    unsigned long long* cnt;     // [0] shape evaluations, [1] far-path pixels, [2] likelihood passes
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -178,9 +175,6 @@ __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, const WarpSmem
     const int npairs = (P + 63) >> 6;
     const int tune_interval = p.tune_interval, thin = p.thin, burn = p.burn, tune_throughout = p.tune_throughout;
     const double ubase = rs.ubase[rs.tile_off[r]];
-    const double lognorm = rs.lognorm[r];
-    const double c_hi = (double)(P - 1);
-    const double w_hi = 0.5 * (double)(P - 1) * (KIND == VAMP_KIND_VOIGT ? FWHM_PER_SIGMA : 1.0);
     const T* __restrict__ gdu = RS<T>::du(rs) + rs.pix_off[r];
     const typename RS<T>::Pair* __restrict__ gduf = RS<T>::duf(rs) + rs.pix_off[r];
     const T* __restrict__ gw = RS<T>::w(rs) + rs.pix_off[r];
@@ -190,22 +184,22 @@ __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, const WarpSmem
     const size_t gb = (size_t)chain * ts;
     for (int i = lane; i < ts; i += 32) {
         ws.th[i] = p.theta[gb + i];
-        ws.best[i] = p.best_theta[gb + i];
-        ws.mean[i] = p.mean[gb + i];
-        ws.m2[i] = p.m2[gb + i];
         ws.asf[i] = p.asf[gb + i];
         ws.psd[i] = p.psd[gb + i];
         ws.acc[i] = p.acc[gb + i];
         ws.rej[i] = p.rej[gb + i];
         ws.acct[i] = p.acc_total[gb + i];
     }
-    for (int i = lane; i < 6 * p.cmax; i += 32) ws.comom[i] = p.comom[(size_t)chain * 6 * p.cmax + i];
-    double best_logp = p.best_logp[chain];
+    if (lane == 0) {
+        ws.sc[0] = p.best_logp[chain];
+        ws.sc[1] = p.sum_lnL[chain];
+        ws.sc[2] = p.sum_lnL2[chain];
+        ws.cnt[0] = ws.cnt[1] = ws.cnt[2] = 0ull;
+    }
     int ntally = p.ntally[chain];
-    double sum_lnL = p.sum_lnL[chain], sum_lnL2 = p.sum_lnL2[chain];
     __syncwarp();
 
-    unsigned long long n_far = 0ull, n_shape = 0ull, n_like = 0ull;
+    unsigned n_far = 0u, n_shape = 0u, n_like = 0u;      // per iteration; flushed to ws.cnt
     // slot table: component c's shape lives in Hbuf[slot(c)*HS ...]; slot n is the spare one
     unsigned long long slots = 0ull;
     for (int c = 0; c <= n; ++c) slots |= (unsigned long long)c << (4 * c);
@@ -244,7 +238,7 @@ __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, const WarpSmem
         lp += log(a) - a;
     }
 
-    WarpRng rng;
+    WarpRng<T> rng;
     {
         const unsigned long long uid = p.chain_uid[chain];
         rng.uid_lo = (uint32_t)uid;
@@ -284,10 +278,10 @@ __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, const WarpSmem
             }
             double z, lu;
             {
-                const double zs = (qslot & 1) ? rng.z1 : rng.z0;
-                const double ls = (qslot & 1) ? rng.lu1 : rng.lu0;
-                z = __shfl_sync(VAMP_FULL_MASK, zs, qslot >> 1);
-                lu = __shfl_sync(VAMP_FULL_MASK, ls, qslot >> 1);
+                const T zs = (qslot & 1) ? rng.z1 : rng.z0;
+                const T ls = (qslot & 1) ? rng.lu1 : rng.lu0;
+                z = (double)__shfl_sync(VAMP_FULL_MASK, zs, qslot >> 1);
+                lu = (double)__shfl_sync(VAMP_FULL_MASK, ls, qslot >> 1);
             }
             if (++qslot == 64) {
                 qslot = 0;
@@ -326,6 +320,8 @@ __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, const WarpSmem
                 }
                 const double cur = (i == 0) ? pA : (i == 1) ? pc : (i == 2) ? pw1 : pw2;
                 prop = cur + z * (double)(ws.asf[idx] * ws.psd[idx]);
+                const double c_hi = (double)(P - 1);
+                const double w_hi = c_hi * (KIND == VAMP_KIND_VOIGT ? 0.5 * FWHM_PER_SIGMA : 0.5);
                 bool ok;
                 if (i == 0) ok = prop > 0.0;
                 else if (i == 1) ok = (prop >= 0.0) && (prop <= c_hi);
@@ -398,16 +394,28 @@ __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, const WarpSmem
         __syncwarp();
 
         // ---- end of iteration: log-posterior of the current state
-        const double lnL = WT ? (-0.5 * Scur + lognorm) : (-Scur * half_inv_var - P * (logsd + 0.91893853320467274178));
+        const double lnL = WT ? (-0.5 * Scur + rs.lognorm[r])
+                              : (-Scur * half_inv_var - P * (logsd + 0.91893853320467274178));
         const double logp = lnL + lp;
-        if (logp > best_logp) {
-            best_logp = logp;
+        const bool better = logp > ws.sc[0];
+        const bool tally = post_burn && (it % thin) == 0;
+        __syncwarp();
+        if (lane == 0) {
+            if (better) ws.sc[0] = logp;
+            if (tally) {
+                ws.sc[1] += lnL;
+                ws.sc[2] += lnL * lnL;
+            }
+            ws.cnt[0] += n_shape;
+            ws.cnt[1] += n_far - n_shape * (unsigned)(64 * npairs - P);   // padding pixels always count as far
+            ws.cnt[2] += n_like;
+        }
+        n_shape = n_far = n_like = 0u;
+        if (better) {
             for (int i2 = lane; i2 < ts; i2 += 32) ws.best[i2] = ws.th[i2];
         }
-        if (post_burn && (it % thin) == 0) {
+        if (tally) {
             ++ntally;
-            sum_lnL += lnL;
-            sum_lnL2 += lnL * lnL;
             const double inv = 1.0 / (double)ntally;
             const double wgt = (double)(ntally - 1) * inv;
             for (int i2 = lane; i2 < 6 * n; i2 += 32) {          // co-moments first (need the old means)
@@ -439,17 +447,13 @@ __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, const WarpSmem
     // ---- state -> global
     for (int i = lane; i < ts; i += 32) {
         p.theta[gb + i] = ws.th[i];
-        p.best_theta[gb + i] = ws.best[i];
-        p.mean[gb + i] = ws.mean[i];
-        p.m2[gb + i] = ws.m2[i];
         p.asf[gb + i] = ws.asf[i];
         p.acc[gb + i] = ws.acc[i];
         p.rej[gb + i] = ws.rej[i];
         p.acc_total[gb + i] = ws.acct[i];
     }
-    for (int i = lane; i < 6 * p.cmax; i += 32) p.comom[(size_t)chain * 6 * p.cmax + i] = ws.comom[i];
     if (lane == 0) {
-        const double lnL = WT ? lnL_noise(Scur, lognorm) : lnL_sd(Scur, sd, P);
+        const double lnL = WT ? lnL_noise(Scur, rs.lognorm[r]) : lnL_sd(Scur, sd, P);
         double lpx = 0.0;
         for (int c = 0; c < n; ++c) {
             const double a = ws.th[VAMP_TH(c, 0)];
@@ -457,15 +461,14 @@ __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, const WarpSmem
         }
         p.lnL[chain] = lnL;
         p.logp[chain] = lnL + lpx;
-        p.best_logp[chain] = best_logp;
+        p.best_logp[chain] = ws.sc[0];
         p.ntally[chain] = ntally;
-        p.sum_lnL[chain] = sum_lnL;
-        p.sum_lnL2[chain] = sum_lnL2;
+        p.sum_lnL[chain] = ws.sc[1];
+        p.sum_lnL2[chain] = ws.sc[2];
         if (p.work) {
-            const unsigned long long pads = (unsigned long long)(64 * npairs - P);   // padding pixels are always "far"
-            p.work[3 * (size_t)chain + 0] += n_shape;               // component evaluations (x P pixels each)
-            p.work[3 * (size_t)chain + 1] += n_far - n_shape * pads; // of their pixels: far-path ones
-            p.work[3 * (size_t)chain + 2] += n_like;                // exp(-tau) + residual passes (x P pixels)
+            p.work[3 * (size_t)chain + 0] += ws.cnt[0];    // component evaluations (x P pixels each)
+            p.work[3 * (size_t)chain + 1] += ws.cnt[1];    // pixels of far-path rows (padding rows excluded below)
+            p.work[3 * (size_t)chain + 2] += ws.cnt[2];    // exp(-tau) + residual passes (x P pixels)
         }
     }
 }
@@ -476,7 +479,7 @@ template <typename T>
 __host__ __device__ inline size_t k2_warp_bytes(int ppl_max, int ncomp_max, int cmax, bool lsf) {
     const int ts = 4 * cmax + 1;
     size_t b = 0;
-    b += align16(sizeof(double) * (4 * ts + 6 * cmax));       // th, best, mean, m2, comom
+    b += align16(sizeof(double) * (ts + 6));                  // th, sc[3], cnt[3]
     b += align16(sizeof(float) * 2 * ts);                      // asf, psd
     b += align16(sizeof(int) * 3 * ts);                        // acc, rej, acct
     b += align16(sizeof(T) * (size_t)(ncomp_max + 2) * 32 * ppl_max); // shape cache (+ spare slot) + base
@@ -485,7 +488,7 @@ __host__ __device__ inline size_t k2_warp_bytes(int ppl_max, int ncomp_max, int 
 }
 
 template <typename T, int KIND, bool WT, bool LSF>
-__global__ void __launch_bounds__(K2_WARPS * 32, (sizeof(T) == 4) ? 5 : 3)
+__global__ void __launch_bounds__(K2_WARPS * 32, (sizeof(T) == 4) ? VAMP_K2_MINBLOCKS : 3)
 k2_mcmc_kernel(McmcDev p, int ppl_max, int ncomp_max) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -501,11 +504,15 @@ k2_mcmc_kernel(McmcDev p, int ppl_max, int ncomp_max) {
     unsigned char* base = smem_raw + head + (size_t)warp * k2_warp_bytes<T>(ppl_max, ncomp_max, p.cmax, LSF);
     WarpSmem ws;
     ws.th = reinterpret_cast<double*>(base);
-    ws.best = ws.th + ts;
-    ws.mean = ws.best + ts;
-    ws.m2 = ws.mean + ts;
-    ws.comom = ws.m2 + ts;
-    base += align16(sizeof(double) * (4 * ts + 6 * p.cmax));
+    ws.sc = ws.th + ts;
+    ws.cnt = reinterpret_cast<unsigned long long*>(ws.sc + 3);
+    base += align16(sizeof(double) * (ts + 6));
+    // best state and tally statistics are touched rarely (improvements, every `thin` iterations):
+    // they stay in global memory so that more chains fit on an SM
+    ws.best = p.best_theta + (size_t)chain * ts;
+    ws.mean = p.mean + (size_t)chain * ts;
+    ws.m2 = p.m2 + (size_t)chain * ts;
+    ws.comom = p.comom + (size_t)chain * 6 * p.cmax;
     ws.asf = reinterpret_cast<float*>(base);
     ws.psd = ws.asf + ts;
     base += align16(sizeof(float) * 2 * ts);
