@@ -255,8 +255,8 @@ int vamp_regions_create(vamp_ctx* ctx, int R, const int* npix, const double* nu,
     const long long NP = poff, NT = toff;
     std::vector<float> du32(NP, 0.f), f32(NP, 1.f), w32(NP, 0.f);
     std::vector<double> du64(NP, 0.0), f64(NP, 1.0), w64(NP, 0.0), ubase(NT, 0.0), lognorm(R, 0.0);
-    std::vector<float> duf32(2 * NP);
-    std::vector<double> duf64(2 * NP);
+    std::vector<float> pdu32(NP), pf32(NP), pw32(NP);      // pair layout (see RegionSetDev)
+    std::vector<double> pdu64(NP), pf64(NP), pw64(NP);
     src = 0;
     for (int r = 0; r < R; ++r) {
         const int P = npix[r];
@@ -300,8 +300,11 @@ int vamp_regions_create(vamp_ctx* ctx, int R, const int* npix, const double* nu,
         src += P;
     }
     for (long long i = 0; i < NP; ++i) {
-        duf32[2 * i] = du32[i]; duf32[2 * i + 1] = f32[i];
-        duf64[2 * i] = du64[i]; duf64[2 * i + 1] = f64[i];
+        // natural pixel i = 64*jj + 32*h + lane  ->  pair element (32*jj + lane), half h
+        const long long jj = i / 64, h = (i / 32) & 1, lane = i & 31;
+        const long long e = 2 * (32 * jj + lane) + h;
+        pdu32[e] = du32[i]; pf32[e] = f32[i]; pw32[e] = w32[i];
+        pdu64[e] = du64[i]; pf64[e] = f64[i]; pw64[e] = w64[i];
     }
     std::vector<float> l32(lsf_taps > 0 ? lsf_taps : 1, 1.f);
     std::vector<double> l64(lsf_taps > 0 ? lsf_taps : 1, 1.0);
@@ -319,8 +322,12 @@ int vamp_regions_create(vamp_ctx* ctx, int R, const int* npix, const double* nu,
     const size_t o_du64 = o; o += al(sizeof(double) * NP);
     const size_t o_f64 = o; o += al(sizeof(double) * NP);
     const size_t o_w64 = o; o += al(sizeof(double) * NP);
-    const size_t o_duf32 = o; o += al(sizeof(float) * 2 * NP);
-    const size_t o_duf64 = o; o += al(sizeof(double) * 2 * NP);
+    const size_t o_pdu32 = o; o += al(sizeof(float) * NP);
+    const size_t o_pf32 = o; o += al(sizeof(float) * NP);
+    const size_t o_pw32 = o; o += al(sizeof(float) * NP);
+    const size_t o_pdu64 = o; o += al(sizeof(double) * NP);
+    const size_t o_pf64 = o; o += al(sizeof(double) * NP);
+    const size_t o_pw64 = o; o += al(sizeof(double) * NP);
     const size_t o_ub = o; o += al(sizeof(double) * NT);
     const size_t o_ln = o; o += al(sizeof(double) * R);
     const size_t o_l32 = o; o += al(sizeof(float) * l32.size());
@@ -343,8 +350,12 @@ int vamp_regions_create(vamp_ctx* ctx, int R, const int* npix, const double* nu,
     VAMP_UP(o_du64, du64.data(), sizeof(double) * NP);
     VAMP_UP(o_f64, f64.data(), sizeof(double) * NP);
     VAMP_UP(o_w64, w64.data(), sizeof(double) * NP);
-    VAMP_UP(o_duf32, duf32.data(), sizeof(float) * 2 * NP);
-    VAMP_UP(o_duf64, duf64.data(), sizeof(double) * 2 * NP);
+    VAMP_UP(o_pdu32, pdu32.data(), sizeof(float) * NP);
+    VAMP_UP(o_pf32, pf32.data(), sizeof(float) * NP);
+    VAMP_UP(o_pw32, pw32.data(), sizeof(float) * NP);
+    VAMP_UP(o_pdu64, pdu64.data(), sizeof(double) * NP);
+    VAMP_UP(o_pf64, pf64.data(), sizeof(double) * NP);
+    VAMP_UP(o_pw64, pw64.data(), sizeof(double) * NP);
     VAMP_UP(o_ub, ubase.data(), sizeof(double) * NT);
     VAMP_UP(o_ln, lognorm.data(), sizeof(double) * R);
     VAMP_UP(o_l32, l32.data(), sizeof(float) * l32.size());
@@ -363,8 +374,12 @@ int vamp_regions_create(vamp_ctx* ctx, int R, const int* npix, const double* nu,
     d.du64 = reinterpret_cast<double*>(base + o_du64);
     d.f64 = reinterpret_cast<double*>(base + o_f64);
     d.w64 = reinterpret_cast<double*>(base + o_w64);
-    d.duf32 = reinterpret_cast<float2*>(base + o_duf32);
-    d.duf64 = reinterpret_cast<double2*>(base + o_duf64);
+    d.pdu32 = reinterpret_cast<float2*>(base + o_pdu32);
+    d.pf32 = reinterpret_cast<float2*>(base + o_pf32);
+    d.pw32 = reinterpret_cast<float2*>(base + o_pw32);
+    d.pdu64 = reinterpret_cast<double2*>(base + o_pdu64);
+    d.pf64 = reinterpret_cast<double2*>(base + o_pf64);
+    d.pw64 = reinterpret_cast<double2*>(base + o_pw64);
     d.ubase = reinterpret_cast<double*>(base + o_ub);
     d.lognorm = reinterpret_cast<double*>(base + o_ln);
     d.lsf32 = reinterpret_cast<float*>(base + o_l32);

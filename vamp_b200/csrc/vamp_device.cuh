@@ -39,8 +39,14 @@ struct RegionSetDev {
     const double* du64;
     const double* f64;
     const double* w64;
-    const float2* duf32;    // [Ppad] (du, flux) interleaved: one 8-byte load per pixel in the chain kernel
-    const double2* duf64;
+    // pair layout for the chain kernel: element [jj*32 + lane] holds pixels (64 jj + lane, 64 jj + 32 + lane),
+    // i.e. the two rows a warp processes together, so one 8/16-byte load feeds a packed f32x2 operation
+    const float2* pdu32;    // [Ppad/2]
+    const float2* pf32;
+    const float2* pw32;
+    const double2* pdu64;
+    const double2* pf64;
+    const double2* pw64;
     const double* ubase;    // [tiles] scaled coordinate of each tile's base
     const double* lognorm;  // [R]   sum_i ln(1/noise_i) - P/2 ln(2 pi)
     const float* lsf32;     // [taps] or nullptr
@@ -55,7 +61,9 @@ template <> struct RS<float> {
     static __device__ __forceinline__ const float* w(const RegionSetDev& r) { return r.w32; }
     static __device__ __forceinline__ const float* lsf(const RegionSetDev& r) { return r.lsf32; }
     typedef float2 Pair;
-    static __device__ __forceinline__ const float2* duf(const RegionSetDev& r) { return r.duf32; }
+    static __device__ __forceinline__ const float2* pdu(const RegionSetDev& r) { return r.pdu32; }
+    static __device__ __forceinline__ const float2* pf(const RegionSetDev& r) { return r.pf32; }
+    static __device__ __forceinline__ const float2* pw(const RegionSetDev& r) { return r.pw32; }
 };
 template <> struct RS<double> {
     static __device__ __forceinline__ const double* du(const RegionSetDev& r) { return r.du64; }
@@ -63,7 +71,9 @@ template <> struct RS<double> {
     static __device__ __forceinline__ const double* w(const RegionSetDev& r) { return r.w64; }
     static __device__ __forceinline__ const double* lsf(const RegionSetDev& r) { return r.lsf64; }
     typedef double2 Pair;
-    static __device__ __forceinline__ const double2* duf(const RegionSetDev& r) { return r.duf64; }
+    static __device__ __forceinline__ const double2* pdu(const RegionSetDev& r) { return r.pdu64; }
+    static __device__ __forceinline__ const double2* pf(const RegionSetDev& r) { return r.pf64; }
+    static __device__ __forceinline__ const double2* pw(const RegionSetDev& r) { return r.pw64; }
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -278,6 +288,106 @@ __device__ __forceinline__ void comp_shape(const CompC<T>& cc, const T (&du)[PPL
 }
 
 // ------------------------------------------------------------------------------------------------
+// Two-wide values.  The chain kernel processes two 32-pixel rows together; in fp32 the pair lives
+// in one 64-bit register and every arithmetic step is ONE packed instruction (sm_100
+// fma/mul/add.rn.f32x2 -> SASS FFMA2/FMUL2/FADD2).  Measured on B200 (tools/micro/ffma2_bench.cu):
+// FFMA2 delivers the same 72-74 TFLOP/s as FFMA with half the issue slots, which is what this
+// issue-bound kernel needs.  In fp64 the pair is two doubles and the same code compiles to scalar ops.
+template <typename T> struct P2;
+template <> struct P2<float> { unsigned long long v; };
+template <> struct P2<double> { double a, b; };
+
+__device__ __forceinline__ P2<float> p2_make(float a, float b) {
+    P2<float> r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ P2<double> p2_make(double a, double b) { P2<double> r; r.a = a; r.b = b; return r; }
+template <typename T> __device__ __forceinline__ P2<T> p2_bc(T a) { return p2_make(a, a); }
+__device__ __forceinline__ float p2_lo(P2<float> x) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(x.v)); return a; }
+__device__ __forceinline__ float p2_hi(P2<float> x) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(x.v)); return b; }
+__device__ __forceinline__ double p2_lo(P2<double> x) { return x.a; }
+__device__ __forceinline__ double p2_hi(P2<double> x) { return x.b; }
+__device__ __forceinline__ P2<float> p2_from(float2 v) { return p2_make(v.x, v.y); }
+__device__ __forceinline__ P2<double> p2_from(double2 v) { return p2_make(v.x, v.y); }
+__device__ __forceinline__ P2<float> p2_fma(P2<float> a, P2<float> b, P2<float> c) {
+    P2<float> d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d.v) : "l"(a.v), "l"(b.v), "l"(c.v));
+    return d;
+}
+__device__ __forceinline__ P2<float> p2_mul(P2<float> a, P2<float> b) {
+    P2<float> d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d.v) : "l"(a.v), "l"(b.v));
+    return d;
+}
+__device__ __forceinline__ P2<float> p2_add(P2<float> a, P2<float> b) {
+    P2<float> d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d.v) : "l"(a.v), "l"(b.v));
+    return d;
+}
+__device__ __forceinline__ P2<float> p2_neg(P2<float> a) { P2<float> d; d.v = a.v ^ 0x8000000080000000ull; return d; }
+__device__ __forceinline__ P2<double> p2_fma(P2<double> a, P2<double> b, P2<double> c) { return p2_make(fma(a.a, b.a, c.a), fma(a.b, b.b, c.b)); }
+__device__ __forceinline__ P2<double> p2_mul(P2<double> a, P2<double> b) { return p2_make(a.a * b.a, a.b * b.b); }
+__device__ __forceinline__ P2<double> p2_add(P2<double> a, P2<double> b) { return p2_make(a.a + b.a, a.b + b.b); }
+__device__ __forceinline__ P2<double> p2_neg(P2<double> a) { return p2_make(-a.a, -a.b); }
+template <typename T> __device__ __forceinline__ P2<T> p2_rcp(P2<T> a) { return p2_make(Real<T>::rcp(p2_lo(a)), Real<T>::rcp(p2_hi(a))); }
+template <typename T> __device__ __forceinline__ P2<T> p2_exp_scaled(P2<T> a) { return p2_make(Real<T>::exp_scaled(p2_lo(a)), Real<T>::exp_scaled(p2_hi(a))); }
+
+// fad_core for two rows (same arithmetic as fad_core, every step one packed instruction)
+template <typename T>
+__device__ __forceinline__ P2<T> fad_core2(P2<T> X, T y, P2<T> S) {
+    const T L = Fad<T>::L();
+    const P2<T> R = p2_rcp<T>(p2_add(S, p2_bc<T>((T(2) * L) * y + L * L)));
+    const P2<T> Zr = p2_mul(p2_fma(S, p2_bc<T>(T(-1)), p2_bc<T>(L * L)), R);
+    const P2<T> Zi = p2_mul(p2_mul(X, p2_bc<T>(T(2) * L)), R);
+    const P2<T> t = p2_add(Zr, Zr);
+    const P2<T> nn = p2_neg(p2_fma(Zr, Zr, p2_mul(Zi, Zi)));          // -|Z|^2
+    P2<T> b1 = p2_bc<T>(Fad<T>::a(0)), b2 = p2_bc<T>(T(0));
+#pragma unroll
+    for (int j = 1; j < Fad<T>::N - 1; ++j) {
+        const P2<T> nb = p2_fma(t, b1, p2_fma(nn, b2, p2_bc<T>(Fad<T>::a(j))));
+        b2 = b1;
+        b1 = nb;
+    }
+    const P2<T> pr = p2_fma(b1, Zr, p2_fma(nn, b2, p2_bc<T>(Fad<T>::a(Fad<T>::N - 1))));
+    const P2<T> pi = p2_mul(b1, Zi);
+    const P2<T> ir = p2_mul(p2_bc<T>(L + y), R), ii = p2_mul(X, R);
+    const P2<T> i2r = p2_fma(ir, ir, p2_neg(p2_mul(ii, ii)));
+    const P2<T> i2i = p2_mul(p2_add(ir, ir), ii);
+    const P2<T> q = p2_fma(pr, i2r, p2_neg(p2_mul(pi, i2i)));
+    return p2_mul(p2_bc<T>(y), p2_fma(p2_bc<T>(T(3.54490770181103205460)), q, ir));
+}
+
+// fad_far for two rows
+template <typename T>
+__device__ __forceinline__ P2<T> fad_far2(P2<T> X, T y, P2<T> S) {
+    const P2<T> RS_ = p2_rcp<T>(S);
+    const P2<T> tr = p2_mul(X, RS_), ti = p2_mul(p2_bc<T>(-y), RS_);
+    const P2<T> vr = p2_fma(tr, tr, p2_neg(p2_mul(ti, ti)));
+    const P2<T> vi = p2_mul(p2_add(tr, tr), ti);
+    const P2<T> nvi = p2_neg(vi);
+    P2<T> nr = p2_bc<T>(Fad<T>::cfn(Fad<T>::CFN - 1)), ni = p2_bc<T>(T(0));
+#pragma unroll
+    for (int k = Fad<T>::CFN - 2; k >= 0; --k) {
+        const P2<T> a = p2_fma(nr, vr, p2_fma(ni, nvi, p2_bc<T>(Fad<T>::cfn(k))));
+        ni = p2_fma(nr, vi, p2_mul(ni, vr));
+        nr = a;
+    }
+    P2<T> dr = p2_bc<T>(Fad<T>::cfd(Fad<T>::CFD - 1)), di = p2_bc<T>(T(0));
+#pragma unroll
+    for (int k = Fad<T>::CFD - 2; k >= 0; --k) {
+        const P2<T> a = p2_fma(dr, vr, p2_fma(di, nvi, p2_bc<T>(Fad<T>::cfd(k))));
+        di = p2_fma(dr, vi, p2_mul(di, vr));
+        dr = a;
+    }
+    const P2<T> er = p2_fma(nr, dr, p2_mul(ni, di));
+    const P2<T> ei = p2_fma(ni, dr, p2_neg(p2_mul(nr, di)));
+    const P2<T> imq = p2_fma(tr, ei, p2_mul(ti, er));
+    const P2<T> rd = p2_rcp<T>(p2_fma(dr, dr, p2_mul(di, di)));
+    return p2_mul(p2_mul(p2_bc<T>(-y), imq), rd);
+}
+
+// ------------------------------------------------------------------------------------------------
 // Row-streaming evaluation (K2 / K3): one 32-pixel row per call, path chosen per ROW.
 // component constants with the divisions done in T (double divisions cost ~20 instructions each
 // and are executed redundantly by every lane once per scalar step)
@@ -330,43 +440,32 @@ __device__ __forceinline__ T row_shape(const CompC<T>& cc, T du, unsigned& nfar)
     return fad_core<T>(x, cc.y, s);
 }
 
-// Two rows at once.  When both rows take the same path (the common case) their two dependent
-// Horner / continued-fraction chains sit in one basic block and interleave (ILP 2).
+// Two rows at once (the chain kernel's unit of work).  Row policy: all 32 pixels far -> continued
+// fraction, otherwise Weideman for the whole row; when both rows agree the pair is evaluated packed.
 template <typename T, int KIND>
-__device__ __forceinline__ void row_shape2(const CompC<T>& cc, T du0, T du1, T& H0, T& H1, unsigned& nfar) {
+__device__ __forceinline__ P2<T> pair_shape(const CompC<T>& cc, P2<T> DU, unsigned& nfar) {
+    const P2<T> D = p2_add(DU, p2_bc<T>(-cc.cb));
+    const P2<T> X = p2_mul(D, p2_bc<T>(cc.g));
     if (KIND == VAMP_KIND_GAUSS) {
-        const T q0 = (du0 - cc.cb) * cc.g, q1 = (du1 - cc.cb) * cc.g;
-        H0 = Real<T>::exp2_neg(q0 * q0);
-        H1 = Real<T>::exp2_neg(q1 * q1);
-        return;
+        const P2<T> Q = p2_mul(X, X);
+        return p2_make(Real<T>::exp2_neg(p2_lo(Q)), Real<T>::exp2_neg(p2_hi(Q)));
     }
-    const T d0 = du0 - cc.cb, d1 = du1 - cc.cb;
-    const T x0 = d0 * cc.g, x1 = d1 * cc.g;
-    const T s0 = Real<T>::fma_(x0, x0, cc.y2), s1 = Real<T>::fma_(x1, x1, cc.y2);
-    // row policy: all 32 pixels far -> continued fraction, otherwise Weideman for the whole row
+    const P2<T> S = p2_fma(X, X, p2_bc<T>(cc.y2));
+    const T s0 = p2_lo(S), s1 = p2_hi(S);
     const bool far0 = __all_sync(VAMP_FULL_MASK, !(s0 < Fad<T>::R2()));
     const bool far1 = __all_sync(VAMP_FULL_MASK, !(s1 < Fad<T>::R2()));
     const bool big = __any_sync(VAMP_FULL_MASK, !(fmax(s0, s1) < Fad<T>::FAR2()));
-    if (big) {
-        H0 = row_shape<T, KIND>(cc, du0, nfar);
-        H1 = row_shape<T, KIND>(cc, du1, nfar);
-    } else if (far0 && far1) {
-        nfar += 64u;
-        H0 = fad_far<T>(x0, cc.y, s0);
-        H1 = fad_far<T>(x1, cc.y, s1);
-    } else if (!far0 && !far1) {
-        H0 = fad_core<T>(x0, cc.y, s0);
-        H1 = fad_core<T>(x1, cc.y, s1);
-    } else {
-        nfar += 32u;
-        if (far0) {
-            H0 = fad_far<T>(x0, cc.y, s0);
-            H1 = fad_core<T>(x1, cc.y, s1);
-        } else {
-            H0 = fad_core<T>(x0, cc.y, s0);
-            H1 = fad_far<T>(x1, cc.y, s1);
-        }
+    if (big) {          // overflow guard (padding pixels, G -> 0)
+        return p2_make(row_shape<T, KIND>(cc, p2_lo(DU), nfar), row_shape<T, KIND>(cc, p2_hi(DU), nfar));
     }
+    if (far0 && far1) {
+        nfar += 64u;
+        return fad_far2<T>(X, cc.y, S);
+    }
+    if (!far0 && !far1) return fad_core2<T>(X, cc.y, S);
+    nfar += 32u;
+    if (far0) return p2_make(fad_far<T>(p2_lo(X), cc.y, s0), fad_core<T>(p2_hi(X), cc.y, s1));
+    return p2_make(fad_core<T>(p2_lo(X), cc.y, s0), fad_far<T>(p2_hi(X), cc.y, s1));
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -26,7 +26,7 @@ namespace {
 
 constexpr int K2_WARPS = 4;
 #ifndef VAMP_K2_MINBLOCKS
-#define VAMP_K2_MINBLOCKS 6
+#define VAMP_K2_MINBLOCKS 5
 #endif
 constexpr double FWHM_PER_SIGMA = 2.35482004503094938202;
 
@@ -93,75 +93,69 @@ template <> __device__ __forceinline__ float real_log<float>(double x) { return 
 template <> __device__ __forceinline__ double real_log<double>(double x) { return log(x); }
 
 // One likelihood pass over the region, two rows (64 pixels) per trip, nothing masked: the
-// region arrays and the shared-memory rows are padded to 64 pixels with neutral values.
+// region arrays and the shared-memory rows are padded to 64 pixels with neutral values, and
+// everything is in PAIR layout (element jj*32 + lane = pixels 64 jj + lane and 64 jj + 32 + lane),
+// so the two rows travel as one packed value through loads, arithmetic and shared memory.
 // FRESH: evaluate the component `cc` and store its shape to Hdst; else read the shape from Hsrc.
 // `An` and `basebuf` are pre-multiplied by NEGK (-log2(e) in fp32) so m = ex2(fma(An, H, base)).
 // Returns sum (f - m)^2 (WT: noise-weighted) of m = exp(-(tau_others + A*H)) [convolved with the LSF].
 template <typename T, int KIND, bool WT, bool LSF, bool FRESH>
-__device__ __forceinline__ double chain_pass(const CompC<T>& cc, T An, const T* __restrict__ Hsrc, T* __restrict__ Hdst,
-                                             const T* __restrict__ basebuf, const typename RS<T>::Pair* __restrict__ gduf,
-                                             const T* __restrict__ gw, int npairs, int P, int lane,
+__device__ __forceinline__ double chain_pass(const CompC<T>& cc, T An, const P2<T>* __restrict__ Hsrc,
+                                             P2<T>* __restrict__ Hdst, const P2<T>* __restrict__ basebuf,
+                                             const typename RS<T>::Pair* __restrict__ gdu,
+                                             const typename RS<T>::Pair* __restrict__ gf,
+                                             const typename RS<T>::Pair* __restrict__ gw, int npairs, int P, int lane,
                                              T* lsf_buf, const T* lsf_s, int taps, unsigned& nfar) {
-    typedef typename RS<T>::Pair Pair;
-    T S0 = T(0), S1 = T(0);
-    int o = lane;                                   // element offset of row 0 of the current pair
-    T* pl = lsf_buf + (taps >> 1);
+    P2<T> S2 = p2_bc<T>(T(0));
+    const P2<T> A2 = p2_bc<T>(An);
+    int o = lane;                                   // pair-layout element of the current row pair
+    T* pl = lsf_buf + (taps >> 1) + lane;
 #pragma unroll 1
-    for (int jj = 0; jj < npairs; ++jj, o += 64) {
-        T H0, H1, f0, f1;
+    for (int jj = 0; jj < npairs; ++jj, o += 32) {
+        P2<T> H;
         if (FRESH) {
-            const Pair v0 = __ldg(gduf + o), v1 = __ldg(gduf + o + 32);
-            f0 = v0.y;
-            f1 = v1.y;
-            row_shape2<T, KIND>(cc, v0.x, v1.x, H0, H1, nfar);
-            Hdst[o] = H0;
-            Hdst[o + 32] = H1;
+            H = pair_shape<T, KIND>(cc, p2_from(__ldg(gdu + o)), nfar);
+            Hdst[o] = H;
         } else {
-            H0 = Hsrc[o];
-            H1 = Hsrc[o + 32];
-            if (!LSF) {
-                f0 = __ldg(&gduf[o].y);
-                f1 = __ldg(&gduf[o + 32].y);
-            }
+            H = Hsrc[o];
         }
-        const T m0 = Real<T>::exp_scaled(Real<T>::fma_(An, H0, basebuf[o]));
-        const T m1 = Real<T>::exp_scaled(Real<T>::fma_(An, H1, basebuf[o + 32]));
+        const P2<T> M = p2_exp_scaled<T>(p2_fma(A2, H, basebuf[o]));
         if (LSF) {
-            pl[o] = m0 - T(1);
-            pl[o + 32] = m1 - T(1);
+            pl[64 * jj] = p2_lo(M) - T(1);
+            pl[64 * jj + 32] = p2_hi(M) - T(1);
         } else {
-            T r0 = f0 - m0, r1 = f1 - m1;
-            if (WT) {
-                r0 *= __ldg(gw + o);
-                r1 *= __ldg(gw + o + 32);
-            }
-            S0 = Real<T>::fma_(r0, r0, S0);
-            S1 = Real<T>::fma_(r1, r1, S1);
+            P2<T> R = p2_add(p2_from(__ldg(gf + o)), p2_neg(M));
+            if (WT) R = p2_mul(R, p2_from(__ldg(gw + o)));
+            S2 = p2_fma(R, R, S2);
         }
     }
+    T S = p2_lo(S2) + p2_hi(S2);
     if (LSF) {
         const int h = taps >> 1;
         for (int i = lane; i < 2 * h; i += 32) lsf_buf[(i < h) ? i : (64 * npairs + i)] = T(0);
         __syncwarp();
         const T* bq = lsf_buf + lane + 2 * h;
+        const T* gfn = reinterpret_cast<const T*>(gf);
+        const T* gwn = reinterpret_cast<const T*>(gw);
         for (int j = 0; j < 2 * npairs; ++j) {
             T acc = T(1);
             for (int t = 0; t < taps; ++t) acc = Real<T>::fma_(lsf_s[t], bq[-t], acc);
             // the convolution leaks into the padding pixels next to the region edge: mask them
             const int px = j * 32 + lane;
-            T rr = (px < P) ? (__ldg(&gduf[px].y) - acc) : T(0);
-            if (WT) rr *= __ldg(gw + px);
-            S0 = Real<T>::fma_(rr, rr, S0);
+            const int e = 2 * (32 * (j >> 1) + lane) + (j & 1);        // natural pixel -> pair layout
+            T rr = (px < P) ? (__ldg(gfn + e) - acc) : T(0);
+            if (WT) rr *= __ldg(gwn + e);
+            S = Real<T>::fma_(rr, rr, S);
             bq += 32;
         }
         __syncwarp();
     }
-    return (double)warp_sum(S0 + S1);
+    return (double)warp_sum(S);
 }
 
 template <typename T, int KIND, bool WT, bool LSF>
-__device__ void mcmc_chain(const McmcDev& p, int chain, int lane, const WarpSmem& ws, T* Hbuf, T* basebuf, T* lsf_buf,
-                           const T* lsf_s, int HS) {
+__device__ void mcmc_chain(const McmcDev& p, int chain, int lane, const WarpSmem& ws, P2<T>* Hbuf, P2<T>* basebuf,
+                           T* lsf_buf, const T* lsf_s, int HS) {
     constexpr int NP = (KIND == VAMP_KIND_VOIGT) ? 4 : 3;
     const RegionSetDev& rs = p.rs;
     const int r = p.item_region[chain];
@@ -175,9 +169,10 @@ __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, const WarpSmem
     const int npairs = (P + 63) >> 6;
     const int tune_interval = p.tune_interval, thin = p.thin, burn = p.burn, tune_throughout = p.tune_throughout;
     const double ubase = rs.ubase[rs.tile_off[r]];
-    const T* __restrict__ gdu = RS<T>::du(rs) + rs.pix_off[r];
-    const typename RS<T>::Pair* __restrict__ gduf = RS<T>::duf(rs) + rs.pix_off[r];
-    const T* __restrict__ gw = RS<T>::w(rs) + rs.pix_off[r];
+    typedef typename RS<T>::Pair Pair;
+    const Pair* __restrict__ gdu = RS<T>::pdu(rs) + (rs.pix_off[r] >> 1);
+    const Pair* __restrict__ gf = RS<T>::pf(rs) + (rs.pix_off[r] >> 1);
+    const Pair* __restrict__ gw = RS<T>::pw(rs) + (rs.pix_off[r] >> 1);
     const T NK = Real<T>::NEGK();
 
     // ---- state -> shared
@@ -208,26 +203,27 @@ __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, const WarpSmem
     // ---- build the shape cache and the current sum of squares
     CompC<T> cz;
     cz.A = cz.cb = cz.g = cz.y = cz.y2 = cz.L2 = T(0);
-    for (int j = 0; j < 2 * npairs; ++j) basebuf[j * 32 + lane] = T(0);
+    for (int jj = 0; jj < npairs; ++jj) basebuf[jj * 32 + lane] = p2_bc<T>(T(0));
     {
         unsigned dummy = 0u;
         for (int c = 0; c < n; ++c) {
             const CompC<T> cc = make_comp<T, KIND>(ws.th[VAMP_TH(c, 0)], ws.th[VAMP_TH(c, 1)], ws.th[VAMP_TH(c, 2)],
                                                    ws.th[VAMP_TH(c, 3)], ubase);
-            T* Hd = Hbuf + slot_of(c) * HS;
-            for (int j = 0; j < 2 * npairs; ++j) {
-                const int px = j * 32 + lane;
-                const T H = row_shape<T, KIND>(cc, __ldg(gdu + px), dummy);
-                Hd[px] = H;
-                basebuf[px] = Real<T>::fma_(NK * cc.A, H, basebuf[px]);
+            P2<T>* Hd = Hbuf + slot_of(c) * HS;
+            const P2<T> A2 = p2_bc<T>(NK * cc.A);
+            for (int jj = 0; jj < npairs; ++jj) {
+                const int o = jj * 32 + lane;
+                const P2<T> H = pair_shape<T, KIND>(cc, p2_from(__ldg(gdu + o)), dummy);
+                Hd[o] = H;
+                basebuf[o] = p2_fma(A2, H, basebuf[o]);
             }
         }
-        T* Hspare = Hbuf + slot_of(n) * HS;
-        for (int j = 0; j < 2 * npairs; ++j) Hspare[j * 32 + lane] = T(0);
+        P2<T>* Hspare = Hbuf + slot_of(n) * HS;
+        for (int jj = 0; jj < npairs; ++jj) Hspare[jj * 32 + lane] = p2_bc<T>(T(0));
         // base holds the full tau here: one cached pass with A = 0 gives the current S
     }
     unsigned nf32 = 0u;
-    double Scur = chain_pass<T, KIND, WT, LSF, false>(cz, T(0), Hbuf + slot_of(n) * HS, nullptr, basebuf, gduf, gw,
+    double Scur = chain_pass<T, KIND, WT, LSF, false>(cz, T(0), Hbuf + slot_of(n) * HS, nullptr, basebuf, gdu, gf, gw,
                                                       npairs, P, lane, lsf_buf, lsf_s, taps, nf32);
     double sd = WT ? 1.0 : ws.th[sdi];
     double logsd = WT ? 0.0 : log(sd);
@@ -296,22 +292,22 @@ __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, const WarpSmem
                 if (i == 0) {
                     // new component: base = tau of the others, rebuilt from the cache (no drift)
                     __syncwarp();
-                    T* bb = basebuf + lane;
+                    P2<T>* bb = basebuf + lane;
                     if (c == 0) {
                         // once per iteration: rebuild from the cache, so rounding never accumulates
-                        for (int j = 0; j < 2 * npairs; ++j) bb[j * 32] = T(0);
+                        for (int jj = 0; jj < npairs; ++jj) bb[jj * 32] = p2_bc<T>(T(0));
                         for (int c2 = 1; c2 < n; ++c2) {
-                            const T A2 = NK * T(ws.th[VAMP_TH(c2, 0)]);
-                            const T* Hs = Hbuf + slot_of(c2) * HS + lane;
-                            for (int j = 0; j < 2 * npairs; ++j) bb[j * 32] = Real<T>::fma_(A2, Hs[j * 32], bb[j * 32]);
+                            const P2<T> A2 = p2_bc<T>(NK * T(ws.th[VAMP_TH(c2, 0)]));
+                            const P2<T>* Hs = Hbuf + slot_of(c2) * HS + lane;
+                            for (int jj = 0; jj < npairs; ++jj) bb[jj * 32] = p2_fma(A2, Hs[jj * 32], bb[jj * 32]);
                         }
                     } else {
                         // next component: base += tau_{c-1} - tau_c  (two FMAs per pixel instead of n - 1)
-                        const T Ap = NK * T(ws.th[VAMP_TH(c - 1, 0)]), Ac = NK * T(ws.th[idx]);
-                        const T* Hp = Hbuf + slot_of(c - 1) * HS + lane;
-                        const T* Hn = Hbuf + slot_of(c) * HS + lane;
-                        for (int j = 0; j < 2 * npairs; ++j)
-                            bb[j * 32] = Real<T>::fma_(-Ac, Hn[j * 32], Real<T>::fma_(Ap, Hp[j * 32], bb[j * 32]));
+                        const P2<T> Ap = p2_bc<T>(NK * T(ws.th[VAMP_TH(c - 1, 0)])), Ac = p2_bc<T>(-NK * T(ws.th[idx]));
+                        const P2<T>* Hp = Hbuf + slot_of(c - 1) * HS + lane;
+                        const P2<T>* Hn = Hbuf + slot_of(c) * HS + lane;
+                        for (int jj = 0; jj < npairs; ++jj)
+                            bb[jj * 32] = p2_fma(Ac, Hn[jj * 32], p2_fma(Ap, Hp[jj * 32], bb[jj * 32]));
                     }
                     pA = ws.th[idx];
                     pc = ws.th[idx + 1];
@@ -331,16 +327,16 @@ __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, const WarpSmem
                     double dprior = 0.0, Snew;
                     const int sc = slot_of(c), sp = slot_of(n);
                     if (i == 0) {
-                        Snew = chain_pass<T, KIND, WT, LSF, false>(cz, NK * T(prop), Hbuf + sc * HS, nullptr, basebuf, gduf,
-                                                                   gw, npairs, P, lane, lsf_buf, lsf_s, taps, nf32);
+                        Snew = chain_pass<T, KIND, WT, LSF, false>(cz, NK * T(prop), Hbuf + sc * HS, nullptr, basebuf, gdu,
+                                                                   gf, gw, npairs, P, lane, lsf_buf, lsf_s, taps, nf32);
                         dprior = (double)real_log<T>((double)(T(prop) * Real<T>::rcp(T(pA)))) - (prop - pA);
                     } else {
                         const CompC<T> cc = make_comp_fast<T, KIND>(pA, (i == 1) ? prop : pc, (i == 2) ? prop : pw1,
                                                                     (i == 3) ? prop : pw2, ubase);
                         ++n_shape;
                         nf32 = 0u;
-                        Snew = chain_pass<T, KIND, WT, LSF, true>(cc, NK * cc.A, nullptr, Hbuf + sp * HS, basebuf, gduf, gw,
-                                                                  npairs, P, lane, lsf_buf, lsf_s, taps, nf32);
+                        Snew = chain_pass<T, KIND, WT, LSF, true>(cc, NK * cc.A, nullptr, Hbuf + sp * HS, basebuf, gdu, gf,
+                                                                  gw, npairs, P, lane, lsf_buf, lsf_s, taps, nf32);
                         n_far += nf32;
                     }
                     ++n_like;
@@ -520,10 +516,10 @@ k2_mcmc_kernel(McmcDev p, int ppl_max, int ncomp_max) {
     ws.rej = ws.acc + ts;
     ws.acct = ws.rej + ts;
     base += align16(sizeof(int) * 3 * ts);
-    const int HS = 32 * ppl_max;
-    T* Hbuf = reinterpret_cast<T*>(base);                       // [(ncomp_max + 1)][HS]
-    T* basebuf = Hbuf + (size_t)(ncomp_max + 1) * HS;           // [HS]
-    base += align16(sizeof(T) * (size_t)(ncomp_max + 2) * HS);
+    const int HS = 16 * ppl_max;                                // row pairs x 32 lanes, in P2 units
+    P2<T>* Hbuf = reinterpret_cast<P2<T>*>(base);               // [(ncomp_max + 1)][HS]
+    P2<T>* basebuf = Hbuf + (size_t)(ncomp_max + 1) * HS;       // [HS]
+    base += align16(sizeof(T) * (size_t)(ncomp_max + 2) * 32 * ppl_max);
     T* lsf_buf = reinterpret_cast<T*>(base);
     mcmc_chain<T, KIND, WT, LSF>(p, chain, lane, ws, Hbuf, basebuf, lsf_buf, lsf_s, HS);
 }
