@@ -36,7 +36,7 @@ def u01(x):
 
 
 class WarpRng:
-    """Per-chain stream of (normal, log-uniform) pairs: lane l of block b owns steps 2l, 2l+1."""
+    """Per-chain stream of (normal, log-uniform) pairs: lane l of block b owns steps l and 32 + l."""
 
     def __init__(self, uid, seed):
         self.uid_lo, self.uid_hi = uid & MASK, (uid >> 32) & MASK
@@ -47,13 +47,13 @@ class WarpRng:
     def get(self, q):
         blk = q >> 6
         if blk != self.blk:
-            self.blk, self.vals = blk, []
+            self.blk, self.vals = blk, [None] * 64
             for lane in range(32):
                 x = philox4x32_10((self.uid_lo, self.uid_hi, blk & MASK, (((blk >> 32) & 0xFFFFFF) << 8) | lane), self.key)
                 rad = math.sqrt(-2.0 * math.log(u01(x[0])))
                 ang = 2.0 * u01(x[1])
-                self.vals.append((rad * math.cos(math.pi * ang), math.log(u01(x[2]))))
-                self.vals.append((rad * math.sin(math.pi * ang), math.log(u01(x[3]))))
+                self.vals[lane] = (rad * math.cos(math.pi * ang), math.log(u01(x[2])))
+                self.vals[32 + lane] = (rad * math.sin(math.pi * ang), math.log(u01(x[3])))
         return self.vals[q & 63]
 
 

@@ -293,6 +293,8 @@ __device__ __forceinline__ void comp_shape(const CompC<T>& cc, const T (&du)[PPL
 // fma/mul/add.rn.f32x2 -> SASS FFMA2/FMUL2/FADD2).  Measured on B200 (tools/micro/ffma2_bench.cu):
 // FFMA2 delivers the same 72-74 TFLOP/s as FFMA with half the issue slots, which is what this
 // issue-bound kernel needs.  In fp64 the pair is two doubles and the same code compiles to scalar ops.
+// Negations are written on the unpacked halves: ptxas folds them into the operand modifiers of the
+// consuming FFMA2/FADD2 (an XOR on the 64-bit register would cost two LOP3 each).
 template <typename T> struct P2;
 template <> struct P2<float> { unsigned long long v; };
 template <> struct P2<double> { double a, b; };
@@ -325,63 +327,77 @@ __device__ __forceinline__ P2<float> p2_add(P2<float> a, P2<float> b) {
     asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d.v) : "l"(a.v), "l"(b.v));
     return d;
 }
-__device__ __forceinline__ P2<float> p2_neg(P2<float> a) { P2<float> d; d.v = a.v ^ 0x8000000080000000ull; return d; }
+__device__ __forceinline__ P2<float> p2_sub(P2<float> a, P2<float> b) {
+    P2<float> d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d.v) : "l"(a.v), "l"(b.v));
+    return d;
+}
+__device__ __forceinline__ P2<float> p2_neg(P2<float> a) { return p2_make(-p2_lo(a), -p2_hi(a)); }
 __device__ __forceinline__ P2<double> p2_fma(P2<double> a, P2<double> b, P2<double> c) { return p2_make(fma(a.a, b.a, c.a), fma(a.b, b.b, c.b)); }
 __device__ __forceinline__ P2<double> p2_mul(P2<double> a, P2<double> b) { return p2_make(a.a * b.a, a.b * b.b); }
 __device__ __forceinline__ P2<double> p2_add(P2<double> a, P2<double> b) { return p2_make(a.a + b.a, a.b + b.b); }
+__device__ __forceinline__ P2<double> p2_sub(P2<double> a, P2<double> b) { return p2_make(a.a - b.a, a.b - b.b); }
 __device__ __forceinline__ P2<double> p2_neg(P2<double> a) { return p2_make(-a.a, -a.b); }
 template <typename T> __device__ __forceinline__ P2<T> p2_rcp(P2<T> a) { return p2_make(Real<T>::rcp(p2_lo(a)), Real<T>::rcp(p2_hi(a))); }
 template <typename T> __device__ __forceinline__ P2<T> p2_exp_scaled(P2<T> a) { return p2_make(Real<T>::exp_scaled(p2_lo(a)), Real<T>::exp_scaled(p2_hi(a))); }
 
-// fad_core for two rows (same arithmetic as fad_core, every step one packed instruction)
+// fad_core for two rows (the arithmetic of fad_core, every step one packed instruction).
+// Z = (L + iz)/(L - iz):  with R = 1/|L - iz|^2 = 1/(s + 2Ly + L^2),
+//   Re Z = (L^2 - s) R,  Im Z = 2 L x R,  |Z|^2 = (s - 2Ly + L^2) R   (no dependence on Re/Im Z).
+// 40 packed operations + 2 MUFU per pixel pair.
 template <typename T>
 __device__ __forceinline__ P2<T> fad_core2(P2<T> X, T y, P2<T> S) {
     const T L = Fad<T>::L();
-    const P2<T> R = p2_rcp<T>(p2_add(S, p2_bc<T>((T(2) * L) * y + L * L)));
-    const P2<T> Zr = p2_mul(p2_fma(S, p2_bc<T>(T(-1)), p2_bc<T>(L * L)), R);
-    const P2<T> Zi = p2_mul(p2_mul(X, p2_bc<T>(T(2) * L)), R);
+    const T L2 = L * L, twoLy = (T(2) * L) * y;
+    const P2<T> R = p2_rcp<T>(p2_add(S, p2_bc<T>(twoLy + L2)));
+    const P2<T> Zr = p2_mul(p2_sub(p2_bc<T>(L2), S), R);
+    const P2<T> XR = p2_mul(X, R);                                      // Im 1/(L - iz)
+    const P2<T> Zi = p2_mul(XR, p2_bc<T>(T(2) * L));
     const P2<T> t = p2_add(Zr, Zr);
-    const P2<T> nn = p2_neg(p2_fma(Zr, Zr, p2_mul(Zi, Zi)));          // -|Z|^2
-    P2<T> b1 = p2_bc<T>(Fad<T>::a(0)), b2 = p2_bc<T>(T(0));
+    const P2<T> nn = p2_mul(p2_sub(p2_bc<T>(twoLy - L2), S), R);        // -|Z|^2
+    P2<T> b1 = p2_fma(t, p2_bc<T>(Fad<T>::a(0)), p2_bc<T>(Fad<T>::a(1))), b2 = p2_bc<T>(Fad<T>::a(0));
 #pragma unroll
-    for (int j = 1; j < Fad<T>::N - 1; ++j) {
+    for (int j = 2; j < Fad<T>::N - 1; ++j) {
         const P2<T> nb = p2_fma(t, b1, p2_fma(nn, b2, p2_bc<T>(Fad<T>::a(j))));
         b2 = b1;
         b1 = nb;
     }
     const P2<T> pr = p2_fma(b1, Zr, p2_fma(nn, b2, p2_bc<T>(Fad<T>::a(Fad<T>::N - 1))));
     const P2<T> pi = p2_mul(b1, Zi);
-    const P2<T> ir = p2_mul(p2_bc<T>(L + y), R), ii = p2_mul(X, R);
-    const P2<T> i2r = p2_fma(ir, ir, p2_neg(p2_mul(ii, ii)));
-    const P2<T> i2i = p2_mul(p2_add(ir, ir), ii);
-    const P2<T> q = p2_fma(pr, i2r, p2_neg(p2_mul(pi, i2i)));
+    const P2<T> ir = p2_mul(p2_bc<T>(L + y), R);                        // Re 1/(L - iz)
+    const P2<T> i2r = p2_sub(p2_mul(ir, ir), p2_mul(XR, XR));
+    const P2<T> i2i = p2_mul(p2_add(ir, ir), XR);
+    const P2<T> q = p2_sub(p2_mul(pr, i2r), p2_mul(pi, i2i));           // Re(p / (L - iz)^2)
     return p2_mul(p2_bc<T>(y), p2_fma(p2_bc<T>(T(3.54490770181103205460)), q, ir));
 }
 
-// fad_far for two rows
+// fad_far for two rows: 28 (fp32) packed operations + 4 MUFU per pixel pair
 template <typename T>
 __device__ __forceinline__ P2<T> fad_far2(P2<T> X, T y, P2<T> S) {
     const P2<T> RS_ = p2_rcp<T>(S);
     const P2<T> tr = p2_mul(X, RS_), ti = p2_mul(p2_bc<T>(-y), RS_);
-    const P2<T> vr = p2_fma(tr, tr, p2_neg(p2_mul(ti, ti)));
+    const P2<T> vr = p2_sub(p2_mul(tr, tr), p2_mul(ti, ti));
     const P2<T> vi = p2_mul(p2_add(tr, tr), ti);
     const P2<T> nvi = p2_neg(vi);
-    P2<T> nr = p2_bc<T>(Fad<T>::cfn(Fad<T>::CFN - 1)), ni = p2_bc<T>(T(0));
+    // Horner in v with real coefficients; the first step has a real accumulator
+    P2<T> nr = p2_fma(p2_bc<T>(Fad<T>::cfn(Fad<T>::CFN - 1)), vr, p2_bc<T>(Fad<T>::cfn(Fad<T>::CFN - 2)));
+    P2<T> ni = p2_mul(p2_bc<T>(Fad<T>::cfn(Fad<T>::CFN - 1)), vi);
 #pragma unroll
-    for (int k = Fad<T>::CFN - 2; k >= 0; --k) {
+    for (int k = Fad<T>::CFN - 3; k >= 0; --k) {
         const P2<T> a = p2_fma(nr, vr, p2_fma(ni, nvi, p2_bc<T>(Fad<T>::cfn(k))));
         ni = p2_fma(nr, vi, p2_mul(ni, vr));
         nr = a;
     }
-    P2<T> dr = p2_bc<T>(Fad<T>::cfd(Fad<T>::CFD - 1)), di = p2_bc<T>(T(0));
+    P2<T> dr = p2_fma(p2_bc<T>(Fad<T>::cfd(Fad<T>::CFD - 1)), vr, p2_bc<T>(Fad<T>::cfd(Fad<T>::CFD - 2)));
+    P2<T> di = p2_mul(p2_bc<T>(Fad<T>::cfd(Fad<T>::CFD - 1)), vi);
 #pragma unroll
-    for (int k = Fad<T>::CFD - 2; k >= 0; --k) {
+    for (int k = Fad<T>::CFD - 3; k >= 0; --k) {
         const P2<T> a = p2_fma(dr, vr, p2_fma(di, nvi, p2_bc<T>(Fad<T>::cfd(k))));
         di = p2_fma(dr, vi, p2_mul(di, vr));
         dr = a;
     }
     const P2<T> er = p2_fma(nr, dr, p2_mul(ni, di));
-    const P2<T> ei = p2_fma(ni, dr, p2_neg(p2_mul(nr, di)));
+    const P2<T> ei = p2_sub(p2_mul(ni, dr), p2_mul(nr, di));
     const P2<T> imq = p2_fma(tr, ei, p2_mul(ti, er));
     const P2<T> rd = p2_rcp<T>(p2_fma(dr, dr, p2_mul(di, di)));
     return p2_mul(p2_mul(p2_bc<T>(-y), imq), rd);
@@ -390,21 +406,27 @@ __device__ __forceinline__ P2<T> fad_far2(P2<T> X, T y, P2<T> S) {
 // ------------------------------------------------------------------------------------------------
 // Row-streaming evaluation (K2 / K3): one 32-pixel row per call, path chosen per ROW.
 // component constants with the divisions done in T (double divisions cost ~20 instructions each
-// and are executed redundantly by every lane once per scalar step)
+// and are executed redundantly by every lane once per scalar step).  g and y are clamped so
+// that the padding coordinate (1e12) never overflows x^2 + y^2: a Gaussian FWHM below
+// 1.7e-6 px (fp32) is a delta function between pixels either way.
+template <typename T> struct PadClamp;
+template <> struct PadClamp<float> { static __device__ __forceinline__ float g() { return 1.0e6f; } static __device__ __forceinline__ float y() { return 1.0e9f; } };
+template <> struct PadClamp<double> { static __device__ __forceinline__ double g() { return 1.0e100; } static __device__ __forceinline__ double y() { return 1.0e100; } };
+
 template <typename T, int KIND>
-__device__ __forceinline__ CompC<T> make_comp_fast(double A, double c, double w1, double w2, double ubase) {
+__device__ __forceinline__ CompC<T> make_comp_fast(T A, T cb, T w1, T w2) {
     CompC<T> cc;
-    cc.A = T(A);
-    cc.cb = T(c - ubase);
+    cc.A = A;
+    cc.cb = cb;
     if (KIND == VAMP_KIND_GAUSS) {
-        cc.g = T(0.84932180028801904272) * Real<T>::rcp(T(w1));
+        cc.g = fmin(T(0.84932180028801904272) * Real<T>::rcp(w1), PadClamp<T>::g());
         cc.y = cc.y2 = cc.L2 = T(0);
     } else {
-        const T ig = Real<T>::rcp(T(w2));
-        cc.g = fmin(T(1.66510922231539551270) * ig, Fad<T>::BIG());
-        cc.y = fmin(T(0.83255461115769775635) * T(w1) * ig, Fad<T>::BIG());
+        const T ig = Real<T>::rcp(w2);
+        cc.g = fmin(T(1.66510922231539551270) * ig, PadClamp<T>::g());
+        cc.y = fmin(T(0.83255461115769775635) * w1 * ig, PadClamp<T>::y());
         cc.y2 = cc.y * cc.y;
-        cc.L2 = T(w1) * T(w1);
+        cc.L2 = w1 * w1;
     }
     return cc;
 }
@@ -440,32 +462,22 @@ __device__ __forceinline__ T row_shape(const CompC<T>& cc, T du, unsigned& nfar)
     return fad_core<T>(x, cc.y, s);
 }
 
-// Two rows at once (the chain kernel's unit of work).  Row policy: all 32 pixels far -> continued
-// fraction, otherwise Weideman for the whole row; when both rows agree the pair is evaluated packed.
+// Two rows at once (the chain kernel's unit of work).  Pair policy: all 64 pixels far -> continued
+// fraction, otherwise Weideman (valid over the whole upper half plane) for the pair.  No overflow
+// guard: make_comp_fast clamps g and y, so padding pixels give H ~ 1e-18 (exp(-tau) = 1 exactly).
+// `far` returns the path taken (for the work counters).
 template <typename T, int KIND>
-__device__ __forceinline__ P2<T> pair_shape(const CompC<T>& cc, P2<T> DU, unsigned& nfar) {
-    const P2<T> D = p2_add(DU, p2_bc<T>(-cc.cb));
-    const P2<T> X = p2_mul(D, p2_bc<T>(cc.g));
+__device__ __forceinline__ P2<T> pair_shape(const CompC<T>& cc, P2<T> DU, bool& far) {
+    const P2<T> X = p2_mul(p2_sub(DU, p2_bc<T>(cc.cb)), p2_bc<T>(cc.g));
     if (KIND == VAMP_KIND_GAUSS) {
         const P2<T> Q = p2_mul(X, X);
+        far = false;
         return p2_make(Real<T>::exp2_neg(p2_lo(Q)), Real<T>::exp2_neg(p2_hi(Q)));
     }
     const P2<T> S = p2_fma(X, X, p2_bc<T>(cc.y2));
-    const T s0 = p2_lo(S), s1 = p2_hi(S);
-    const bool far0 = __all_sync(VAMP_FULL_MASK, !(s0 < Fad<T>::R2()));
-    const bool far1 = __all_sync(VAMP_FULL_MASK, !(s1 < Fad<T>::R2()));
-    const bool big = __any_sync(VAMP_FULL_MASK, !(fmax(s0, s1) < Fad<T>::FAR2()));
-    if (big) {          // overflow guard (padding pixels, G -> 0)
-        return p2_make(row_shape<T, KIND>(cc, p2_lo(DU), nfar), row_shape<T, KIND>(cc, p2_hi(DU), nfar));
-    }
-    if (far0 && far1) {
-        nfar += 64u;
-        return fad_far2<T>(X, cc.y, S);
-    }
-    if (!far0 && !far1) return fad_core2<T>(X, cc.y, S);
-    nfar += 32u;
-    if (far0) return p2_make(fad_far<T>(p2_lo(X), cc.y, s0), fad_core<T>(p2_hi(X), cc.y, s1));
-    return p2_make(fad_core<T>(p2_lo(X), cc.y, s0), fad_far<T>(p2_hi(X), cc.y, s1));
+    far = __all_sync(VAMP_FULL_MASK, !(fmin(p2_lo(S), p2_hi(S)) < Fad<T>::R2()));
+    if (far) return fad_far2<T>(X, cc.y, S);
+    return fad_core2<T>(X, cc.y, S);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -30,20 +30,44 @@ constexpr int K2_WARPS = 4;
 #endif
 constexpr double FWHM_PER_SIGMA = 2.35482004503094938202;
 
+// ------------------------------------------------------------------------------------------------
+// Per-chain random stream.  One Philox4x32-10 call per lane yields the (normal, log-uniform)
+// pairs of TWO steps of a 64-step block: lane l owns steps l (z0, lu0) and 32 + l (z1, lu1), so
+// the hand-out is a plain shuffle from lane (step & 31) of the current half's registers.
+// Kept in the kernel's precision (the fp32 kernel runs Box-Muller on the MUFU units).
+template <typename T> struct RngMath;
+template <> struct RngMath<double> {
+    static __device__ __forceinline__ void fill(const uint4& x, double& z0, double& z1, double& l0, double& l1) {
+        const double rad = sqrt(-2.0 * log(u01(x.x)));
+        double sn, cs;
+        sincospi(2.0 * u01(x.y), &sn, &cs);
+        z0 = rad * cs;
+        z1 = rad * sn;
+        l0 = log(u01(x.z));
+        l1 = log(u01(x.w));
+    }
+};
+template <> struct RngMath<float> {
+    static __device__ __forceinline__ float u(uint32_t x) { return fmaf((float)x, 2.3283064365386962890625e-10f, 1.16415321826934814453125e-10f); }
+    static __device__ __forceinline__ void fill(const uint4& x, float& z0, float& z1, float& l0, float& l1) {
+        const float rad = sqrtf(-2.0f * __logf(u(x.x)));
+        float sn, cs;
+        __sincosf(6.283185307179586f * u(x.y), &sn, &cs);
+        z0 = rad * cs;
+        z1 = rad * sn;
+        l0 = __logf(u(x.z));
+        l1 = __logf(u(x.w));
+    }
+};
+
 template <typename T>
 struct WarpRng {
-    T z0, z1, lu0, lu1;      // kept in the kernel's precision: half the registers in the fp32 kernel
+    T z0, z1, lu0, lu1;
     uint32_t uid_lo, uid_hi, k0, k1;
     __device__ __forceinline__ void refill(unsigned long long blk, int lane) {
         const uint4 x = philox4x32_10(make_uint4(uid_lo, uid_hi, (uint32_t)blk, ((uint32_t)(blk >> 32) << 8) | (uint32_t)lane),
                                       make_uint2(k0, k1));
-        const double rad = sqrt(-2.0 * log(u01(x.x)));
-        double sn, cs;
-        sincospi(2.0 * u01(x.y), &sn, &cs);
-        z0 = T(rad * cs);
-        z1 = T(rad * sn);
-        lu0 = T(log(u01(x.z)));
-        lu1 = T(log(u01(x.w)));
+        RngMath<T>::fill(x, z0, z1, lu0, lu1);
     }
 };
 
@@ -58,104 +82,148 @@ __device__ __forceinline__ float tune_factor(float rate) {
     return 1.0f;
 }
 
-struct WarpSmem {          // pointers into this warp's shared-memory slice
-    double* th;
-    double* best;
-    double* mean;
-    double* m2;
-    double* comom;
-    float* asf;
-    float* psd;
-    int* acc;
-    int* rej;
-    int* acct;
-    double* sc;                  // [0] best_logp, [1] sum_lnL, [2] sum_lnL2
-    unsigned long long* cnt;     // [0] shape evaluations, [1] far-path pixels, [2] likelihood passes
+template <typename T> struct StepMath;
+template <> struct StepMath<float> {
+    static __device__ __forceinline__ float log_(float x) { return __logf(x); }
+};
+template <> struct StepMath<double> {
+    static __device__ __forceinline__ double log_(double x) { return log(x); }
 };
 
+__host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
+
 // ------------------------------------------------------------------------------------------------
-// Row-streaming chain kernel.
-//
-// First version of this kernel kept the lane's pixels in registers and fully unrolled the
-// per-row Voigt evaluation for PPL = 1/2/4/8: 34 k SASS instructions (544 KB) per kernel, and ncu
-// showed the warps stalled on instruction fetch (stall_no_instruction 7.4 warps per issue,
-// issue-active 32 %, profiles/r1_k2_a_unrolled_baseline.txt).  This version streams the rows
-// (32 pixels each, two rows in flight for ILP) through ONE copy of the core / far code:
-//   * du, flux (and 1/noise) of a row come from global memory - 3 KB per region, always L1 hits;
-//   * the per-component shape cache, the tau of the other components ("base") and the
-//     proposed shape live in warp-private shared memory, lane-private slots (no syncs);
-//   * accepting a centroid/width step flips a slot index instead of copying the shape.
-// The hot loop is now a few hundred instructions and the register footprint is halved.
+// Shared-memory slice of one chain (= warp), sized for one 256-pixel tile so that every pixel
+// buffer sits at a compile-time offset from ONE running address register.
+//   pixel buffers (PAIR layout: element 32 jj + lane holds pixels 64 jj + lane and 64 jj + 32 + lane):
+//     du | flux | base (tau of the other components, pre-multiplied by -log2 e) | [1/noise] |
+//     shape cache: ncomp_max + 1 slots (one spare: a proposal is evaluated into the spare slot and
+//     accepting it swaps two slot indices instead of copying)
+//   scalar state: theta (kernel precision), proposal scale asf * psd, acc / rej / acc_total counters,
+//     slot table.
+template <typename T, bool WT>
+struct K2Lay {
+    static constexpr int NE = VAMP_TILE_PIX / 2;
+    static constexpr int SLOT = NE * (int)sizeof(P2<T>);
+    static constexpr int DU = 0, F = SLOT, BASE = 2 * SLOT, W = 3 * SLOT, H = (WT ? 4 : 3) * SLOT;
+    static __host__ __device__ size_t lsf_bytes(bool lsf) {
+        return lsf ? align16(sizeof(T) * (VAMP_TILE_PIX + VAMP_MAX_LSF_TAPS)) : 0;
+    }
+    static __host__ __device__ size_t bytes(int ncomp_max, int cmax, bool lsf) {
+        const int ts = 4 * cmax + 1;
+        return (size_t)H + (size_t)(ncomp_max + 1) * SLOT + lsf_bytes(lsf) + align16(sizeof(T) * ts) +
+               align16(sizeof(float) * ts) + 3 * align16(sizeof(int) * ts) + align16(sizeof(int) * (ncomp_max + 1));
+    }
+};
 
 template <typename T>
-__device__ __forceinline__ T real_log(double x);
-template <> __device__ __forceinline__ float real_log<float>(double x) { return __logf((float)x); }
-template <> __device__ __forceinline__ double real_log<double>(double x) { return log(x); }
+struct LsfCtx {
+    T* buf;            // warp-private [VAMP_TILE_PIX + taps]
+    const T* taps_s;   // block-shared taps
+    int taps, P;
+};
 
-// One likelihood pass over the region, two rows (64 pixels) per trip, nothing masked: the
-// region arrays and the shared-memory rows are padded to 64 pixels with neutral values, and
-// everything is in PAIR layout (element jj*32 + lane = pixels 64 jj + lane and 64 jj + 32 + lane),
-// so the two rows travel as one packed value through loads, arithmetic and shared memory.
-// FRESH: evaluate the component `cc` and store its shape to Hdst; else read the shape from Hsrc.
-// `An` and `basebuf` are pre-multiplied by NEGK (-log2(e) in fp32) so m = ex2(fma(An, H, base)).
-// Returns sum (f - m)^2 (WT: noise-weighted) of m = exp(-(tau_others + A*H)) [convolved with the LSF].
-template <typename T, int KIND, bool WT, bool LSF, bool FRESH>
-__device__ __forceinline__ double chain_pass(const CompC<T>& cc, T An, const P2<T>* __restrict__ Hsrc,
-                                             P2<T>* __restrict__ Hdst, const P2<T>* __restrict__ basebuf,
-                                             const typename RS<T>::Pair* __restrict__ gdu,
-                                             const typename RS<T>::Pair* __restrict__ gf,
-                                             const typename RS<T>::Pair* __restrict__ gw, int npairs, int P, int lane,
-                                             T* lsf_buf, const T* lsf_s, int taps, unsigned& nfar) {
-    P2<T> S2 = p2_bc<T>(T(0));
+// Residual sum of squares from a model row-pair buffer in natural order (LSF path only):
+// buf[h + p] holds m_p - 1; out = 1 + sum_t lsf[t] (m - 1)[p + h - t], zero outside [0, P).
+template <typename T, bool WT>
+__device__ __forceinline__ T lsf_residuals(const LsfCtx<T>& lc, const unsigned char* wb, int npairs, int lane) {
+    typedef K2Lay<T, WT> Lay;
+    const int h = lc.taps >> 1;
+    for (int i = lane; i < 2 * h; i += 32) lc.buf[(i < h) ? i : (64 * npairs + i)] = T(0);
+    __syncwarp();
+    const T* bq = lc.buf + lane + 2 * h;
+    const T* fn = reinterpret_cast<const T*>(wb + Lay::F);
+    const T* wn = reinterpret_cast<const T*>(wb + Lay::W);
+    T S = T(0);
+    for (int j = 0; j < 2 * npairs; ++j) {
+        T acc = T(1);
+        for (int t = 0; t < lc.taps; ++t) acc = Real<T>::fma_(lc.taps_s[t], bq[-t], acc);
+        // the convolution leaks into the padding pixels next to the region edge: mask them
+        const int px = j * 32 + lane;
+        const int e = 2 * (32 * (j >> 1) + lane) + (j & 1);        // natural pixel -> pair layout
+        T rr = (px < lc.P) ? (fn[e] - acc) : T(0);
+        if (WT) rr *= wn[e];
+        S = Real<T>::fma_(rr, rr, S);
+        bq += 32;
+    }
+    __syncwarp();
+    return S;
+}
+
+// One likelihood pass with the component's CACHED shape (amplitude steps, initial state):
+// m = ex2(An * H + base), returns sum (w (f - m))^2 over the region, identical in every lane.
+template <typename T, bool WT, bool LSF>
+__device__ __forceinline__ T pass_cached(T An, const P2<T>* __restrict__ Hc, const unsigned char* wb, int npairs, int lane,
+                                         const LsfCtx<T>& lc) {
+    typedef K2Lay<T, WT> Lay;
+    const P2<T>* pf = reinterpret_cast<const P2<T>*>(wb + Lay::F) + lane;
+    const P2<T>* pb = reinterpret_cast<const P2<T>*>(wb + Lay::BASE) + lane;
+    const P2<T>* pw = reinterpret_cast<const P2<T>*>(wb + Lay::W) + lane;
     const P2<T> A2 = p2_bc<T>(An);
-    int o = lane;                                   // pair-layout element of the current row pair
-    T* pl = lsf_buf + (taps >> 1) + lane;
+    P2<T> S2 = p2_bc<T>(T(0));
 #pragma unroll 1
-    for (int jj = 0; jj < npairs; ++jj, o += 32) {
-        P2<T> H;
-        if (FRESH) {
-            H = pair_shape<T, KIND>(cc, p2_from(__ldg(gdu + o)), nfar);
-            Hdst[o] = H;
-        } else {
-            H = Hsrc[o];
-        }
-        const P2<T> M = p2_exp_scaled<T>(p2_fma(A2, H, basebuf[o]));
+    for (int e = 0; e < 32 * npairs; e += 32) {
+        const P2<T> M = p2_exp_scaled<T>(p2_fma(A2, Hc[e], pb[e]));
         if (LSF) {
-            pl[64 * jj] = p2_lo(M) - T(1);
-            pl[64 * jj + 32] = p2_hi(M) - T(1);
+            lc.buf[(lc.taps >> 1) + lane + 2 * e] = p2_lo(M) - T(1);
+            lc.buf[(lc.taps >> 1) + lane + 2 * e + 32] = p2_hi(M) - T(1);
         } else {
-            P2<T> R = p2_add(p2_from(__ldg(gf + o)), p2_neg(M));
-            if (WT) R = p2_mul(R, p2_from(__ldg(gw + o)));
+            P2<T> R = p2_sub(pf[e], M);
+            if (WT) R = p2_mul(R, pw[e]);
             S2 = p2_fma(R, R, S2);
         }
     }
     T S = p2_lo(S2) + p2_hi(S2);
-    if (LSF) {
-        const int h = taps >> 1;
-        for (int i = lane; i < 2 * h; i += 32) lsf_buf[(i < h) ? i : (64 * npairs + i)] = T(0);
-        __syncwarp();
-        const T* bq = lsf_buf + lane + 2 * h;
-        const T* gfn = reinterpret_cast<const T*>(gf);
-        const T* gwn = reinterpret_cast<const T*>(gw);
-        for (int j = 0; j < 2 * npairs; ++j) {
-            T acc = T(1);
-            for (int t = 0; t < taps; ++t) acc = Real<T>::fma_(lsf_s[t], bq[-t], acc);
-            // the convolution leaks into the padding pixels next to the region edge: mask them
-            const int px = j * 32 + lane;
-            const int e = 2 * (32 * (j >> 1) + lane) + (j & 1);        // natural pixel -> pair layout
-            T rr = (px < P) ? (__ldg(gfn + e) - acc) : T(0);
-            if (WT) rr *= __ldg(gwn + e);
-            S = Real<T>::fma_(rr, rr, S);
-            bq += 32;
-        }
-        __syncwarp();
-    }
-    return (double)warp_sum(S);
+    if (LSF) S = lsf_residuals<T, WT>(lc, wb, npairs, lane);
+    return warp_sum(S);
 }
 
+// One likelihood pass that EVALUATES the component `cc` (centroid / width steps): the new shape
+// goes to the spare slot Hs.  `nfar` counts pixels that took the continued-fraction path.
 template <typename T, int KIND, bool WT, bool LSF>
-__device__ void mcmc_chain(const McmcDev& p, int chain, int lane, const WarpSmem& ws, P2<T>* Hbuf, P2<T>* basebuf,
-                           T* lsf_buf, const T* lsf_s, int HS) {
+__device__ __forceinline__ T pass_fresh(const CompC<T>& cc, T An, P2<T>* __restrict__ Hs, const unsigned char* wb, int npairs,
+                                        int lane, const LsfCtx<T>& lc, unsigned& nfar, bool& last_far) {
+    typedef K2Lay<T, WT> Lay;
+    const P2<T>* pd = reinterpret_cast<const P2<T>*>(wb + Lay::DU) + lane;
+    const P2<T>* pf = reinterpret_cast<const P2<T>*>(wb + Lay::F) + lane;
+    const P2<T>* pb = reinterpret_cast<const P2<T>*>(wb + Lay::BASE) + lane;
+    const P2<T>* pw = reinterpret_cast<const P2<T>*>(wb + Lay::W) + lane;
+    const P2<T> A2 = p2_bc<T>(An);
+    P2<T> S2 = p2_bc<T>(T(0));
+    bool far = false;
+#pragma unroll 1
+    for (int e = 0; e < 32 * npairs; e += 32) {
+        const P2<T> H = pair_shape<T, KIND>(cc, pd[e], far);
+        nfar += far ? 64u : 0u;
+        Hs[e] = H;
+        const P2<T> M = p2_exp_scaled<T>(p2_fma(A2, H, pb[e]));
+        if (LSF) {
+            lc.buf[(lc.taps >> 1) + lane + 2 * e] = p2_lo(M) - T(1);
+            lc.buf[(lc.taps >> 1) + lane + 2 * e + 32] = p2_hi(M) - T(1);
+        } else {
+            P2<T> R = p2_sub(pf[e], M);
+            if (WT) R = p2_mul(R, pw[e]);
+            S2 = p2_fma(R, R, S2);
+        }
+    }
+    last_far = far;
+    T S = p2_lo(S2) + p2_hi(S2);
+    if (LSF) S = lsf_residuals<T, WT>(lc, wb, npairs, lane);
+    return warp_sum(S);
+}
+
+// ------------------------------------------------------------------------------------------------
+// The chain.  PyMC 2's scalar Metropolis-within-Gibbs (oracle/sampler.py; replayed step for step
+// by oracle/chain_replay.py): per iteration every component's amplitude, centroid and width(s)
+// are stepped in order, then sd.  An amplitude step reuses the cached shape, a centroid / width
+// step re-evaluates ONE component over the region (the economy PyMC 2's LazyFunction cache gives
+// the reference), `base` carries the other components' tau and moves to the next component with
+// two FMAs per pixel.  The step logic runs in the kernel's precision; acceptance counters are
+// gathered in a per-component bit mask and written by lanes 0..3 once per component.
+template <typename T, int KIND, bool WT, bool LSF>
+__device__ void mcmc_chain(const McmcDev& p, int chain, int lane, unsigned char* wb, int ncomp_max, const T* lsf_s) {
+    typedef K2Lay<T, WT> Lay;
+    typedef typename RS<T>::Pair Pair;
     constexpr int NP = (KIND == VAMP_KIND_VOIGT) ? 4 : 3;
     const RegionSetDev& rs = p.rs;
     const int r = p.item_region[chain];
@@ -163,77 +231,96 @@ __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, const WarpSmem
     const int n = p.item_ncomp[chain];
     const int ts = p.tstride;
     const int sdi = 4 * p.cmax;
-    const int ncs = NP * n;                        // component steps per iteration
-    const int k = ncs + (WT ? 0 : 1);
-    const int taps = rs.lsf_taps;
+    const int k = NP * n + (WT ? 0 : 1);
     const int npairs = (P + 63) >> 6;
+    const int npad = 64 * npairs - P;
     const int tune_interval = p.tune_interval, thin = p.thin, burn = p.burn, tune_throughout = p.tune_throughout;
-    const double ubase = rs.ubase[rs.tile_off[r]];
-    typedef typename RS<T>::Pair Pair;
-    const Pair* __restrict__ gdu = RS<T>::pdu(rs) + (rs.pix_off[r] >> 1);
-    const Pair* __restrict__ gf = RS<T>::pf(rs) + (rs.pix_off[r] >> 1);
-    const Pair* __restrict__ gw = RS<T>::pw(rs) + (rs.pix_off[r] >> 1);
     const T NK = Real<T>::NEGK();
-
-    // ---- state -> shared
     const size_t gb = (size_t)chain * ts;
+
+    // ---- carve the slice
+    P2<T>* const Hbuf = reinterpret_cast<P2<T>*>(wb + Lay::H) + lane;           // slot s at Hbuf + s * NE
+    unsigned char* sp_ = wb + Lay::H + (size_t)(ncomp_max + 1) * Lay::SLOT;
+    LsfCtx<T> lc;
+    lc.buf = reinterpret_cast<T*>(sp_);
+    lc.taps_s = lsf_s;
+    lc.taps = rs.lsf_taps;
+    lc.P = P;
+    sp_ += Lay::lsf_bytes(LSF);
+    T* const th = reinterpret_cast<T*>(sp_);
+    sp_ += align16(sizeof(T) * ts);
+    float* const scl = reinterpret_cast<float*>(sp_);
+    sp_ += align16(sizeof(float) * ts);
+    int* const acc = reinterpret_cast<int*>(sp_);
+    sp_ += align16(sizeof(int) * ts);
+    int* const rej = reinterpret_cast<int*>(sp_);
+    sp_ += align16(sizeof(int) * ts);
+    int* const acct = reinterpret_cast<int*>(sp_);
+    sp_ += align16(sizeof(int) * ts);
+    int* const slot = reinterpret_cast<int*>(sp_);
+
+    // ---- region and state -> shared
+    {
+        const Pair* gdu = RS<T>::pdu(rs) + (rs.pix_off[r] >> 1);
+        const Pair* gf = RS<T>::pf(rs) + (rs.pix_off[r] >> 1);
+        const Pair* gw = RS<T>::pw(rs) + (rs.pix_off[r] >> 1);
+        P2<T>* sd_ = reinterpret_cast<P2<T>*>(wb + Lay::DU) + lane;
+        P2<T>* sf_ = reinterpret_cast<P2<T>*>(wb + Lay::F) + lane;
+        P2<T>* sb_ = reinterpret_cast<P2<T>*>(wb + Lay::BASE) + lane;
+        P2<T>* sw_ = reinterpret_cast<P2<T>*>(wb + Lay::W) + lane;
+        for (int e = 0; e < 32 * npairs; e += 32) {
+            sd_[e] = p2_from(__ldg(gdu + e + lane));
+            sf_[e] = p2_from(__ldg(gf + e + lane));
+            if (WT) sw_[e] = p2_from(__ldg(gw + e + lane));
+            sb_[e] = p2_bc<T>(T(0));
+            Hbuf[n * Lay::NE + e] = p2_bc<T>(T(0));                 // spare slot
+        }
+    }
     for (int i = lane; i < ts; i += 32) {
-        ws.th[i] = p.theta[gb + i];
-        ws.asf[i] = p.asf[gb + i];
-        ws.psd[i] = p.psd[gb + i];
-        ws.acc[i] = p.acc[gb + i];
-        ws.rej[i] = p.rej[gb + i];
-        ws.acct[i] = p.acc_total[gb + i];
+        th[i] = T(p.theta[gb + i]);
+        scl[i] = p.asf[gb + i] * p.psd[gb + i];
+        acc[i] = p.acc[gb + i];
+        rej[i] = p.rej[gb + i];
+        acct[i] = p.acc_total[gb + i];
     }
-    if (lane == 0) {
-        ws.sc[0] = p.best_logp[chain];
-        ws.sc[1] = p.sum_lnL[chain];
-        ws.sc[2] = p.sum_lnL2[chain];
-        ws.cnt[0] = ws.cnt[1] = ws.cnt[2] = 0ull;
-    }
-    int ntally = p.ntally[chain];
+    for (int i = lane; i <= n; i += 32) slot[i] = i;
     __syncwarp();
 
-    unsigned n_far = 0u, n_shape = 0u, n_like = 0u;      // per iteration; flushed to ws.cnt
-    // slot table: component c's shape lives in Hbuf[slot(c)*HS ...]; slot n is the spare one
-    unsigned long long slots = 0ull;
-    for (int c = 0; c <= n; ++c) slots |= (unsigned long long)c << (4 * c);
-    auto slot_of = [&](int c) -> int { return (int)((slots >> (4 * c)) & 15ull); };
+    // centroid relative to the coordinate-tile base; the base is split so the fp32 kernel loses nothing
+    const double ubase = rs.ubase[rs.tile_off[r]];
+    const T ub_hi = T(ubase), ub_lo = T(ubase - (double)ub_hi);
+    auto cbase = [&](T c) -> T { return (c - ub_hi) - ub_lo; };
 
-    // ---- build the shape cache and the current sum of squares
-    CompC<T> cz;
-    cz.A = cz.cb = cz.g = cz.y = cz.y2 = cz.L2 = T(0);
-    for (int jj = 0; jj < npairs; ++jj) basebuf[jj * 32 + lane] = p2_bc<T>(T(0));
+    // ---- build the shape cache; base holds the FULL tau here, one cached pass with A = 0 gives S
     {
-        unsigned dummy = 0u;
+        P2<T>* sb_ = reinterpret_cast<P2<T>*>(wb + Lay::BASE) + lane;
+        const P2<T>* sd_ = reinterpret_cast<const P2<T>*>(wb + Lay::DU) + lane;
         for (int c = 0; c < n; ++c) {
-            const CompC<T> cc = make_comp<T, KIND>(ws.th[VAMP_TH(c, 0)], ws.th[VAMP_TH(c, 1)], ws.th[VAMP_TH(c, 2)],
-                                                   ws.th[VAMP_TH(c, 3)], ubase);
-            P2<T>* Hd = Hbuf + slot_of(c) * HS;
+            const CompC<T> cc = make_comp_fast<T, KIND>(th[VAMP_TH(c, 0)], cbase(th[VAMP_TH(c, 1)]), th[VAMP_TH(c, 2)],
+                                                        th[VAMP_TH(c, 3)]);
             const P2<T> A2 = p2_bc<T>(NK * cc.A);
-            for (int jj = 0; jj < npairs; ++jj) {
-                const int o = jj * 32 + lane;
-                const P2<T> H = pair_shape<T, KIND>(cc, p2_from(__ldg(gdu + o)), dummy);
-                Hd[o] = H;
-                basebuf[o] = p2_fma(A2, H, basebuf[o]);
+            bool far;
+            for (int e = 0; e < 32 * npairs; e += 32) {
+                const P2<T> H = pair_shape<T, KIND>(cc, sd_[e], far);
+                Hbuf[c * Lay::NE + e] = H;
+                sb_[e] = p2_fma(A2, H, sb_[e]);
             }
         }
-        P2<T>* Hspare = Hbuf + slot_of(n) * HS;
-        for (int jj = 0; jj < npairs; ++jj) Hspare[jj * 32 + lane] = p2_bc<T>(T(0));
-        // base holds the full tau here: one cached pass with A = 0 gives the current S
     }
-    unsigned nf32 = 0u;
-    double Scur = chain_pass<T, KIND, WT, LSF, false>(cz, T(0), Hbuf + slot_of(n) * HS, nullptr, basebuf, gdu, gf, gw,
-                                                      npairs, P, lane, lsf_buf, lsf_s, taps, nf32);
-    double sd = WT ? 1.0 : ws.th[sdi];
-    double logsd = WT ? 0.0 : log(sd);
-    double half_inv_var = WT ? 0.5 : 0.5 / (sd * sd);
-    double lp = 0.0;                                          // sum_c (ln A_c - A_c), kept incrementally
+    T Scur = pass_cached<T, WT, LSF>(T(0), Hbuf + n * Lay::NE, wb, npairs, lane, lc);
+    T sd = WT ? T(1) : th[sdi];
+    T logsd = WT ? T(0) : StepMath<T>::log_(sd);
+    T hiv = WT ? T(0.5) : T(0.5) / (sd * sd);                 // 1 / (2 sd^2)
+    T lp = T(0);                                              // sum_c (ln A_c - A_c), kept incrementally
     for (int c = 0; c < n; ++c) {
-        const double a = ws.th[VAMP_TH(c, 0)];
-        lp += log(a) - a;
+        const T a = th[VAMP_TH(c, 0)];
+        lp += StepMath<T>::log_(a) - a;
     }
+    double best_logp = p.best_logp[chain], sum_lnL = p.sum_lnL[chain], sum_lnL2 = p.sum_lnL2[chain];
+    int ntally = p.ntally[chain];
+    unsigned long long w_shape = 0ull, w_far = 0ull, w_like = 0ull;
 
+    // ---- random stream: step counter q = 64 qblk + qs
     WarpRng<T> rng;
     {
         const unsigned long long uid = p.chain_uid[chain];
@@ -242,286 +329,269 @@ __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, const WarpSmem
         rng.k0 = (uint32_t)p.seed;
         rng.k1 = (uint32_t)(p.seed >> 32);
     }
-    // step counter q = 64 * qblk + qslot; a (normal, log-uniform) pair per step
     unsigned long long qblk = ((unsigned long long)p.it0 * (unsigned long long)k) >> 6;
-    int qslot = (int)(((unsigned long long)p.it0 * (unsigned long long)k) & 63ull);
-    bool need_fill = true;                 // (re)fill at the first step and whenever a 64-step block starts
+    int qs = (int)(((unsigned long long)p.it0 * (unsigned long long)k) & 63ull);
+    rng.refill(qblk, lane);
+    T zc = (qs < 32) ? rng.z0 : rng.z1, luc = (qs < 32) ? rng.lu0 : rng.lu1;
+    auto draw = [&](T& z, T& lu) {
+        z = __shfl_sync(VAMP_FULL_MASK, zc, qs);               // source lane = qs mod 32
+        lu = __shfl_sync(VAMP_FULL_MASK, luc, qs);
+        ++qs;
+        if ((qs & 31) == 0) {
+            if (qs == 64) {
+                qs = 0;
+                ++qblk;
+                rng.refill(qblk, lane);
+                zc = rng.z0;
+                luc = rng.lu0;
+            } else {
+                zc = rng.z1;
+                luc = rng.lu1;
+            }
+        }
+    };
+
+    const T c_hi = T(P - 1);
+    const T w_hi = T((double)(P - 1) * (KIND == VAMP_KIND_VOIGT ? 0.5 * FWHM_PER_SIGMA : 0.5));
+    P2<T>* const pbase = reinterpret_cast<P2<T>*>(wb + Lay::BASE) + lane;
+    bool fresh_base = true;                 // rebuild base from the cache (first iteration, then every 8th)
 
     for (int it = p.it0; it < p.it1; ++it) {
         // ---- tuning (PyMC 2: every tune_interval iterations; optionally only during burn-in)
         if (it > 0 && (it % tune_interval) == 0 && (tune_throughout || it <= burn)) {
             for (int i = lane; i < ts; i += 32) {
-                const int a = ws.acc[i], b = ws.rej[i];
+                const int a = acc[i], b = rej[i];
+                float f = p.asf[gb + i];
                 if (a + b > 0) {
-                    const float nf = ws.asf[i] * tune_factor((float)a / (float)(a + b));
-                    if (nf > 0.0f) ws.asf[i] = nf;
+                    const float nf = f * tune_factor((float)a / (float)(a + b));
+                    if (nf > 0.0f) f = nf;
                 }
-                ws.acc[i] = 0;
-                ws.rej[i] = 0;
+                p.asf[gb + i] = f;
+                scl[i] = f * p.psd[gb + i];
+                acc[i] = 0;
+                rej[i] = 0;
             }
             __syncwarp();
         }
         const bool post_burn = it >= burn;
+        unsigned n_shape = 0u, n_far = 0u, n_like = 0u;
+        int hprev = 0;                        // slot of component c - 1
 
-        int c = 0, i = 0;
-        double pA = 0.0, pc = 0.0, pw1 = 0.0, pw2 = 0.0;
 #pragma unroll 1
-        for (int st = 0; st < k; ++st) {
-            // ---- one (normal, log-uniform) pair; the only RNG call site of the kernel
-            if (need_fill) {
-                rng.refill(qblk, lane);
-                need_fill = false;
-            }
-            double z, lu;
-            {
-                const T zs = (qslot & 1) ? rng.z1 : rng.z0;
-                const T ls = (qslot & 1) ? rng.lu1 : rng.lu0;
-                z = (double)__shfl_sync(VAMP_FULL_MASK, zs, qslot >> 1);
-                lu = (double)__shfl_sync(VAMP_FULL_MASK, ls, qslot >> 1);
-            }
-            if (++qslot == 64) {
-                qslot = 0;
-                ++qblk;
-                need_fill = true;
-            }
-            bool accept = false;
-            int idx;
-            double prop;
-            if (st < ncs) {
-                idx = VAMP_TH(c, i);
-                if (i == 0) {
-                    // new component: base = tau of the others, rebuilt from the cache (no drift)
-                    __syncwarp();
-                    P2<T>* bb = basebuf + lane;
-                    if (c == 0) {
-                        // once per iteration: rebuild from the cache, so rounding never accumulates
-                        for (int jj = 0; jj < npairs; ++jj) bb[jj * 32] = p2_bc<T>(T(0));
-                        for (int c2 = 1; c2 < n; ++c2) {
-                            const P2<T> A2 = p2_bc<T>(NK * T(ws.th[VAMP_TH(c2, 0)]));
-                            const P2<T>* Hs = Hbuf + slot_of(c2) * HS + lane;
-                            for (int jj = 0; jj < npairs; ++jj) bb[jj * 32] = p2_fma(A2, Hs[jj * 32], bb[jj * 32]);
-                        }
-                    } else {
-                        // next component: base += tau_{c-1} - tau_c  (two FMAs per pixel instead of n - 1)
-                        const P2<T> Ap = p2_bc<T>(NK * T(ws.th[VAMP_TH(c - 1, 0)])), Ac = p2_bc<T>(-NK * T(ws.th[idx]));
-                        const P2<T>* Hp = Hbuf + slot_of(c - 1) * HS + lane;
-                        const P2<T>* Hn = Hbuf + slot_of(c) * HS + lane;
-                        for (int jj = 0; jj < npairs; ++jj)
-                            bb[jj * 32] = p2_fma(Ac, Hn[jj * 32], p2_fma(Ap, Hp[jj * 32], bb[jj * 32]));
+        for (int c = 0; c < n; ++c) {
+            const int i0 = VAMP_TH(c, 0);
+            T pA = th[i0], pc = th[i0 + 1], pw1 = th[i0 + 2], pw2 = (NP == 4) ? th[i0 + 3] : T(0);
+            int hc = slot[c], hs = slot[n];
+            // ---- base = tau of the other components
+            if (c == 0) {
+                if (fresh_base) {
+                    // rebuilt from the cache so that rounding never accumulates
+                    for (int e = 0; e < 32 * npairs; e += 32) pbase[e] = p2_bc<T>(T(0));
+                    for (int c2 = 1; c2 < n; ++c2) {
+                        const P2<T> A2 = p2_bc<T>(NK * th[VAMP_TH(c2, 0)]);
+                        const P2<T>* Hs2 = Hbuf + slot[c2] * Lay::NE;
+                        for (int e = 0; e < 32 * npairs; e += 32) pbase[e] = p2_fma(A2, Hs2[e], pbase[e]);
                     }
-                    pA = ws.th[idx];
-                    pc = ws.th[idx + 1];
-                    pw1 = ws.th[idx + 2];
-                    pw2 = ws.th[idx + 3];
-                }
-                const double cur = (i == 0) ? pA : (i == 1) ? pc : (i == 2) ? pw1 : pw2;
-                prop = cur + z * (double)(ws.asf[idx] * ws.psd[idx]);
-                const double c_hi = (double)(P - 1);
-                const double w_hi = c_hi * (KIND == VAMP_KIND_VOIGT ? 0.5 * FWHM_PER_SIGMA : 0.5);
-                bool ok;
-                if (i == 0) ok = prop > 0.0;
-                else if (i == 1) ok = (prop >= 0.0) && (prop <= c_hi);
-                else if (KIND == VAMP_KIND_VOIGT && i == 2) ok = (prop >= 0.0) && (prop <= w_hi);
-                else ok = (prop > 0.0) && (prop <= w_hi);
-                if (ok) {
-                    double dprior = 0.0, Snew;
-                    const int sc = slot_of(c), sp = slot_of(n);
-                    if (i == 0) {
-                        Snew = chain_pass<T, KIND, WT, LSF, false>(cz, NK * T(prop), Hbuf + sc * HS, nullptr, basebuf, gdu,
-                                                                   gf, gw, npairs, P, lane, lsf_buf, lsf_s, taps, nf32);
-                        dprior = (double)real_log<T>((double)(T(prop) * Real<T>::rcp(T(pA)))) - (prop - pA);
-                    } else {
-                        const CompC<T> cc = make_comp_fast<T, KIND>(pA, (i == 1) ? prop : pc, (i == 2) ? prop : pw1,
-                                                                    (i == 3) ? prop : pw2, ubase);
-                        ++n_shape;
-                        nf32 = 0u;
-                        Snew = chain_pass<T, KIND, WT, LSF, true>(cc, NK * cc.A, nullptr, Hbuf + sp * HS, basebuf, gdu, gf,
-                                                                  gw, npairs, P, lane, lsf_buf, lsf_s, taps, nf32);
-                        n_far += nf32;
-                    }
-                    ++n_like;
-                    accept = lu < (Scur - Snew) * half_inv_var + dprior;      // false for NaN
-                    if (accept) {
-                        Scur = Snew;
-                        if (i == 0) {
-                            pA = prop;
-                            lp += dprior;
-                        } else {
-                            if (i == 1) pc = prop;
-                            else if (i == 2) pw1 = prop;
-                            else pw2 = prop;
-                            // the proposed shape becomes the component's shape: swap slot indices
-                            slots &= ~((15ull << (4 * c)) | (15ull << (4 * n)));
-                            slots |= ((unsigned long long)sp << (4 * c)) | ((unsigned long long)sc << (4 * n));
-                        }
-                    }
-                }
-                if (++i == NP) {
-                    i = 0;
-                    ++c;
+                } else {
+                    // from the last component of the previous iteration back to the first
+                    const P2<T> Ap = p2_bc<T>(NK * th[VAMP_TH(n - 1, 0)]), Ac = p2_bc<T>(-NK * pA);
+                    const P2<T>* Hp = Hbuf + slot[n - 1] * Lay::NE;
+                    const P2<T>* Hn = Hbuf + hc * Lay::NE;
+                    if (n > 1)
+                        for (int e = 0; e < 32 * npairs; e += 32)
+                            pbase[e] = p2_fma(Ac, Hn[e], p2_fma(Ap, Hp[e], pbase[e]));
                 }
             } else {
-                idx = sdi;
-                prop = sd + z * (double)(ws.asf[sdi] * ws.psd[sdi]);
-                if (prop > 0.0 && prop <= 1.0) {
-                    const double lprop = log(prop);
-                    const double hv = 0.5 / (prop * prop);
-                    accept = lu < -Scur * (hv - half_inv_var) - P * (lprop - logsd);
-                    if (accept) {
-                        sd = prop;
-                        logsd = lprop;
-                        half_inv_var = hv;
+                // next component: base += tau_{c-1} - tau_c  (two FMAs per pixel instead of n - 1)
+                const P2<T> Ap = p2_bc<T>(NK * th[i0 - 4]), Ac = p2_bc<T>(-NK * pA);
+                const P2<T>* Hp = Hbuf + hprev * Lay::NE;
+                const P2<T>* Hn = Hbuf + hc * Lay::NE;
+                for (int e = 0; e < 32 * npairs; e += 32) pbase[e] = p2_fma(Ac, Hn[e], p2_fma(Ap, Hp[e], pbase[e]));
+            }
+            unsigned am = 0u;                 // accept bits of this component's steps
+
+            // ---- amplitude: cached shape
+            {
+                T z, lu;
+                draw(z, lu);
+                const T prop = pA + z * T(scl[i0]);
+                if (prop > T(0)) {
+                    const T Snew = pass_cached<T, WT, LSF>(NK * prop, Hbuf + hc * Lay::NE, wb, npairs, lane, lc);
+                    const T dprior = StepMath<T>::log_(prop * Real<T>::rcp(pA)) - (prop - pA);
+                    ++n_like;
+                    if (lu < (Scur - Snew) * hiv + dprior) {          // false for NaN
+                        Scur = Snew;
+                        pA = prop;
+                        lp += dprior;
+                        am = 1u;
                     }
                 }
             }
-            {   // counters and state: every lane computes, lane 0 stores (no divergent branch)
-                const int na = ws.acc[idx] + (accept ? 1 : 0);
-                const int nr = ws.rej[idx] + (accept ? 0 : 1);
-                const int nt = ws.acct[idx] + ((accept && post_burn) ? 1 : 0);
-                const double nv = accept ? prop : ws.th[idx];
-                if (lane == 0) {
-                    ws.acc[idx] = na;
-                    ws.rej[idx] = nr;
-                    ws.acct[idx] = nt;
-                    ws.th[idx] = nv;
+            // ---- centroid and width(s): evaluate the proposed shape into the spare slot
+#pragma unroll 1
+            for (int i = 1; i < NP; ++i) {
+                T z, lu;
+                draw(z, lu);
+                const T cur = (i == 1) ? pc : (i == 2) ? pw1 : pw2;
+                const T prop = cur + z * T(scl[i0 + i]);
+                const T hi = (i == 1) ? c_hi : w_hi;
+                const bool ok = (prop <= hi) && ((i == NP - 1) ? (prop > T(0)) : (prop >= T(0)));
+                if (ok) {
+                    const T qc = (i == 1) ? prop : pc, q1 = (i == 2) ? prop : pw1, q2 = (i == 3) ? prop : pw2;
+                    const CompC<T> cc = make_comp_fast<T, KIND>(pA, cbase(qc), q1, q2);
+                    unsigned nf = 0u;
+                    bool last_far;
+                    const T Snew = pass_fresh<T, KIND, WT, LSF>(cc, NK * pA, Hbuf + hs * Lay::NE, wb, npairs, lane, lc, nf,
+                                                                last_far);
+                    n_far += nf - (last_far ? (unsigned)npad : 0u);
+                    ++n_shape;
+                    ++n_like;
+                    if (lu < (Scur - Snew) * hiv) {
+                        Scur = Snew;
+                        pc = qc;
+                        pw1 = q1;
+                        pw2 = q2;
+                        const int tmp = hc;         // the proposed shape becomes the component's shape
+                        hc = hs;
+                        hs = tmp;
+                        am |= 1u << i;
+                    }
                 }
             }
+            // ---- component epilogue: counters and state, lanes 0..NP-1
+            __syncwarp();
+            if (lane < NP) {
+                const int idx = i0 + lane;
+                const int bit = (int)((am >> lane) & 1u);
+                acc[idx] += bit;
+                rej[idx] += 1 - bit;
+                acct[idx] += post_burn ? bit : 0;
+                th[idx] = (lane == 0) ? pA : (lane == 1) ? pc : (lane == 2) ? pw1 : pw2;
+            }
+            slot[c] = hc;
+            slot[n] = hs;
+            hprev = hc;
+            __syncwarp();
         }
-        __syncwarp();
+        fresh_base = ((it + 1) & 7) == 0;
+
+        if (!WT) {
+            // ---- sd: no model evaluation
+            T z, lu;
+            draw(z, lu);
+            const T prop = sd + z * T(scl[sdi]);
+            bool a_sd = false;
+            if (prop > T(0) && prop <= T(1)) {
+                const T lprop = StepMath<T>::log_(prop);
+                const T hv = T(0.5) / (prop * prop);
+                a_sd = lu < -Scur * (hv - hiv) - T(P) * (lprop - logsd);
+                if (a_sd) {
+                    sd = prop;
+                    logsd = lprop;
+                    hiv = hv;
+                }
+            }
+            if (lane == 0) {
+                acc[sdi] += a_sd ? 1 : 0;
+                rej[sdi] += a_sd ? 0 : 1;
+                acct[sdi] += (a_sd && post_burn) ? 1 : 0;
+                th[sdi] = sd;
+            }
+            __syncwarp();
+        }
+        w_shape += n_shape;
+        w_far += n_far;
+        w_like += n_like;
 
         // ---- end of iteration: log-posterior of the current state
-        const double lnL = WT ? (-0.5 * Scur + rs.lognorm[r])
-                              : (-Scur * half_inv_var - P * (logsd + 0.91893853320467274178));
-        const double logp = lnL + lp;
-        const bool better = logp > ws.sc[0];
-        const bool tally = post_burn && (it % thin) == 0;
-        __syncwarp();
-        if (lane == 0) {
-            if (better) ws.sc[0] = logp;
-            if (tally) {
-                ws.sc[1] += lnL;
-                ws.sc[2] += lnL * lnL;
-            }
-            ws.cnt[0] += n_shape;
-            ws.cnt[1] += n_far - n_shape * (unsigned)(64 * npairs - P);   // padding pixels always count as far
-            ws.cnt[2] += n_like;
+        const double lnL = WT ? (-0.5 * (double)Scur + rs.lognorm[r])
+                              : (-(double)Scur * (double)hiv - P * ((double)logsd + 0.91893853320467274178));
+        const double logp = lnL + (double)lp;
+        if (logp > best_logp) {
+            best_logp = logp;
+            for (int i2 = lane; i2 < ts; i2 += 32) p.best_theta[gb + i2] = (double)th[i2];
         }
-        n_shape = n_far = n_like = 0u;
-        if (better) {
-            for (int i2 = lane; i2 < ts; i2 += 32) ws.best[i2] = ws.th[i2];
-        }
-        if (tally) {
+        if (post_burn && (it % thin) == 0) {
+            sum_lnL += lnL;
+            sum_lnL2 += lnL * lnL;
             ++ntally;
             const double inv = 1.0 / (double)ntally;
             const double wgt = (double)(ntally - 1) * inv;
+            double* mean = p.mean + gb;
+            double* m2 = p.m2 + gb;
+            double* comom = p.comom + (size_t)chain * 6 * p.cmax;
             for (int i2 = lane; i2 < 6 * n; i2 += 32) {          // co-moments first (need the old means)
                 const int cc2 = i2 / 6, pr = i2 - 6 * cc2;
                 const int a = (pr < 3) ? 0 : (pr < 5 ? 1 : 2);
                 const int b = (pr < 3) ? pr + 1 : (pr < 5 ? pr - 1 : 3);
-                const double da = ws.th[VAMP_TH(cc2, a)] - ws.mean[VAMP_TH(cc2, a)];
-                const double db = ws.th[VAMP_TH(cc2, b)] - ws.mean[VAMP_TH(cc2, b)];
-                ws.comom[i2] += wgt * da * db;
+                const double da = (double)th[VAMP_TH(cc2, a)] - mean[VAMP_TH(cc2, a)];
+                const double db = (double)th[VAMP_TH(cc2, b)] - mean[VAMP_TH(cc2, b)];
+                comom[i2] += wgt * da * db;
             }
             __syncwarp();
             for (int i2 = lane; i2 < ts; i2 += 32) {
-                const double x = ws.th[i2];
-                const double d = x - ws.mean[i2];
-                const double mn = ws.mean[i2] + d * inv;
-                ws.mean[i2] = mn;
-                ws.m2[i2] += d * (x - mn);
+                const double x = (double)th[i2];
+                const double d = x - mean[i2];
+                const double mn = mean[i2] + d * inv;
+                mean[i2] = mn;
+                m2[i2] += d * (x - mn);
             }
             if (p.trace) {
-                const int slot = ntally - 1;
-                if (slot < p.trace_cap)
+                const int slot_t = ntally - 1;
+                if (slot_t < p.trace_cap)
                     for (int i2 = lane; i2 < ts; i2 += 32)
-                        p.trace[((size_t)chain * p.trace_cap + slot) * ts + i2] = ws.th[i2];
+                        p.trace[((size_t)chain * p.trace_cap + slot_t) * ts + i2] = (double)th[i2];
             }
+            __syncwarp();
         }
-        __syncwarp();
     }
 
     // ---- state -> global
+    __syncwarp();
     for (int i = lane; i < ts; i += 32) {
-        p.theta[gb + i] = ws.th[i];
-        p.asf[gb + i] = ws.asf[i];
-        p.acc[gb + i] = ws.acc[i];
-        p.rej[gb + i] = ws.rej[i];
-        p.acc_total[gb + i] = ws.acct[i];
+        p.theta[gb + i] = (double)th[i];
+        p.acc[gb + i] = acc[i];
+        p.rej[gb + i] = rej[i];
+        p.acc_total[gb + i] = acct[i];
     }
     if (lane == 0) {
-        const double lnL = WT ? lnL_noise(Scur, rs.lognorm[r]) : lnL_sd(Scur, sd, P);
+        const double lnL = WT ? lnL_noise((double)Scur, rs.lognorm[r]) : lnL_sd((double)Scur, (double)sd, P);
         double lpx = 0.0;
         for (int c = 0; c < n; ++c) {
-            const double a = ws.th[VAMP_TH(c, 0)];
+            const double a = (double)th[VAMP_TH(c, 0)];
             lpx += log(a) - a;
         }
         p.lnL[chain] = lnL;
         p.logp[chain] = lnL + lpx;
-        p.best_logp[chain] = ws.sc[0];
+        p.best_logp[chain] = best_logp;
         p.ntally[chain] = ntally;
-        p.sum_lnL[chain] = ws.sc[1];
-        p.sum_lnL2[chain] = ws.sc[2];
+        p.sum_lnL[chain] = sum_lnL;
+        p.sum_lnL2[chain] = sum_lnL2;
         if (p.work) {
-            p.work[3 * (size_t)chain + 0] += ws.cnt[0];    // component evaluations (x P pixels each)
-            p.work[3 * (size_t)chain + 1] += ws.cnt[1];    // pixels of far-path rows (padding rows excluded below)
-            p.work[3 * (size_t)chain + 2] += ws.cnt[2];    // exp(-tau) + residual passes (x P pixels)
+            p.work[3 * (size_t)chain + 0] += w_shape;    // component evaluations (x P pixels each)
+            p.work[3 * (size_t)chain + 1] += w_far;      // pixels evaluated on the continued-fraction path
+            p.work[3 * (size_t)chain + 2] += w_like;     // exp(-tau) + residual passes (x P pixels)
         }
     }
 }
 
-__host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
-
-template <typename T>
-__host__ __device__ inline size_t k2_warp_bytes(int ppl_max, int ncomp_max, int cmax, bool lsf) {
-    const int ts = 4 * cmax + 1;
-    size_t b = 0;
-    b += align16(sizeof(double) * (ts + 6));                  // th, sc[3], cnt[3]
-    b += align16(sizeof(float) * 2 * ts);                      // asf, psd
-    b += align16(sizeof(int) * 3 * ts);                        // acc, rej, acct
-    b += align16(sizeof(T) * (size_t)(ncomp_max + 2) * 32 * ppl_max); // shape cache (+ spare slot) + base
-    if (lsf) b += align16(sizeof(T) * (32 * ppl_max + VAMP_MAX_LSF_TAPS));
-    return b;
-}
-
 template <typename T, int KIND, bool WT, bool LSF>
-__global__ void __launch_bounds__(K2_WARPS * 32, (sizeof(T) == 4) ? VAMP_K2_MINBLOCKS : 3)
-k2_mcmc_kernel(McmcDev p, int ppl_max, int ncomp_max) {
+__global__ void __launch_bounds__(K2_WARPS * 32, (sizeof(T) == 4) ? VAMP_K2_MINBLOCKS : 2)
+k2_mcmc_kernel(McmcDev p, int ncomp_max) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     T* lsf_s = reinterpret_cast<T*>(smem_raw);
-    const size_t head = align16(sizeof(T) * VAMP_MAX_LSF_TAPS);
+    const size_t head = LSF ? align16(sizeof(T) * VAMP_MAX_LSF_TAPS) : 0;
     if (LSF) {
         for (int i = threadIdx.x; i < p.rs.lsf_taps; i += blockDim.x) lsf_s[i] = RS<T>::lsf(p.rs)[i];
         __syncthreads();
     }
-    const int chain = blockIdx.x * K2_WARPS + warp;
-    if (chain >= p.B) return;
-    const int ts = p.tstride;
-    unsigned char* base = smem_raw + head + (size_t)warp * k2_warp_bytes<T>(ppl_max, ncomp_max, p.cmax, LSF);
-    WarpSmem ws;
-    ws.th = reinterpret_cast<double*>(base);
-    ws.sc = ws.th + ts;
-    ws.cnt = reinterpret_cast<unsigned long long*>(ws.sc + 3);
-    base += align16(sizeof(double) * (ts + 6));
-    // best state and tally statistics are touched rarely (improvements, every `thin` iterations):
-    // they stay in global memory so that more chains fit on an SM
-    ws.best = p.best_theta + (size_t)chain * ts;
-    ws.mean = p.mean + (size_t)chain * ts;
-    ws.m2 = p.m2 + (size_t)chain * ts;
-    ws.comom = p.comom + (size_t)chain * 6 * p.cmax;
-    ws.asf = reinterpret_cast<float*>(base);
-    ws.psd = ws.asf + ts;
-    base += align16(sizeof(float) * 2 * ts);
-    ws.acc = reinterpret_cast<int*>(base);
-    ws.rej = ws.acc + ts;
-    ws.acct = ws.rej + ts;
-    base += align16(sizeof(int) * 3 * ts);
-    const int HS = 16 * ppl_max;                                // row pairs x 32 lanes, in P2 units
-    P2<T>* Hbuf = reinterpret_cast<P2<T>*>(base);               // [(ncomp_max + 1)][HS]
-    P2<T>* basebuf = Hbuf + (size_t)(ncomp_max + 1) * HS;       // [HS]
-    base += align16(sizeof(T) * (size_t)(ncomp_max + 2) * 32 * ppl_max);
-    T* lsf_buf = reinterpret_cast<T*>(base);
-    mcmc_chain<T, KIND, WT, LSF>(p, chain, lane, ws, Hbuf, basebuf, lsf_buf, lsf_s, HS);
+    // launch order: the host sorts chains by ascending cost; the longest chains go first so the
+    // tail of the grid is made of short ones
+    const int chain = p.B - 1 - (blockIdx.x * K2_WARPS + warp);
+    if (chain < 0) return;
+    unsigned char* wb = smem_raw + head + (size_t)warp * K2Lay<T, WT>::bytes(ncomp_max, p.cmax, LSF);
+    mcmc_chain<T, KIND, WT, LSF>(p, chain, lane, wb, ncomp_max, lsf_s);
 }
 
 // ---- initial states -------------------------------------------------------------------------
@@ -579,15 +649,14 @@ __global__ void init_state_kernel(McmcDev p) {
 }
 
 template <typename T, int KIND, bool WT, bool LSF>
-cudaError_t launch_k2_t(const McmcDev& p, int max_npix, int max_ncomp, cudaStream_t st) {
-    const int ppl_max = 2 * ((max_npix + 63) / 64);          // rows, in pairs of 32-pixel rows
-    const size_t smem = align16(sizeof(T) * VAMP_MAX_LSF_TAPS) + K2_WARPS * k2_warp_bytes<T>(ppl_max, max_ncomp, p.cmax, LSF);
+cudaError_t launch_k2_t(const McmcDev& p, int max_ncomp, cudaStream_t st) {
+    const size_t smem = (LSF ? align16(sizeof(T) * VAMP_MAX_LSF_TAPS) : 0) + K2_WARPS * K2Lay<T, WT>::bytes(max_ncomp, p.cmax, LSF);
     auto kern = k2_mcmc_kernel<T, KIND, WT, LSF>;
     if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int grid = (p.B + K2_WARPS - 1) / K2_WARPS;
-    kern<<<grid, K2_WARPS * 32, smem, st>>>(p, ppl_max, max_ncomp);
+    kern<<<grid, K2_WARPS * 32, smem, st>>>(p, max_ncomp);
     return cudaGetLastError();
 }
 
@@ -614,8 +683,8 @@ cudaError_t VAMP_INST_NAME(vamp_launch_k2)(const McmcDev& p, int max_npix, int m
     if (max_npix > VAMP_TILE_PIX) return cudaErrorInvalidValue;
     const bool lsf = p.rs.lsf_taps > 1;
     if (p.sd_free)
-        return lsf ? launch_k2_t<InstT, InstKind, false, true>(p, max_npix, max_ncomp, st)
-                   : launch_k2_t<InstT, InstKind, false, false>(p, max_npix, max_ncomp, st);
-    return lsf ? launch_k2_t<InstT, InstKind, true, true>(p, max_npix, max_ncomp, st)
-               : launch_k2_t<InstT, InstKind, true, false>(p, max_npix, max_ncomp, st);
+        return lsf ? launch_k2_t<InstT, InstKind, false, true>(p, max_ncomp, st)
+                   : launch_k2_t<InstT, InstKind, false, false>(p, max_ncomp, st);
+    return lsf ? launch_k2_t<InstT, InstKind, true, true>(p, max_ncomp, st)
+               : launch_k2_t<InstT, InstKind, true, false>(p, max_ncomp, st);
 }
