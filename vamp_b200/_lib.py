@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvamp_b200.so")
+LIB_PATH = os.environ.get("VAMP_B200_LIB") or os.path.join(_HERE, "libvamp_b200.so")   # env override: kernel experiments
 
 VAMP_F32, VAMP_F64 = 0, 1
 VAMP_GAUSS, VAMP_VOIGT = 0, 1

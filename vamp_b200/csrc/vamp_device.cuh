@@ -132,6 +132,10 @@ template <> struct Fad<float> {
     static __device__ __forceinline__ float a(int i) { return WEID_A_F32[i]; }
     static __device__ __forceinline__ float cfn(int i) { return CF_NUM_F32[i]; }
     static __device__ __forceinline__ float cfd(int i) { return CF_DEN_F32[i]; }
+    // compile-time-index forms: the coefficient becomes an instruction immediate
+    static __device__ __forceinline__ constexpr float ac(int i) { return WEID_A_F32_c(i); }
+    static __device__ __forceinline__ constexpr float cfnc(int i) { return CF_NUM_F32_c(i); }
+    static __device__ __forceinline__ constexpr float cfdc(int i) { return CF_DEN_F32_c(i); }
     static __device__ __forceinline__ float R2() { return 32.0f; }
     static __device__ __forceinline__ float FAR2() { return 1.0e8f; }
     static __device__ __forceinline__ float BIG() { return 1.0e18f; }
@@ -143,6 +147,9 @@ template <> struct Fad<double> {
     static __device__ __forceinline__ double a(int i) { return WEID_A_F64[i]; }
     static __device__ __forceinline__ double cfn(int i) { return CF_NUM_F64[i]; }
     static __device__ __forceinline__ double cfd(int i) { return CF_DEN_F64[i]; }
+    static __device__ __forceinline__ constexpr double ac(int i) { return WEID_A_F64_c(i); }
+    static __device__ __forceinline__ constexpr double cfnc(int i) { return CF_NUM_F64_c(i); }
+    static __device__ __forceinline__ constexpr double cfdc(int i) { return CF_DEN_F64_c(i); }
     static __device__ __forceinline__ double R2() { return 64.0; }
     static __device__ __forceinline__ double FAR2() { return 1.0e16; }
     static __device__ __forceinline__ double BIG() { return 1.0e150; }
@@ -355,14 +362,14 @@ __device__ __forceinline__ P2<T> fad_core2(P2<T> X, T y, P2<T> S) {
     const P2<T> Zi = p2_mul(XR, p2_bc<T>(T(2) * L));
     const P2<T> t = p2_add(Zr, Zr);
     const P2<T> nn = p2_mul(p2_sub(p2_bc<T>(twoLy - L2), S), R);        // -|Z|^2
-    P2<T> b1 = p2_fma(t, p2_bc<T>(Fad<T>::a(0)), p2_bc<T>(Fad<T>::a(1))), b2 = p2_bc<T>(Fad<T>::a(0));
+    P2<T> b1 = p2_fma(t, p2_bc<T>(Fad<T>::ac(0)), p2_bc<T>(Fad<T>::ac(1))), b2 = p2_bc<T>(Fad<T>::ac(0));
 #pragma unroll
     for (int j = 2; j < Fad<T>::N - 1; ++j) {
-        const P2<T> nb = p2_fma(t, b1, p2_fma(nn, b2, p2_bc<T>(Fad<T>::a(j))));
+        const P2<T> nb = p2_fma(t, b1, p2_fma(nn, b2, p2_bc<T>(Fad<T>::ac(j))));
         b2 = b1;
         b1 = nb;
     }
-    const P2<T> pr = p2_fma(b1, Zr, p2_fma(nn, b2, p2_bc<T>(Fad<T>::a(Fad<T>::N - 1))));
+    const P2<T> pr = p2_fma(b1, Zr, p2_fma(nn, b2, p2_bc<T>(Fad<T>::ac(Fad<T>::N - 1))));
     const P2<T> pi = p2_mul(b1, Zi);
     const P2<T> ir = p2_mul(p2_bc<T>(L + y), R);                        // Re 1/(L - iz)
     const P2<T> i2r = p2_sub(p2_mul(ir, ir), p2_mul(XR, XR));
@@ -380,19 +387,19 @@ __device__ __forceinline__ P2<T> fad_far2(P2<T> X, T y, P2<T> S) {
     const P2<T> vi = p2_mul(p2_add(tr, tr), ti);
     const P2<T> nvi = p2_neg(vi);
     // Horner in v with real coefficients; the first step has a real accumulator
-    P2<T> nr = p2_fma(p2_bc<T>(Fad<T>::cfn(Fad<T>::CFN - 1)), vr, p2_bc<T>(Fad<T>::cfn(Fad<T>::CFN - 2)));
-    P2<T> ni = p2_mul(p2_bc<T>(Fad<T>::cfn(Fad<T>::CFN - 1)), vi);
+    P2<T> nr = p2_fma(p2_bc<T>(Fad<T>::cfnc(Fad<T>::CFN - 1)), vr, p2_bc<T>(Fad<T>::cfnc(Fad<T>::CFN - 2)));
+    P2<T> ni = p2_mul(p2_bc<T>(Fad<T>::cfnc(Fad<T>::CFN - 1)), vi);
 #pragma unroll
     for (int k = Fad<T>::CFN - 3; k >= 0; --k) {
-        const P2<T> a = p2_fma(nr, vr, p2_fma(ni, nvi, p2_bc<T>(Fad<T>::cfn(k))));
+        const P2<T> a = p2_fma(nr, vr, p2_fma(ni, nvi, p2_bc<T>(Fad<T>::cfnc(k))));
         ni = p2_fma(nr, vi, p2_mul(ni, vr));
         nr = a;
     }
-    P2<T> dr = p2_fma(p2_bc<T>(Fad<T>::cfd(Fad<T>::CFD - 1)), vr, p2_bc<T>(Fad<T>::cfd(Fad<T>::CFD - 2)));
-    P2<T> di = p2_mul(p2_bc<T>(Fad<T>::cfd(Fad<T>::CFD - 1)), vi);
+    P2<T> dr = p2_fma(p2_bc<T>(Fad<T>::cfdc(Fad<T>::CFD - 1)), vr, p2_bc<T>(Fad<T>::cfdc(Fad<T>::CFD - 2)));
+    P2<T> di = p2_mul(p2_bc<T>(Fad<T>::cfdc(Fad<T>::CFD - 1)), vi);
 #pragma unroll
     for (int k = Fad<T>::CFD - 3; k >= 0; --k) {
-        const P2<T> a = p2_fma(dr, vr, p2_fma(di, nvi, p2_bc<T>(Fad<T>::cfd(k))));
+        const P2<T> a = p2_fma(dr, vr, p2_fma(di, nvi, p2_bc<T>(Fad<T>::cfdc(k))));
         di = p2_fma(dr, vi, p2_mul(di, vr));
         dr = a;
     }
@@ -465,19 +472,34 @@ __device__ __forceinline__ T row_shape(const CompC<T>& cc, T du, unsigned& nfar)
 // Two rows at once (the chain kernel's unit of work).  Pair policy: all 64 pixels far -> continued
 // fraction, otherwise Weideman (valid over the whole upper half plane) for the pair.  No overflow
 // guard: make_comp_fast clamps g and y, so padding pixels give H ~ 1e-18 (exp(-tau) = 1 exactly).
-// `far` returns the path taken (for the work counters).
+// Split in two so the chain kernel can classify pair j + 1 (load, 3 packed operations, vote)
+// under the arithmetic of pair j.
+template <typename T, int KIND>
+__device__ __forceinline__ void pair_classify(const CompC<T>& cc, P2<T> DU, P2<T>& X, P2<T>& S, bool& far) {
+    X = p2_mul(p2_sub(DU, p2_bc<T>(cc.cb)), p2_bc<T>(cc.g));
+    if (KIND == VAMP_KIND_GAUSS) {
+        S = p2_mul(X, X);
+        far = false;
+    } else {
+        S = p2_fma(X, X, p2_bc<T>(cc.y2));
+        far = __all_sync(VAMP_FULL_MASK, !(fmin(p2_lo(S), p2_hi(S)) < Fad<T>::R2()));
+    }
+}
+template <typename T, int KIND>
+__device__ __forceinline__ P2<T> pair_eval(const CompC<T>& cc, P2<T> X, P2<T> S, bool far, unsigned& nfar) {
+    if (KIND == VAMP_KIND_GAUSS) return p2_make(Real<T>::exp2_neg(p2_lo(S)), Real<T>::exp2_neg(p2_hi(S)));
+    if (far) {
+        nfar += 64u;
+        return fad_far2<T>(X, cc.y, S);
+    }
+    return fad_core2<T>(X, cc.y, S);
+}
 template <typename T, int KIND>
 __device__ __forceinline__ P2<T> pair_shape(const CompC<T>& cc, P2<T> DU, bool& far) {
-    const P2<T> X = p2_mul(p2_sub(DU, p2_bc<T>(cc.cb)), p2_bc<T>(cc.g));
-    if (KIND == VAMP_KIND_GAUSS) {
-        const P2<T> Q = p2_mul(X, X);
-        far = false;
-        return p2_make(Real<T>::exp2_neg(p2_lo(Q)), Real<T>::exp2_neg(p2_hi(Q)));
-    }
-    const P2<T> S = p2_fma(X, X, p2_bc<T>(cc.y2));
-    far = __all_sync(VAMP_FULL_MASK, !(fmin(p2_lo(S), p2_hi(S)) < Fad<T>::R2()));
-    if (far) return fad_far2<T>(X, cc.y, S);
-    return fad_core2<T>(X, cc.y, S);
+    P2<T> X, S;
+    unsigned dummy = 0u;
+    pair_classify<T, KIND>(cc, DU, X, S, far);
+    return pair_eval<T, KIND>(cc, X, S, far, dummy);
 }
 
 // ------------------------------------------------------------------------------------------------

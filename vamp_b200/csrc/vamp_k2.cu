@@ -26,8 +26,15 @@ namespace {
 
 constexpr int K2_WARPS = 4;
 #ifndef VAMP_K2_MINBLOCKS
-#define VAMP_K2_MINBLOCKS 5
+#define VAMP_K2_MINBLOCKS 6
 #endif
+#ifndef VAMP_K2_UNROLL
+#define VAMP_K2_UNROLL 0          // 1: pixel passes fully unrolled over the 4 row pairs of a tile, 2: by two, 0: rolled
+#endif
+#ifndef VAMP_K2_STEPUNROLL
+#define VAMP_K2_STEPUNROLL 1      // 1: the centroid / width steps of a component are unrolled (no selects)
+#endif
+constexpr int K2_PAIRS = VAMP_TILE_PIX / 64;
 constexpr double FWHM_PER_SIGMA = 2.35482004503094938202;
 
 // ------------------------------------------------------------------------------------------------
@@ -60,17 +67,6 @@ template <> struct RngMath<float> {
     }
 };
 
-template <typename T>
-struct WarpRng {
-    T z0, z1, lu0, lu1;
-    uint32_t uid_lo, uid_hi, k0, k1;
-    __device__ __forceinline__ void refill(unsigned long long blk, int lane) {
-        const uint4 x = philox4x32_10(make_uint4(uid_lo, uid_hi, (uint32_t)blk, ((uint32_t)(blk >> 32) << 8) | (uint32_t)lane),
-                                      make_uint2(k0, k1));
-        RngMath<T>::fill(x, z0, z1, lu0, lu1);
-    }
-};
-
 // PyMC 2.3 Metropolis.tune switch (oracle/sampler.py:pymc2_tune)
 __device__ __forceinline__ float tune_factor(float rate) {
     if (rate < 0.001f) return 0.1f;
@@ -82,9 +78,14 @@ __device__ __forceinline__ float tune_factor(float rate) {
     return 1.0f;
 }
 
+// natural log in the step logic: the fp32 kernel uses the raw MUFU lg2 (arguments are O(1))
 template <typename T> struct StepMath;
 template <> struct StepMath<float> {
-    static __device__ __forceinline__ float log_(float x) { return __logf(x); }
+    static __device__ __forceinline__ float log_(float x) {
+        float r;
+        asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+        return r * 0.693147180559945309f;
+    }
 };
 template <> struct StepMath<double> {
     static __device__ __forceinline__ double log_(double x) { return log(x); }
@@ -93,26 +94,43 @@ template <> struct StepMath<double> {
 __host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
 // ------------------------------------------------------------------------------------------------
-// Shared-memory slice of one chain (= warp), sized for one 256-pixel tile so that every pixel
-// buffer sits at a compile-time offset from ONE running address register.
-//   pixel buffers (PAIR layout: element 32 jj + lane holds pixels 64 jj + lane and 64 jj + 32 + lane):
-//     du | flux | base (tau of the other components, pre-multiplied by -log2 e) | [1/noise] |
+// Shared memory.  Pixel buffers are in PAIR layout (element 32 jj + lane holds pixels 64 jj + lane
+// and 64 jj + 32 + lane) and sized for one 256-pixel tile, so every buffer sits at a compile-time
+// offset from a base register.
+//   region slice, shared by the warps of a CTA (they almost always fit the same region, see
+//     k2_mcmc_kernel):  du | flux | [1/noise]
+//   chain slice (one per warp):  base (tau of the other components, pre-multiplied by -log2 e) |
 //     shape cache: ncomp_max + 1 slots (one spare: a proposal is evaluated into the spare slot and
-//     accepting it swaps two slot indices instead of copying)
-//   scalar state: theta (kernel precision), proposal scale asf * psd, acc / rej / acc_total counters,
-//     slot table.
+//     accepting it swaps two slot indices instead of copying) | [LSF staging] |
+//     sd record | one record per component
+template <typename T>
+struct alignas(16) CompRec {       // 64 bytes (fp32) / 80 bytes (fp64)
+    T th[4];                       // amplitude, centroid, w1, w2 (kernel precision)
+    float scl[4];                  // proposal scale asf * psd
+    int acc[4];                    // accepted since the last tune
+    int slot;                      // shape-cache slot of this component
+    float g, y;                    // make_comp_fast constants of (w1, w2) - a centroid step reuses them
+    int pad;
+};
+template <typename T>
+struct alignas(16) SdRec {
+    T th;
+    float scl;
+    int acc;
+};
+
 template <typename T, bool WT>
 struct K2Lay {
     static constexpr int NE = VAMP_TILE_PIX / 2;
     static constexpr int SLOT = NE * (int)sizeof(P2<T>);
-    static constexpr int DU = 0, F = SLOT, BASE = 2 * SLOT, W = 3 * SLOT, H = (WT ? 4 : 3) * SLOT;
+    static constexpr int DU = 0, F = SLOT, W = 2 * SLOT, REGION = (WT ? 3 : 2) * SLOT;
+    static constexpr int BASE = 0, H = SLOT;
     static __host__ __device__ size_t lsf_bytes(bool lsf) {
         return lsf ? align16(sizeof(T) * (VAMP_TILE_PIX + VAMP_MAX_LSF_TAPS)) : 0;
     }
-    static __host__ __device__ size_t bytes(int ncomp_max, int cmax, bool lsf) {
-        const int ts = 4 * cmax + 1;
-        return (size_t)H + (size_t)(ncomp_max + 1) * SLOT + lsf_bytes(lsf) + align16(sizeof(T) * ts) +
-               align16(sizeof(float) * ts) + 3 * align16(sizeof(int) * ts) + align16(sizeof(int) * (ncomp_max + 1));
+    static __host__ __device__ size_t bytes(int ncomp_max, bool lsf) {
+        return (size_t)H + (size_t)(ncomp_max + 1) * SLOT + lsf_bytes(lsf) + sizeof(SdRec<T>) +
+               (size_t)ncomp_max * sizeof(CompRec<T>);
     }
 };
 
@@ -126,14 +144,14 @@ struct LsfCtx {
 // Residual sum of squares from a model row-pair buffer in natural order (LSF path only):
 // buf[h + p] holds m_p - 1; out = 1 + sum_t lsf[t] (m - 1)[p + h - t], zero outside [0, P).
 template <typename T, bool WT>
-__device__ __forceinline__ T lsf_residuals(const LsfCtx<T>& lc, const unsigned char* wb, int npairs, int lane) {
+__device__ __forceinline__ T lsf_residuals(const LsfCtx<T>& lc, const unsigned char* rb, int npairs, int lane) {
     typedef K2Lay<T, WT> Lay;
     const int h = lc.taps >> 1;
     for (int i = lane; i < 2 * h; i += 32) lc.buf[(i < h) ? i : (64 * npairs + i)] = T(0);
     __syncwarp();
     const T* bq = lc.buf + lane + 2 * h;
-    const T* fn = reinterpret_cast<const T*>(wb + Lay::F);
-    const T* wn = reinterpret_cast<const T*>(wb + Lay::W);
+    const T* fn = reinterpret_cast<const T*>(rb + Lay::F);
+    const T* wn = reinterpret_cast<const T*>(rb + Lay::W);
     T S = T(0);
     for (int j = 0; j < 2 * npairs; ++j) {
         T acc = T(1);
@@ -150,52 +168,50 @@ __device__ __forceinline__ T lsf_residuals(const LsfCtx<T>& lc, const unsigned c
     return S;
 }
 
-// One likelihood pass with the component's CACHED shape (amplitude steps, initial state):
-// m = ex2(An * H + base), returns sum (w (f - m))^2 over the region, identical in every lane.
-template <typename T, bool WT, bool LSF>
-__device__ __forceinline__ T pass_cached(T An, const P2<T>* __restrict__ Hc, const unsigned char* wb, int npairs, int lane,
-                                         const LsfCtx<T>& lc) {
-    typedef K2Lay<T, WT> Lay;
-    const P2<T>* pf = reinterpret_cast<const P2<T>*>(wb + Lay::F) + lane;
-    const P2<T>* pb = reinterpret_cast<const P2<T>*>(wb + Lay::BASE) + lane;
-    const P2<T>* pw = reinterpret_cast<const P2<T>*>(wb + Lay::W) + lane;
-    const P2<T> A2 = p2_bc<T>(An);
-    P2<T> S2 = p2_bc<T>(T(0));
-#pragma unroll 1
-    for (int e = 0; e < 32 * npairs; e += 32) {
-        const P2<T> M = p2_exp_scaled<T>(p2_fma(A2, Hc[e], pb[e]));
-        if (LSF) {
-            lc.buf[(lc.taps >> 1) + lane + 2 * e] = p2_lo(M) - T(1);
-            lc.buf[(lc.taps >> 1) + lane + 2 * e + 32] = p2_hi(M) - T(1);
-        } else {
-            P2<T> R = p2_sub(pf[e], M);
-            if (WT) R = p2_mul(R, pw[e]);
-            S2 = p2_fma(R, R, S2);
-        }
-    }
-    T S = p2_lo(S2) + p2_hi(S2);
-    if (LSF) S = lsf_residuals<T, WT>(lc, wb, npairs, lane);
-    return warp_sum(S);
+#ifndef VAMP_K2_NOINLINE_EVAL
+#define VAMP_K2_NOINLINE_EVAL 0
+#endif
+// out-of-line copy of the rational functions (experiment: one body shared by all unrolled call sites)
+template <typename T, int KIND>
+__device__ __noinline__ P2<T> pair_eval_call(P2<T> X, P2<T> S, T y, bool far) {
+    if (KIND == VAMP_KIND_GAUSS) return p2_make(Real<T>::exp2_neg(p2_lo(S)), Real<T>::exp2_neg(p2_hi(S)));
+    if (far) return fad_far2<T>(X, y, S);
+    return fad_core2<T>(X, y, S);
 }
 
-// One likelihood pass that EVALUATES the component `cc` (centroid / width steps): the new shape
-// goes to the spare slot Hs.  `nfar` counts pixels that took the continued-fraction path.
-template <typename T, int KIND, bool WT, bool LSF>
-__device__ __forceinline__ T pass_fresh(const CompC<T>& cc, T An, P2<T>* __restrict__ Hs, const unsigned char* wb, int npairs,
-                                        int lane, const LsfCtx<T>& lc, unsigned& nfar, bool& last_far) {
+// One likelihood pass over the region.  FRESH: evaluate the component `cc` (centroid / width
+// steps) and store its shape to the spare slot Hs; otherwise reuse the cached shape Hc (amplitude
+// steps, initial state).  m = ex2(An * H + base); returns sum (w (f - m))^2, identical in every lane.
+// The trips over the row pairs are fully unrolled (a tile has at most 4): every shared-memory
+// address is base register + immediate and consecutive pairs overlap in the schedule.
+// `nfar` counts pixels that took the continued-fraction path (padding excluded by the caller).
+template <typename T, int KIND, bool WT, bool LSF, bool FRESH>
+__device__ __forceinline__ T chain_pass(const CompC<T>& cc, T An, const P2<T>* __restrict__ Hc, P2<T>* __restrict__ Hs,
+                                        const unsigned char* rb, const unsigned char* wb, int npairs, int lane,
+                                        const LsfCtx<T>& lc, unsigned& nfar, bool& last_far) {
     typedef K2Lay<T, WT> Lay;
-    const P2<T>* pd = reinterpret_cast<const P2<T>*>(wb + Lay::DU) + lane;
-    const P2<T>* pf = reinterpret_cast<const P2<T>*>(wb + Lay::F) + lane;
+    const P2<T>* pd = reinterpret_cast<const P2<T>*>(rb + Lay::DU) + lane;
+    const P2<T>* pf = reinterpret_cast<const P2<T>*>(rb + Lay::F) + lane;
+    const P2<T>* pw = reinterpret_cast<const P2<T>*>(rb + Lay::W) + lane;
     const P2<T>* pb = reinterpret_cast<const P2<T>*>(wb + Lay::BASE) + lane;
-    const P2<T>* pw = reinterpret_cast<const P2<T>*>(wb + Lay::W) + lane;
     const P2<T> A2 = p2_bc<T>(An);
     P2<T> S2 = p2_bc<T>(T(0));
     bool far = false;
-#pragma unroll 1
-    for (int e = 0; e < 32 * npairs; e += 32) {
-        const P2<T> H = pair_shape<T, KIND>(cc, pd[e], far);
-        nfar += far ? 64u : 0u;
-        Hs[e] = H;
+    auto trip = [&](int e) {
+        P2<T> H;
+        if (FRESH) {
+            P2<T> X, S;
+            pair_classify<T, KIND>(cc, pd[e], X, S, far);
+#if VAMP_K2_NOINLINE_EVAL
+            nfar += far ? 64u : 0u;
+            H = pair_eval_call<T, KIND>(X, S, cc.y, far);
+#else
+            H = pair_eval<T, KIND>(cc, X, S, far, nfar);
+#endif
+            Hs[e] = H;
+        } else {
+            H = Hc[e];
+        }
         const P2<T> M = p2_exp_scaled<T>(p2_fma(A2, H, pb[e]));
         if (LSF) {
             lc.buf[(lc.taps >> 1) + lane + 2 * e] = p2_lo(M) - T(1);
@@ -205,10 +221,24 @@ __device__ __forceinline__ T pass_fresh(const CompC<T>& cc, T An, P2<T>* __restr
             if (WT) R = p2_mul(R, pw[e]);
             S2 = p2_fma(R, R, S2);
         }
+    };
+#if VAMP_K2_UNROLL == 1
+#pragma unroll
+    for (int jj = 0; jj < K2_PAIRS; ++jj)
+        if (jj < npairs) trip(32 * jj);
+#elif VAMP_K2_UNROLL == 2
+#pragma unroll 1
+    for (int e = 0; e < 32 * npairs; e += 64) {
+        trip(e);
+        if (e + 32 < 32 * npairs) trip(e + 32);
     }
+#else
+#pragma unroll 1
+    for (int e = 0; e < 32 * npairs; e += 32) trip(e);
+#endif
     last_far = far;
     T S = p2_lo(S2) + p2_hi(S2);
-    if (LSF) S = lsf_residuals<T, WT>(lc, wb, npairs, lane);
+    if (LSF) S = lsf_residuals<T, WT>(lc, rb, npairs, lane);
     return warp_sum(S);
 }
 
@@ -218,12 +248,15 @@ __device__ __forceinline__ T pass_fresh(const CompC<T>& cc, T An, P2<T>* __restr
 // are stepped in order, then sd.  An amplitude step reuses the cached shape, a centroid / width
 // step re-evaluates ONE component over the region (the economy PyMC 2's LazyFunction cache gives
 // the reference), `base` carries the other components' tau and moves to the next component with
-// two FMAs per pixel.  The step logic runs in the kernel's precision; acceptance counters are
-// gathered in a per-component bit mask and written by lanes 0..3 once per component.
+// two FMAs per pixel.  The step logic runs in the kernel's precision.  Bookkeeping is kept off
+// the step path: a component's parameters, scales and counters are one 64-byte record (one
+// vector load at the start, one read-modify-write at the end of the component), rejections are
+// derived (every parameter is proposed exactly once per iteration) and the post-burn acceptance
+// total is settled at tune / burn / exit events.
 template <typename T, int KIND, bool WT, bool LSF>
-__device__ void mcmc_chain(const McmcDev& p, int chain, int lane, unsigned char* wb, int ncomp_max, const T* lsf_s) {
+__device__ void mcmc_chain(const McmcDev& p, int chain, int lane, const unsigned char* rb, unsigned char* wb, int ncomp_max,
+                           const T* lsf_s) {
     typedef K2Lay<T, WT> Lay;
-    typedef typename RS<T>::Pair Pair;
     constexpr int NP = (KIND == VAMP_KIND_VOIGT) ? 4 : 3;
     const RegionSetDev& rs = p.rs;
     const int r = p.item_region[chain];
@@ -234,12 +267,13 @@ __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, unsigned char*
     const int k = NP * n + (WT ? 0 : 1);
     const int npairs = (P + 63) >> 6;
     const int npad = 64 * npairs - P;
-    const int tune_interval = p.tune_interval, thin = p.thin, burn = p.burn, tune_throughout = p.tune_throughout;
+    const int burn = p.burn;
     const T NK = Real<T>::NEGK();
     const size_t gb = (size_t)chain * ts;
 
     // ---- carve the slice
     P2<T>* const Hbuf = reinterpret_cast<P2<T>*>(wb + Lay::H) + lane;           // slot s at Hbuf + s * NE
+    P2<T>* const pbase = reinterpret_cast<P2<T>*>(wb + Lay::BASE) + lane;
     unsigned char* sp_ = wb + Lay::H + (size_t)(ncomp_max + 1) * Lay::SLOT;
     LsfCtx<T> lc;
     lc.buf = reinterpret_cast<T*>(sp_);
@@ -247,43 +281,33 @@ __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, unsigned char*
     lc.taps = rs.lsf_taps;
     lc.P = P;
     sp_ += Lay::lsf_bytes(LSF);
-    T* const th = reinterpret_cast<T*>(sp_);
-    sp_ += align16(sizeof(T) * ts);
-    float* const scl = reinterpret_cast<float*>(sp_);
-    sp_ += align16(sizeof(float) * ts);
-    int* const acc = reinterpret_cast<int*>(sp_);
-    sp_ += align16(sizeof(int) * ts);
-    int* const rej = reinterpret_cast<int*>(sp_);
-    sp_ += align16(sizeof(int) * ts);
-    int* const acct = reinterpret_cast<int*>(sp_);
-    sp_ += align16(sizeof(int) * ts);
-    int* const slot = reinterpret_cast<int*>(sp_);
+    SdRec<T>* const sdrec = reinterpret_cast<SdRec<T>*>(sp_);
+    CompRec<T>* const recs = reinterpret_cast<CompRec<T>*>(sp_ + sizeof(SdRec<T>));
 
-    // ---- region and state -> shared
-    {
-        const Pair* gdu = RS<T>::pdu(rs) + (rs.pix_off[r] >> 1);
-        const Pair* gf = RS<T>::pf(rs) + (rs.pix_off[r] >> 1);
-        const Pair* gw = RS<T>::pw(rs) + (rs.pix_off[r] >> 1);
-        P2<T>* sd_ = reinterpret_cast<P2<T>*>(wb + Lay::DU) + lane;
-        P2<T>* sf_ = reinterpret_cast<P2<T>*>(wb + Lay::F) + lane;
-        P2<T>* sb_ = reinterpret_cast<P2<T>*>(wb + Lay::BASE) + lane;
-        P2<T>* sw_ = reinterpret_cast<P2<T>*>(wb + Lay::W) + lane;
-        for (int e = 0; e < 32 * npairs; e += 32) {
-            sd_[e] = p2_from(__ldg(gdu + e + lane));
-            sf_[e] = p2_from(__ldg(gf + e + lane));
-            if (WT) sw_[e] = p2_from(__ldg(gw + e + lane));
-            sb_[e] = p2_bc<T>(T(0));
-            Hbuf[n * Lay::NE + e] = p2_bc<T>(T(0));                 // spare slot
-        }
+    // is parameter i of the flat layout sampled by this chain?
+    auto is_free = [&](int i) -> bool { return (i == sdi) ? !WT : ((i < 4 * n) && ((i & 3) < NP)); };
+
+    // ---- state -> shared (the region slice was filled by the CTA)
+    for (int e = 0; e < 32 * npairs; e += 32) {
+        pbase[e] = p2_bc<T>(T(0));
+        Hbuf[n * Lay::NE + e] = p2_bc<T>(T(0));                     // spare slot
     }
-    for (int i = lane; i < ts; i += 32) {
-        th[i] = T(p.theta[gb + i]);
-        scl[i] = p.asf[gb + i] * p.psd[gb + i];
-        acc[i] = p.acc[gb + i];
-        rej[i] = p.rej[gb + i];
-        acct[i] = p.acc_total[gb + i];
+    for (int i = lane; i < 4 * n; i += 32) {
+        CompRec<T>& rc = recs[i >> 2];
+        rc.th[i & 3] = T(p.theta[gb + i]);
+        rc.scl[i & 3] = p.asf[gb + i] * p.psd[gb + i];
+        rc.acc[i & 3] = p.acc[gb + i];
+        if ((i & 3) == 0) rc.slot = i >> 2;
     }
-    for (int i = lane; i <= n; i += 32) slot[i] = i;
+    if (lane == 0) {
+        sdrec->th = T(p.theta[gb + sdi]);
+        sdrec->scl = p.asf[gb + sdi] * p.psd[gb + sdi];
+        sdrec->acc = p.acc[gb + sdi];
+    }
+    // proposals per parameter since the counters were last reset (the same for every parameter)
+    int tot = p.acc[gb] + p.rej[gb];
+    if (p.it0 > burn)                        // this launch continues a post-burn counting interval:
+        for (int i = lane; i < ts; i += 32) p.acc_total[gb + i] -= p.acc[gb + i];   // settled again at tune / exit
     __syncwarp();
 
     // centroid relative to the coordinate-tile base; the base is split so the fp32 kernel loses nothing
@@ -293,46 +317,55 @@ __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, unsigned char*
 
     // ---- build the shape cache; base holds the FULL tau here, one cached pass with A = 0 gives S
     {
-        P2<T>* sb_ = reinterpret_cast<P2<T>*>(wb + Lay::BASE) + lane;
-        const P2<T>* sd_ = reinterpret_cast<const P2<T>*>(wb + Lay::DU) + lane;
+        const P2<T>* sd_ = reinterpret_cast<const P2<T>*>(rb + Lay::DU) + lane;
         for (int c = 0; c < n; ++c) {
-            const CompC<T> cc = make_comp_fast<T, KIND>(th[VAMP_TH(c, 0)], cbase(th[VAMP_TH(c, 1)]), th[VAMP_TH(c, 2)],
-                                                        th[VAMP_TH(c, 3)]);
+            CompRec<T>& rc = recs[c];
+            const CompC<T> cc = make_comp_fast<T, KIND>(rc.th[0], cbase(rc.th[1]), rc.th[2], rc.th[3]);
+            rc.g = (float)cc.g;       // fp32 kernel only (see the centroid step); harmless otherwise
+            rc.y = (float)cc.y;
             const P2<T> A2 = p2_bc<T>(NK * cc.A);
             bool far;
             for (int e = 0; e < 32 * npairs; e += 32) {
                 const P2<T> H = pair_shape<T, KIND>(cc, sd_[e], far);
                 Hbuf[c * Lay::NE + e] = H;
-                sb_[e] = p2_fma(A2, H, sb_[e]);
+                pbase[e] = p2_fma(A2, H, pbase[e]);
             }
         }
     }
-    T Scur = pass_cached<T, WT, LSF>(T(0), Hbuf + n * Lay::NE, wb, npairs, lane, lc);
-    T sd = WT ? T(1) : th[sdi];
+    CompC<T> cz;
+    cz.A = cz.cb = cz.g = cz.y = cz.y2 = cz.L2 = T(0);
+    unsigned dummy = 0u;
+    bool dummy_far;
+    T Scur = chain_pass<T, KIND, WT, LSF, false>(cz, T(0), Hbuf + n * Lay::NE, nullptr, rb, wb, npairs, lane, lc, dummy, dummy_far);
+    T sd = WT ? T(1) : sdrec->th;
     T logsd = WT ? T(0) : StepMath<T>::log_(sd);
     T hiv = WT ? T(0.5) : T(0.5) / (sd * sd);                 // 1 / (2 sd^2)
     T lp = T(0);                                              // sum_c (ln A_c - A_c), kept incrementally
     for (int c = 0; c < n; ++c) {
-        const T a = th[VAMP_TH(c, 0)];
+        const T a = recs[c].th[0];
         lp += StepMath<T>::log_(a) - a;
     }
-    double best_logp = p.best_logp[chain], sum_lnL = p.sum_lnL[chain], sum_lnL2 = p.sum_lnL2[chain];
+    const T lognorm = WT ? T(rs.lognorm[r]) : T(0);
+    T best_logp = T(p.best_logp[chain]);
     int ntally = p.ntally[chain];
     unsigned long long w_shape = 0ull, w_far = 0ull, w_like = 0ull;
 
     // ---- random stream: step counter q = 64 qblk + qs
-    WarpRng<T> rng;
-    {
-        const unsigned long long uid = p.chain_uid[chain];
-        rng.uid_lo = (uint32_t)uid;
-        rng.uid_hi = (uint32_t)(uid >> 32);
-        rng.k0 = (uint32_t)p.seed;
-        rng.k1 = (uint32_t)(p.seed >> 32);
-    }
+    const unsigned long long uid = p.chain_uid[chain];
     unsigned long long qblk = ((unsigned long long)p.it0 * (unsigned long long)k) >> 6;
     int qs = (int)(((unsigned long long)p.it0 * (unsigned long long)k) & 63ull);
-    rng.refill(qblk, lane);
-    T zc = (qs < 32) ? rng.z0 : rng.z1, luc = (qs < 32) ? rng.lu0 : rng.lu1;
+    T zc, luc, zn, lun;                     // current / next half of the 64-step block
+    auto refill = [&]() {
+        const uint4 x = philox4x32_10(make_uint4((uint32_t)uid, (uint32_t)(uid >> 32), (uint32_t)qblk,
+                                                 ((uint32_t)(qblk >> 32) << 8) | (uint32_t)lane),
+                                      make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32)));
+        RngMath<T>::fill(x, zc, zn, luc, lun);
+    };
+    refill();
+    if (qs >= 32) {
+        zc = zn;
+        luc = lun;
+    }
     auto draw = [&](T& z, T& lu) {
         z = __shfl_sync(VAMP_FULL_MASK, zc, qs);               // source lane = qs mod 32
         lu = __shfl_sync(VAMP_FULL_MASK, luc, qs);
@@ -341,69 +374,83 @@ __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, unsigned char*
             if (qs == 64) {
                 qs = 0;
                 ++qblk;
-                rng.refill(qblk, lane);
-                zc = rng.z0;
-                luc = rng.lu0;
+                refill();
             } else {
-                zc = rng.z1;
-                luc = rng.lu1;
+                zc = zn;
+                luc = lun;
             }
         }
     };
 
     const T c_hi = T(P - 1);
-    const T w_hi = T((double)(P - 1) * (KIND == VAMP_KIND_VOIGT ? 0.5 * FWHM_PER_SIGMA : 0.5));
-    P2<T>* const pbase = reinterpret_cast<P2<T>*>(wb + Lay::BASE) + lane;
-    bool fresh_base = true;                 // rebuild base from the cache (first iteration, then every 8th)
+    const T w_hi = T(P - 1) * T(KIND == VAMP_KIND_VOIGT ? 0.5 * FWHM_PER_SIGMA : 0.5);
+    // countdowns instead of modulo tests in the iteration loop
+    const int tune_interval = p.tune_interval, thin = p.thin;
+    int to_tune = (p.it0 % tune_interval == 0) ? 0 : tune_interval - p.it0 % tune_interval;   // iterations until it % ti == 0
+    int to_thin = (p.it0 % thin == 0) ? 0 : thin - p.it0 % thin;
+    int hs = n;                             // the spare shape slot
+    int rebuild = 0;                        // base is rebuilt from the cache when this reaches 0
 
     for (int it = p.it0; it < p.it1; ++it) {
         // ---- tuning (PyMC 2: every tune_interval iterations; optionally only during burn-in)
-        if (it > 0 && (it % tune_interval) == 0 && (tune_throughout || it <= burn)) {
-            for (int i = lane; i < ts; i += 32) {
-                const int a = acc[i], b = rej[i];
-                float f = p.asf[gb + i];
-                if (a + b > 0) {
-                    const float nf = f * tune_factor((float)a / (float)(a + b));
-                    if (nf > 0.0f) f = nf;
+        if (to_tune == 0) {
+            to_tune = tune_interval;
+            if (it > 0 && (p.tune_throughout || it <= burn)) {
+                for (int i = lane; i < ts; i += 32) {
+                    if (!is_free(i)) continue;
+                    int* pa = (i == sdi) ? &sdrec->acc : &recs[i >> 2].acc[i & 3];
+                    float* ps = (i == sdi) ? &sdrec->scl : &recs[i >> 2].scl[i & 3];
+                    const int a = *pa;
+                    float f = p.asf[gb + i];
+                    if (tot > 0) {
+                        const float nf = f * tune_factor((float)a / (float)tot);
+                        if (nf > 0.0f) f = nf;
+                    }
+                    p.asf[gb + i] = f;
+                    *ps = f * p.psd[gb + i];
+                    if (it > burn) p.acc_total[gb + i] += a;
+                    *pa = 0;
                 }
-                p.asf[gb + i] = f;
-                scl[i] = f * p.psd[gb + i];
-                acc[i] = 0;
-                rej[i] = 0;
+                tot = 0;
+                __syncwarp();
             }
-            __syncwarp();
         }
-        const bool post_burn = it >= burn;
+        --to_tune;
+        if (it == burn) {                    // accepted steps count towards acc_total from here on
+            for (int i = lane; i < ts; i += 32)
+                if (is_free(i)) p.acc_total[gb + i] -= (i == sdi) ? sdrec->acc : recs[i >> 2].acc[i & 3];
+        }
         unsigned n_shape = 0u, n_far = 0u, n_like = 0u;
         int hprev = 0;                        // slot of component c - 1
 
 #pragma unroll 1
         for (int c = 0; c < n; ++c) {
-            const int i0 = VAMP_TH(c, 0);
-            T pA = th[i0], pc = th[i0 + 1], pw1 = th[i0 + 2], pw2 = (NP == 4) ? th[i0 + 3] : T(0);
-            int hc = slot[c], hs = slot[n];
+            CompRec<T>& rc = recs[c];
+            T pA = rc.th[0], pc = rc.th[1], pw1 = rc.th[2], pw2 = rc.th[3];
+            const T sA = T(rc.scl[0]), sC = T(rc.scl[1]), sW1 = T(rc.scl[2]), sW2 = T(rc.scl[3]);
+            int hc = rc.slot;
             // ---- base = tau of the other components
             if (c == 0) {
-                if (fresh_base) {
-                    // rebuilt from the cache so that rounding never accumulates
+                if (rebuild == 0) {
+                    // rebuilt from the cache (first iteration, then every 8th) so that rounding never accumulates
+                    rebuild = 8;
                     for (int e = 0; e < 32 * npairs; e += 32) pbase[e] = p2_bc<T>(T(0));
                     for (int c2 = 1; c2 < n; ++c2) {
-                        const P2<T> A2 = p2_bc<T>(NK * th[VAMP_TH(c2, 0)]);
-                        const P2<T>* Hs2 = Hbuf + slot[c2] * Lay::NE;
+                        const P2<T> A2 = p2_bc<T>(NK * recs[c2].th[0]);
+                        const P2<T>* Hs2 = Hbuf + recs[c2].slot * Lay::NE;
                         for (int e = 0; e < 32 * npairs; e += 32) pbase[e] = p2_fma(A2, Hs2[e], pbase[e]);
                     }
-                } else {
+                } else if (n > 1) {
                     // from the last component of the previous iteration back to the first
-                    const P2<T> Ap = p2_bc<T>(NK * th[VAMP_TH(n - 1, 0)]), Ac = p2_bc<T>(-NK * pA);
-                    const P2<T>* Hp = Hbuf + slot[n - 1] * Lay::NE;
+                    const P2<T> Ap = p2_bc<T>(NK * recs[n - 1].th[0]), Ac = p2_bc<T>(-NK * pA);
+                    const P2<T>* Hp = Hbuf + recs[n - 1].slot * Lay::NE;
                     const P2<T>* Hn = Hbuf + hc * Lay::NE;
-                    if (n > 1)
-                        for (int e = 0; e < 32 * npairs; e += 32)
-                            pbase[e] = p2_fma(Ac, Hn[e], p2_fma(Ap, Hp[e], pbase[e]));
+                    for (int e = 0; e < 32 * npairs; e += 32) pbase[e] = p2_fma(Ac, Hn[e], p2_fma(Ap, Hp[e], pbase[e]));
                 }
+                --rebuild;
             } else {
                 // next component: base += tau_{c-1} - tau_c  (two FMAs per pixel instead of n - 1)
-                const P2<T> Ap = p2_bc<T>(NK * th[i0 - 4]), Ac = p2_bc<T>(-NK * pA);
+                const P2<T> Ap = p2_bc<T>(NK * recs[c - 1].th[0]), Ac = p2_bc<T>(-NK * pA);
                 const P2<T>* Hp = Hbuf + hprev * Lay::NE;
                 const P2<T>* Hn = Hbuf + hc * Lay::NE;
                 for (int e = 0; e < 32 * npairs; e += 32) pbase[e] = p2_fma(Ac, Hn[e], p2_fma(Ap, Hp[e], pbase[e]));
@@ -414,9 +461,10 @@ __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, unsigned char*
             {
                 T z, lu;
                 draw(z, lu);
-                const T prop = pA + z * T(scl[i0]);
+                const T prop = pA + z * sA;
                 if (prop > T(0)) {
-                    const T Snew = pass_cached<T, WT, LSF>(NK * prop, Hbuf + hc * Lay::NE, wb, npairs, lane, lc);
+                    const T Snew = chain_pass<T, KIND, WT, LSF, false>(cz, NK * prop, Hbuf + hc * Lay::NE, nullptr, rb, wb, npairs,
+                                                                       lane, lc, dummy, dummy_far);
                     const T dprior = StepMath<T>::log_(prop * Real<T>::rcp(pA)) - (prop - pA);
                     ++n_like;
                     if (lu < (Scur - Snew) * hiv + dprior) {          // false for NaN
@@ -428,21 +476,37 @@ __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, unsigned char*
                 }
             }
             // ---- centroid and width(s): evaluate the proposed shape into the spare slot
+#if VAMP_K2_STEPUNROLL
+            T cg = T(rc.g), cy = T(rc.y);     // constants of the current (w1, w2), fp32 kernel
+#pragma unroll
+#else
 #pragma unroll 1
+#endif
             for (int i = 1; i < NP; ++i) {
                 T z, lu;
                 draw(z, lu);
                 const T cur = (i == 1) ? pc : (i == 2) ? pw1 : pw2;
-                const T prop = cur + z * T(scl[i0 + i]);
+                const T prop = cur + z * ((i == 1) ? sC : (i == 2) ? sW1 : sW2);
                 const T hi = (i == 1) ? c_hi : w_hi;
                 const bool ok = (prop <= hi) && ((i == NP - 1) ? (prop > T(0)) : (prop >= T(0)));
                 if (ok) {
                     const T qc = (i == 1) ? prop : pc, q1 = (i == 2) ? prop : pw1, q2 = (i == 3) ? prop : pw2;
-                    const CompC<T> cc = make_comp_fast<T, KIND>(pA, cbase(qc), q1, q2);
+                    CompC<T> cc;
+#if VAMP_K2_STEPUNROLL
+                    if (i == 1 && sizeof(T) == 4) {       // widths unchanged: reuse g, y (the fp64 kernel recomputes:
+                        cc.A = pA;                        // the record holds them in float)
+                        cc.cb = cbase(qc);
+                        cc.g = cg;
+                        cc.y = cy;
+                        cc.y2 = cy * cy;
+                        cc.L2 = T(0);
+                    } else
+#endif
+                        cc = make_comp_fast<T, KIND>(pA, cbase(qc), q1, q2);
                     unsigned nf = 0u;
                     bool last_far;
-                    const T Snew = pass_fresh<T, KIND, WT, LSF>(cc, NK * pA, Hbuf + hs * Lay::NE, wb, npairs, lane, lc, nf,
-                                                                last_far);
+                    const T Snew = chain_pass<T, KIND, WT, LSF, true>(cc, NK * pA, nullptr, Hbuf + hs * Lay::NE, rb, wb, npairs, lane,
+                                                                      lc, nf, last_far);
                     n_far += nf - (last_far ? (unsigned)npad : 0u);
                     ++n_shape;
                     ++n_like;
@@ -451,6 +515,10 @@ __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, unsigned char*
                         pc = qc;
                         pw1 = q1;
                         pw2 = q2;
+#if VAMP_K2_STEPUNROLL
+                        cg = cc.g;
+                        cy = cc.y;
+#endif
                         const int tmp = hc;         // the proposed shape becomes the component's shape
                         hc = hs;
                         hs = tmp;
@@ -458,44 +526,41 @@ __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, unsigned char*
                     }
                 }
             }
-            // ---- component epilogue: counters and state, lanes 0..NP-1
+            // ---- component epilogue: every lane writes the same record (same addresses, same values)
             __syncwarp();
-            if (lane < NP) {
-                const int idx = i0 + lane;
-                const int bit = (int)((am >> lane) & 1u);
-                acc[idx] += bit;
-                rej[idx] += 1 - bit;
-                acct[idx] += post_burn ? bit : 0;
-                th[idx] = (lane == 0) ? pA : (lane == 1) ? pc : (lane == 2) ? pw1 : pw2;
-            }
-            slot[c] = hc;
-            slot[n] = hs;
+            rc.th[0] = pA;
+            rc.th[1] = pc;
+            rc.th[2] = pw1;
+            if (NP == 4) rc.th[3] = pw2;
+            rc.acc[0] += (int)(am & 1u);
+            rc.acc[1] += (int)((am >> 1) & 1u);
+            rc.acc[2] += (int)((am >> 2) & 1u);
+            if (NP == 4) rc.acc[3] += (int)((am >> 3) & 1u);
+            rc.slot = hc;
+#if VAMP_K2_STEPUNROLL
+            rc.g = (float)cg;
+            rc.y = (float)cy;
+#endif
             hprev = hc;
             __syncwarp();
         }
-        fresh_base = ((it + 1) & 7) == 0;
+        ++tot;
 
         if (!WT) {
             // ---- sd: no model evaluation
             T z, lu;
             draw(z, lu);
-            const T prop = sd + z * T(scl[sdi]);
-            bool a_sd = false;
+            const T prop = sd + z * T(sdrec->scl);
             if (prop > T(0) && prop <= T(1)) {
                 const T lprop = StepMath<T>::log_(prop);
                 const T hv = T(0.5) / (prop * prop);
-                a_sd = lu < -Scur * (hv - hiv) - T(P) * (lprop - logsd);
-                if (a_sd) {
+                if (lu < -Scur * (hv - hiv) - T(P) * (lprop - logsd)) {
                     sd = prop;
                     logsd = lprop;
                     hiv = hv;
+                    sdrec->acc += 1;
+                    sdrec->th = sd;
                 }
-            }
-            if (lane == 0) {
-                acc[sdi] += a_sd ? 1 : 0;
-                rej[sdi] += a_sd ? 0 : 1;
-                acct[sdi] += (a_sd && post_burn) ? 1 : 0;
-                th[sdi] = sd;
             }
             __syncwarp();
         }
@@ -504,69 +569,78 @@ __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, unsigned char*
         w_like += n_like;
 
         // ---- end of iteration: log-posterior of the current state
-        const double lnL = WT ? (-0.5 * (double)Scur + rs.lognorm[r])
-                              : (-(double)Scur * (double)hiv - P * ((double)logsd + 0.91893853320467274178));
-        const double logp = lnL + (double)lp;
+        const T lnL = WT ? (T(-0.5) * Scur + lognorm) : (-Scur * hiv - T(P) * (logsd + T(0.91893853320467274178)));
+        const T logp = lnL + lp;
         if (logp > best_logp) {
             best_logp = logp;
-            for (int i2 = lane; i2 < ts; i2 += 32) p.best_theta[gb + i2] = (double)th[i2];
+            for (int i2 = lane; i2 < ts; i2 += 32)
+                if (is_free(i2)) p.best_theta[gb + i2] = (double)((i2 == sdi) ? sdrec->th : recs[i2 >> 2].th[i2 & 3]);
         }
-        if (post_burn && (it % thin) == 0) {
-            sum_lnL += lnL;
-            sum_lnL2 += lnL * lnL;
-            ++ntally;
-            const double inv = 1.0 / (double)ntally;
-            const double wgt = (double)(ntally - 1) * inv;
-            double* mean = p.mean + gb;
-            double* m2 = p.m2 + gb;
-            double* comom = p.comom + (size_t)chain * 6 * p.cmax;
-            for (int i2 = lane; i2 < 6 * n; i2 += 32) {          // co-moments first (need the old means)
-                const int cc2 = i2 / 6, pr = i2 - 6 * cc2;
-                const int a = (pr < 3) ? 0 : (pr < 5 ? 1 : 2);
-                const int b = (pr < 3) ? pr + 1 : (pr < 5 ? pr - 1 : 3);
-                const double da = (double)th[VAMP_TH(cc2, a)] - mean[VAMP_TH(cc2, a)];
-                const double db = (double)th[VAMP_TH(cc2, b)] - mean[VAMP_TH(cc2, b)];
-                comom[i2] += wgt * da * db;
+        if (to_thin == 0) {
+            to_thin = thin;
+            if (it >= burn) {
+                auto th_of = [&](int i2) -> double {
+                    return is_free(i2) ? (double)((i2 == sdi) ? sdrec->th : recs[i2 >> 2].th[i2 & 3]) : 0.0;
+                };
+                if (lane == 0) {
+                    p.sum_lnL[chain] += (double)lnL;
+                    p.sum_lnL2[chain] += (double)lnL * (double)lnL;
+                }
+                ++ntally;
+                const double inv = 1.0 / (double)ntally;
+                const double wgt = (double)(ntally - 1) * inv;
+                double* mean = p.mean + gb;
+                double* m2 = p.m2 + gb;
+                double* comom = p.comom + (size_t)chain * 6 * p.cmax;
+                for (int i2 = lane; i2 < 6 * n; i2 += 32) {          // co-moments first (need the old means)
+                    const int cc2 = i2 / 6, pr = i2 - 6 * cc2;
+                    const int a = (pr < 3) ? 0 : (pr < 5 ? 1 : 2);
+                    const int b = (pr < 3) ? pr + 1 : (pr < 5 ? pr - 1 : 3);
+                    const double da = th_of(VAMP_TH(cc2, a)) - mean[VAMP_TH(cc2, a)];
+                    const double db = th_of(VAMP_TH(cc2, b)) - mean[VAMP_TH(cc2, b)];
+                    comom[i2] += wgt * da * db;
+                }
+                __syncwarp();
+                for (int i2 = lane; i2 < ts; i2 += 32) {
+                    const double x = th_of(i2);
+                    const double d = x - mean[i2];
+                    const double mn = mean[i2] + d * inv;
+                    mean[i2] = mn;
+                    m2[i2] += d * (x - mn);
+                }
+                if (p.trace) {
+                    const int slot_t = ntally - 1;
+                    if (slot_t < p.trace_cap)
+                        for (int i2 = lane; i2 < ts; i2 += 32)
+                            p.trace[((size_t)chain * p.trace_cap + slot_t) * ts + i2] = th_of(i2);
+                }
+                __syncwarp();
             }
-            __syncwarp();
-            for (int i2 = lane; i2 < ts; i2 += 32) {
-                const double x = (double)th[i2];
-                const double d = x - mean[i2];
-                const double mn = mean[i2] + d * inv;
-                mean[i2] = mn;
-                m2[i2] += d * (x - mn);
-            }
-            if (p.trace) {
-                const int slot_t = ntally - 1;
-                if (slot_t < p.trace_cap)
-                    for (int i2 = lane; i2 < ts; i2 += 32)
-                        p.trace[((size_t)chain * p.trace_cap + slot_t) * ts + i2] = (double)th[i2];
-            }
-            __syncwarp();
         }
+        --to_thin;
     }
 
     // ---- state -> global
     __syncwarp();
     for (int i = lane; i < ts; i += 32) {
-        p.theta[gb + i] = (double)th[i];
-        p.acc[gb + i] = acc[i];
-        p.rej[gb + i] = rej[i];
-        p.acc_total[gb + i] = acct[i];
+        if (!is_free(i)) continue;
+        const int a = (i == sdi) ? sdrec->acc : recs[i >> 2].acc[i & 3];
+        p.theta[gb + i] = (double)((i == sdi) ? sdrec->th : recs[i >> 2].th[i & 3]);
+        p.acc[gb + i] = a;
+        p.rej[gb + i] = tot - a;
+        if (p.it1 > burn) p.acc_total[gb + i] += a;
     }
     if (lane == 0) {
         const double lnL = WT ? lnL_noise((double)Scur, rs.lognorm[r]) : lnL_sd((double)Scur, (double)sd, P);
         double lpx = 0.0;
         for (int c = 0; c < n; ++c) {
-            const double a = (double)th[VAMP_TH(c, 0)];
+            const double a = (double)recs[c].th[0];
             lpx += log(a) - a;
         }
         p.lnL[chain] = lnL;
         p.logp[chain] = lnL + lpx;
-        p.best_logp[chain] = best_logp;
+        p.best_logp[chain] = (double)best_logp;
         p.ntally[chain] = ntally;
-        p.sum_lnL[chain] = sum_lnL;
-        p.sum_lnL2[chain] = sum_lnL2;
         if (p.work) {
             p.work[3 * (size_t)chain + 0] += w_shape;    // component evaluations (x P pixels each)
             p.work[3 * (size_t)chain + 1] += w_far;      // pixels evaluated on the continued-fraction path
@@ -575,23 +649,52 @@ __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, unsigned char*
     }
 }
 
+// One warp per chain, K2_WARPS chains per CTA.  The host sorts chains by (pixel class, component
+// count, model), so the warps of a CTA almost always fit the same region: the region's pixels
+// (du, flux, 1/noise) are staged ONCE per CTA and shared, which is what lets a sixth CTA fit on an
+// SM.  A CTA whose warps belong to different regions (group boundaries) processes its distinct
+// regions one after the other - rare, and always correct.
 template <typename T, int KIND, bool WT, bool LSF>
 __global__ void __launch_bounds__(K2_WARPS * 32, (sizeof(T) == 4) ? VAMP_K2_MINBLOCKS : 2)
 k2_mcmc_kernel(McmcDev p, int ncomp_max) {
+    typedef K2Lay<T, WT> Lay;
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int s_region[K2_WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     T* lsf_s = reinterpret_cast<T*>(smem_raw);
     const size_t head = LSF ? align16(sizeof(T) * VAMP_MAX_LSF_TAPS) : 0;
     if (LSF) {
         for (int i = threadIdx.x; i < p.rs.lsf_taps; i += blockDim.x) lsf_s[i] = RS<T>::lsf(p.rs)[i];
-        __syncthreads();
     }
     // launch order: the host sorts chains by ascending cost; the longest chains go first so the
     // tail of the grid is made of short ones
     const int chain = p.B - 1 - (blockIdx.x * K2_WARPS + warp);
-    if (chain < 0) return;
-    unsigned char* wb = smem_raw + head + (size_t)warp * K2Lay<T, WT>::bytes(ncomp_max, p.cmax, LSF);
-    mcmc_chain<T, KIND, WT, LSF>(p, chain, lane, wb, ncomp_max, lsf_s);
+    const int my_region = (chain >= 0) ? p.item_region[chain] : -1;
+    if (lane == 0) s_region[warp] = my_region;
+    __syncthreads();
+    unsigned char* rb = smem_raw + head;
+    unsigned char* wb = rb + Lay::REGION + (size_t)warp * Lay::bytes(ncomp_max, LSF);
+    for (int round = 0; round < K2_WARPS; ++round) {
+        const int rr = s_region[round];
+        bool skip = rr < 0;
+        for (int j = 0; j < round; ++j) skip = skip || (s_region[j] == rr);
+        if (skip) continue;                              // CTA-uniform
+        if (round > 0) __syncthreads();                  // the previous region's chains are done
+        {
+            const RegionSetDev& rs = p.rs;
+            const int off = rs.pix_off[rr] >> 1, ne = 32 * ((rs.npix[rr] + 63) >> 6);
+            P2<T>* sd_ = reinterpret_cast<P2<T>*>(rb + Lay::DU);
+            P2<T>* sf_ = reinterpret_cast<P2<T>*>(rb + Lay::F);
+            P2<T>* sw_ = reinterpret_cast<P2<T>*>(rb + Lay::W);
+            for (int e = threadIdx.x; e < ne; e += blockDim.x) {
+                sd_[e] = p2_from(__ldg(RS<T>::pdu(rs) + off + e));
+                sf_[e] = p2_from(__ldg(RS<T>::pf(rs) + off + e));
+                if (WT) sw_[e] = p2_from(__ldg(RS<T>::pw(rs) + off + e));
+            }
+        }
+        __syncthreads();
+        if (my_region == rr) mcmc_chain<T, KIND, WT, LSF>(p, chain, lane, rb, wb, ncomp_max, lsf_s);
+    }
 }
 
 // ---- initial states -------------------------------------------------------------------------
@@ -650,7 +753,8 @@ __global__ void init_state_kernel(McmcDev p) {
 
 template <typename T, int KIND, bool WT, bool LSF>
 cudaError_t launch_k2_t(const McmcDev& p, int max_ncomp, cudaStream_t st) {
-    const size_t smem = (LSF ? align16(sizeof(T) * VAMP_MAX_LSF_TAPS) : 0) + K2_WARPS * K2Lay<T, WT>::bytes(max_ncomp, p.cmax, LSF);
+    const size_t smem = (LSF ? align16(sizeof(T) * VAMP_MAX_LSF_TAPS) : 0) + K2Lay<T, WT>::REGION +
+                        K2_WARPS * K2Lay<T, WT>::bytes(max_ncomp, LSF);
     auto kern = k2_mcmc_kernel<T, KIND, WT, LSF>;
     if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
