@@ -59,6 +59,45 @@ def test_chain_replay_fp64(ctx, voigt, sd_free, P, n, lsf):
         assert lnL[b] == pytest.approx(ref["lnL"], rel=1e-9, abs=1e-7)
 
 
+def test_chain_replay_mixed_regions_per_cta(ctx):
+    """CTAs whose warps belong to different regions (the region slice is staged once per CTA
+    and the distinct regions of a CTA are processed in turn): every chain still reproduces the
+    replay of its own region, for ragged region sizes and odd chain counts."""
+    voigt, sd_free = True, True
+    sizes, ns = [70, 200, 33], [1, 2, 1]
+    regl = [synth.make_region(P, n, 40.0, 500 + P, voigt=voigt) for P, n in zip(sizes, ns)]
+    regs = engine.Regions(ctx, [(r["nu"], r["flux"], r["noise"]) for r in regl])
+    item_region = np.array([0, 0, 0, 1, 1, 2, 2, 2, 2, 0, 1], np.int32)       # 11 chains: 3 CTAs, all mixed
+    item_ncomp = np.array([ns[r] for r in item_region], np.int32)
+    B, iters, burn, thin, tune = len(item_region), 60, 20, 4, 10
+    uid = (np.arange(B, dtype=np.uint64) + np.uint64(900))
+    seed = 77
+    cmax = 2
+    s = engine.Sampler(regs, item_region, item_ncomp, uid, voigt=voigt, sd_free=sd_free, dtype="f64", seed=seed, burn=burn,
+                       thin=thin, tune_interval=tune, tune_throughout=True, trace_cap=(iters - burn) // thin + 2, cmax=cmax)
+    s.init()
+    th0 = s.get("theta").copy()
+    s.run(25)
+    s.run(iters - 25)
+    th, ntal, tr, acc, rej, acct = s.get("theta"), s.get("ntally"), s.get("trace"), s.get("acc"), s.get("rej"), s.get("acc_total")
+    for b in range(B):
+        r = int(item_region[b])
+        u = _scaled_grid(regs, r)
+        ref = CR.replay_chain(u, regl[r]["flux"], regl[r]["noise"], th0[b], ns[r], voigt, sd_free, int(uid[b]), seed, iters,
+                              burn, thin, tune, True, cmax, record_every_step=True)
+        assert ntal[b] == ref["ntally"]
+        np.testing.assert_allclose(th[b], ref["theta"], rtol=1e-8, atol=1e-10, err_msg="chain %d" % b)
+        np.testing.assert_allclose(tr[b, : ntal[b]], ref["trace"], rtol=1e-8, atol=1e-10)
+        # counters: acc + rej = proposals since the last tune; acc_total = accepted steps of iterations >= burn
+        k = 4 * ns[r] + 1
+        steps = np.array([(i, a) for i, _, a in ref["steps"]]).reshape(iters, k, 2)
+        free = steps[0, :, 0]
+        np.testing.assert_array_equal(acct[b][free], steps[burn:, :, 1].sum(axis=0))
+        last_tune = (iters - 1) // tune * tune
+        np.testing.assert_array_equal(acc[b][free], steps[last_tune:, :, 1].sum(axis=0))
+        np.testing.assert_array_equal((acc[b] + rej[b])[free], np.full(k, iters - last_tune))
+
+
 def test_chain_fp32_tracks_fp64_initially(ctx):
     """fp32 and fp64 chains share the RNG stream: identical accept/reject history at first."""
     reg = synth.config_c2()

@@ -416,9 +416,19 @@ __device__ __forceinline__ P2<T> fad_far2(P2<T> X, T y, P2<T> S) {
 // and are executed redundantly by every lane once per scalar step).  g and y are clamped so
 // that the padding coordinate (1e12) never overflows x^2 + y^2: a Gaussian FWHM below
 // 1.7e-6 px (fp32) is a delta function between pixels either way.
+// 1/G is clamped (g and y together, so y/x = L/(2 d) - the Lorentzian limit - is preserved):
+//   K2 (regions <= 256 px, padding coordinate 1e12):  1/G <= 6e5   ->  x <= 1e18, x^2 + y^2 finite in fp32
+//   K1 (regions <= 2^17 px, no padding reads):          1/G <= 6e13  ->  x <= 1.3e19
+// A Gaussian FWHM below the clamp is a delta function between pixels either way.
 template <typename T> struct PadClamp;
-template <> struct PadClamp<float> { static __device__ __forceinline__ float g() { return 1.0e6f; } static __device__ __forceinline__ float y() { return 1.0e9f; } };
-template <> struct PadClamp<double> { static __device__ __forceinline__ double g() { return 1.0e100; } static __device__ __forceinline__ double y() { return 1.0e100; } };
+template <> struct PadClamp<float> {
+    static __device__ __forceinline__ float ig() { return 6.0e5f; }
+    static __device__ __forceinline__ float ig_k1() { return 6.0e13f; }
+};
+template <> struct PadClamp<double> {
+    static __device__ __forceinline__ double ig() { return 1.0e100; }
+    static __device__ __forceinline__ double ig_k1() { return 1.0e100; }
+};
 
 template <typename T, int KIND>
 __device__ __forceinline__ CompC<T> make_comp_fast(T A, T cb, T w1, T w2) {
@@ -426,14 +436,33 @@ __device__ __forceinline__ CompC<T> make_comp_fast(T A, T cb, T w1, T w2) {
     cc.A = A;
     cc.cb = cb;
     if (KIND == VAMP_KIND_GAUSS) {
-        cc.g = fmin(T(0.84932180028801904272) * Real<T>::rcp(w1), PadClamp<T>::g());
+        cc.g = T(0.84932180028801904272) * fmin(Real<T>::rcp(w1), PadClamp<T>::ig());
         cc.y = cc.y2 = cc.L2 = T(0);
     } else {
-        const T ig = Real<T>::rcp(w2);
-        cc.g = fmin(T(1.66510922231539551270) * ig, PadClamp<T>::g());
-        cc.y = fmin(T(0.83255461115769775635) * w1 * ig, PadClamp<T>::y());
+        const T ig = fmin(Real<T>::rcp(w2), PadClamp<T>::ig());
+        cc.g = T(1.66510922231539551270) * ig;
+        cc.y = T(0.83255461115769775635) * w1 * ig;
         cc.y2 = cc.y * cc.y;
         cc.L2 = w1 * w1;
+    }
+    return cc;
+}
+
+// K1's component constants: divisions in double (one per item and component), same clamp policy.
+template <typename T, int KIND>
+__device__ __forceinline__ CompC<T> make_comp_k1(double A, double c, double w1, double w2, double ubase) {
+    CompC<T> cc;
+    cc.A = T(A);
+    cc.cb = T(c - ubase);
+    if (KIND == VAMP_KIND_GAUSS) {
+        cc.g = T(0.84932180028801904272 * fmin(1.0 / w1, (double)PadClamp<T>::ig_k1()));
+        cc.y = cc.y2 = cc.L2 = T(0);
+    } else {
+        const double ig = fmin(1.0 / w2, (double)PadClamp<T>::ig_k1());
+        cc.g = T(1.66510922231539551270 * ig);
+        cc.y = T(0.83255461115769775635 * w1 * ig);
+        cc.y2 = cc.y * cc.y;
+        cc.L2 = T(w1 * w1);
     }
     return cc;
 }
@@ -592,22 +621,51 @@ constexpr int InstKind = VAMP_INST_VOIGT ? VAMP_KIND_VOIGT : VAMP_KIND_GAUSS;
 
 // Full model evaluation for a warp-owned item: tau summed over components in registers,
 // m = exp(-tau), optional LSF.  Leaves the model flux in m[].
+// Rows are processed two at a time in the packed two-row form (pair_classify / pair_eval: one
+// FFMA2 per step for both rows, path chosen per 64-pixel pair); a single-row tile (<= 32 px)
+// takes the scalar form.
 template <typename T, int KIND, int PPL>
 __device__ __forceinline__ void eval_model(const LaneTile<T, PPL>& t, const double* __restrict__ theta, int ncomp,
                                            double ubase, T (&m)[PPL], T* lsf_buf, const T* lsf_s, int taps, int lane) {
-    T tau[PPL];
+    if (PPL == 1) {
+        T tau[PPL];
 #pragma unroll
-    for (int j = 0; j < PPL; ++j) tau[j] = T(0);
-    for (int c = 0; c < ncomp; ++c) {
-        const CompC<T> cc = make_comp<T, KIND>(theta[VAMP_TH(c, 0)], theta[VAMP_TH(c, 1)], theta[VAMP_TH(c, 2)],
-                                               theta[VAMP_TH(c, 3)], ubase);
-        T H[PPL];
-        comp_shape<T, KIND, PPL>(cc, t.du, H);
+        for (int j = 0; j < PPL; ++j) tau[j] = T(0);
+        for (int c = 0; c < ncomp; ++c) {
+            const CompC<T> cc = make_comp<T, KIND>(theta[VAMP_TH(c, 0)], theta[VAMP_TH(c, 1)], theta[VAMP_TH(c, 2)],
+                                                   theta[VAMP_TH(c, 3)], ubase);
+            T H[PPL];
+            comp_shape<T, KIND, PPL>(cc, t.du, H);
 #pragma unroll
-        for (int j = 0; j < PPL; ++j) tau[j] = Real<T>::fma_(cc.A, H[j], tau[j]);
+            for (int j = 0; j < PPL; ++j) tau[j] = Real<T>::fma_(cc.A, H[j], tau[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < PPL; ++j) m[j] = Real<T>::exp_neg(tau[j]);
+    } else {
+        constexpr int NPR = (PPL + 1) / 2;
+        P2<T> tau2[NPR];
+#pragma unroll
+        for (int jj = 0; jj < NPR; ++jj) tau2[jj] = p2_bc<T>(T(0));
+        unsigned nfar = 0u;
+        for (int c = 0; c < ncomp; ++c) {
+            const CompC<T> cc = make_comp_k1<T, KIND>(theta[VAMP_TH(c, 0)], theta[VAMP_TH(c, 1)], theta[VAMP_TH(c, 2)],
+                                                      theta[VAMP_TH(c, 3)], ubase);
+            const P2<T> A2 = p2_bc<T>(Real<T>::NEGK() * cc.A);
+#pragma unroll
+            for (int jj = 0; jj < NPR; ++jj) {
+                P2<T> X, S;
+                bool far;
+                pair_classify<T, KIND>(cc, p2_make(t.du[2 * jj], t.du[(2 * jj + 1 < PPL) ? 2 * jj + 1 : 2 * jj]), X, S, far);
+                tau2[jj] = p2_fma(A2, pair_eval<T, KIND>(cc, X, S, far, nfar), tau2[jj]);
+            }
+        }
+#pragma unroll
+        for (int jj = 0; jj < NPR; ++jj) {
+            const P2<T> M = p2_exp_scaled<T>(tau2[jj]);
+            m[2 * jj] = p2_lo(M);
+            if (2 * jj + 1 < PPL) m[2 * jj + 1] = p2_hi(M);
+        }
     }
-#pragma unroll
-    for (int j = 0; j < PPL; ++j) m[j] = Real<T>::exp_neg(tau[j]);
     if (taps > 1) lsf_apply<T, PPL>(m, t.valid, lsf_buf, lsf_s, taps, lane);
 }
 

@@ -123,8 +123,8 @@ k1_cta_kernel(RegionSetDev rs, int B, int nchunk_max, const int* __restrict__ it
     const int ntile = (P + VAMP_TILE_PIX - 1) / VAMP_TILE_PIX;
     for (int i = tid; i < taps; i += 256) lsf_s[i] = RS<T>::lsf(rs)[i];
     for (int c = tid; c < ncomp; c += 256) {
-        const CompC<T> cc = make_comp<T, KIND>(th[VAMP_TH(c, 0)], th[VAMP_TH(c, 1)], th[VAMP_TH(c, 2)],
-                                               th[VAMP_TH(c, 3)], 0.0);
+        const CompC<T> cc = make_comp_k1<T, KIND>(th[VAMP_TH(c, 0)], th[VAMP_TH(c, 1)], th[VAMP_TH(c, 2)],
+                                                  th[VAMP_TH(c, 3)], 0.0);
         cs[c].A = cc.A; cs[c].g = cc.g; cs[c].y = cc.y; cs[c].y2 = cc.y2; cs[c].L2 = cc.L2;
     }
     for (int i = tid; i < ROWS * ncomp; i += 256) {
@@ -138,7 +138,7 @@ k1_cta_kernel(RegionSetDev rs, int B, int nchunk_max, const int* __restrict__ it
     (void)tile0;
 
     // ---- own pixels: g = g0 + j*256 + tid
-    T du[PPL], f[PPL], w[PPL], tau[PPL], m[PPL];
+    T du[PPL], f[PPL], w[PPL], m[PPL];
     unsigned valid = 0u;
 #pragma unroll
     for (int j = 0; j < PPL; ++j) {
@@ -148,21 +148,34 @@ k1_cta_kernel(RegionSetDev rs, int B, int nchunk_max, const int* __restrict__ it
         f[j] = ok ? RS<T>::f(rs)[off + g] : T(1);
         w[j] = ok ? RS<T>::w(rs)[off + g] : T(0);
         valid |= ok ? (1u << j) : 0u;
-        tau[j] = T(0);
     }
-    for (int c = 0; c < ncomp; ++c) {
-        CompC<T> cc;
-        cc.A = cs[c].A; cc.g = cs[c].g; cc.y = cs[c].y; cc.y2 = cs[c].y2; cc.L2 = cs[c].L2;
-        T dd[PPL], H[PPL];
+    {
+        // packed two-row form: rows (2 jj, 2 jj + 1) of this thread travel together, one path per warp and pair
+        P2<T> tau2[PPL / 2];
 #pragma unroll
-        for (int j = 0; j < PPL; ++j) dd[j] = du[j] - cb[j * ncomp + c];
-        cc.cb = T(0);
-        comp_shape<T, KIND, PPL>(cc, dd, H);
+        for (int jj = 0; jj < PPL / 2; ++jj) tau2[jj] = p2_bc<T>(T(0));
+        unsigned nfar = 0u;
+        for (int c = 0; c < ncomp; ++c) {
+            CompC<T> cc;
+            cc.A = cs[c].A; cc.g = cs[c].g; cc.y = cs[c].y; cc.y2 = cs[c].y2; cc.L2 = cs[c].L2;
+            cc.cb = T(0);
+            const P2<T> A2 = p2_bc<T>(Real<T>::NEGK() * cc.A);
 #pragma unroll
-        for (int j = 0; j < PPL; ++j) tau[j] = Real<T>::fma_(cc.A, H[j], tau[j]);
+            for (int jj = 0; jj < PPL / 2; ++jj) {
+                P2<T> X, S;
+                bool far;
+                pair_classify<T, KIND>(cc, p2_make(du[2 * jj] - cb[(2 * jj) * ncomp + c], du[2 * jj + 1] - cb[(2 * jj + 1) * ncomp + c]),
+                                       X, S, far);
+                tau2[jj] = p2_fma(A2, pair_eval<T, KIND>(cc, X, S, far, nfar), tau2[jj]);
+            }
+        }
+#pragma unroll
+        for (int jj = 0; jj < PPL / 2; ++jj) {
+            const P2<T> M = p2_exp_scaled<T>(tau2[jj]);
+            m[2 * jj] = p2_lo(M);
+            m[2 * jj + 1] = p2_hi(M);
+        }
     }
-#pragma unroll
-    for (int j = 0; j < PPL; ++j) m[j] = Real<T>::exp_neg(tau[j]);
 
     if (LSF) {
 #pragma unroll

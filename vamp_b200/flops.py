@@ -4,34 +4,36 @@ Used by ``bench.py`` for ``roofline.achieved`` and stated in DESIGN.md section 5
 ncu ``smsp__sass_thread_inst_executed_op_{fadd,fmul,ffma}_pred_on`` (profiles/).
 Counts follow ``vamp_b200/csrc/vamp_device.cuh`` line by line.
 
-fp32 ``fad_core`` (Weideman N = 12, real second-order recurrence), per pixel:
-    r = rcp(s + 2L*y + L*L)            FMA + ADD + MUFU           = 4
-    Zr = (L*L - s) * r                 ADD + MUL                  = 2
-    Zi = 2L * x * r                    2 MUL                      = 2
-    t = 2 Zr, n = |Z|^2                ADD, MUL + FMA             = 4
-    10 recurrence steps (2 FMA)        10 * 4                     = 40
-    pr (2 FMA), pi (MUL)                                          = 5
-    ir, ii                             ADD + 2 MUL                = 3
-    i2r, i2i                           MUL + FMA, 2 MUL           = 5
+fp32 ``fad_core2`` (Weideman N = 12, real second-order recurrence; K2's packed two-row form), per pixel:
+    R = rcp(s + (2Ly + L^2))           ADD + MUFU                 = 2     (2Ly + L^2: once per component)
+    Zr = (L^2 - s) R                   SUB + MUL                  = 2
+    XR = x R, Zi = 2L XR               2 MUL                      = 2
+    t = 2 Zr, -|Z|^2 = (2Ly-L^2-s) R   ADD, SUB + MUL             = 3
+    b1 = t a0 + a1                     FMA                        = 2
+    9 recurrence steps (2 FMA)         9 * 4                      = 36
+    pr (2 FMA), pi (MUL), ir (MUL)                                = 6
+    i2r, i2i                           MUL + FMA, ADD + MUL       = 5
     q, H                               MUL + FMA, FMA + MUL       = 6
-                                                                   ---- 71
-fp32 ``fad_far`` (4-level continued fraction):
+                                                                   ---- 64
+fp32 ``fad_far2`` (4-level continued fraction as N(v)/D(v), v = 1/z^2):
     rs, tr, ti                         MUFU + 2 MUL               = 3
-    vr, vi                             MUL + FMA, 2 MUL           = 5
-    N(v), D(v): 2 Horner steps each    4 * 7                      = 28
+    vr, vi                             MUL + FMA, ADD + MUL       = 5
+    N(v), D(v): real first step (FMA + MUL) + one complex Horner step (3 FMA + MUL)   2 * 10 = 20
     er, ei, imq                        3 * (MUL + FMA)            = 9
     |D|^2, rcp, -y*imq*rcp             MUL + FMA + MUFU + 2 MUL   = 6
-                                                                   ---- 51
+                                                                   ---- 43
 common per shape pixel: d = du - cb, x = d*g, s = fma(x,x,y2)     = 4
 per likelihood pixel:  v = fma(An,H,base) (tau pre-scaled by -log2 e), ex2 (MUFU), r = f - m, S = fma(r,r,S)  = 6
     (+ 1 for the noise weight, + 2 per LSF tap)
-fp64: same structure with N = 32 (30 recurrence steps) and 9 CF levels (4 + 5 Horner steps); the
-    reciprocal and exp are multi-instruction sequences, counted as 10 and 30 flops.
+fp64: same structure with N = 32 (29 recurrence steps) and 9 CF levels (N: 1 real + 3 complex steps, D: 1 real +
+    4 complex steps); a reciprocal and an exp are multi-instruction sequences, counted as 10 and 30 flops.
+(K1 uses the same packed forms + one FMA per component for the tau accumulation; K3 evaluates one row at a
+ time with the scalar forms ``fad_core`` / ``fad_far``: + 7 / + 8.)
 """
 
-F32 = {"core": 71.0, "far": 51.0, "shape_common": 4.0, "like": 6.0}
-F64 = {"core": 13 + 2 + 2 + 4 + 30 * 4 + 5 + 3 + 5 + 6, "far": 3 + 5 + 9 * 7 + 9 + 6 + 18, "shape_common": 4.0,
-       "like": 36.0}
+F32 = {"core": 64.0, "far": 43.0, "shape_common": 4.0, "like": 6.0}
+F64 = {"core": (2 + 9) + 2 + 2 + 3 + 2 + 29 * 4 + 6 + 5 + 6, "far": (3 + 9) + 5 + (3 + 3 * 7) + (3 + 4 * 7) + 9 + (6 + 9),
+       "shape_common": 4.0, "like": 36.0}
 GAUSS = {"shape": 5.0}      # d, q = d*g, q*q, exp2 (MUFU): SUB + MUL + MUL + MUFU + neg
 
 
