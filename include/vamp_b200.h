@@ -32,7 +32,10 @@ extern "C" {
 
 #define VAMP_ABI_VERSION 1
 
-enum { VAMP_F32 = 0, VAMP_F64 = 1 };          /* arithmetic of the pixel math */
+enum { VAMP_F32 = 0, VAMP_F64 = 1,            /* arithmetic of the pixel math */
+       VAMP_MIXED = 2 };                       /* vamp_map_dev only: fp32 objective during the simplex search,
+                                                  float64 simplex and float64 lnL / chi^2 / BIC at the optimum,
+                                                  one warp per start (the schedule for thousands of starts) */
 enum { VAMP_GAUSS = 0, VAMP_VOIGT = 1 };      /* VPfit(voigt=False|True) */
 
 typedef struct vamp_ctx vamp_ctx;
@@ -121,7 +124,7 @@ typedef struct vamp_mcmc_args {
 int vamp_mcmc_init_dev(vamp_ctx* ctx, const vamp_regions* regions, int kind, const vamp_mcmc_args* a, int from_prior);
 int vamp_mcmc_run_dev(vamp_ctx* ctx, const vamp_regions* regions, int dtype, int kind, const vamp_mcmc_args* a);
 
-/* K3 - batched Nelder-Mead MAP + BIC, one warp per start.  Replaces
+/* K3 - batched Nelder-Mead MAP + BIC (one CTA per start; one warp per start with VAMP_MIXED).  Replaces
  * mc.MAP(model).fit(iterlim, tol) and map.BIC (vpfits.py:357-358, 419-427). */
 typedef struct vamp_map_args {
     int n_starts;

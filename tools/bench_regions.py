@@ -1,0 +1,51 @@
+"""BASELINE config C4 (scaled down): R mixed synthetic regions (P ~ U{32..256}, 1-8 true components, S/N 10/30/100)
+fitted with ``fit_regions`` - sharded over the ranks when launched under torchrun.
+    python tools/bench_regions.py [R] [chains_per_restart]      (or torchrun --nproc-per-node N ...)
+Prints regions/s (max over ranks) and the K2 / K3 split of rank 0."""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from vamp_b200 import engine, synth
+from vamp_b200.fit_regions import fit_regions
+
+R = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+cpr = int(sys.argv[2]) if len(sys.argv) > 2 else 8
+world, rank, lrank = int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0))
+torch.cuda.set_device(lrank)
+if world > 1:
+    import torch.distributed as dist
+    dist.init_process_group("nccl", device_id=torch.device("cuda", lrank))
+ctx = engine.default_context(lrank)
+regs = [synth.config_c4_region(10_000 + i) for i in range(R)]
+host = [(r["nu"], r["flux"], r["noise"]) for r in regs]
+ntrue = np.array([len(r["truth"]) for r in regs])
+marks = {"k2": 0.0, "k3": 0.0}
+orig_run, orig_map = engine.Sampler.run, engine.Sampler._map
+evs = []
+def run(self, iters):
+    a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+    a.record(); orig_run(self, iters); b.record(); evs.append(("k2", a, b))
+def _map(self, *a_, **k):
+    a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+    a.record(); r = orig_map(self, *a_, **k); b.record(); evs.append(("k3", a, b)); return r
+engine.Sampler.run, engine.Sampler._map = run, _map
+for rep in range(2):
+    evs.clear()
+    st = {}
+    torch.cuda.synchronize()
+    if world > 1: dist.barrier()
+    t0 = time.perf_counter()
+    res = fit_regions(host, uids=[10_000 + i for i in range(R)], voigt=True, iterations=3000, burn=300, thin=15, restarts=3,
+                      chains_per_restart=cpr, window=3, nmax=8, seed=rep, stats=st, polish_dtype=os.environ.get("POLISH", "auto"))
+    torch.cuda.synchronize()
+    if world > 1: dist.barrier()
+    dt = time.perf_counter() - t0
+    k2 = sum(a.elapsed_time(b) for n, a, b in evs if n == "k2"); k3 = sum(a.elapsed_time(b) for n, a, b in evs if n == "k3")
+    if rank == 0:
+        nfit = np.array([r.n for r in res])
+        print("rep %d: %d regions on %d GPU(s): %.2f s -> %.1f regions/s | rank0 K2 %.0f ms K3 %.0f ms rounds %d chains %d | "
+              "n == truth %.2f, |n - truth| <= 1 %.2f, status0 %.2f" % (
+                  rep, R, world, dt, R / dt, k2, k3, st.get("launches", 0) // 4, st.get("chains", 0),
+                  np.mean(nfit == ntrue), np.mean(np.abs(nfit - ntrue) <= 1), np.mean([r.status == 0 for r in res])), flush=True)
+if world > 1:
+    dist.destroy_process_group()

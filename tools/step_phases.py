@@ -24,7 +24,8 @@ for k in range(int(sys.argv[1]) if len(sys.argv) > 1 else 4):
     torch.cuda.synchronize()
     t0 = time.perf_counter(); marks.append(("start", ev()))
     mb = batch.fit_models(regs, models, voigt=True, iterations=3000, burn=300, thin=15, restarts=4, chains_per_restart=1024,
-                          polish_top=4, dtype="f32", seed=2000 + k, region_uids=[2], keep_sampler=True)
+                          polish_top=4, dtype="f32", seed=2000 + k, region_uids=[2], keep_sampler=True,
+                          polish_dtype=os.environ.get("POLISH", "f64"))
     marks.append(("end", ev())); torch.cuda.synchronize(); wall = time.perf_counter() - t0
     d = dict(marks)
     print("step %d: wall %.1f ms | pre-K2 %.1f  K2 %.1f  K2->K3 %.1f  K3 %.1f  post %.1f | nm iters max %d mean %.0f" % (

@@ -10,7 +10,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("VAMP_B200_LIB") or os.path.join(_HERE, "libvamp_b200.so")   # env override: kernel experiments
 
-VAMP_F32, VAMP_F64 = 0, 1
+VAMP_F32, VAMP_F64, VAMP_MIXED = 0, 1, 2
 VAMP_GAUSS, VAMP_VOIGT = 0, 1
 
 c_int_p = C.POINTER(C.c_int)

@@ -549,7 +549,13 @@ int vamp_map_dev(vamp_ctx* ctx, const vamp_regions* rg, int dtype, int kind, con
     p.out_bic = a->out_bic;
     p.out_iters = a->out_iters;
     p.out_nfev = a->out_nfev;
-    VAMP_CUDA(VAMP_DISPATCH4(vamp_launch_k3, dtype, kind, p, rg->max_npix, a->max_ncomp, ctx->stream));
+    if (dtype == VAMP_MIXED && rg->dev.lsf_taps <= 1) {
+        VAMP_CUDA(kind == VAMP_VOIGT ? vamp_launch_k3w_mixed_voigt(p, rg->max_npix, a->max_ncomp, ctx->stream)
+                                     : vamp_launch_k3w_mixed_gauss(p, rg->max_npix, a->max_ncomp, ctx->stream));
+        return 0;
+    }
+    // (VAMP_MIXED on an LSF region set: the CTA schedule in float64)
+    VAMP_CUDA(VAMP_DISPATCH4(vamp_launch_k3, dtype == VAMP_MIXED ? VAMP_F64 : dtype, kind, p, rg->max_npix, a->max_ncomp, ctx->stream));
     return 0;
 }
 

@@ -449,16 +449,18 @@ __device__ __forceinline__ CompC<T> make_comp_fast(T A, T cb, T w1, T w2) {
 }
 
 // K1's component constants: divisions in double (one per item and component), same clamp policy.
-template <typename T, int KIND>
+// PADDED: the caller reads the padded pair-layout arrays (padding coordinate 1e12): K2's clamp.
+template <typename T, int KIND, bool PADDED = false>
 __device__ __forceinline__ CompC<T> make_comp_k1(double A, double c, double w1, double w2, double ubase) {
     CompC<T> cc;
     cc.A = T(A);
     cc.cb = T(c - ubase);
+    const double igmax = PADDED ? (double)PadClamp<T>::ig() : (double)PadClamp<T>::ig_k1();
     if (KIND == VAMP_KIND_GAUSS) {
-        cc.g = T(0.84932180028801904272 * fmin(1.0 / w1, (double)PadClamp<T>::ig_k1()));
+        cc.g = T(0.84932180028801904272 * fmin(1.0 / w1, igmax));
         cc.y = cc.y2 = cc.L2 = T(0);
     } else {
-        const double ig = fmin(1.0 / w2, (double)PadClamp<T>::ig_k1());
+        const double ig = fmin(1.0 / w2, igmax);
         cc.g = T(1.66510922231539551270 * ig);
         cc.y = T(0.83255461115769775635 * w1 * ig);
         cc.y2 = cc.y * cc.y;

@@ -184,33 +184,31 @@ __device__ void nm_run(const MapDev& p, int s, double* sm, T* mbuf, const T* lsf
     double fb = 0, fw = 0, fw2 = 0;
     const int maxfun = p.maxfun > 0 ? p.maxfun : 0x7fffffff;
     while (true) {
-        // ---- order statistics: best, worst, second worst (ties as a stable sort would order them)
+        // ---- order statistics in one pass: best (first minimum), worst and second worst (last maxima,
+        //      the order a stable sort gives); tiny (<= 34 values), identical in every thread
         fb = INFINITY; fw = -INFINITY; fw2 = -INFINITY; ib = iw = iw2 = 0;
-        for (int v = 0; v < nv; ++v) {          // tiny (<= 34), identical in every thread
+        for (int v = 0; v < nv; ++v) {
             const double x = fsim[v];
             if (x < fb) { fb = x; ib = v; }
-        }
-        for (int v = 0; v < nv; ++v) {
-            const double x = fsim[v];
-            if (x >= fw) { fw = x; iw = v; }
-        }
-        for (int v = 0; v < nv; ++v) {
-            if (v == iw) continue;
-            const double x = fsim[v];
-            if (x >= fw2) { fw2 = x; iw2 = v; }
+            if (x >= fw) { fw2 = fw; iw2 = iw; fw = x; iw = v; }
+            else if (x >= fw2) { fw2 = x; iw2 = v; }
         }
         if (!(nfev < maxfun && iters < p.maxiter)) break;
-        // ---- convergence test (identical in every thread: all read the same shared simplex)
-        double dx = 0.0;
-        for (int i = 0; i < ts; ++i) {
-            if (!is_free(i)) continue;
-            const double b = sim[(size_t)ib * ts + i];
-            for (int v = 0; v < nv; ++v) dx = fmax(dx, fabs(sim[(size_t)v * ts + i] - b));
-            if (dx > p.xtol) break;
-        }
+        // ---- convergence test (identical in every thread: all read the same shared simplex).  Both
+        //      conditions must hold, so the O(k nv) coordinate spread is only formed once the function
+        //      spread is within ftol.
         double df = 0.0;
         for (int v = 0; v < nv; ++v) df = fmax(df, fabs(fsim[v] - fb));
-        if (dx <= p.xtol && df <= p.ftol) break;
+        if (df <= p.ftol) {
+            double dx = 0.0;
+            for (int i = 0; i < ts; ++i) {
+                if (!is_free(i)) continue;
+                const double b = sim[(size_t)ib * ts + i];
+                for (int v = 0; v < nv; ++v) dx = fmax(dx, fabs(sim[(size_t)v * ts + i] - b));
+                if (dx > p.xtol) break;
+            }
+            if (dx <= p.xtol) break;
+        }
 
         // ---- centroid of all but the worst
         for (int i = tid; i < ts; i += K3_THREADS) {
@@ -304,6 +302,274 @@ k3_map_kernel(MapDev p, int kmax) {
     nm_run<T, KIND>(p, s, sm, mbuf, lsf_s);
 }
 
+
+// ================================================================================================
+// K3w - the throughput schedule: ONE WARP per start, objective in fp32 (packed two-row Faddeeva,
+// same code as K2), simplex and Nelder-Mead logic in float64, and the reported lnL / chi^2 / BIC
+// re-evaluated in float64 at the optimum.  With thousands of starts (10^5 regions x candidates
+// x restarts) the CTA-per-start schedule above leaves most of an SM waiting on one simplex; here
+// every warp is busy and 16+ simplexes share an SM.  Lanes own pixels during an evaluation and
+// coordinates during the simplex updates.
+#if VAMP_INST_F64 == 0
+constexpr int K3W_WARPS = 4;
+#ifndef VAMP_K3W_SWITCH
+#define VAMP_K3W_SWITCH 0.01
+#endif
+#ifndef VAMP_K3W_MINBLOCKS
+#define VAMP_K3W_MINBLOCKS 4
+#endif
+constexpr double K3W_SWITCH = VAMP_K3W_SWITCH;     // function spread at which the search moves to the float64 objective
+
+template <typename T>
+struct CompK { T A, cb, g, y; };          // per-component constants staged in shared memory
+
+__host__ __device__ inline size_t k3w_warp_bytes(int kmax, int ts, int ncomp_max) {
+    return k3_align16(sizeof(double) * ((size_t)(kmax + 1) * ts + (kmax + 1) + 3 * ts)) +
+           k3_align16(sizeof(CompK<double>) * ncomp_max);
+}
+
+// -logp of `th` (full layout, shared memory); +inf outside the prior support.  All lanes get the
+// same value.  T = float: search precision; T = double: reporting precision.
+template <typename T, int KIND>
+__device__ __noinline__ double k3w_objective(const MapDev& p, const double* th, int r, int P, int n, int lane, void* ccbuf,
+                                             double c_hi, double w_hi, double ubase, double& lnL, double& chi2) {
+    constexpr int NP = (KIND == VAMP_KIND_VOIGT) ? 4 : 3;
+    typedef typename RS<T>::Pair Pair;
+    const RegionSetDev& rs = p.rs;
+    const int sdi = 4 * p.cmax;
+    CompK<T>* ccs = reinterpret_cast<CompK<T>*>(ccbuf);
+    // ---- bounds, prior and component constants: lane c handles component c (c + 32, ...)
+    bool ok = true;
+    double lp = 0.0;
+    for (int c = lane; c < n; c += 32) {
+        const double a = th[VAMP_TH(c, 0)], ce = th[VAMP_TH(c, 1)], w1 = th[VAMP_TH(c, 2)], w2 = th[VAMP_TH(c, 3)];
+        ok = ok && (a > 0.0) && (ce >= 0.0) && (ce <= c_hi);
+        if (NP == 4) ok = ok && (w1 >= 0.0) && (w1 <= w_hi) && (w2 > 0.0) && (w2 <= w_hi);
+        else ok = ok && (w1 > 0.0) && (w1 <= w_hi);
+        lp += log(a) - a;
+        const CompC<T> cc = make_comp_k1<T, KIND, true>(a, ce, w1, w2, ubase);
+        ccs[c].A = Real<T>::NEGK() * cc.A;
+        ccs[c].cb = cc.cb;
+        ccs[c].g = cc.g;
+        ccs[c].y = cc.y;
+    }
+    double sd = 1.0;
+    if (p.sd_free) {
+        sd = th[sdi];
+        ok = ok && (sd > 0.0) && (sd <= 1.0);
+    }
+    ok = __all_sync(VAMP_FULL_MASK, ok);
+    if (!ok) { lnL = -INFINITY; chi2 = INFINITY; return INFINITY; }
+    lp = warp_sum(lp);
+    __syncwarp();
+    // ---- model and residuals, two rows per trip (pair layout of the region set)
+    const int npairs = (P + 63) >> 6;
+    const Pair* gdu = RS<T>::pdu(rs) + (rs.pix_off[r] >> 1) + lane;
+    const Pair* gf = RS<T>::pf(rs) + (rs.pix_off[r] >> 1) + lane;
+    const Pair* gw = RS<T>::pw(rs) + (rs.pix_off[r] >> 1) + lane;
+    P2<T> S2 = p2_bc<T>(T(0)), X2 = p2_bc<T>(T(0));
+    unsigned nfar = 0u;
+#pragma unroll 1
+    for (int e = 0; e < 32 * npairs; e += 32) {
+        const P2<T> DU = p2_from(__ldg(gdu + e));
+        P2<T> tau = p2_bc<T>(T(0));
+#pragma unroll 1
+        for (int c = 0; c < n; ++c) {
+            CompC<T> cc;
+            cc.A = ccs[c].A;
+            cc.cb = ccs[c].cb;
+            cc.g = ccs[c].g;
+            cc.y = ccs[c].y;
+            cc.y2 = cc.y * cc.y;
+            cc.L2 = T(0);
+            P2<T> X, S;
+            bool far;
+            pair_classify<T, KIND>(cc, DU, X, S, far);
+            tau = p2_fma(p2_bc<T>(cc.A), pair_eval<T, KIND>(cc, X, S, far, nfar), tau);
+        }
+        // padding pixels: du = 1e12 gives tau = 0 exactly, flux 1, weight 0 (vamp_regions_create)
+        const P2<T> R = p2_sub(p2_from(__ldg(gf + e)), p2_exp_scaled<T>(tau));
+        S2 = p2_fma(R, R, S2);
+        const P2<T> RW = p2_mul(R, p2_from(__ldg(gw + e)));
+        X2 = p2_fma(RW, RW, X2);
+    }
+    const double Sd = (double)warp_sum(p2_lo(S2) + p2_hi(S2)), Xd = (double)warp_sum(p2_lo(X2) + p2_hi(X2));
+    chi2 = Xd;
+    lnL = p.sd_free ? lnL_sd(Sd, sd, P) : lnL_noise(Xd, rs.lognorm[r]);
+    const double f = -(lnL + lp);
+    return (f == f) ? f : INFINITY;
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(K3W_WARPS * 32, VAMP_K3W_MINBLOCKS)
+k3w_map_kernel(MapDev p, int kmax, int ncomp_max) {
+    constexpr int NP = (KIND == VAMP_KIND_VOIGT) ? 4 : 3;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int s = blockIdx.x * K3W_WARPS + warp;
+    if (s >= p.S) return;
+    const int ts = p.tstride;
+    unsigned char* wbase = smem_raw + (size_t)warp * k3w_warp_bytes(kmax, ts, ncomp_max);
+    const RegionSetDev& rs = p.rs;
+    const int r = p.item_region[s];
+    const int P = rs.npix[r];
+    const int n = p.item_ncomp[s];
+    const int sdi = 4 * p.cmax;
+    const double ubase = rs.ubase[rs.tile_off[r]];
+    const double c_hi = (double)(P - 1);
+    const double w_hi = 0.5 * (double)(P - 1) * (KIND == VAMP_KIND_VOIGT ? FWHM_PER_SIGMA : 1.0);
+    const int k = NP * n + (p.sd_free ? 1 : 0);
+    const int nv = k + 1;
+    auto is_free = [&](int i) -> bool {
+        if (i == sdi) return p.sd_free != 0;
+        return (i < 4 * n) && ((i & 3) < NP);
+    };
+    auto free_pos = [&](int j) -> int { return (j == NP * n) ? sdi : 4 * (j / NP) + (j % NP); };
+
+    double* sim = reinterpret_cast<double*>(wbase);   // [nv][ts]
+    double* fsim = sim + (size_t)nv * ts;              // [nv]
+    double* xbar = fsim + nv;                          // [ts]
+    double* xt = xbar + ts;                            // [ts]
+    double* xr = xt + ts;                              // [ts]
+    void* ccbuf = wbase + k3_align16(sizeof(double) * ((size_t)(kmax + 1) * ts + (kmax + 1) + 3 * ts));
+    double lnL = 0.0, chi2 = 0.0;
+    // Two stages: the fp32 objective differs from float64 by 1e-4 .. 1e-3 in logp, pixel-to-pixel jumps up
+    // to 2e-3 (measured, tools/noise_scan.py) - the size of the stopping tolerance - so once the simplex's
+    // function spread is within K3W_SWITCH the search continues on the float64 objective (all vertices
+    // re-evaluated).  Before that every comparison is far above the noise and the two objectives decide alike.
+    bool fine = false;
+    auto F = [&](const double* th) -> double {
+        return fine ? k3w_objective<double, KIND>(p, th, r, P, n, lane, ccbuf, c_hi, w_hi, ubase, lnL, chi2)
+                    : k3w_objective<float, KIND>(p, th, r, P, n, lane, ccbuf, c_hi, w_hi, ubase, lnL, chi2);
+    };
+
+    // ---- initial simplex (scipy: vertex j+1 perturbs coordinate j by 5 %, or 0.00025 if zero)
+    for (int v = 0; v < nv; ++v) {
+        const int pj = v > 0 ? free_pos(v - 1) : -1;
+        for (int i = lane; i < ts; i += 32) {
+            double x = p.theta[(size_t)s * ts + i];
+            if (i == pj) x = (x != 0.0) ? 1.05 * x : 0.00025;
+            sim[(size_t)v * ts + i] = x;
+        }
+    }
+    __syncwarp();
+    int nfev = 0;
+    for (int v = 0; v < nv; ++v) {
+        const double fv = F(sim + (size_t)v * ts);
+        ++nfev;
+        if (lane == 0) fsim[v] = fv;
+    }
+    __syncwarp();
+
+    int iters = 1, ib = 0, iw = 0, iw2 = 0;
+    double fb = 0, fw = 0, fw2 = 0;
+    const int maxfun = p.maxfun > 0 ? p.maxfun : 0x7fffffff;
+    while (true) {
+        fb = INFINITY; fw = -INFINITY; fw2 = -INFINITY; ib = iw = iw2 = 0;
+        for (int v = 0; v < nv; ++v) {
+            const double x = fsim[v];
+            if (x < fb) { fb = x; ib = v; }
+            if (x >= fw) { fw2 = fw; iw2 = iw; fw = x; iw = v; }
+            else if (x >= fw2) { fw2 = x; iw2 = v; }
+        }
+        if (!(nfev < maxfun && iters < p.maxiter)) break;
+        double df = 0.0;
+        for (int v = 0; v < nv; ++v) df = fmax(df, fabs(fsim[v] - fb));
+        if (!fine && df <= K3W_SWITCH) {
+            fine = true;
+            for (int v = 0; v < nv; ++v) {
+                const double fv = F(sim + (size_t)v * ts);
+                ++nfev;
+                if (lane == 0) fsim[v] = fv;
+            }
+            __syncwarp();
+            continue;                              // order statistics again, on float64 values
+        }
+        if (df <= p.ftol) {
+            double dx = 0.0;                       // lane i: spread of coordinate i
+            for (int i = lane; i < ts; i += 32) {
+                if (!is_free(i)) continue;
+                const double b = sim[(size_t)ib * ts + i];
+                for (int v = 0; v < nv; ++v) dx = fmax(dx, fabs(sim[(size_t)v * ts + i] - b));
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) dx = fmax(dx, __shfl_xor_sync(VAMP_FULL_MASK, dx, o));
+            if (dx <= p.xtol) break;
+        }
+        // ---- centroid of all but the worst (lane-parallel over coordinates)
+        for (int i = lane; i < ts; i += 32) {
+            double a = 0.0;
+            for (int v = 0; v < nv; ++v)
+                if (v != iw) a += sim[(size_t)v * ts + i];
+            xbar[i] = is_free(i) ? a / (double)k : sim[(size_t)ib * ts + i];
+        }
+        __syncwarp();
+        const double* xw = sim + (size_t)iw * ts;
+        auto combine = [&](double* dst, double ca, double cb_) {
+            for (int i = lane; i < ts; i += 32) dst[i] = is_free(i) ? ca * xbar[i] + cb_ * xw[i] : xbar[i];
+            __syncwarp();
+        };
+        auto replace_worst = [&](const double* src, double fv) {
+            for (int i = lane; i < ts; i += 32) sim[(size_t)iw * ts + i] = src[i];
+            if (lane == 0) fsim[iw] = fv;
+            __syncwarp();
+        };
+        combine(xr, 2.0, -1.0);
+        const double fxr = F(xr);
+        ++nfev;
+        bool shrink = false;
+        if (fxr < fb) {
+            combine(xt, 3.0, -2.0);
+            const double fxe = F(xt);
+            ++nfev;
+            if (fxe < fxr) replace_worst(xt, fxe);
+            else replace_worst(xr, fxr);
+        } else if (fxr < fw2) {
+            replace_worst(xr, fxr);
+        } else if (fxr < fw) {
+            combine(xt, 1.5, -0.5);
+            const double fxc = F(xt);
+            ++nfev;
+            if (fxc <= fxr) replace_worst(xt, fxc);
+            else shrink = true;
+        } else {
+            combine(xt, 0.5, 0.5);
+            const double fxcc = F(xt);
+            ++nfev;
+            if (fxcc < fw) replace_worst(xt, fxcc);
+            else shrink = true;
+        }
+        if (shrink) {
+            for (int v = 0; v < nv; ++v) {
+                if (v == ib) continue;
+                for (int i = lane; i < ts; i += 32) {
+                    const double b = sim[(size_t)ib * ts + i];
+                    sim[(size_t)v * ts + i] = b + 0.5 * (sim[(size_t)v * ts + i] - b);
+                }
+                __syncwarp();
+                const double fv = F(sim + (size_t)v * ts);
+                ++nfev;
+                if (lane == 0) fsim[v] = fv;
+            }
+            __syncwarp();
+        }
+        ++iters;
+    }
+    // ---- report in float64 at the best vertex
+    fine = true;
+    const double fbest = F(sim + (size_t)ib * ts);
+    for (int i = lane; i < ts; i += 32) p.theta[(size_t)s * ts + i] = sim[(size_t)ib * ts + i];
+    if (lane == 0) {
+        p.out_logp[s] = -fbest;
+        p.out_lnL[s] = lnL;
+        p.out_chi2[s] = chi2;
+        p.out_bic[s] = (double)k * log((double)P) - 2.0 * lnL;
+        p.out_iters[s] = iters;
+        p.out_nfev[s] = nfev;
+    }
+}
+#endif  // VAMP_INST_F64 == 0
+
 }  // namespace
 
 cudaError_t VAMP_INST_NAME(vamp_launch_k3)(const MapDev& p, int max_npix, int max_ncomp, cudaStream_t st) {
@@ -321,3 +587,20 @@ cudaError_t VAMP_INST_NAME(vamp_launch_k3)(const MapDev& p, int max_npix, int ma
     kern<<<p.S, K3_THREADS, smem, st>>>(p, kmax);
     return cudaGetLastError();
 }
+
+#if VAMP_INST_F64 == 0
+// mixed-precision warp-per-start schedule (vamp_map_dev dtype VAMP_MIXED); LSF regions use the CTA schedule
+cudaError_t VAMP_CAT3(vamp_launch_k3w, mixed, VAMP_KN)(const MapDev& p, int max_npix, int max_ncomp, cudaStream_t st) {
+    if (p.S <= 0) return cudaSuccess;
+    if (max_npix > VAMP_TILE_PIX || p.rs.lsf_taps > 1) return cudaErrorInvalidValue;
+    const int NP = (InstKind == VAMP_KIND_VOIGT) ? 4 : 3;
+    const int kmax = NP * max_ncomp + 1;
+    const size_t smem = K3W_WARPS * k3w_warp_bytes(kmax, p.tstride, max_ncomp);
+    if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
+    auto kern = k3w_map_kernel<InstKind>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<(p.S + K3W_WARPS - 1) / K3W_WARPS, K3W_WARPS * 32, smem, st>>>(p, kmax, max_ncomp);
+    return cudaGetLastError();
+}
+#endif

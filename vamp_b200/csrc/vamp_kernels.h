@@ -77,3 +77,6 @@ struct MapDev {
     int* out_nfev;                       // [S]
 };
 VAMP_DECL4(cudaError_t, vamp_launch_k3, const MapDev& p, int max_npix, int max_ncomp, cudaStream_t st)
+// warp-per-start schedule: fp32 objective, float64 simplex and float64 final evaluation (dtype VAMP_MIXED)
+cudaError_t vamp_launch_k3w_mixed_gauss(const MapDev& p, int max_npix, int max_ncomp, cudaStream_t st);
+cudaError_t vamp_launch_k3w_mixed_voigt(const MapDev& p, int max_npix, int max_ncomp, cudaStream_t st);

@@ -13,7 +13,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import VAMP_F32, VAMP_F64, VAMP_GAUSS, VAMP_VOIGT, McmcArgs, MapArgs, check
+from ._lib import VAMP_F32, VAMP_F64, VAMP_MIXED, VAMP_GAUSS, VAMP_VOIGT, McmcArgs, MapArgs, check
 
 FWHM_PER_SIGMA = 2.0 * np.sqrt(2.0 * np.log(2.0))
 _DTYPES = {"f32": VAMP_F32, "f64": VAMP_F64, "float32": VAMP_F32, "float64": VAMP_F64, VAMP_F32: VAMP_F32,
@@ -378,7 +378,8 @@ class Sampler:
         a.out_logp, a.out_lnL, a.out_chi2, a.out_bic = (out["logp"].data_ptr(), out["lnL"].data_ptr(),
                                                         out["chi2"].data_ptr(), out["bic"].data_ptr())
         a.out_iters, a.out_nfev = out["iters"].data_ptr(), out["nfev"].data_ptr()
-        code = self.dtype if dtype is None else dtype_code(dtype)
+        # "mixed": fp32 objective in the simplex search, float64 simplex + float64 report, one warp per start
+        code = self.dtype if dtype is None else (VAMP_MIXED if dtype == "mixed" else dtype_code(dtype))
         check(self.lib.vamp_map_dev(self.ctx.handle, self.regions.handle, code, self.kind, C.byref(a)))
         out["theta"] = th
         return out

@@ -42,6 +42,9 @@ def lpt_partition(costs, world_size):
     return [sorted(p) for p in parts]
 
 
+MIXED_POLISH_STARTS = 2048
+
+
 class RegionResult:
     """Per-region outcome: chosen ``n``, the BIC / reduced-chi^2 ladder, the MAP parameters of
     the kept fit (physical units) and posterior mean / std of its winning chain."""
@@ -93,7 +96,7 @@ def unpack_record(rec, nmax, G, cmax):
 
 def fit_local(regions_host, uids, voigt=False, sd_free=True, iterations=3000, burn=300, thin=15, restarts=3,
               chains_per_restart=32, window=3, max_rounds=4, chi_limit=1.5, dtype="f32", seed=0, lsf=None,
-              n0=None, nmax=12, ctx=None, polish_top=4, tune_interval=50, stats=None, cmax_rec=None):
+              n0=None, nmax=12, ctx=None, polish_top=4, tune_interval=50, stats=None, cmax_rec=None, polish_dtype="f64"):
     """Fit the given regions on this process's GPU.  Returns ``[R, record_len]`` float64."""
     ctx = ctx or engine.default_context()
     R = len(regions_host)
@@ -123,7 +126,7 @@ def fit_local(regions_host, uids, voigt=False, sd_free=True, iterations=3000, bu
                     owner.append(i)
         mb = batch.fit_models(regs, models, voigt=voigt, sd_free=sd_free, iterations=iterations, burn=burn, thin=thin,
                               restarts=G, chains_per_restart=chains_per_restart, polish_top=polish_top, dtype=dtype,
-                              seed=seed, region_uids=uids, tune_interval=tune_interval)
+                              seed=seed, region_uids=uids, tune_interval=tune_interval, polish_dtype=polish_dtype)
         if stats is not None:
             stats["voigt_evals"] = stats.get("voigt_evals", 0) + mb.voigt_evals
             stats["voigt_evals_actual"] = stats.get("voigt_evals_actual", 0) + mb.work["shape_pix"]
@@ -196,6 +199,12 @@ def fit_regions(regions_host, uids=None, distributed=None, fit_fn=None, **kw):
     cmax_rec = (max(n0) if n0 else 1) + nmax
     rec_len = _record_len(nmax, G, cmax_rec)
     use_dist = dist.is_available() and dist.is_initialized() if distributed is None else bool(distributed)
+    if kw.get("polish_dtype", "auto") == "auto" and fit_fn is None:
+        # K3 schedule from the GLOBAL number of starts (the same on every rank and for every world size):
+        # thousands of starts -> one warp per start, fp32 search stage + float64 finish ("mixed");
+        # a few -> one CTA per start in float64 (latency)
+        starts = R * window * G * kw.get("polish_top", 4)
+        kw["polish_dtype"] = "mixed" if (starts >= MIXED_POLISH_STARTS and kw.get("lsf") is None) else "f64"
     fit_fn = fit_fn or fit_local
     if not use_dist:
         recs = fit_fn(regions_host, uids, n0=n0, cmax_rec=cmax_rec, **kw)
