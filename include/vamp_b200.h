@@ -143,6 +143,18 @@ typedef struct vamp_map_args {
 } vamp_map_args;
 int vamp_map_dev(vamp_ctx* ctx, const vamp_regions* regions, int dtype, int kind, const vamp_map_args* a);
 
+/* K4 - detection ratio of whole sightlines (batched matched filter).  Replaces the equivalent-width
+ * loops and the 2 x 9 Gaussian convolutions of VPspectrum.compute_detection_regions
+ * (vamp_1.0/vpspectrum.py:92-122; the vectorised twin is vamp_2.0/vamp_src/dataset/preprocess.py:45-126):
+ * out[s, i] = max over std in [std_min, std_max) of flux_func / sqrt(noise_func), -inf at the two end
+ * pixels.  float64.  [n_spectra, stride] row-major arrays; npix[s] <= stride pixels of row s are
+ * used (NULL: all rows have `stride` pixels).  The sequential region selection
+ * (vpspectrum.py:124-174) is host logic (vamp_b200/vpspectrum.py:select_regions). */
+int vamp_detect_dev(vamp_ctx* ctx, int n_spectra, int stride, const int* npix, int max_npix, const double* wavelength,
+                    const double* flux, const double* noise, int std_min, int std_max, double* out_det_ratio);
+int vamp_detect_host(vamp_ctx* ctx, int n_spectra, int stride, const int* npix, const double* wavelength,
+                     const double* flux, const double* noise, int std_min, int std_max, double* out_det_ratio);
+
 /* One component's optical depth tau(x) on an arbitrary HOST grid, evaluated in float64 on the
  * device: VPfit.VoigtFunction(x, centroid, amplitude, L_fwhm, G_fwhm) (vpfits.py:58-76; kind =
  * VAMP_VOIGT, w1 = L_fwhm, w2 = G_fwhm) or VPfit.GaussFunction(x, amplitude, centroid, sigma)

@@ -127,6 +127,29 @@ def load():
     return types.SimpleNamespace(**_CACHE)
 
 
+def load_spectrum_class():
+    """The reference's ``VPspectrum`` class (vamp_1.0/vpspectrum.py), exec'd from where it lies with
+    inert stubs for pymc / matplotlib / h5py and the truncated ``vpregion`` module (the file itself
+    is a SyntaxError on Python 3).  ``compute_detection_regions`` and ``split_difficult_region``
+    then run the reference's own lines."""
+    if "VPspectrum" in _CACHE:
+        return _CACHE["VPspectrum"]
+    ref = load()
+    v1 = os.path.join(REFERENCE_ROOT, "vamp_1.0")
+    saved = _install_stubs()
+    fake_region = types.ModuleType("vpregion")
+    fake_region.VPregion = ref.VPregion
+    saved_mods = {k: sys.modules.get(k) for k in ("physics", "vpfits", "vpregion")}
+    sys.modules.update({"physics": ref.physics, "vpfits": ref.vpfits, "vpregion": fake_region})
+    try:
+        mod = _load("_ref_vpspectrum", os.path.join(v1, "vpspectrum.py"))
+    finally:
+        _restore(saved)
+        _restore(saved_mods)
+    _CACHE["VPspectrum"] = mod.VPspectrum
+    return mod.VPspectrum
+
+
 def read_simba_fixture(name):
     """Raw-offset reader for vamp_1.0/data/simba_*.h5 (no h5py here):
     contiguous little-endian float64[1000] datasets."""

@@ -180,6 +180,45 @@ def make_simba(ref):
     np.savez_compressed(os.path.join(OUT, "simba.npz"), **out)
 
 
+def make_detect(ref):
+    """Detection regions (vpspectrum.py:67-174) from the reference's own ``compute_detection_regions`` on
+    the two simba sightlines and on seeded synthetic sightlines (odd and even lengths, several
+    thresholds / widths, ``extend`` on and off)."""
+    import contextlib
+    import io
+    VPspectrum = LR.load_spectrum_class()
+    out = {}
+    cases = []
+    for fname in ("simba_CII1036.h5", "simba_H1215.h5"):
+        fx = LR.read_simba_fixture(fname)
+        cases.append((fname.split(".")[0], fx["wavelength"], fx["flux"], fx["noise"]))
+    rng = np.random.default_rng(20260101)
+    for k, P in enumerate((257, 600, 1001, 90)):
+        wave = 1215.0 + 0.0203 * np.arange(P)
+        tau = np.zeros(P)
+        for _ in range(max(1, P // 120)):
+            c, s, a = rng.uniform(0.1, 0.9) * P, rng.uniform(2.0, 9.0), rng.uniform(0.3, 3.0)
+            tau += a * np.exp(-0.5 * ((np.arange(P) - c) / s) ** 2)
+        snr = (20.0, 50.0, 100.0, 30.0)[k]
+        noise = np.full(P, 1.0 / snr) * rng.uniform(0.8, 1.2, P)
+        flux = np.exp(-tau) + rng.normal(0.0, 1.0, P) * noise
+        cases.append(("synth%d" % k, wave, flux, noise))
+    settings = [dict(min_region_width=2, N_sigma=4.0, extend=False), dict(min_region_width=2, N_sigma=4.0, extend=True),
+                dict(min_region_width=5, N_sigma=6.0, extend=False), dict(min_region_width=2, N_sigma=3.0, extend=False, std_min=3, std_max=8)]
+    for name, wave, flux, noise in cases:
+        out[name + "/wavelength"], out[name + "/flux"], out[name + "/noise"] = wave, flux, noise
+        for j, kw in enumerate(settings):
+            sp = VPspectrum(1215.0)
+            sp.wavelength_array, sp.flux_array, sp.noise_array = wave.copy(), flux.copy(), noise.copy()
+            with contextlib.redirect_stdout(io.StringIO()), np.errstate(all="ignore"):
+                sp.compute_detection_regions(**kw)
+            out["%s/s%d/region_pixels" % (name, j)] = np.array(sp.region_pixels, dtype=np.int64).reshape(-1, 2)
+    out["names"] = np.array([c[0] for c in cases])
+    out["settings"] = np.array([repr(sorted(kw.items())) for kw in settings])
+    np.savez_compressed(os.path.join(OUT, "detect.npz"), **out)
+    return {n: [out["%s/s%d/region_pixels" % (n, j)].tolist() for j in range(len(settings))] for n in out["names"]}
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = LR.load()
@@ -187,6 +226,8 @@ def main():
     make_physics(ref)
     make_wofz_mp()
     make_simba(ref)
+    det = make_detect(ref)
+    print("detection regions:", {k: v[0] for k, v in det.items()})
     print("wrote %d profile cases + physics + wofz_mp + simba to %s" % (n, OUT))
 
 

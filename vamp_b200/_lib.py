@@ -56,6 +56,9 @@ SIGNATURES = {
     "vamp_regions_destroy": (C.c_int, [C.c_void_p]),
     "vamp_regions_info": (C.c_int, [C.c_void_p, c_int_p, c_int_p, C.POINTER(C.c_longlong)]),
     "vamp_regions_scale": (C.c_int, [C.c_void_p, c_dbl_p, c_dbl_p]),
+    "vamp_detect_dev": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.c_int, C.c_int, C.c_void_p]),
+    "vamp_detect_host": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_int_p, c_dbl_p, c_dbl_p, c_dbl_p, C.c_int, C.c_int, c_dbl_p]),
     "vamp_loglike_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                    C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong]),
     "vamp_loglike_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, c_int_p, c_int_p, C.c_int,

@@ -45,6 +45,7 @@ def _jobs():
                 obj = os.path.join(OBJ, "%s_%s_%s.o" % (base, "f64" if f64 else "f32", "voigt" if voigt else "gauss"))
                 defs = ["-DVAMP_INST_F64=%d" % f64, "-DVAMP_INST_VOIGT=%d" % voigt]
                 jobs.append((src, obj, defs, hdr))
+    jobs.append((os.path.join(CSRC, "vamp_k4.cu"), os.path.join(OBJ, "vamp_k4.o"), [], hdr))
     jobs.append((os.path.join(CSRC, "vamp_cabi.cu"), os.path.join(OBJ, "vamp_cabi.o"), [], hdr))
     return jobs
 

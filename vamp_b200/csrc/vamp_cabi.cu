@@ -559,6 +559,50 @@ int vamp_map_dev(vamp_ctx* ctx, const vamp_regions* rg, int dtype, int kind, con
     return 0;
 }
 
+int vamp_detect_dev(vamp_ctx* ctx, int n_spectra, int stride, const int* npix, int max_npix, const double* wavelength,
+                    const double* flux, const double* noise, int std_min, int std_max, double* out_det_ratio) {
+    if (!ctx || !wavelength || !flux || !noise || !out_det_ratio) return fail(-1, "null argument");
+    if (n_spectra < 0 || stride < 1 || max_npix < 1 || max_npix > stride) return fail(-2, "bad sizes: n=%d stride=%d max_npix=%d", n_spectra, stride, max_npix);
+    if (std_min < 1 || std_max <= std_min || std_max > 33) return fail(-2, "std range [%d, %d) not in 1 <= std_min < std_max <= 33", std_min, std_max);
+    if (n_spectra > 65535) return fail(-2, "at most 65535 sightlines per call (got %d)", n_spectra);
+    VAMP_CUDA(cudaSetDevice(ctx->device));
+    VAMP_CUDA(vamp_launch_k4(n_spectra, stride, max_npix, npix, wavelength, flux, noise, std_min, std_max, out_det_ratio,
+                             ctx->stream));
+    return 0;
+}
+
+int vamp_detect_host(vamp_ctx* ctx, int n_spectra, int stride, const int* npix, const double* wavelength,
+                     const double* flux, const double* noise, int std_min, int std_max, double* out_det_ratio) {
+    if (!ctx || !wavelength || !flux || !noise || !out_det_ratio) return fail(-1, "null argument");
+    if (n_spectra <= 0) return 0;
+    if (stride < 1) return fail(-2, "bad stride %d", stride);
+    int max_npix = stride;
+    if (npix) {
+        max_npix = 0;
+        for (int i = 0; i < n_spectra; ++i) {
+            if (npix[i] < 0 || npix[i] > stride) return fail(-2, "npix[%d] = %d outside [0, stride]", i, npix[i]);
+            max_npix = npix[i] > max_npix ? npix[i] : max_npix;
+        }
+        if (max_npix == 0) return 0;
+    }
+    VAMP_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const size_t nb = sizeof(double) * (size_t)n_spectra * stride;
+    for (int k = 0; k < 4; ++k) VAMP_CUDA(ctx->scratch[k].reserve(nb));
+    VAMP_CUDA(ctx->scratch[4].reserve(sizeof(int) * (size_t)n_spectra));
+    VAMP_CUDA(cudaMemcpyAsync(ctx->scratch[0].p, wavelength, nb, cudaMemcpyHostToDevice, st));
+    VAMP_CUDA(cudaMemcpyAsync(ctx->scratch[1].p, flux, nb, cudaMemcpyHostToDevice, st));
+    VAMP_CUDA(cudaMemcpyAsync(ctx->scratch[2].p, noise, nb, cudaMemcpyHostToDevice, st));
+    if (npix) VAMP_CUDA(cudaMemcpyAsync(ctx->scratch[4].p, npix, sizeof(int) * (size_t)n_spectra, cudaMemcpyHostToDevice, st));
+    const int rc = vamp_detect_dev(ctx, n_spectra, stride, npix ? (const int*)ctx->scratch[4].p : nullptr, max_npix,
+                                   (const double*)ctx->scratch[0].p, (const double*)ctx->scratch[1].p,
+                                   (const double*)ctx->scratch[2].p, std_min, std_max, (double*)ctx->scratch[3].p);
+    if (rc) return rc;
+    VAMP_CUDA(cudaMemcpyAsync(out_det_ratio, ctx->scratch[3].p, nb, cudaMemcpyDeviceToHost, st));
+    VAMP_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
 int vamp_faddeeva_host(vamp_ctx* ctx, int dtype, int n, const double* x, const double* y, double* out_H) {
     if (!ctx || !x || !y || !out_H) return fail(-1, "null argument");
     if (n <= 0) return 0;

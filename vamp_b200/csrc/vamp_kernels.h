@@ -80,3 +80,7 @@ VAMP_DECL4(cudaError_t, vamp_launch_k3, const MapDev& p, int max_npix, int max_n
 // warp-per-start schedule: fp32 objective, float64 simplex and float64 final evaluation (dtype VAMP_MIXED)
 cudaError_t vamp_launch_k3w_mixed_gauss(const MapDev& p, int max_npix, int max_ncomp, cudaStream_t st);
 cudaError_t vamp_launch_k3w_mixed_voigt(const MapDev& p, int max_npix, int max_ncomp, cudaStream_t st);
+
+// ---- K4 (vamp_k4.cu): detection ratio of sightlines (batched matched filter), float64
+cudaError_t vamp_launch_k4(int S, int stride, int max_npix, const int* npix, const double* wavelength, const double* flux,
+                           const double* noise, int std_min, int std_max, double* out_det, cudaStream_t st);

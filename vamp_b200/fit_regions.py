@@ -54,10 +54,14 @@ class RegionResult:
 
 
 def _record_len(nmax, G, cmax):
-    return 6 + 2 * nmax * G + 1 + 3 * cmax * 4 + 3
+    return 6 + 2 * nmax * G + 1 + 3 * cmax * 4 + 3 + 1 + cmax
 
 
-def pack_record(uid, status, n0, kept, exit_n, tables, nmax, G, cmax, theta, sd, mean, std, sd_mean, sd_std, lnL):
+def pack_record(uid, status, n0, kept, exit_n, tables, nmax, G, cmax, theta, sd, mean, std, sd_mean, sd_std, lnL,
+                chi2=np.nan, cov_aw=None):
+    """Fixed-geometry float64 record of one region (the unit of the result all-gather).  ``chi2``:
+    noise-weighted chi^2 of the kept fit; ``cov_aw``: posterior covariance of (amplitude, Gaussian
+    width) per component (physical units) - what ``chain_covariance`` / ``ErrorN`` consume."""
     rec = np.full(_record_len(nmax, G, cmax), np.nan)
     rec[0:6] = [uid, status, n0, kept, exit_n, len(tables)]
     bic = np.full((nmax, G), np.nan)
@@ -75,6 +79,11 @@ def pack_record(uid, status, n0, kept, exit_n, tables, nmax, G, cmax, theta, sd,
         rec[o: o + cmax * 4] = a.reshape(-1); o += cmax * 4
     rec[o: o + 3] = [np.nan if sd is None else sd, np.nan if sd_mean is None else sd_mean,
                      np.nan if sd_std is None else sd_std]
+    o += 3
+    rec[o] = chi2
+    if cov_aw is not None:
+        k = min(len(cov_aw), cmax)
+        rec[o + 1: o + 1 + k] = np.asarray(cov_aw, dtype=np.float64)[:k]
     return rec
 
 
@@ -88,7 +97,10 @@ def unpack_record(rec, nmax, G, cmax):
     for _ in range(3):
         arrs.append(rec[o: o + cmax * 4].reshape(cmax, 4)[:kept].copy()); o += cmax * 4
     sd, sd_mean, sd_std = rec[o: o + 3]
-    return RegionResult(uid=uid, status=status, n0=n0, n=kept, exit_n=exit_n,
+    o += 3
+    chi2 = rec[o]
+    cov_aw = rec[o + 1: o + 1 + cmax][:kept].copy()
+    return RegionResult(uid=uid, status=status, n0=n0, n=kept, exit_n=exit_n, chi2=chi2, cov_aw=cov_aw,
                         bic={n0 + i: bic[i].copy() for i in range(min(ncand, nmax))},
                         red_chi={n0 + i: red[i].copy() for i in range(min(ncand, nmax))},
                         lnL=lnL, theta=arrs[0], mean=arrs[1], std=arrs[2], sd=sd, sd_mean=sd_mean, sd_std=sd_std)
@@ -153,10 +165,16 @@ def fit_local(regions_host, uids, voigt=False, sd_free=True, iterations=3000, bu
         kept, exit_n, status = outcome[i]
         mb, m = fits[i][kept]
         g = int(np.nanargmin(mb.bic[m])) if np.any(np.isfinite(mb.bic[m])) else 0
+        # covariance of (amplitude, Gaussian width) from the co-moments of the winning chain: Gauss (A, sigma) =
+        # pair 1, Voigt (A, G_fwhm) = pair 2 converted to sigma; widths are in scaled units on the device
+        pair = 2 if voigt else 1
+        fac = mb.scale[m] * (1.0 / (2.0 * np.sqrt(2.0 * np.log(2.0))) if voigt else 1.0)
+        cov_aw = mb.comom[m, g, :kept, pair] / max(int(mb.ntally[m, g]) - 1, 1) * fac      # np.cov normalisation
         out[i] = pack_record(uids[i], status, n0[i], kept, exit_n, tables[i], nmax, G, cmax_rec,
                              mb.theta[m, g, :kept], None if mb.sd is None else mb.sd[m, g], mb.mean[m, g, :kept],
                              mb.std[m, g, :kept], None if mb.sd_mean is None else mb.sd_mean[m, g],
-                             None if mb.sd_std is None else mb.sd_std[m, g], mb.lnL[m, g])
+                             None if mb.sd_std is None else mb.sd_std[m, g], mb.lnL[m, g], chi2=mb.chi2[m, g],
+                             cov_aw=cov_aw)
     return out
 
 

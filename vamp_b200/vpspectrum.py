@@ -1,0 +1,312 @@
+"""``VPspectrum`` - a whole sightline: detection regions -> region fits -> physical parameters
+(the role of vamp_1.0/vpspectrum.py).
+
+Same constructor arguments, attribute names (``region_pixels``, ``region_waves``, ``params``,
+``flux_model``, ``regions`` ...) and dictionary keys as the reference class, GPU-shaped inside:
+
+* ``compute_detection_regions`` (vpspectrum.py:67-174): the equivalent widths and the 2 x 9
+  Gaussian convolutions run as one batched kernel (K4, ``vamp_detect_host``) - also for many
+  sightlines at once (``detection_ratio_batch``); the sequential selection is ``select_regions``.
+* ``fit_spectrum`` (vpspectrum.py:243-430): all regions of the sightline (and all candidate
+  component counts, restarts and chains of each) are fitted together by ``fit_regions``; the
+  reference's retry loop becomes rounds over the regions that have not reached ``chi_limit`` yet.
+  N, b, EW and their errors come from ``physics.py`` on the MAP parameters and the device-side
+  posterior moments.
+
+The reference file has undefined names on some paths (``attempt_n``, ``n``, ``min_region_size``,
+``forced_number_regions`` at vpspectrum.py:203,216,308,317) and asks the MCMC statistics for
+``est_sigma_i`` in Voigt mode (KeyError, :401-410); the intended behaviour is implemented here
+(Voigt widths are ``GaussianWidth(G_fwhm)``, vpspectrum.py:376-377).  HDF5 I/O needs ``h5py``
+(not a dependency): ``set_spectrum`` takes arrays, ``write_file`` falls back to ``.npz``.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib, engine
+from .fit_regions import estimate_n, fit_regions
+from .physics import (ColumnDensity, DopplerParameter, EquivalentWidthFlux, EquivalentWidthTau, ErrorB, ErrorN,
+                      Freq2wave, Tau2flux, Wave2freq)
+from .vpfits import VPfit
+
+
+def detection_ratio_batch(wavelengths, fluxes, noises, std_min=2, std_max=11, ctx=None):
+    """Detection ratio of ``S`` sightlines (sequences of 1-D float64 arrays, ragged lengths allowed)
+    in one K4 launch.  Returns a list of arrays (``-inf`` at the end pixels, vpspectrum.py:92-122)."""
+    ctx = ctx or engine.default_context()
+    ctx.use_current_stream()
+    S = len(wavelengths)
+    if S == 0:
+        return []
+    npix = np.array([len(w) for w in wavelengths], dtype=np.int32)
+    stride = int(npix.max())
+    pack = lambda arrs: np.ascontiguousarray(
+        np.stack([np.pad(np.asarray(a, dtype=np.float64), (0, stride - len(a))) for a in arrs]))
+    wl, fl, ns = pack(wavelengths), pack(fluxes), pack(noises)
+    out = np.empty_like(wl)
+    for s0 in range(0, S, 65535):
+        s1 = min(S, s0 + 65535)
+        _lib.check(ctx.lib.vamp_detect_host(ctx.handle, s1 - s0, stride, _lib.as_int_p(npix[s0:s1]), _lib.as_dbl_p(wl[s0:s1]),
+                                            _lib.as_dbl_p(fl[s0:s1]), _lib.as_dbl_p(ns[s0:s1]), int(std_min), int(std_max),
+                                            _lib.as_dbl_p(out[s0:s1])))
+    return [out[s, : npix[s]].copy() for s in range(S)]
+
+
+def select_regions(det_ratio, flux, noise, min_region_width=2, N_sigma=4.0, extend=False):
+    """The sequential part of ``compute_detection_regions`` (vpspectrum.py:124-174): threshold the
+    detection ratio, optionally extend to the continuum, merge with the following region when they
+    overlap, keep regions that contain a pixel ``N_sigma`` noise deviations deep, pad by 3 pixels.
+    Returns ``[[start, end], ...]`` (pixel indices)."""
+    P = len(flux)
+    start, endpoints = 0, []
+    for i in range(P):
+        if start == 0 and det_ratio[i] > N_sigma and flux[i] < 1.0:
+            start = i
+        elif start != 0 and (det_ratio[i] < N_sigma or flux[i] > 1.0):
+            if (i - start) > min_region_width:
+                endpoints.append([start, i])
+            start = 0
+    if extend:
+        expanded = []
+        for s, e in endpoints:
+            while s > 0 and flux[s] < 1.0:
+                s -= 1
+            while e < P - 1 and flux[e] < 1.0:
+                e += 1
+            expanded.append([s, e])
+    else:
+        expanded = endpoints
+    pixels, buffer = [], 3
+    for i, (s, e) in enumerate(expanded):
+        if i < len(expanded) - 1 and e > expanded[i + 1][0]:
+            e = expanded[i + 1][1]
+        deep = np.nonzero(1.0 - np.asarray(flux[s:e]) > np.abs(noise[s:e]) * N_sigma)[0]
+        if deep.size:
+            if s >= buffer:
+                s -= buffer
+            if e < P - buffer:
+                e += buffer
+            pixels.append([int(s), int(e)])
+    return pixels
+
+
+class VPspectrum():
+
+    def __init__(self, line, spectrum_file=None, out_folder=None, voigt=False, chi_limit=1.5, mcmc_cov=False,
+                 get_mcmc_err=True, convergence_attempts=10, chi_sq_maximum=10., max_single_region_components=15,
+                 ideal_single_region_components=5, min_region_percentage=2., **fit_kwargs):
+        """vpspectrum.py:23-55.  ``fit_kwargs`` (new): GPU controls forwarded to ``fit_regions``
+        (iterations, burn, thin, restarts, chains_per_restart, window, nmax, dtype, seed, lsf ...)."""
+        self.line = line
+        self.spectrum_file = spectrum_file
+        self.out_folder = out_folder
+        self.voigt = voigt
+        self.chi_limit = chi_limit
+        self.mcmc_cov = mcmc_cov
+        self.get_mcmc_err = get_mcmc_err
+        self.convergence_attempts = convergence_attempts
+        self.chi_sq_maximum = chi_sq_maximum
+        self.max_single_region_components = max_single_region_components
+        self.ideal_single_region_components = ideal_single_region_components
+        self.min_region_percentage = min_region_percentage
+        self.fit_kwargs = fit_kwargs
+        self.verbose = False
+        self.difficult_fit = False
+        if spectrum_file is not None:
+            self.read_from_spectrum_file()
+
+    # ------------------------------------------------------------------ input
+    def set_spectrum(self, wavelength, flux, noise):
+        """Arrays instead of a file (what ``read_from_spectrum_file`` fills, vpspectrum.py:58-64)."""
+        self.wavelength_array = np.asarray(wavelength, dtype=np.float64)
+        self.flux_array = np.asarray(flux, dtype=np.float64)
+        self.noise_array = np.asarray(noise, dtype=np.float64)
+        if not (len(self.wavelength_array) == len(self.flux_array) == len(self.noise_array)):
+            raise ValueError("wavelength / flux / noise lengths differ")
+        self.frequency_array = Wave2freq(self.wavelength_array)
+        return self
+
+    def read_from_spectrum_file(self):
+        """vpspectrum.py:58-64: HDF5 with ``wavelength``, ``noise``, ``flux`` datasets."""
+        try:
+            import h5py
+        except ImportError as e:
+            raise ImportError("reading %r needs h5py; use set_spectrum(wavelength, flux, noise)" % self.spectrum_file) from e
+        with h5py.File(self.spectrum_file, 'r') as data:
+            self.set_spectrum(np.array(data['wavelength'][:]), np.array(data['flux'][:]), np.array(data['noise'][:]))
+
+    # ------------------------------------------------------------------ detection
+    def compute_detection_regions(self, min_region_width=2, N_sigma=4.0, extend=False, std_min=2, std_max=11):
+        """vpspectrum.py:67-174.  Fills ``region_pixels`` / ``region_waves`` (and ``det_ratio``)."""
+        self.num_pixels = len(self.wavelength_array)
+        self.det_ratio = detection_ratio_batch([self.wavelength_array], [self.flux_array], [self.noise_array],
+                                               std_min, std_max)[0]
+        self.region_pixels = select_regions(self.det_ratio, self.flux_array, self.noise_array, min_region_width, N_sigma,
+                                            extend)
+        self.region_waves = [[self.wavelength_array[s], self.wavelength_array[e]] for s, e in self.region_pixels]
+        if self.verbose:
+            print('Found {} detection regions.'.format(len(self.region_pixels)))
+
+    def split_difficult_region(self):
+        """vpspectrum.py:177-241: a single region with more than ``max_single_region_components``
+        estimated lines is split at its highest-flux pixels, at least ``min_region_percentage`` of
+        the region apart, into ``n // ideal_single_region_components`` contiguous regions."""
+        self.difficult_fit = False
+        if len(self.region_pixels) != 1:
+            return
+        start, end = self.region_pixels[0]
+        flux = self.flux_array[start:end]
+        n = estimate_n(np.flip(flux, 0))
+        if n <= self.max_single_region_components:
+            return
+        self.difficult_fit = True
+        forced = max(1, n // self.ideal_single_region_components)
+        k = min(len(flux), 10 * forced)
+        ind = np.argpartition(flux, -k)[-k:]
+        ind_sorted = np.flip(ind[np.argsort(flux[ind])], axis=0)          # highest flux first
+        min_size = len(flux) * (self.min_region_percentage / 100.0)
+        points = [start, end]
+        for i in ind_sorted:
+            if len(points) == forced + 1:
+                break
+            p = start + int(i)
+            if all(abs(p - q) >= min_size for q in points):
+                points.append(p)
+        points.sort()
+        self.region_pixels = [[points[i], points[i + 1]] for i in range(len(points) - 1)]
+        self.region_waves = [[self.wavelength_array[s], self.wavelength_array[e]] for s, e in self.region_pixels]
+
+    # ------------------------------------------------------------------ fit
+    def _region_arrays(self, start, end):
+        """vpspectrum.py:274-279: flipped so that frequency ascends."""
+        return (np.flip(self.frequency_array[start:end], 0), np.flip(self.flux_array[start:end], 0),
+                np.flip(self.noise_array[start:end], 0), np.flip(self.wavelength_array[start:end], 0))
+
+    def fit_spectrum(self):
+        """vpspectrum.py:243-430.  Returns ``params`` (``b, b_std, N, N_std, EW, centers,
+        region_numbers``); ``flux_model`` holds the model flux and the per-region fits."""
+        if not hasattr(self, "region_pixels"):
+            self.compute_detection_regions(min_region_width=2)
+            self.split_difficult_region()
+        R = len(self.region_pixels)
+        self.params = {'b': np.array([]), 'b_std': np.array([]), 'N': np.array([]), 'N_std': np.array([]),
+                       'EW': np.array([]), 'centers': np.array([]), 'region_numbers': np.array([])}
+        self.flux_model = {'total': np.ones(len(self.flux_array)), 'chi_squared': np.zeros(R),
+                           'region_pixels': self.region_pixels, 'amplitude': np.array([]), 'sigmas': np.array([]),
+                           'centers': np.array([]), 'region_numbers': np.array([]), 'EW': np.zeros(R),
+                           'std_a': np.array([]), 'std_s': np.array([]), 'std_c': np.array([]), 'cov_as': np.array([]),
+                           'difficult_fit': self.difficult_fit}
+        self.regions = []
+        if R == 0:
+            return self.params
+        arrays = [self._region_arrays(s, e) for s, e in self.region_pixels]
+        host = [(a[0], a[1], a[2]) for a in arrays]
+        n_est = [estimate_n(a[1]) for a in arrays]
+        # ---- rounds over the regions that have not converged (the reference's per-region attempt loop)
+        attempts_left = []
+        for n in n_est:
+            if n > self.max_single_region_components:                     # vpspectrum.py:289-295
+                self.flux_model['difficult_fit'] = True
+                attempts_left.append(1 if n > 1.5 * self.max_single_region_components else 2)
+            else:
+                attempts_left.append(self.convergence_attempts)
+        best = [None] * R
+        best_chi = [-1.0] * R
+        history = [[] for _ in range(R)]                                  # (n fitted, reduced chi^2) per attempt
+        n0 = list(n_est)
+        kw = dict(self.fit_kwargs)
+        base_seed = int(kw.pop("seed", 0))
+        rnd = 0
+        while True:
+            todo = [i for i in range(R) if attempts_left[i] > 0]
+            if not todo:
+                break
+            for i in todo:                                                # force more lines after repeated failures
+                same = [c for n, c in history[i] if n == n0[i]]          # (vpspectrum.py:306-322)
+                if len(same) > 2 and min(same) > self.chi_sq_maximum:
+                    n0[i] += 1
+            res = fit_regions([host[i] for i in todo], uids=[(rnd << 20) | i for i in todo], voigt=self.voigt,
+                              n0=[n0[i] for i in todo], seed=base_seed + rnd, distributed=False,
+                              chi_limit=self.chi_limit, **kw)
+            for i, r in zip(todo, res):
+                P = len(host[i][1])
+                freedom = P - 3 * r.n                                     # region.set_freedom() after the fit
+                chi = float(r.chi2) / freedom if freedom > 0 else float("inf")
+                history[i].append((r.n, chi))
+                if best[i] is None or chi < best_chi[i]:
+                    best[i], best_chi[i] = r, chi
+                attempts_left[i] -= 1
+                limit = self.chi_limit * (3.0 if n0[i] > self.max_single_region_components else 1.0)
+                if best_chi[i] < limit:
+                    attempts_left[i] = 0
+            rnd += 1
+        # ---- harvest (vpspectrum.py:352-426)
+        for j, ((start, end), (nu, fluxes, noise, waves), r) in enumerate(zip(self.region_pixels, arrays, best)):
+            n = r.n
+            th = r.theta                                                  # [n, 4] (amplitude, centroid, w1, w2) in Hz
+            profiles = []
+            for k in range(n):
+                if self.voigt:
+                    profiles.append(VPfit.VoigtFunction(nu, th[k, 1], th[k, 0], th[k, 2], th[k, 3]))
+                else:
+                    profiles.append(VPfit.GaussFunction(nu, th[k, 0], th[k, 1], th[k, 2]))
+            total = Tau2flux(np.sum(profiles, axis=0))
+            self.flux_model['chi_squared'][j] = best_chi[j]
+            self.flux_model['total'][start:end] = np.flip(total, 0)
+            self.flux_model['region_' + str(j) + '_wave'] = np.flip(waves, 0)
+            self.flux_model['region_' + str(j) + '_flux'] = np.array([np.flip(Tau2flux(p), 0) for p in profiles])
+            self.flux_model['EW'][j] = EquivalentWidthFlux(edges=self.flux_model['region_' + str(j) + '_wave'],
+                                                           fluxes=self.flux_model['region_' + str(j) + '_flux'])
+            heights = th[:, 0].copy()
+            centers = Freq2wave(th[:, 1])
+            region_numbers = np.arange(n)
+            sigmas = VPfit.GaussianWidth(th[:, 3]) if self.voigt else th[:, 2].copy()
+            std_a = r.std[:, 0]
+            std_s = VPfit.GaussianWidth(r.std[:, 3]) if self.voigt else r.std[:, 2]
+            std_c = r.std[:, 1]
+            for key, val in (('amplitude', heights), ('centers', centers), ('region_numbers', region_numbers),
+                             ('sigmas', sigmas)):
+                self.flux_model[key] = np.append(self.flux_model[key], val)
+            if self.mcmc_cov:                                             # vpspectrum.py:384-397
+                for key, val in (('std_a', std_a), ('std_s', std_s), ('std_c', std_c), ('cov_as', r.cov_aw)):
+                    self.flux_model[key] = np.append(self.flux_model[key], val)
+                self.params['N_std'] = np.append(self.params['N_std'], ErrorN(heights, sigmas, std_a, std_s, r.cov_aw))
+            elif self.get_mcmc_err:                                       # vpspectrum.py:399-418
+                self.flux_model['std_s'] = np.append(self.flux_model['std_s'], std_s)
+                self.flux_model['std_a'] = np.append(self.flux_model['std_a'], std_a)
+                self.params['b_std'] = np.append(self.params['b_std'], ErrorB(std_s, self.line))
+                self.params['N_std'] = np.append(self.params['N_std'],
+                                                 ErrorN(amplitude=heights, sigma=sigmas, std_a=std_a, std_s=std_s,
+                                                        cov_as=np.zeros(n)))
+            self.params['b'] = np.append(self.params['b'], DopplerParameter(sigmas, self.line))
+            self.params['N'] = np.append(self.params['N'], ColumnDensity(heights, sigmas))
+            self.params['centers'] = np.append(self.params['centers'], centers)
+            self.params['region_numbers'] = np.append(self.params['region_numbers'], region_numbers)
+            for k in range(n):
+                self.params['EW'] = np.append(self.params['EW'], EquivalentWidthTau(profiles[k], [waves[0], waves[-1]]))
+            r.attempt_n = [h[0] for h in history[j]]
+            r.attempt_chi_squareds = [h[1] for h in history[j]]
+            r.best_chi_squared = best_chi[j]
+            self.regions.append(r)
+        if self.out_folder is not None:
+            name = (self.spectrum_file or "spectrum").split('/', -1)[-1]
+            name = name[:name.find('.')] if '.' in name else name
+            self.output_filename = self.out_folder + name + ('_voigt_' if self.voigt else '_gauss_')
+            self.write_file()
+        return self.params
+
+    # ------------------------------------------------------------------ output
+    def write_file(self):
+        """vpspectrum.py:528-538: ``*params.h5`` and ``*flux_model.h5`` (``.npz`` without h5py)."""
+        try:
+            import h5py
+        except ImportError:
+            np.savez(self.output_filename + 'params.npz', **{k: np.array(v) for k, v in self.params.items()})
+            np.savez(self.output_filename + 'flux_model.npz', **{k: np.array(v) for k, v in self.flux_model.items()})
+            return
+        with h5py.File(self.output_filename + 'params.h5', 'a') as f:
+            for p in self.params.keys():
+                f.create_dataset(p, data=np.array(self.params[p]))
+        with h5py.File(self.output_filename + 'flux_model.h5', 'a') as f:
+            for p in self.flux_model.keys():
+                f.create_dataset(p, data=np.array(self.flux_model[p]))
