@@ -30,9 +30,10 @@ def test_geweke_flags_drift():
     rng = np.random.default_rng(1)
     flat = rng.normal(0, 1, 4000)
     z = DG.geweke(flat)
-    assert z.shape == (20, 2) and np.mean(np.abs(z[:, 1]) < 2.0) > 0.9
+    # PyMC 2 normalises by the slice variances (not the variance of the means): |z| << 1 for a flat chain
+    assert z.shape == (20, 2) and np.all(np.abs(z[:, 1]) < 0.3)
     drift = flat + np.linspace(3, 0, 4000)
-    assert np.abs(DG.geweke(drift)[0, 1]) > 2.0
+    assert np.abs(DG.geweke(drift)[0, 1]) > 1.0
 
 
 def test_ess_and_dic():
