@@ -22,9 +22,9 @@ ntrue = np.array([len(r["truth"]) for r in regs])
 marks = {"k2": 0.0, "k3": 0.0}
 orig_run, orig_map = engine.Sampler.run, engine.Sampler._map
 evs = []
-def run(self, iters):
+def run(self, iters, *a_, **k_):
     a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
-    a.record(); orig_run(self, iters); b.record(); evs.append(("k2", a, b))
+    a.record(); orig_run(self, iters, *a_, **k_); b.record(); evs.append(("k2", a, b))
 def _map(self, *a_, **k):
     a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
     a.record(); r = orig_map(self, *a_, **k); b.record(); evs.append(("k3", a, b)); return r

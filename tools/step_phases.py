@@ -13,8 +13,8 @@ orig_run, orig_map = engine.Sampler.run, engine.Sampler._map
 marks = []
 def ev():
     e = torch.cuda.Event(enable_timing=True); e.record(); return e
-def run(self, iters):
-    marks.append(("k2_start", ev())); orig_run(self, iters); marks.append(("k2_end", ev()))
+def run(self, iters, *a_, **k_):
+    marks.append(("k2_start", ev())); orig_run(self, iters, *a_, **k_); marks.append(("k2_end", ev()))
 def _map(self, *a, **k):
     marks.append(("k3_start", ev())); r = orig_map(self, *a, **k); marks.append(("k3_end", ev())); return r
 engine.Sampler.run, engine.Sampler._map = run, _map

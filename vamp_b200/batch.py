@@ -35,7 +35,7 @@ class ModelBatch:
 def fit_models(regions, models, voigt=False, sd_free=True, iterations=3000, burn=300, thin=15, restarts=3,
                chains_per_restart=32, polish_top=4, dtype="f32", seed=0, region_uids=None, tune_interval=50,
                tune_throughout=True, keep_sampler=False, trace=False, maxiter=None, xtol=1e-4, ftol=1e-3,
-               polish_dtype="f64"):
+               polish_dtype="f64", overlap=False):
     """Fit ``models = [(region_index, n), ...]`` on the device-resident ``regions``.
 
     Per model and restart group: prior-drawn starts -> ``iterations`` of K2 Metropolis ->
@@ -53,9 +53,11 @@ def fit_models(regions, models, voigt=False, sd_free=True, iterations=3000, burn
     item_region = np.repeat(np.array([r for r, _ in models], dtype=np.int32), per)
     item_ncomp = np.repeat(np.array([n for _, n in models], dtype=np.int32), per)
     uid = np.concatenate([chain_uids(region_uids[r], n, G, Cn) for r, n in models])
-    # launch order: homogeneous CTAs (same pixel class and component count) finish together
+    # sampler rows sorted by (component count, pixel class, model): CTAs are homogeneous, a kernel launches its
+    # rows from the end (most expensive chains first), and the chains of one component count are contiguous,
+    # so every count can run as its own launch on its own stream (below)
     ppl = (regions.npix[item_region] + 31) // 32
-    order = np.lexsort((np.arange(M * per), item_ncomp, ppl))
+    order = np.lexsort((np.arange(M * per), ppl, item_ncomp))
     inv = np.empty_like(order)
     inv[order] = np.arange(order.size)
     cap = max(0, (int(iterations) - int(burn) + int(thin) - 1) // max(int(thin), 1) + 1) if trace else 0
@@ -63,27 +65,68 @@ def fit_models(regions, models, voigt=False, sd_free=True, iterations=3000, burn
                        dtype=dtype, seed=seed, burn=burn, thin=thin, tune_interval=tune_interval,
                        tune_throughout=tune_throughout, trace_cap=cap, cmax=cmax)
     s.init()
-    s.run(iterations)
     dev = s.ctx.torch_device
     d_inv = torch.from_numpy(inv).to(dev)
-    # ---- top-K chains of every (model, restart) by best log-posterior, on the device
     K = max(1, min(int(polish_top), Cn))
-    best_logp = s.t["best_logp"][d_inv].view(M * G, Cn)
-    best_logp = torch.nan_to_num(best_logp, nan=-float("inf"))
-    top = best_logp.topk(K, dim=1).indices                                   # [M*G, K] chain-in-group
-    flat = (torch.arange(M * G, device=dev)[:, None] * Cn + top).reshape(-1)  # logical chain ids
-    phys = d_inv[flat]                                                        # sampler rows
-    starts = s.t["best_theta"][phys].contiguous()
-    res = s._map(starts, s.t["item_region"][phys].contiguous(), s.t["item_ncomp"][phys].contiguous(), cmax,
-                 int(maxiter or iterations), 0, xtol, ftol, polish_dtype)
-    logp = torch.nan_to_num(res["logp"].view(M * G, K), nan=-float("inf"))
-    win = logp.argmax(dim=1)                                                  # [M*G]
-    pick = torch.arange(M * G, device=dev) * K + win
-    out = {k: res[k][pick].view(M, G).cpu().numpy() for k in ("logp", "lnL", "chi2", "bic")}
-    out["iters"] = res["iters"][pick].view(M, G).cpu().numpy()
-    theta_map = res["theta"][pick].cpu().numpy()                              # [M*G, ts] scaled
-    primary_rows = phys.view(M * G, K)[torch.arange(M * G, device=dev), win]  # sampler row of the winning chain
-    prow = primary_rows.cpu().numpy()
+    MG = M * G
+    f64 = torch.float64
+    res = {k: torch.empty(MG, dtype=f64, device=dev) for k in ("logp", "lnL", "chi2", "bic")}
+    res["iters"] = torch.empty(MG, dtype=torch.int32, device=dev)
+    res["theta"] = torch.empty((MG, s.ts), dtype=f64, device=dev)
+    primary_rows = torch.empty(MG, dtype=torch.int64, device=dev)
+
+    def polish(model_ids):
+        """Top-K chains of every (model, restart) by best log-posterior -> K3 -> winner per (model, restart);
+        everything on the device and on the current stream."""
+        mid = torch.as_tensor(np.asarray(model_ids, dtype=np.int64), device=dev)
+        mg = (mid[:, None] * G + torch.arange(G, device=dev)[None, :]).reshape(-1)        # (model, restart) ids
+        chains = (mg[:, None] * Cn + torch.arange(Cn, device=dev)[None, :])               # logical chain ids [mg, Cn]
+        rows = d_inv[chains]                                                             # sampler rows
+        blp = torch.nan_to_num(s.t["best_logp"][rows], nan=-float("inf"))
+        top = blp.topk(K, dim=1).indices
+        phys = torch.gather(rows, 1, top).reshape(-1)
+        starts = s.t["best_theta"][phys].contiguous()
+        r = s._map(starts, s.t["item_region"][phys].contiguous(), s.t["item_ncomp"][phys].contiguous(),
+                   int(max(models[m][1] for m in model_ids)), int(maxiter or iterations), 0, xtol, ftol, polish_dtype)
+        logp = torch.nan_to_num(r["logp"].view(-1, K), nan=-float("inf"))
+        win = logp.argmax(dim=1)
+        pick = torch.arange(mg.numel(), device=dev) * K + win
+        for k in ("logp", "lnL", "chi2", "bic", "iters", "theta"):
+            res[k][mg] = r[k][pick]
+        primary_rows[mg] = phys[pick]
+
+    # ---- default: ONE sampler launch over all chains (longest first), then one polish launch.
+    #      ``overlap=True`` (experiment, kept for the record): one launch group per component count on its own
+    #      stream with the group's polish on a high-priority stream, so that a finished group's K3 (few CTAs,
+    #      latency bound) hides under the groups still sampling.  Measured on B200 it is SLOWER - C2 step 472 ->
+    #      601 ms (706 ms with stream priorities standing in for the launch order): concurrent grids with
+    #      different shared-memory footprints do not share an SM well and the longest-first order is lost.
+    counts = sorted({n for _, n in models}, reverse=True)
+    sorted_nc = item_ncomp[order]
+    main = torch.cuda.current_stream(dev)
+    if overlap and len(counts) > 1:
+        side = []
+        for rank, n in enumerate(counts):
+            a, b = int(np.searchsorted(sorted_nc, n, "left")), int(np.searchsorted(sorted_nc, n, "right"))
+            # stream priorities stand in for the launch order of a single grid: pending CTAs of the more
+            # expensive groups are scheduled first (CUDA clamps to the device's priority range, 0 .. -5 on B200)
+            st, hp = torch.cuda.Stream(dev, priority=min(0, rank - 4)), torch.cuda.Stream(dev, priority=-5)
+            st.wait_stream(main)
+            with torch.cuda.stream(st):
+                s.run(iterations, rows=(a, b), max_ncomp=n, advance=False)
+            hp.wait_stream(st)
+            with torch.cuda.stream(hp):
+                polish([m for m in range(M) if models[m][1] == n])
+            side.append(hp)
+        for hp in side:
+            main.wait_stream(hp)
+        s.iteration += int(iterations)
+    else:
+        s.run(iterations)
+        polish(list(range(M)))
+    out = {k: res[k].view(M, G).cpu().numpy() for k in ("logp", "lnL", "chi2", "bic", "iters")}
+    theta_map = res["theta"].cpu().numpy()                                    # [M*G, ts] scaled
+    prow = primary_rows.cpu().numpy()                                         # sampler row of the winning chain
     ts = s.ts
     comps_s = theta_map[:, : 4 * cmax].reshape(M * G, cmax, 4)
     reg_of = np.repeat(np.array([r for r, _ in models]), G)

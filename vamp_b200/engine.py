@@ -297,17 +297,24 @@ class Sampler:
             "work": torch.zeros((B, 3), dtype=torch.int64, device=dev),
         }
 
-    def _args(self, it0=0, it1=0):
+    def _args(self, it0=0, it1=0, rows=None, max_ncomp=None):
+        """``rows = (a, b)``: the launch covers sampler rows [a, b) only (every per-chain array is
+        addressed from row a) - used to run model groups on separate streams."""
+        a0, b0 = (0, self.B) if rows is None else (int(rows[0]), int(rows[1]))
         a = McmcArgs()
-        a.n_chains, a.cmax, a.max_ncomp, a.sd_free = self.B, self.cmax, self.max_ncomp, int(self.sd_free)
+        a.n_chains, a.cmax, a.sd_free = b0 - a0, self.cmax, int(self.sd_free)
+        a.max_ncomp = self.max_ncomp if max_ncomp is None else int(max_ncomp)
         a.it0, a.it1, a.burn, a.thin = int(it0), int(it1), self.burn, self.thin
         a.tune_interval, a.tune_throughout, a.seed = self.tune_interval, self.tune_throughout, self.seed
         for name in ("item_region", "item_ncomp", "chain_uid", "theta", "asf", "psd", "acc", "rej", "acc_total", "logp",
                      "lnL", "best_theta", "best_logp", "mean", "m2", "comom", "ntally", "sum_lnL", "sum_lnL2"):
-            setattr(a, name, self.t[name].data_ptr())
-        a.trace = self.t["trace"].data_ptr() if self.t["trace"] is not None else None
+            t = self.t[name]
+            setattr(a, name, t.data_ptr() + a0 * t.stride(0) * t.element_size())
+        tr = self.t["trace"]
+        a.trace = (tr.data_ptr() + a0 * tr.stride(0) * tr.element_size()) if tr is not None else None
         a.trace_cap = self.trace_cap
-        a.work = self.t["work"].data_ptr()
+        w = self.t["work"]
+        a.work = w.data_ptr() + a0 * w.stride(0) * w.element_size()
         return a
 
     def init(self, theta0_scaled=None):
@@ -321,12 +328,15 @@ class Sampler:
                                           0 if theta0_scaled is not None else 1))
         self.iteration = 0
 
-    def run(self, iters):
-        """Advance every chain by ``iters`` iterations (asynchronous on the current stream)."""
+    def run(self, iters, rows=None, max_ncomp=None, advance=True):
+        """Advance every chain (or sampler rows ``[a, b)``) by ``iters`` iterations, asynchronously on
+        the current torch stream.  ``advance=False`` leaves the iteration counter alone (the caller
+        launches several row groups for the same iteration range)."""
         self.ctx.use_current_stream()
-        a = self._args(self.iteration, self.iteration + int(iters))
+        a = self._args(self.iteration, self.iteration + int(iters), rows, max_ncomp)
         check(self.lib.vamp_mcmc_run_dev(self.ctx.handle, self.regions.handle, self.dtype, self.kind, C.byref(a)))
-        self.iteration += int(iters)
+        if advance:
+            self.iteration += int(iters)
 
     def n_free(self, ncomp):
         return self.np_per * ncomp + (1 if self.sd_free else 0)
@@ -366,6 +376,7 @@ class Sampler:
 
     def _map(self, th, d_ir, d_in, max_ncomp, maxiter, maxfun, xtol, ftol, dtype=None):
         torch = _torch()
+        self.ctx.use_current_stream()
         dev = self.ctx.torch_device
         S = th.shape[0]
         out = {k: torch.empty(S, dtype=torch.float64, device=dev) for k in ("logp", "lnL", "chi2", "bic")}
