@@ -125,3 +125,20 @@ def test_simba_fixture_regions(ctx):
         chi = region.fit.ReducedChisquared(flux, region.fit.total.value, noise, region.freedom)
         assert chi < 2.5, (j, chi, region.n)
         assert 1 <= len(region.fit.estimated_profiles) <= 4     # notebook ladder ended at n = 2, 1, 1
+
+
+def test_fit_regions_polish_schedules_agree(ctx):
+    """The many-region polish schedule (one warp per start, fp32 search stage, float64 finish) selects the same
+    component counts and the same optimum as the float64 CTA schedule."""
+    from vamp_b200.fit_regions import fit_regions
+    regs = [synth.make_region(P, n, 60.0, 3100 + i, voigt=False) for i, (P, n) in enumerate([(96, 1), (160, 2), (64, 1), (200, 2)])]
+    host = [(r["nu"], r["flux"], r["noise"]) for r in regs]
+    kw = dict(uids=[50, 51, 52, 53], voigt=False, iterations=1200, burn=300, thin=5, restarts=3, chains_per_restart=16,
+              window=2, nmax=4, n0=[1, 1, 1, 1], seed=9, distributed=False)
+    a = fit_regions(host, polish_dtype="f64", **kw)
+    b = fit_regions(host, polish_dtype="mixed", **kw)
+    assert [r.n for r in a] == [r.n for r in b]
+    for ra, rb in zip(a, b):
+        assert rb.lnL == pytest.approx(ra.lnL, abs=2e-2)
+        np.testing.assert_allclose(rb.theta, ra.theta, rtol=2e-3)
+        assert rb.chi2 == pytest.approx(ra.chi2, rel=1e-3)

@@ -26,10 +26,13 @@ namespace {
 
 constexpr int K2_WARPS = 4;
 #ifndef VAMP_K2_MINBLOCKS
-#define VAMP_K2_MINBLOCKS 6
+#define VAMP_K2_MINBLOCKS 5
 #endif
 #ifndef VAMP_K2_UNROLL
 #define VAMP_K2_UNROLL 0          // 1: pixel passes fully unrolled over the 4 row pairs of a tile, 2: by two, 0: rolled
+#endif
+#ifndef VAMP_K2_QUAD
+#define VAMP_K2_QUAD 1            // 1: the pixel passes take two row pairs (128 pixels) per trip
 #endif
 #ifndef VAMP_K2_STEPUNROLL
 #define VAMP_K2_STEPUNROLL 1      // 1: the centroid / width steps of a component are unrolled (no selects)
@@ -222,7 +225,59 @@ __device__ __forceinline__ T chain_pass(const CompC<T>& cc, T An, const P2<T>* _
             S2 = p2_fma(R, R, S2);
         }
     };
-#if VAMP_K2_UNROLL == 1
+#if VAMP_K2_QUAD
+    // Two row pairs (128 pixels) per trip: half the loop / address / vote overhead per pixel and two
+    // independent dependency chains for the scheduler to interleave.  One path per quad (all 128 pixels
+    // far -> continued fraction, else Weideman).  Regions are padded to whole quads (see mcmc_chain).
+    P2<T> S2b = p2_bc<T>(T(0));
+#pragma unroll 1
+    for (int e = 0; e < 32 * npairs; e += 64) {
+        P2<T> H0, H1;
+        if (FRESH) {
+            const P2<T> cb2 = p2_bc<T>(cc.cb), g2 = p2_bc<T>(cc.g);
+            const P2<T> X0 = p2_mul(p2_sub(pd[e], cb2), g2), X1 = p2_mul(p2_sub(pd[e + 32], cb2), g2);
+            if (KIND == VAMP_KIND_GAUSS) {
+                const P2<T> Q0 = p2_mul(X0, X0), Q1 = p2_mul(X1, X1);
+                H0 = p2_make(Real<T>::exp2_neg(p2_lo(Q0)), Real<T>::exp2_neg(p2_hi(Q0)));
+                H1 = p2_make(Real<T>::exp2_neg(p2_lo(Q1)), Real<T>::exp2_neg(p2_hi(Q1)));
+            } else {
+                const P2<T> y22 = p2_bc<T>(cc.y2);
+                const P2<T> S0 = p2_fma(X0, X0, y22), S1 = p2_fma(X1, X1, y22);
+                const T smin = fmin(fmin(p2_lo(S0), p2_hi(S0)), fmin(p2_lo(S1), p2_hi(S1)));
+                far = __all_sync(VAMP_FULL_MASK, !(smin < Fad<T>::R2()));
+                if (far) {
+                    nfar += 128u;
+                    H0 = fad_far2<T>(X0, cc.y, S0);
+                    H1 = fad_far2<T>(X1, cc.y, S1);
+                } else {
+                    H0 = fad_core2<T>(X0, cc.y, S0);
+                    H1 = fad_core2<T>(X1, cc.y, S1);
+                }
+            }
+            Hs[e] = H0;
+            Hs[e + 32] = H1;
+        } else {
+            H0 = Hc[e];
+            H1 = Hc[e + 32];
+        }
+        const P2<T> M0 = p2_exp_scaled<T>(p2_fma(A2, H0, pb[e])), M1 = p2_exp_scaled<T>(p2_fma(A2, H1, pb[e + 32]));
+        if (LSF) {
+            lc.buf[(lc.taps >> 1) + lane + 2 * e] = p2_lo(M0) - T(1);
+            lc.buf[(lc.taps >> 1) + lane + 2 * e + 32] = p2_hi(M0) - T(1);
+            lc.buf[(lc.taps >> 1) + lane + 2 * e + 64] = p2_lo(M1) - T(1);
+            lc.buf[(lc.taps >> 1) + lane + 2 * e + 96] = p2_hi(M1) - T(1);
+        } else {
+            P2<T> R0 = p2_sub(pf[e], M0), R1 = p2_sub(pf[e + 32], M1);
+            if (WT) {
+                R0 = p2_mul(R0, pw[e]);
+                R1 = p2_mul(R1, pw[e + 32]);
+            }
+            S2 = p2_fma(R0, R0, S2);
+            S2b = p2_fma(R1, R1, S2b);
+        }
+    }
+    S2 = p2_add(S2, S2b);
+#elif VAMP_K2_UNROLL == 1
 #pragma unroll
     for (int jj = 0; jj < K2_PAIRS; ++jj)
         if (jj < npairs) trip(32 * jj);
@@ -265,7 +320,9 @@ __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, const unsigned
     const int ts = p.tstride;
     const int sdi = 4 * p.cmax;
     const int k = NP * n + (WT ? 0 : 1);
-    const int npairs = (P + 63) >> 6;
+    // row pairs swept by every per-pixel loop: with quad trips the region is padded to whole quads (padding
+    // pixels - du 1e12, flux 1, weight 0 - contribute exactly nothing)
+    const int npairs = VAMP_K2_QUAD ? 2 * ((P + 127) >> 7) : (P + 63) >> 6;
     const int npad = 64 * npairs - P;
     const int burn = p.burn;
     const T NK = Real<T>::NEGK();
@@ -683,13 +740,15 @@ k2_mcmc_kernel(McmcDev p, int ncomp_max) {
         {
             const RegionSetDev& rs = p.rs;
             const int off = rs.pix_off[rr] >> 1, ne = 32 * ((rs.npix[rr] + 63) >> 6);
+            const int nq = VAMP_K2_QUAD ? 64 * ((rs.npix[rr] + 127) >> 7) : ne;       // whole quads: pad the rest
             P2<T>* sd_ = reinterpret_cast<P2<T>*>(rb + Lay::DU);
             P2<T>* sf_ = reinterpret_cast<P2<T>*>(rb + Lay::F);
             P2<T>* sw_ = reinterpret_cast<P2<T>*>(rb + Lay::W);
-            for (int e = threadIdx.x; e < ne; e += blockDim.x) {
-                sd_[e] = p2_from(__ldg(RS<T>::pdu(rs) + off + e));
-                sf_[e] = p2_from(__ldg(RS<T>::pf(rs) + off + e));
-                if (WT) sw_[e] = p2_from(__ldg(RS<T>::pw(rs) + off + e));
+            for (int e = threadIdx.x; e < nq; e += blockDim.x) {
+                const bool in = e < ne;
+                sd_[e] = in ? p2_from(__ldg(RS<T>::pdu(rs) + off + e)) : p2_bc<T>(T(1.0e12));
+                sf_[e] = in ? p2_from(__ldg(RS<T>::pf(rs) + off + e)) : p2_bc<T>(T(1));
+                if (WT) sw_[e] = in ? p2_from(__ldg(RS<T>::pw(rs) + off + e)) : p2_bc<T>(T(0));
             }
         }
         __syncthreads();
