@@ -24,9 +24,10 @@ constexpr double FWHM_PER_SIGMA = 2.35482004503094938202;
 __host__ __device__ inline size_t k3_align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
 template <typename T>
-__host__ __device__ inline size_t k3_smem_bytes(int kmax, int ts, bool lsf) {
+__host__ __device__ inline size_t k3_smem_bytes(int kmax, int ts, bool lsf, int ncmax) {
     size_t b = 0;
     b += k3_align16(sizeof(double) * ((size_t)(kmax + 1) * ts + (kmax + 1) + 4 * ts + 4 * K3_WARPS));
+    b += k3_align16(sizeof(CompC<T>) * K3_WARPS * (size_t)ncmax);
     if (lsf) b += k3_align16(sizeof(T) * (VAMP_TILE_PIX + 2 * VAMP_MAX_LSF_TAPS));
     return b;
 }
@@ -42,6 +43,8 @@ struct Objective {
     const T* gw;
     double* red;           // [4 * K3_WARPS] shared
     T* mbuf;               // LSF staging (shared)
+    CompC<T>* ccw;         // [K3_WARPS][ncmax] per-warp component constants (shared)
+    int ncmax;
     const T* lsf_s;
     double lnL, chi2;      // of the last evaluation
 
@@ -49,21 +52,29 @@ struct Objective {
     // Called by ALL threads of the CTA with the same theta; returns the same value everywhere.
     __device__ __noinline__ double operator()(const double* th) {
         constexpr int NP = (KIND == VAMP_KIND_VOIGT) ? 4 : 3;
+        // Bounds, prior and component constants: lane c of EVERY warp handles component c (c + 32, ...), so the
+        // float64 log and the divisions of make_comp run once in parallel instead of n times in sequence
+        // (they were a third of an evaluation's latency); each warp stages its constants in its own slice.
         bool ok = true;
         double lp = 0.0;
-        for (int c = 0; c < n; ++c) {
+        CompC<T>* ccs = ccw + warp * ncmax;
+        for (int c = lane; c < n; c += 32) {
             const double a = th[VAMP_TH(c, 0)], ce = th[VAMP_TH(c, 1)], w1 = th[VAMP_TH(c, 2)], w2 = th[VAMP_TH(c, 3)];
             ok = ok && (a > 0.0) && (ce >= 0.0) && (ce <= c_hi);
             if (NP == 4) ok = ok && (w1 >= 0.0) && (w1 <= w_hi) && (w2 > 0.0) && (w2 <= w_hi);
             else ok = ok && (w1 > 0.0) && (w1 <= w_hi);
             lp += log(a) - a;
+            ccs[c] = make_comp<T, KIND>(a, ce, w1, w2, ubase);
         }
         double sd = 1.0;
         if (p.sd_free) {
             sd = th[sdi];
             ok = ok && (sd > 0.0) && (sd <= 1.0);
         }
+        ok = __all_sync(VAMP_FULL_MASK, ok);
         if (!ok) { lnL = -INFINITY; chi2 = INFINITY; return INFINITY; }
+        lp = warp_sum(lp);
+        __syncwarp();
         const int h = taps >> 1;
         T S = T(0), X = T(0);
         unsigned dummy = 0u;
@@ -72,8 +83,7 @@ struct Objective {
             const T du = __ldg(gdu + px);                 // rows are padded with neutral pixels
             T tau = T(0);
             for (int c = 0; c < n; ++c) {
-                const CompC<T> cc = make_comp<T, KIND>(th[VAMP_TH(c, 0)], th[VAMP_TH(c, 1)], th[VAMP_TH(c, 2)],
-                                                       th[VAMP_TH(c, 3)], ubase);
+                const CompC<T> cc = ccs[c];
                 tau = Real<T>::fma_(cc.A, row_shape<T, KIND>(cc, du, dummy), tau);
             }
             const T m = Real<T>::exp_neg(tau);
@@ -115,7 +125,7 @@ struct Objective {
 };
 
 template <typename T, int KIND>
-__device__ void nm_run(const MapDev& p, int s, double* sm, T* mbuf, const T* lsf_s) {
+__device__ void nm_run(const MapDev& p, int s, double* sm, CompC<T>* ccw, int ncmax, T* mbuf, const T* lsf_s) {
     constexpr int NP = (KIND == VAMP_KIND_VOIGT) ? 4 : 3;
     const RegionSetDev& rs = p.rs;
     const int ts = p.tstride;
@@ -137,6 +147,8 @@ __device__ void nm_run(const MapDev& p, int s, double* sm, T* mbuf, const T* lsf
     f.gf = RS<T>::f(rs) + rs.pix_off[r];
     f.gw = RS<T>::w(rs) + rs.pix_off[r];
     f.mbuf = mbuf;
+    f.ccw = ccw;
+    f.ncmax = ncmax;
     f.lsf_s = lsf_s;
 
     const int n = f.n;
@@ -284,7 +296,7 @@ __device__ void nm_run(const MapDev& p, int s, double* sm, T* mbuf, const T* lsf
 
 template <typename T, int KIND>
 __global__ void __launch_bounds__(K3_THREADS)
-k3_map_kernel(MapDev p, int kmax) {
+k3_map_kernel(MapDev p, int kmax, int ncmax) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const bool LSF = p.rs.lsf_taps > 1;
     T* lsf_s = reinterpret_cast<T*>(smem_raw);
@@ -297,9 +309,11 @@ k3_map_kernel(MapDev p, int kmax) {
     if (s >= p.S) return;
     unsigned char* base = smem_raw + head;
     double* sm = reinterpret_cast<double*>(base);
-    T* mbuf = reinterpret_cast<T*>(base + k3_align16(sizeof(double) * ((size_t)(kmax + 1) * p.tstride + (kmax + 1) +
-                                                                        4 * p.tstride + 4 * K3_WARPS)));
-    nm_run<T, KIND>(p, s, sm, mbuf, lsf_s);
+    base += k3_align16(sizeof(double) * ((size_t)(kmax + 1) * p.tstride + (kmax + 1) + 4 * p.tstride + 4 * K3_WARPS));
+    CompC<T>* ccw = reinterpret_cast<CompC<T>*>(base);
+    base += k3_align16(sizeof(CompC<T>) * K3_WARPS * (size_t)ncmax);
+    T* mbuf = reinterpret_cast<T*>(base);
+    nm_run<T, KIND>(p, s, sm, ccw, ncmax, mbuf, lsf_s);
 }
 
 
@@ -579,12 +593,12 @@ cudaError_t VAMP_INST_NAME(vamp_launch_k3)(const MapDev& p, int max_npix, int ma
     const bool LSF = p.rs.lsf_taps > 1;
     const int NP = (InstKind == VAMP_KIND_VOIGT) ? 4 : 3;
     const int kmax = NP * max_ncomp + 1;
-    const size_t smem = k3_align16(sizeof(T) * VAMP_MAX_LSF_TAPS) + k3_smem_bytes<T>(kmax, p.tstride, LSF);
+    const size_t smem = k3_align16(sizeof(T) * VAMP_MAX_LSF_TAPS) + k3_smem_bytes<T>(kmax, p.tstride, LSF, max_ncomp);
     if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
     auto kern = k3_map_kernel<T, InstKind>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    kern<<<p.S, K3_THREADS, smem, st>>>(p, kmax);
+    kern<<<p.S, K3_THREADS, smem, st>>>(p, kmax, max_ncomp);
     return cudaGetLastError();
 }
 
