@@ -297,14 +297,18 @@ def run_gpu(args):
     # algorithmic HBM bytes of one K2 launch: spectrum tile per chain + chain state in/out
     P = 256
     ts = 4 * N_CAND + 1
-    alg_bytes = chains * (P * 8 + 2 * (ts * (8 * 4 + 4 * 2 + 4 * 3) + 6 * N_CAND * 8 + 64))
+    # spectrum tile (du, flux: 8 B/px) once per CTA of 4 chains + chain state in and out
+    alg_bytes = chains * (P * 8 // 4 + 2 * (ts * (8 * 4 + 4 * 2 + 4 * 3) + 6 * N_CAND * 8 + 64))
+    # dram__bytes_read.sum + dram__bytes_write.sum of this launch (same grid, 3000 iterations) from one
+    # `ncu --set full` capture of `bench.py --steps 1 --warmup 1`: profiles/r1_k2_bench_launch_full.txt
+    K2_DRAM_TRAFFIC_BYTES = 34.698496e6 + 3.837952e6
     roofline = {"bound": "fp32", "kernel": "k2_mcmc_kernel<float, VOIGT>", "achieved": achieved_tf, "peak": peak_tf,
                 "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
                 "peak_source": "SMs x 128 x 2 x sm_max_mhz (MEASURED_PEAKS.json %s MHz, %d SMs)" % (sm_max, nsm),
                 "kernel_ms": k2_time * 1e3, "algorithmic_flops_per_launch": flops_k2,
                 "evals_per_launch": work_k2["shape_pix"], "far_path_fraction": work_k2["far_pix"] / max(work_k2["shape_pix"], 1),
                 "kernel_evals_per_sec": work_k2["shape_pix"] / k2_time,
-                "traffic": None,
+                "traffic": K2_DRAM_TRAFFIC_BYTES, "traffic_unit": "bytes per launch (ncu dram read + write)",
                 "hbm": {"achieved_gbs": alg_bytes / k2_time / 1e9, "peak_gbs": hbm_peak,
                         "algorithmic_bytes_per_launch": alg_bytes}}
     if clk.get("sm_mhz"):
