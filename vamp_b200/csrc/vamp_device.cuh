@@ -649,9 +649,25 @@ __device__ __forceinline__ void eval_model(const LaneTile<T, PPL>& t, const doub
 #pragma unroll
         for (int jj = 0; jj < NPR; ++jj) tau2[jj] = p2_bc<T>(T(0));
         unsigned nfar = 0u;
-        for (int c = 0; c < ncomp; ++c) {
-            const CompC<T> cc = make_comp_k1<T, KIND>(theta[VAMP_TH(c, 0)], theta[VAMP_TH(c, 1)], theta[VAMP_TH(c, 2)],
-                                                      theta[VAMP_TH(c, 3)], ubase);
+        for (int c0 = 0; c0 < ncomp; c0 += 32) {
+            // lane l forms the constants of component c0 + l (the float64 divisions run once per component, in
+            // parallel, instead of ncomp times per lane) and they are handed out with shuffles
+            CompC<T> mine;
+            mine.A = mine.cb = mine.g = mine.y = mine.y2 = mine.L2 = T(0);
+            if (c0 + lane < ncomp) {
+                const int c = c0 + lane;
+                mine = make_comp_k1<T, KIND>(theta[VAMP_TH(c, 0)], theta[VAMP_TH(c, 1)], theta[VAMP_TH(c, 2)],
+                                             theta[VAMP_TH(c, 3)], ubase);
+            }
+            const int cend = (ncomp - c0 < 32) ? ncomp - c0 : 32;
+            for (int l = 0; l < cend; ++l) {
+            CompC<T> cc;
+            cc.A = __shfl_sync(VAMP_FULL_MASK, mine.A, l);
+            cc.cb = __shfl_sync(VAMP_FULL_MASK, mine.cb, l);
+            cc.g = __shfl_sync(VAMP_FULL_MASK, mine.g, l);
+            cc.y = __shfl_sync(VAMP_FULL_MASK, mine.y, l);
+            cc.y2 = cc.y * cc.y;
+            cc.L2 = T(0);
             const P2<T> A2 = p2_bc<T>(Real<T>::NEGK() * cc.A);
 #pragma unroll
             for (int jj = 0; jj < NPR; ++jj) {
@@ -659,6 +675,7 @@ __device__ __forceinline__ void eval_model(const LaneTile<T, PPL>& t, const doub
                 bool far;
                 pair_classify<T, KIND>(cc, p2_make(t.du[2 * jj], t.du[(2 * jj + 1 < PPL) ? 2 * jj + 1 : 2 * jj]), X, S, far);
                 tau2[jj] = p2_fma(A2, pair_eval<T, KIND>(cc, X, S, far, nfar), tau2[jj]);
+            }
             }
         }
 #pragma unroll
