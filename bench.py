@@ -73,15 +73,19 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Statistics over the samples that arrived in [t0, t1] (host perf_counter): the sampler is started
+        before the warm-up so that nvidia-smi's start-up (which can stall kernel submission for 0.1-0.3 s)
+        never falls inside a timed region."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.25)
         self.proc.terminate()
         sm, mx, reasons = [], None, set()
-        for r in self.rows:
+        rows = [r for t, r in self.rows if (t0 is None or t >= t0) and (t1 is None or t <= t1 + 0.3)]
+        for r in rows:
             try:
                 sm.append(float(r[1]))
                 mx = float(r[2])
@@ -153,6 +157,58 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def k1_point(ctx, engine, flops, synth, peak_tf, P=256, C=8, B=262144):
+    """One likelihood-only launch (K1, fp32): 2^18 parameter vectors x 8 Voigt components x 256 pixels,
+    posterior-like parameters.  Algorithmic flops from vamp_b200/flops.py with the path mix of the kernel's own
+    pair policy (all 64 pixels of a row pair at |z|^2 >= 32 -> continued fraction) evaluated on the host."""
+    import torch
+    from vamp_b200 import _lib
+    dev = ctx.torch_device
+    reg = synth.make_region(P, 8, 50.0, 7000 + P + C, voigt=True)
+    regs = engine.Regions(ctx, [(reg["nu"], reg["flux"], reg["noise"])])
+    rng = np.random.default_rng(5)
+    nb = 4096
+    th = np.stack([synth.prior_draw_theta(reg["nu"], C, True, rng, posterior_like=reg["truth"]) for _ in range(nb)])
+    ths = regs.to_scaled(th, np.zeros(nb, np.int32))
+    u = (reg["nu"] - regs.nu0[0]) / regs.scale[0]
+    du = (u - u[(P - 1) // 2]).reshape(P // 64, 64)                       # row pairs
+    cb = ths[:, :, 1] - u[(P - 1) // 2]
+    g, y = 1.66510922231539551270 / ths[:, :, 3], 0.83255461115769775635 * ths[:, :, 2] / ths[:, :, 3]
+    smin = (np.abs(du[None, None] - cb[:, :, None, None]).min(axis=3) * g[:, :, None]) ** 2 + (y ** 2)[:, :, None]
+    far_frac = float(np.mean(smin >= 32.0))
+    d_th = torch.from_numpy(np.tile(engine.pack_theta(ths, None, C), (B // nb, 1))).to(dev)
+    d_ir = torch.zeros(B, dtype=torch.int32, device=dev)
+    d_in = torch.full((B,), C, dtype=torch.int32, device=dev)
+    d_sd = torch.full((B,), 0.02, dtype=torch.float64, device=dev)
+    d_lnL = torch.empty(B, dtype=torch.float64, device=dev)
+    d_chi = torch.empty(B, dtype=torch.float64, device=dev)
+
+    def run():
+        _lib.check(ctx.lib.vamp_loglike_dev(ctx.handle, regs.handle, _lib.VAMP_F32, _lib.VAMP_VOIGT, B, d_ir.data_ptr(),
+                                            d_in.data_ptr(), C, d_th.data_ptr(), 4 * C + 1, d_sd.data_ptr(), d_lnL.data_ptr(),
+                                            d_chi.data_ptr(), None, P))
+    for _ in range(3):
+        run()
+    torch.cuda.synchronize()
+    ms = []
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        run()
+        e1.record()
+        torch.cuda.synchronize()
+        ms.append(e0.elapsed_time(e1))
+    t = float(np.median(ms)) * 1e-3
+    evals = float(P) * C * B
+    f = flops.F32
+    fl = evals * (far_frac * f["far"] + (1 - far_frac) * f["core"] + f["shape_common"] + 2) + float(P) * B * (f["like"] + 1)
+    regs.close()
+    return {"workload": "K1 fp32: %d parameter vectors x %d Voigt components x %d px, posterior-like" % (B, C, P),
+            "evals_per_sec": evals / t, "kernel_ms": t * 1e3, "far_path_fraction": far_frac,
+            "achieved_tflops": fl / t / 1e12, "frac_of_fp32_peak": fl / t / 1e12 / peak_tf,
+            "hbm_gbs": B * (P * 12 / 8 + 32 * C + 16) / t / 1e9}
+
+
 # ------------------------------------------------------------------------------------------ GPU arm
 def run_gpu(args):
     import torch
@@ -192,6 +248,8 @@ def run_gpu(args):
                               seed=seed, region_uids=[region_id], keep_sampler=True)
         return mb
 
+    clocks = ClockSampler(local_rank)
+    clocks.start()
     # warm-up (also measures the algorithmic work and the K2 / K3 kernel times with events on the stream)
     k2_ms, k3_ms = [], []
     mb = None
@@ -216,18 +274,21 @@ def run_gpu(args):
     work_k2 = s.work()
     flops_k2 = flops.k2_flops(work_k2, "f32", voigt=True)
 
-    clocks = ClockSampler(local_rank)
+    del mb, s                              # nothing from the warm-up stays allocated during the timed region
     barrier()
-    clocks.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_host0 = time.perf_counter()
     e0.record()
     evals = 0.0
     last = None
+    step_ev = [e0]
     for k in range(args.steps):
         flush.fill_(float(k))
-        last = device_step(seed=2000 + k)
+        last = None                        # release the previous fit first: the caching allocator then reuses its
+        last = device_step(seed=2000 + k)  # blocks instead of growing (a cudaMalloc inside the timed region)
         evals += last.work["shape_pix"]
+        step_ev.append(torch.cuda.Event(enable_timing=True))
+        step_ev[-1].record()
         if world > 1:                      # gather the BIC tables (the only data-path exchange)
             t = torch.from_numpy(np.ascontiguousarray(last.bic)).to(dev)
             out = torch.empty((world,) + tuple(t.shape), dtype=t.dtype, device=dev)
@@ -235,8 +296,8 @@ def run_gpu(args):
     e1.record()
     barrier()
     dev_s = e0.elapsed_time(e1) * 1e-3
-    wall_s = time.perf_counter() - t_host0
-    clk = clocks.stop()
+    t_host1 = time.perf_counter()
+    wall_s = t_host1 - t_host0
     tt = torch.tensor([dev_s, evals], dtype=torch.float64, device=dev)
     if world > 1:
         tmax = tt.clone()
@@ -276,6 +337,7 @@ def run_gpu(args):
         b = e2e_t.clone()
         dist.all_reduce(b, op=dist.ReduceOp.SUM)
         e2e_s, e2e_evals = float(a[0]), float(b[1])
+    clk = clocks.stop(t_host0, time.perf_counter())       # samples of both timed regions (device step and e2e)
     h2d = int(sum(a.nbytes for a in host_regions[0]) + 4)
     rec_bytes = int(8 * (6 + 2 * N_CAND * RESTARTS + 1 + 3 * (1 + N_CAND) * 4 + 3))
 
@@ -314,6 +376,10 @@ def run_gpu(args):
     if clk.get("sm_mhz"):
         roofline["frac_at_observed_clock"] = achieved_tf / flops.fp32_peak_tflops(nsm, clk["sm_mhz"])
 
+    # -------- K1, the fused likelihood kernel on its own (BASELINE config C5, one point): the same Voigt arithmetic
+    #          without the Metropolis bookkeeping - the figure to hold against the FP32 roofline
+    k1 = k1_point(ctx, engine, flops, synth, peak_tf)
+
     cpu_v, cpu_e, cpu_w = reference_sample(1, 60, seed=7)
     cpu_baseline = {"value": cpu_v, "unit": UNIT, "cores": 1, "kind": "port",
                     "sample": "restated PyMC2 scalar Metropolis over the reference density (numpy + scipy wofz), C2 region, "
@@ -325,11 +391,12 @@ def run_gpu(args):
             "e2e": {"value": e2e_evals / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": rec_bytes,
                     "ms_per_step": 1e3 * e2e_s / max(args.steps, 1)},
             "gpu_launches": 4 * args.steps,
-            "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "k1_likelihood": k1,
             "regions_per_sec": world * args.steps / dev_s,
             "chains_per_step": chains * world,
             "selected_n": int(batch.ladder_replay(1, {n: (last.bic[n - 1], last.chi2[n - 1] / 253.0) for n in range(1, N_CAND + 1)})[0]),
-            "host_wall_s": wall_s}
+            "host_wall_s": wall_s,
+            "step_ms": [round(step_ev[k].elapsed_time(step_ev[k + 1]), 2) for k in range(args.steps)]}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
