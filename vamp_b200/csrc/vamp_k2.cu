@@ -28,12 +28,6 @@ constexpr int K2_WARPS = 4;
 #ifndef VAMP_K2_MINBLOCKS
 #define VAMP_K2_MINBLOCKS 5
 #endif
-#ifndef VAMP_K2_UNROLL
-#define VAMP_K2_UNROLL 0          // 1: pixel passes fully unrolled over the 4 row pairs of a tile, 2: by two, 0: rolled
-#endif
-#ifndef VAMP_K2_QUAD
-#define VAMP_K2_QUAD 1            // 1: the pixel passes take two row pairs (128 pixels) per trip
-#endif
 #ifndef VAMP_K2_STEPUNROLL
 #define VAMP_K2_STEPUNROLL 1      // 1: the centroid / width steps of a component are unrolled (no selects)
 #endif
@@ -171,71 +165,89 @@ __device__ __forceinline__ T lsf_residuals(const LsfCtx<T>& lc, const unsigned c
     return S;
 }
 
-#ifndef VAMP_K2_NOINLINE_EVAL
-#define VAMP_K2_NOINLINE_EVAL 0
-#endif
-// out-of-line copy of the rational functions (experiment: one body shared by all unrolled call sites)
-template <typename T, int KIND>
-__device__ __noinline__ P2<T> pair_eval_call(P2<T> X, P2<T> S, T y, bool far) {
-    if (KIND == VAMP_KIND_GAUSS) return p2_make(Real<T>::exp2_neg(p2_lo(S)), Real<T>::exp2_neg(p2_hi(S)));
-    if (far) return fad_far2<T>(X, y, S);
-    return fad_core2<T>(X, y, S);
+// Shared-memory accessors on 32-bit shared-space addresses (ld/st.shared with an immediate offset).
+// The hot passes address every pixel buffer as  base register + compile-time offset : going through C++
+// pointers made the compiler re-derive the CTA's shared-window base (S2R SR_CgaCtaId, shifts, LEA, IMAD -
+// ~13 instructions) at the top of every pass.
+template <typename T> struct SM;
+template <> struct SM<float> {
+    template <int OFF> static __device__ __forceinline__ P2<float> ld(unsigned a) {
+        P2<float> v;
+        asm volatile("ld.shared.b64 %0, [%1+%2];" : "=l"(v.v) : "r"(a), "n"(OFF) : "memory");
+        return v;
+    }
+    template <int OFF> static __device__ __forceinline__ void st(unsigned a, P2<float> v) {
+        asm volatile("st.shared.b64 [%0+%1], %2;" ::"r"(a), "n"(OFF), "l"(v.v) : "memory");
+    }
+};
+template <> struct SM<double> {
+    template <int OFF> static __device__ __forceinline__ P2<double> ld(unsigned a) {
+        P2<double> v;
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+%3];" : "=d"(v.a), "=d"(v.b) : "r"(a), "n"(OFF) : "memory");
+        return v;
+    }
+    template <int OFF> static __device__ __forceinline__ void st(unsigned a, P2<double> v) {
+        asm volatile("st.shared.v2.f64 [%0+%1], {%2, %3};" ::"r"(a), "n"(OFF), "d"(v.a), "d"(v.b) : "memory");
+    }
+};
+
+// Component record (CompRec<T>) through shared addresses: one vector load per field group at the start of a
+// component, one read-modify-write at its end.
+template <typename T> struct RecIO;
+template <> struct RecIO<float> {
+    static __device__ __forceinline__ void ld_th(unsigned a, float& t0, float& t1, float& t2, float& t3) {
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(t0), "=f"(t1), "=f"(t2), "=f"(t3) : "r"(a) : "memory");
+    }
+    static __device__ __forceinline__ void st_th(unsigned a, float t0, float t1, float t2, float t3) {
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(t0), "f"(t1), "f"(t2), "f"(t3) : "memory");
+    }
+};
+template <> struct RecIO<double> {
+    static __device__ __forceinline__ void ld_th(unsigned a, double& t0, double& t1, double& t2, double& t3) {
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(t0), "=d"(t1) : "r"(a) : "memory");
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+16];" : "=d"(t2), "=d"(t3) : "r"(a) : "memory");
+    }
+    static __device__ __forceinline__ void st_th(unsigned a, double t0, double t1, double t2, double t3) {
+        asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(t0), "d"(t1) : "memory");
+        asm volatile("st.shared.v2.f64 [%0+16], {%1, %2};" ::"r"(a), "d"(t2), "d"(t3) : "memory");
+    }
+};
+template <int OFF>
+__device__ __forceinline__ void sm_ld4(unsigned a, unsigned& x, unsigned& y, unsigned& z, unsigned& w) {
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4+%5];" : "=r"(x), "=r"(y), "=r"(z), "=r"(w) : "r"(a), "n"(OFF) : "memory");
+}
+template <int OFF>
+__device__ __forceinline__ void sm_st4(unsigned a, unsigned x, unsigned y, unsigned z, unsigned w) {
+    asm volatile("st.shared.v4.b32 [%0+%1], {%2, %3, %4, %5};" ::"r"(a), "n"(OFF), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
 }
 
-// One likelihood pass over the region.  FRESH: evaluate the component `cc` (centroid / width
-// steps) and store its shape to the spare slot Hs; otherwise reuse the cached shape Hc (amplitude
-// steps, initial state).  m = ex2(An * H + base); returns sum (w (f - m))^2, identical in every lane.
-// The trips over the row pairs are fully unrolled (a tile has at most 4): every shared-memory
-// address is base register + immediate and consecutive pairs overlap in the schedule.
-// `nfar` counts pixels that took the continued-fraction path (padding excluded by the caller).
+// One likelihood pass over the region, two row pairs (128 pixels) per trip: half the loop / vote /
+// address overhead per pixel of a pair-wise loop and two independent dependency chains per trip.
+// FRESH: evaluate the component `cc` (centroid / width steps) and store its shape to the spare slot
+// (address ahs); otherwise reuse the cached shape at ahc (amplitude steps, initial state).
+// m = ex2(An * H + base); returns sum (w (f - m))^2, identical in every lane.  One path per quad (all
+// 128 pixels far -> continued fraction, else Weideman); regions are padded to whole quads with neutral
+// pixels (mcmc_chain).  ar / aw: shared addresses of this lane's element 0 in the region slice and in
+// the chain slice.  `nfar` counts pixels that took the continued-fraction path (padding included; the
+// caller corrects with `last_far`).
 template <typename T, int KIND, bool WT, bool LSF, bool FRESH>
-__device__ __forceinline__ T chain_pass(const CompC<T>& cc, T An, const P2<T>* __restrict__ Hc, P2<T>* __restrict__ Hs,
-                                        const unsigned char* rb, const unsigned char* wb, int npairs, int lane,
-                                        const LsfCtx<T>& lc, unsigned& nfar, bool& last_far) {
+__device__ __forceinline__ T chain_pass(const CompC<T>& cc, T An, unsigned ahc, unsigned ahs, unsigned ar, unsigned aw,
+                                        const unsigned char* rb, int npairs, int lane, const LsfCtx<T>& lc, unsigned& nfar,
+                                        bool& last_far) {
     typedef K2Lay<T, WT> Lay;
-    const P2<T>* pd = reinterpret_cast<const P2<T>*>(rb + Lay::DU) + lane;
-    const P2<T>* pf = reinterpret_cast<const P2<T>*>(rb + Lay::F) + lane;
-    const P2<T>* pw = reinterpret_cast<const P2<T>*>(rb + Lay::W) + lane;
-    const P2<T>* pb = reinterpret_cast<const P2<T>*>(wb + Lay::BASE) + lane;
+    constexpr int SZ = (int)sizeof(P2<T>);
+    constexpr int ROW = 32 * SZ;                       // bytes between the two pairs of a quad
     const P2<T> A2 = p2_bc<T>(An);
-    P2<T> S2 = p2_bc<T>(T(0));
+    P2<T> S2 = p2_bc<T>(T(0)), S2b = p2_bc<T>(T(0));
     bool far = false;
-    auto trip = [&](int e) {
-        P2<T> H;
-        if (FRESH) {
-            P2<T> X, S;
-            pair_classify<T, KIND>(cc, pd[e], X, S, far);
-#if VAMP_K2_NOINLINE_EVAL
-            nfar += far ? 64u : 0u;
-            H = pair_eval_call<T, KIND>(X, S, cc.y, far);
-#else
-            H = pair_eval<T, KIND>(cc, X, S, far, nfar);
-#endif
-            Hs[e] = H;
-        } else {
-            H = Hc[e];
-        }
-        const P2<T> M = p2_exp_scaled<T>(p2_fma(A2, H, pb[e]));
-        if (LSF) {
-            lc.buf[(lc.taps >> 1) + lane + 2 * e] = p2_lo(M) - T(1);
-            lc.buf[(lc.taps >> 1) + lane + 2 * e + 32] = p2_hi(M) - T(1);
-        } else {
-            P2<T> R = p2_sub(pf[e], M);
-            if (WT) R = p2_mul(R, pw[e]);
-            S2 = p2_fma(R, R, S2);
-        }
-    };
-#if VAMP_K2_QUAD
-    // Two row pairs (128 pixels) per trip: half the loop / address / vote overhead per pixel and two
-    // independent dependency chains for the scheduler to interleave.  One path per quad (all 128 pixels
-    // far -> continued fraction, else Weideman).  Regions are padded to whole quads (see mcmc_chain).
-    P2<T> S2b = p2_bc<T>(T(0));
+    const unsigned end = ar + (unsigned)(npairs * ROW);
 #pragma unroll 1
-    for (int e = 0; e < 32 * npairs; e += 64) {
+    for (; ar < end; ar += 2 * ROW, aw += 2 * ROW, ahc += 2 * ROW, ahs += 2 * ROW) {
         P2<T> H0, H1;
         if (FRESH) {
             const P2<T> cb2 = p2_bc<T>(cc.cb), g2 = p2_bc<T>(cc.g);
-            const P2<T> X0 = p2_mul(p2_sub(pd[e], cb2), g2), X1 = p2_mul(p2_sub(pd[e + 32], cb2), g2);
+            const P2<T> X0 = p2_mul(p2_sub(SM<T>::template ld<Lay::DU>(ar), cb2), g2);
+            const P2<T> X1 = p2_mul(p2_sub(SM<T>::template ld<Lay::DU + ROW>(ar), cb2), g2);
             if (KIND == VAMP_KIND_GAUSS) {
                 const P2<T> Q0 = p2_mul(X0, X0), Q1 = p2_mul(X1, X1);
                 H0 = p2_make(Real<T>::exp2_neg(p2_lo(Q0)), Real<T>::exp2_neg(p2_hi(Q0)));
@@ -254,43 +266,31 @@ __device__ __forceinline__ T chain_pass(const CompC<T>& cc, T An, const P2<T>* _
                     H1 = fad_core2<T>(X1, cc.y, S1);
                 }
             }
-            Hs[e] = H0;
-            Hs[e + 32] = H1;
+            SM<T>::template st<0>(ahs, H0);
+            SM<T>::template st<ROW>(ahs, H1);
         } else {
-            H0 = Hc[e];
-            H1 = Hc[e + 32];
+            H0 = SM<T>::template ld<0>(ahc);
+            H1 = SM<T>::template ld<ROW>(ahc);
         }
-        const P2<T> M0 = p2_exp_scaled<T>(p2_fma(A2, H0, pb[e])), M1 = p2_exp_scaled<T>(p2_fma(A2, H1, pb[e + 32]));
+        const P2<T> M0 = p2_exp_scaled<T>(p2_fma(A2, H0, SM<T>::template ld<Lay::BASE>(aw)));
+        const P2<T> M1 = p2_exp_scaled<T>(p2_fma(A2, H1, SM<T>::template ld<Lay::BASE + ROW>(aw)));
         if (LSF) {
+            const int e = (int)(npairs * ROW - (end - ar)) / SZ;          // pair-layout element of this quad
             lc.buf[(lc.taps >> 1) + lane + 2 * e] = p2_lo(M0) - T(1);
             lc.buf[(lc.taps >> 1) + lane + 2 * e + 32] = p2_hi(M0) - T(1);
             lc.buf[(lc.taps >> 1) + lane + 2 * e + 64] = p2_lo(M1) - T(1);
             lc.buf[(lc.taps >> 1) + lane + 2 * e + 96] = p2_hi(M1) - T(1);
         } else {
-            P2<T> R0 = p2_sub(pf[e], M0), R1 = p2_sub(pf[e + 32], M1);
+            P2<T> R0 = p2_sub(SM<T>::template ld<Lay::F>(ar), M0), R1 = p2_sub(SM<T>::template ld<Lay::F + ROW>(ar), M1);
             if (WT) {
-                R0 = p2_mul(R0, pw[e]);
-                R1 = p2_mul(R1, pw[e + 32]);
+                R0 = p2_mul(R0, SM<T>::template ld<Lay::W>(ar));
+                R1 = p2_mul(R1, SM<T>::template ld<Lay::W + ROW>(ar));
             }
             S2 = p2_fma(R0, R0, S2);
             S2b = p2_fma(R1, R1, S2b);
         }
     }
     S2 = p2_add(S2, S2b);
-#elif VAMP_K2_UNROLL == 1
-#pragma unroll
-    for (int jj = 0; jj < K2_PAIRS; ++jj)
-        if (jj < npairs) trip(32 * jj);
-#elif VAMP_K2_UNROLL == 2
-#pragma unroll 1
-    for (int e = 0; e < 32 * npairs; e += 64) {
-        trip(e);
-        if (e + 32 < 32 * npairs) trip(e + 32);
-    }
-#else
-#pragma unroll 1
-    for (int e = 0; e < 32 * npairs; e += 32) trip(e);
-#endif
     last_far = far;
     T S = p2_lo(S2) + p2_hi(S2);
     if (LSF) S = lsf_residuals<T, WT>(lc, rb, npairs, lane);
@@ -322,7 +322,7 @@ __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, const unsigned
     const int k = NP * n + (WT ? 0 : 1);
     // row pairs swept by every per-pixel loop: with quad trips the region is padded to whole quads (padding
     // pixels - du 1e12, flux 1, weight 0 - contribute exactly nothing)
-    const int npairs = VAMP_K2_QUAD ? 2 * ((P + 127) >> 7) : (P + 63) >> 6;
+    const int npairs = 2 * ((P + 127) >> 7);
     const int npad = 64 * npairs - P;
     const int burn = p.burn;
     const T NK = Real<T>::NEGK();
@@ -331,6 +331,12 @@ __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, const unsigned
     // ---- carve the slice
     P2<T>* const Hbuf = reinterpret_cast<P2<T>*>(wb + Lay::H) + lane;           // slot s at Hbuf + s * NE
     P2<T>* const pbase = reinterpret_cast<P2<T>*>(wb + Lay::BASE) + lane;
+    // 32-bit shared addresses of this lane's element 0 (region slice, chain slice), made opaque so that they
+    // stay in registers instead of being re-derived from the shared-window base at every use
+    unsigned ar0 = (unsigned)__cvta_generic_to_shared(rb) + (unsigned)(lane * sizeof(P2<T>));
+    unsigned aw0 = (unsigned)__cvta_generic_to_shared(wb) + (unsigned)(lane * sizeof(P2<T>));
+    asm volatile("" : "+r"(ar0), "+r"(aw0));
+    auto slot_addr = [&](int sl) -> unsigned { return aw0 + (unsigned)(Lay::H + sl * Lay::SLOT); };
     unsigned char* sp_ = wb + Lay::H + (size_t)(ncomp_max + 1) * Lay::SLOT;
     LsfCtx<T> lc;
     lc.buf = reinterpret_cast<T*>(sp_);
@@ -340,6 +346,8 @@ __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, const unsigned
     sp_ += Lay::lsf_bytes(LSF);
     SdRec<T>* const sdrec = reinterpret_cast<SdRec<T>*>(sp_);
     CompRec<T>* const recs = reinterpret_cast<CompRec<T>*>(sp_ + sizeof(SdRec<T>));
+    unsigned arec0 = (unsigned)__cvta_generic_to_shared(recs);
+    asm volatile("" : "+r"(arec0));
 
     // is parameter i of the flat layout sampled by this chain?
     auto is_free = [&](int i) -> bool { return (i == sdi) ? !WT : ((i < 4 * n) && ((i & 3) < NP)); };
@@ -393,7 +401,7 @@ __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, const unsigned
     cz.A = cz.cb = cz.g = cz.y = cz.y2 = cz.L2 = T(0);
     unsigned dummy = 0u;
     bool dummy_far;
-    T Scur = chain_pass<T, KIND, WT, LSF, false>(cz, T(0), Hbuf + n * Lay::NE, nullptr, rb, wb, npairs, lane, lc, dummy, dummy_far);
+    T Scur = chain_pass<T, KIND, WT, LSF, false>(cz, T(0), slot_addr(n), 0u, ar0, aw0, rb, npairs, lane, lc, dummy, dummy_far);
     T sd = WT ? T(1) : sdrec->th;
     T logsd = WT ? T(0) : StepMath<T>::log_(sd);
     T hiv = WT ? T(0.5) : T(0.5) / (sd * sd);                 // 1 / (2 sd^2)
@@ -479,38 +487,51 @@ __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, const unsigned
         }
         unsigned n_shape = 0u, n_far = 0u, n_like = 0u;
         int hprev = 0;                        // slot of component c - 1
+        T Aprev = T(0);                       // its amplitude
 
 #pragma unroll 1
         for (int c = 0; c < n; ++c) {
-            CompRec<T>& rc = recs[c];
-            T pA = rc.th[0], pc = rc.th[1], pw1 = rc.th[2], pw2 = rc.th[3];
-            const T sA = T(rc.scl[0]), sC = T(rc.scl[1]), sW1 = T(rc.scl[2]), sW2 = T(rc.scl[3]);
-            int hc = rc.slot;
-            // ---- base = tau of the other components
-            if (c == 0) {
-                if (rebuild == 0) {
-                    // rebuilt from the cache (first iteration, then every 8th) so that rounding never accumulates
-                    rebuild = 8;
-                    for (int e = 0; e < 32 * npairs; e += 32) pbase[e] = p2_bc<T>(T(0));
-                    for (int c2 = 1; c2 < n; ++c2) {
-                        const P2<T> A2 = p2_bc<T>(NK * recs[c2].th[0]);
-                        const P2<T>* Hs2 = Hbuf + recs[c2].slot * Lay::NE;
-                        for (int e = 0; e < 32 * npairs; e += 32) pbase[e] = p2_fma(A2, Hs2[e], pbase[e]);
+            constexpr int O_SCL = (int)(4 * sizeof(T)), O_ACC = O_SCL + 16, O_SLOT = O_ACC + 16;     // CompRec<T> layout
+            const unsigned arec = arec0 + (unsigned)(c * sizeof(CompRec<T>));
+            T pA, pc, pw1, pw2;
+            RecIO<T>::ld_th(arec, pA, pc, pw1, pw2);
+            unsigned u0, u1, u2, u3, v0, v1, v2, v3;
+            sm_ld4<O_SCL>(arec, u0, u1, u2, u3);
+            sm_ld4<O_SLOT>(arec, v0, v1, v2, v3);
+            const T sA = T(__uint_as_float(u0)), sC = T(__uint_as_float(u1)), sW1 = T(__uint_as_float(u2)), sW2 = T(__uint_as_float(u3));
+            int hc = (int)v0;
+            // ---- base = tau of the other components (shared-address form, see SM<T>)
+            {
+                constexpr int ROW = 32 * (int)sizeof(P2<T>);
+                const unsigned endw = aw0 + (unsigned)(npairs * ROW);
+                if (c == 0) {
+                    if (rebuild == 0) {
+                        // rebuilt from the cache (first iteration, then every 8th) so that rounding never accumulates
+                        rebuild = 8;
+                        for (unsigned a = aw0; a < endw; a += ROW) SM<T>::template st<Lay::BASE>(a, p2_bc<T>(T(0)));
+                        for (int c2 = 1; c2 < n; ++c2) {
+                            const P2<T> A2 = p2_bc<T>(NK * recs[c2].th[0]);
+                            unsigned ah = slot_addr(recs[c2].slot);
+                            for (unsigned a = aw0; a < endw; a += ROW, ah += ROW)
+                                SM<T>::template st<Lay::BASE>(a, p2_fma(A2, SM<T>::template ld<0>(ah), SM<T>::template ld<Lay::BASE>(a)));
+                        }
+                    } else if (n > 1) {
+                        // from the last component of the previous iteration back to the first
+                        const P2<T> Ap = p2_bc<T>(NK * recs[n - 1].th[0]), Ac = p2_bc<T>(-NK * pA);
+                        unsigned ap = slot_addr(recs[n - 1].slot), an = slot_addr(hc);
+                        for (unsigned a = aw0; a < endw; a += ROW, ap += ROW, an += ROW)
+                            SM<T>::template st<Lay::BASE>(a, p2_fma(Ac, SM<T>::template ld<0>(an),
+                                                                   p2_fma(Ap, SM<T>::template ld<0>(ap), SM<T>::template ld<Lay::BASE>(a))));
                     }
-                } else if (n > 1) {
-                    // from the last component of the previous iteration back to the first
-                    const P2<T> Ap = p2_bc<T>(NK * recs[n - 1].th[0]), Ac = p2_bc<T>(-NK * pA);
-                    const P2<T>* Hp = Hbuf + recs[n - 1].slot * Lay::NE;
-                    const P2<T>* Hn = Hbuf + hc * Lay::NE;
-                    for (int e = 0; e < 32 * npairs; e += 32) pbase[e] = p2_fma(Ac, Hn[e], p2_fma(Ap, Hp[e], pbase[e]));
+                    --rebuild;
+                } else {
+                    // next component: base += tau_{c-1} - tau_c  (two FMAs per pixel instead of n - 1)
+                    const P2<T> Ap = p2_bc<T>(NK * Aprev), Ac = p2_bc<T>(-NK * pA);
+                    unsigned ap = slot_addr(hprev), an = slot_addr(hc);
+                    for (unsigned a = aw0; a < endw; a += ROW, ap += ROW, an += ROW)
+                        SM<T>::template st<Lay::BASE>(a, p2_fma(Ac, SM<T>::template ld<0>(an),
+                                                               p2_fma(Ap, SM<T>::template ld<0>(ap), SM<T>::template ld<Lay::BASE>(a))));
                 }
-                --rebuild;
-            } else {
-                // next component: base += tau_{c-1} - tau_c  (two FMAs per pixel instead of n - 1)
-                const P2<T> Ap = p2_bc<T>(NK * recs[c - 1].th[0]), Ac = p2_bc<T>(-NK * pA);
-                const P2<T>* Hp = Hbuf + hprev * Lay::NE;
-                const P2<T>* Hn = Hbuf + hc * Lay::NE;
-                for (int e = 0; e < 32 * npairs; e += 32) pbase[e] = p2_fma(Ac, Hn[e], p2_fma(Ap, Hp[e], pbase[e]));
             }
             unsigned am = 0u;                 // accept bits of this component's steps
 
@@ -520,8 +541,8 @@ __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, const unsigned
                 draw(z, lu);
                 const T prop = pA + z * sA;
                 if (prop > T(0)) {
-                    const T Snew = chain_pass<T, KIND, WT, LSF, false>(cz, NK * prop, Hbuf + hc * Lay::NE, nullptr, rb, wb, npairs,
-                                                                       lane, lc, dummy, dummy_far);
+                    const T Snew = chain_pass<T, KIND, WT, LSF, false>(cz, NK * prop, slot_addr(hc), 0u, ar0, aw0, rb, npairs, lane,
+                                                                       lc, dummy, dummy_far);
                     const T dprior = StepMath<T>::log_(prop * Real<T>::rcp(pA)) - (prop - pA);
                     ++n_like;
                     if (lu < (Scur - Snew) * hiv + dprior) {          // false for NaN
@@ -534,7 +555,7 @@ __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, const unsigned
             }
             // ---- centroid and width(s): evaluate the proposed shape into the spare slot
 #if VAMP_K2_STEPUNROLL
-            T cg = T(rc.g), cy = T(rc.y);     // constants of the current (w1, w2), fp32 kernel
+            T cg = T(__uint_as_float(v1)), cy = T(__uint_as_float(v2));     // constants of the current (w1, w2), fp32 kernel
 #pragma unroll
 #else
 #pragma unroll 1
@@ -562,8 +583,8 @@ __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, const unsigned
                         cc = make_comp_fast<T, KIND>(pA, cbase(qc), q1, q2);
                     unsigned nf = 0u;
                     bool last_far;
-                    const T Snew = chain_pass<T, KIND, WT, LSF, true>(cc, NK * pA, nullptr, Hbuf + hs * Lay::NE, rb, wb, npairs, lane,
-                                                                      lc, nf, last_far);
+                    const T Snew = chain_pass<T, KIND, WT, LSF, true>(cc, NK * pA, 0u, slot_addr(hs), ar0, aw0, rb, npairs, lane, lc,
+                                                                      nf, last_far);
                     n_far += nf - (last_far ? (unsigned)npad : 0u);
                     ++n_shape;
                     ++n_like;
@@ -585,19 +606,15 @@ __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, const unsigned
             }
             // ---- component epilogue: every lane writes the same record (same addresses, same values)
             __syncwarp();
-            rc.th[0] = pA;
-            rc.th[1] = pc;
-            rc.th[2] = pw1;
-            if (NP == 4) rc.th[3] = pw2;
-            rc.acc[0] += (int)(am & 1u);
-            rc.acc[1] += (int)((am >> 1) & 1u);
-            rc.acc[2] += (int)((am >> 2) & 1u);
-            if (NP == 4) rc.acc[3] += (int)((am >> 3) & 1u);
-            rc.slot = hc;
+            RecIO<T>::st_th(arec, pA, pc, pw1, pw2);
+            sm_ld4<O_ACC>(arec, u0, u1, u2, u3);
+            sm_st4<O_ACC>(arec, u0 + (am & 1u), u1 + ((am >> 1) & 1u), u2 + ((am >> 2) & 1u), u3 + ((am >> 3) & 1u));
 #if VAMP_K2_STEPUNROLL
-            rc.g = (float)cg;
-            rc.y = (float)cy;
+            sm_st4<O_SLOT>(arec, (unsigned)hc, __float_as_uint((float)cg), __float_as_uint((float)cy), 0u);
+#else
+            sm_st4<O_SLOT>(arec, (unsigned)hc, v1, v2, 0u);
 #endif
+            Aprev = pA;
             hprev = hc;
             __syncwarp();
         }
@@ -740,7 +757,7 @@ k2_mcmc_kernel(McmcDev p, int ncomp_max) {
         {
             const RegionSetDev& rs = p.rs;
             const int off = rs.pix_off[rr] >> 1, ne = 32 * ((rs.npix[rr] + 63) >> 6);
-            const int nq = VAMP_K2_QUAD ? 64 * ((rs.npix[rr] + 127) >> 7) : ne;       // whole quads: pad the rest
+            const int nq = 64 * ((rs.npix[rr] + 127) >> 7);                           // whole quads: pad the rest
             P2<T>* sd_ = reinterpret_cast<P2<T>*>(rb + Lay::DU);
             P2<T>* sf_ = reinterpret_cast<P2<T>*>(rb + Lay::F);
             P2<T>* sw_ = reinterpret_cast<P2<T>*>(rb + Lay::W);
