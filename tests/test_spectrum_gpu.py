@@ -62,13 +62,13 @@ def test_detection_edge_cases(ctx):
         assert np.array_equal(d[np.isinf(ref)], ref[np.isinf(ref)])
 
 
-def _sightline(P=900, seed=11, snr=60.0):
+def _sightline(P=900, seed=11, snr=60.0, centers=(150.0, 420.0, 470.0, 760.0)):
     rng = np.random.default_rng(seed)
     wave = 1215.0 + 0.0203 * np.arange(P)                 # ~5 km/s pixels
     nu = physics.Wave2freq(wave)
     truth = []
     tau = np.zeros(P)
-    for c in (150.0, 420.0, 470.0, 760.0):
+    for c in centers:
         amp, sig_px = rng.uniform(0.8, 2.5), rng.uniform(4.0, 8.0)
         sig = abs(nu[int(c)] - nu[int(c) + 1]) * sig_px
         tau += amp * np.exp(-0.5 * ((nu - nu[int(c)]) / sig) ** 2)
@@ -103,3 +103,23 @@ def test_fit_spectrum_end_to_end(ctx):
         comp = fm["region_%d_flux" % j]
         np.testing.assert_allclose(np.prod(comp, axis=0), fm["total"][s:e], rtol=1e-9)
         assert fm["EW"][j] > 0
+
+
+def test_fit_spectrum_lsf_convolved(ctx):
+    """BASELINE config C3 in miniature: an LSF-convolved sightline (Gaussian LSF, FWHM 2 px, 7 taps) split into
+    regions and fitted with the LSF inside the model - the recovered widths are the intrinsic ones."""
+    lsf = synth.gaussian_lsf(2.0, 7)
+    wave, flux0, noise, truth, clean = _sightline(P=700, seed=23, snr=80.0, centers=(140.0, 380.0, 560.0))
+    h = lsf.size // 2
+    conv = 1.0 + np.convolve(np.concatenate([np.zeros(h), clean - 1.0, np.zeros(h)]), lsf, "valid")
+    rng = np.random.default_rng(5)
+    flux = conv + rng.normal(0, 1.0 / 80.0, len(wave))
+    sp = VS.VPspectrum(1215.0, voigt=False, chi_limit=1.5, convergence_attempts=2, iterations=1500, burn=300, thin=5,
+                       restarts=3, chains_per_restart=16, window=2, nmax=4, seed=2, lsf=lsf).set_spectrum(wave, flux, noise)
+    params = sp.fit_spectrum()
+    assert np.all(sp.flux_model["chi_squared"] < 1.6)
+    for amp, cen, sig in truth:
+        k = int(np.argmin(np.abs(params["centers"] - physics.Freq2wave(cen))))
+        assert abs(params["centers"][k] - physics.Freq2wave(cen)) < 0.5 * 0.0203
+        # b from the intrinsic width: a fit without the LSF in the model would be broadened by ~(0.85 px)^2 in quadrature
+        assert params["b"][k] == pytest.approx(physics.DopplerParameter(sig, 1215.0), rel=0.12)
