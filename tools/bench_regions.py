@@ -29,7 +29,7 @@ def _map(self, *a_, **k):
     a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
     a.record(); r = orig_map(self, *a_, **k); b.record(); evs.append(("k3", a, b)); return r
 engine.Sampler.run, engine.Sampler._map = run, _map
-for rep in range(2):
+for rep in range(int(os.environ.get("REPS", 3))):
     evs.clear()
     st = {}
     torch.cuda.synchronize()

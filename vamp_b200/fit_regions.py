@@ -45,6 +45,12 @@ def lpt_partition(costs, world_size):
 MIXED_POLISH_STARTS = 2048
 
 
+def default_polish_top(chains_per_restart):
+    """How many of a restart group's chains get the Nelder-Mead polish (the reference polishes its single chain,
+    vpfits.py:419-426): the best quarter, at least 1 and at most 4."""
+    return max(1, min(4, int(chains_per_restart) // 4))
+
+
 class RegionResult:
     """Per-region outcome: chosen ``n``, the BIC / reduced-chi^2 ladder, the MAP parameters of
     the kept fit (physical units) and posterior mean / std of its winning chain."""
@@ -108,11 +114,13 @@ def unpack_record(rec, nmax, G, cmax):
 
 def fit_local(regions_host, uids, voigt=False, sd_free=True, iterations=3000, burn=300, thin=15, restarts=3,
               chains_per_restart=32, window=3, max_rounds=4, chi_limit=1.5, dtype="f32", seed=0, lsf=None,
-              n0=None, nmax=12, ctx=None, polish_top=4, tune_interval=50, stats=None, cmax_rec=None, polish_dtype="f64"):
+              n0=None, nmax=12, ctx=None, polish_top=None, tune_interval=50, stats=None, cmax_rec=None, polish_dtype="f64"):
     """Fit the given regions on this process's GPU.  Returns ``[R, record_len]`` float64."""
     ctx = ctx or engine.default_context()
     R = len(regions_host)
     G = int(restarts)
+    if polish_top is None:                       # chains polished per restart group: a quarter of them, 1 .. 4
+        polish_top = default_polish_top(chains_per_restart)
     n0 = [estimate_n(r[1]) for r in regions_host] if n0 is None else [int(v) for v in n0]
     cap = [max(1, (len(r[1]) - 1) // 2) for r in regions_host]
     freedom = [len(regions_host[i][1]) - 3 * n0[i] for i in range(R)]        # vpregion.py:37-39, frozen at n0
@@ -221,7 +229,7 @@ def fit_regions(regions_host, uids=None, distributed=None, fit_fn=None, **kw):
         # K3 schedule from the GLOBAL number of starts (the same on every rank and for every world size):
         # thousands of starts -> one warp per start, fp32 search stage + float64 finish ("mixed");
         # a few -> one CTA per start in float64 (latency)
-        starts = R * window * G * kw.get("polish_top", 4)
+        starts = R * window * G * (kw.get("polish_top") or default_polish_top(kw.get("chains_per_restart", 32)))
         kw["polish_dtype"] = "mixed" if (starts >= MIXED_POLISH_STARTS and kw.get("lsf") is None) else "f64"
     fit_fn = fit_fn or fit_local
     if not use_dist:
