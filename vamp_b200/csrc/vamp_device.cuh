@@ -410,6 +410,66 @@ __device__ __forceinline__ P2<T> fad_far2(P2<T> X, T y, P2<T> S) {
     return p2_mul(p2_mul(p2_bc<T>(-y), imq), rd);
 }
 
+// Same two rational functions with a different y in each half: K3 evaluates TWO COMPONENTS of one pixel row
+// as one two-wide value, which gives its latency-bound float64 objective two independent dependency chains
+// (in float64 a P2 operation is simply two adjacent scalar operations).
+template <typename T>
+__device__ __forceinline__ P2<T> fad_core2y(P2<T> X, P2<T> Y, P2<T> S) {
+    const T L = Fad<T>::L();
+    const P2<T> L2 = p2_bc<T>(L * L), twoLY = p2_mul(p2_bc<T>(T(2) * L), Y);
+    const P2<T> R = p2_rcp<T>(p2_add(S, p2_add(twoLY, L2)));
+    const P2<T> Zr = p2_mul(p2_sub(L2, S), R);
+    const P2<T> XR = p2_mul(X, R);
+    const P2<T> Zi = p2_mul(XR, p2_bc<T>(T(2) * L));
+    const P2<T> t = p2_add(Zr, Zr);
+    const P2<T> nn = p2_mul(p2_sub(p2_sub(twoLY, L2), S), R);
+    P2<T> b1 = p2_fma(t, p2_bc<T>(Fad<T>::ac(0)), p2_bc<T>(Fad<T>::ac(1))), b2 = p2_bc<T>(Fad<T>::ac(0));
+#pragma unroll
+    for (int j = 2; j < Fad<T>::N - 1; ++j) {
+        const P2<T> nb = p2_fma(t, b1, p2_fma(nn, b2, p2_bc<T>(Fad<T>::ac(j))));
+        b2 = b1;
+        b1 = nb;
+    }
+    const P2<T> pr = p2_fma(b1, Zr, p2_fma(nn, b2, p2_bc<T>(Fad<T>::ac(Fad<T>::N - 1))));
+    const P2<T> pi = p2_mul(b1, Zi);
+    const P2<T> ir = p2_mul(p2_add(p2_bc<T>(L), Y), R);
+    const P2<T> i2r = p2_sub(p2_mul(ir, ir), p2_mul(XR, XR));
+    const P2<T> i2i = p2_mul(p2_add(ir, ir), XR);
+    const P2<T> q = p2_sub(p2_mul(pr, i2r), p2_mul(pi, i2i));
+    return p2_mul(Y, p2_fma(p2_bc<T>(T(3.54490770181103205460)), q, ir));
+}
+
+template <typename T>
+__device__ __forceinline__ P2<T> fad_far2y(P2<T> X, P2<T> Y, P2<T> S) {
+    const P2<T> RS_ = p2_rcp<T>(S);
+    const P2<T> mY = p2_neg(Y);
+    const P2<T> tr = p2_mul(X, RS_), ti = p2_mul(mY, RS_);
+    const P2<T> vr = p2_sub(p2_mul(tr, tr), p2_mul(ti, ti));
+    const P2<T> vi = p2_mul(p2_add(tr, tr), ti);
+    const P2<T> nvi = p2_neg(vi);
+    P2<T> nr = p2_fma(p2_bc<T>(Fad<T>::cfnc(Fad<T>::CFN - 1)), vr, p2_bc<T>(Fad<T>::cfnc(Fad<T>::CFN - 2)));
+    P2<T> ni = p2_mul(p2_bc<T>(Fad<T>::cfnc(Fad<T>::CFN - 1)), vi);
+#pragma unroll
+    for (int k = Fad<T>::CFN - 3; k >= 0; --k) {
+        const P2<T> a = p2_fma(nr, vr, p2_fma(ni, nvi, p2_bc<T>(Fad<T>::cfnc(k))));
+        ni = p2_fma(nr, vi, p2_mul(ni, vr));
+        nr = a;
+    }
+    P2<T> dr = p2_fma(p2_bc<T>(Fad<T>::cfdc(Fad<T>::CFD - 1)), vr, p2_bc<T>(Fad<T>::cfdc(Fad<T>::CFD - 2)));
+    P2<T> di = p2_mul(p2_bc<T>(Fad<T>::cfdc(Fad<T>::CFD - 1)), vi);
+#pragma unroll
+    for (int k = Fad<T>::CFD - 3; k >= 0; --k) {
+        const P2<T> a = p2_fma(dr, vr, p2_fma(di, nvi, p2_bc<T>(Fad<T>::cfdc(k))));
+        di = p2_fma(dr, vi, p2_mul(di, vr));
+        dr = a;
+    }
+    const P2<T> er = p2_fma(nr, dr, p2_mul(ni, di));
+    const P2<T> ei = p2_sub(p2_mul(ni, dr), p2_mul(nr, di));
+    const P2<T> imq = p2_fma(tr, ei, p2_mul(ti, er));
+    const P2<T> rd = p2_rcp<T>(p2_fma(dr, dr, p2_mul(di, di)));
+    return p2_mul(p2_mul(mY, imq), rd);
+}
+
 // ------------------------------------------------------------------------------------------------
 // Row-streaming evaluation (K2 / K3): one 32-pixel row per call, path chosen per ROW.
 // component constants with the divisions done in T (double divisions cost ~20 instructions each

@@ -64,7 +64,7 @@ struct Objective {
             if (NP == 4) ok = ok && (w1 >= 0.0) && (w1 <= w_hi) && (w2 > 0.0) && (w2 <= w_hi);
             else ok = ok && (w1 > 0.0) && (w1 <= w_hi);
             lp += log(a) - a;
-            ccs[c] = make_comp<T, KIND>(a, ce, w1, w2, ubase);
+            ccs[c] = make_comp_k1<T, KIND, true>(a, ce, w1, w2, ubase);      // clamped 1/G: the padding coordinate stays finite
         }
         double sd = 1.0;
         if (p.sd_free) {
@@ -82,9 +82,25 @@ struct Objective {
             const int px = row * 32 + lane;
             const T du = __ldg(gdu + px);                 // rows are padded with neutral pixels
             T tau = T(0);
-            for (int c = 0; c < n; ++c) {
-                const CompC<T> cc = ccs[c];
-                tau = Real<T>::fma_(cc.A, row_shape<T, KIND>(cc, du, dummy), tau);
+            // two components at a time as the halves of a two-wide value (two independent dependency chains: this
+            // kernel is bound by the latency of one evaluation); one path per component pair and row
+            for (int c = 0; c < n; c += 2) {
+                const CompC<T> c0 = ccs[c];
+                CompC<T> c1 = c0;
+                c1.A = T(0);
+                if (c + 1 < n) c1 = ccs[c + 1];
+                const P2<T> X = p2_mul(p2_sub(p2_bc<T>(du), p2_make(c0.cb, c1.cb)), p2_make(c0.g, c1.g));
+                P2<T> H;
+                if (KIND == VAMP_KIND_GAUSS) {
+                    const P2<T> Q = p2_mul(X, X);
+                    H = p2_make(Real<T>::exp2_neg(p2_lo(Q)), Real<T>::exp2_neg(p2_hi(Q)));
+                } else {
+                    const P2<T> Y = p2_make(c0.y, c1.y);
+                    const P2<T> S2 = p2_fma(X, X, p2_mul(Y, Y));
+                    const bool far = __all_sync(VAMP_FULL_MASK, !(fmin(p2_lo(S2), p2_hi(S2)) < Fad<T>::R2()));
+                    H = far ? fad_far2y<T>(X, Y, S2) : fad_core2y<T>(X, Y, S2);
+                }
+                tau = Real<T>::fma_(c0.A, p2_lo(H), Real<T>::fma_(c1.A, p2_hi(H), tau));
             }
             const T m = Real<T>::exp_neg(tau);
             if (taps > 1) {
