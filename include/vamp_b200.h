@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define VAMP_ABI_VERSION 1
+#define VAMP_ABI_VERSION 2   /* 2: vamp_detect_*, VAMP_MIXED for vamp_map_dev */
 
 enum { VAMP_F32 = 0, VAMP_F64 = 1,            /* arithmetic of the pixel math */
        VAMP_MIXED = 2 };                       /* vamp_map_dev only: fp32 objective during the simplex search,

@@ -114,3 +114,10 @@ def test_chain_uids_unique_and_world_independent():
     c = batch.chain_uids(12346, 3, 3, 32)
     allu = np.concatenate([a, b, c])
     assert len(np.unique(allu)) == allu.size
+
+
+def test_empty_inputs_need_no_device():
+    """No regions (an empty catalogue, or a rank whose shard is empty): an empty result, no GPU touched."""
+    assert FR.fit_regions([], distributed=False) == []
+    out = FR.fit_local([], [], cmax_rec=5, nmax=4, restarts=3)
+    assert out.shape == (0, FR._record_len(4, 3, 5))

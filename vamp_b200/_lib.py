@@ -96,7 +96,7 @@ def load():
         fn = getattr(lib, name)      # AttributeError if the symbol is missing
         fn.restype = res
         fn.argtypes = args
-    if lib.vamp_abi_version() != 1:
+    if lib.vamp_abi_version() != 2:
         raise VampError("libvamp_b200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -116,9 +116,12 @@ def fit_local(regions_host, uids, voigt=False, sd_free=True, iterations=3000, bu
               chains_per_restart=32, window=3, max_rounds=4, chi_limit=1.5, dtype="f32", seed=0, lsf=None,
               n0=None, nmax=12, ctx=None, polish_top=None, tune_interval=50, stats=None, cmax_rec=None, polish_dtype="f64"):
     """Fit the given regions on this process's GPU.  Returns ``[R, record_len]`` float64."""
-    ctx = ctx or engine.default_context()
     R = len(regions_host)
     G = int(restarts)
+    if R == 0:                                   # nothing to fit (an empty shard): no device work, no context
+        cm = int(cmax_rec or 1 + nmax)
+        return np.zeros((0, _record_len(nmax, G, cm)))
+    ctx = ctx or engine.default_context()
     if polish_top is None:                       # chains polished per restart group: a quarter of them, 1 .. 4
         polish_top = default_polish_top(chains_per_restart)
     n0 = [estimate_n(r[1]) for r in regions_host] if n0 is None else [int(v) for v in n0]
