@@ -48,7 +48,7 @@ WORKLOAD = ("C2: 256-px synthetic blended Voigt region (3 true components, S/N 5
 
 def config_dict(n_gpus):
     return {"workload": WORKLOAD, "pixels": 256, "candidates": "1..6", "chains_per_candidate": RESTARTS * CHAINS_PER_RESTART,
-            "iterations": ITERS, "burn": BURN, "thin": THIN, "regions_per_gpu": 1, "parallelism": "regions sharded, %d rank(s)" % n_gpus,
+            "iterations": ITERS, "burn": BURN, "thin": THIN, "regions_per_gpu": 1, "parallelism": "regions sharded, %d rank(s); weak scaling: one C2 region per GPU (same spectrum, own chains)" % n_gpus,
             "l2": "flushed between steps (512 MiB write); working set is compute-bound and far below L2"}
 
 
@@ -232,8 +232,11 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    region_id = 2 + rank                    # weak scaling: one C2 region per GPU, keyed by global id
-    reg = synth.config_c2(region_id=region_id)
+    # weak scaling, fixed per-GPU work: every GPU fits the SAME C2 spectrum (region 2) with its own chains - the
+    # Philox streams are keyed by the global uid 2 + rank - so the max over ranks measures the machine, not the
+    # difference between one synthetic region and another (region 2 vs 9 differ by ~5 % in accepted work)
+    region_id = 2 + rank
+    reg = synth.config_c2(region_id=2)
     host_regions = [(reg["nu"], reg["flux"], reg["noise"])]
     models = [(0, n) for n in range(1, N_CAND + 1)]
     flush = torch.empty(512 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
