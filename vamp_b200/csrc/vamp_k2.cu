@@ -7,8 +7,9 @@
 // host round trip, no kernel-per-iteration, and no HBM traffic beyond the initial spectrum
 // load and the optional tallies.
 //
-// Per chain (= warp):
-//   * pixels p = j*32 + lane live in registers (flux, coordinate, running tau);
+// Per chain (= warp), 4 chains per CTA:
+//   * the region's pixels (du, flux, [1/noise]) are staged once per CTA in shared memory, in pair
+//     layout, and the lanes sweep them two row pairs (128 pixels) per trip with packed f32x2 math;
 //   * the unit-amplitude shape H_c of every component is cached in warp-private shared
 //     memory, so a single-parameter step re-evaluates ONE component (P Voigt evaluations) -
 //     the same economy PyMC 2's LazyFunction cache gives the reference - and an amplitude or
@@ -16,9 +17,10 @@
 //   * sum (f-m)^2 is reduced with xor shuffles: every lane holds the identical value and takes
 //     the identical accept decision (no divergence, no broadcast);
 //   * Philox4x32-10 keyed by (seed, global chain id): lane l draws the Box-Muller pair and the
-//     two log-uniforms of steps 2l, 2l+1 of a 64-step block, handed out with shuffles;
+//     two log-uniforms of steps l and 32 + l of a 64-step block, handed out with one shuffle each;
 //   * tallies (i >= burn and i % thin == 0) feed Welford means / co-moments (the reference's
 //     mcmc.stats() and chain_covariance, vpfits.py:432-456) and an optional trace.
+// DESIGN.md section 4 has the measured history of this kernel and what bounds it.
 #include "vamp_device.cuh"
 #include "vamp_kernels.h"
 
@@ -31,7 +33,6 @@ constexpr int K2_WARPS = 4;
 #ifndef VAMP_K2_STEPUNROLL
 #define VAMP_K2_STEPUNROLL 1      // 1: the centroid / width steps of a component are unrolled (no selects)
 #endif
-constexpr int K2_PAIRS = VAMP_TILE_PIX / 64;
 constexpr double FWHM_PER_SIGMA = 2.35482004503094938202;
 
 // ------------------------------------------------------------------------------------------------
