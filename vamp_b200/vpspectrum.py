@@ -176,6 +176,28 @@ class VPspectrum():
         self.region_pixels = [[points[i], points[i + 1]] for i in range(len(points) - 1)]
         self.region_waves = [[self.wavelength_array[s], self.wavelength_array[e]] for s, e in self.region_pixels]
 
+    def split_long_regions(self, max_pixels=256):
+        """New (GPU constraint): the sampler kernels hold one region per 256-pixel coordinate tile.  A longer
+        detection region is cut where the flux comes closest to the continuum (the same choice
+        ``split_difficult_region`` makes, vpspectrum.py:200-232): recursively at the highest-flux pixel of the
+        middle half, so both parts keep at least a quarter of the pixels.  Absorbers separated by continuum are
+        independent, which is what makes regions the unit of the fit in the first place."""
+        out = []
+        stack = [list(r) for r in reversed(self.region_pixels)]
+        while stack:
+            s, e = stack.pop()
+            if e - s <= max_pixels:
+                out.append([s, e])
+                continue
+            lo, hi = s + (e - s) // 4, e - (e - s) // 4
+            cut = lo + int(np.argmax(self.flux_array[lo:hi]))
+            stack.append([cut, e])
+            stack.append([s, cut])
+        if len(out) != len(self.region_pixels):
+            self.region_pixels = out
+            self.region_waves = [[self.wavelength_array[s], self.wavelength_array[min(e, len(self.wavelength_array) - 1)]]
+                                 for s, e in out]
+
     # ------------------------------------------------------------------ fit
     def _region_arrays(self, start, end):
         """vpspectrum.py:274-279: flipped so that frequency ascends."""
@@ -188,6 +210,7 @@ class VPspectrum():
         if not hasattr(self, "region_pixels"):
             self.compute_detection_regions(min_region_width=2)
             self.split_difficult_region()
+        self.split_long_regions()
         R = len(self.region_pixels)
         self.params = {'b': np.array([]), 'b_std': np.array([]), 'N': np.array([]), 'N_std': np.array([]),
                        'EW': np.array([]), 'centers': np.array([]), 'region_numbers': np.array([])}
