@@ -378,6 +378,8 @@ def run_gpu(args):
                         "algorithmic_bytes_per_launch": alg_bytes}}
     if clk.get("sm_mhz"):
         roofline["frac_at_observed_clock"] = achieved_tf / flops.fp32_peak_tflops(nsm, clk["sm_mhz"])
+    # measured FMA-chain burst on this pool's B200s (tools/micro/ffma2_bench.cu: FFMA 72.3, FFMA2 74.0 TFLOP/s)
+    roofline["frac_of_measured_ffma2_burst"] = achieved_tf / 74.0
 
     # -------- K1, the fused likelihood kernel on its own (BASELINE config C5, one point): the same Voigt arithmetic
     #          without the Metropolis bookkeeping - the figure to hold against the FP32 roofline
