@@ -85,9 +85,18 @@ def fit_models(regions, models, voigt=False, sd_free=True, iterations=3000, burn
         blp = torch.nan_to_num(s.t["best_logp"][rows], nan=-float("inf"))
         top = blp.topk(K, dim=1).indices
         phys = torch.gather(rows, 1, top).reshape(-1)
-        starts = s.t["best_theta"][phys].contiguous()
-        r = s._map(starts, s.t["item_region"][phys].contiguous(), s.t["item_ncomp"][phys].contiguous(),
+        # launch order of the polish: cheapest starts first in memory, the kernels take their work from the END of
+        # the list (as K2 does), so the long simplexes (many components, 3000 iterations) start first and the tail
+        # of the launch is made of short ones
+        ncs = s.t["item_ncomp"][phys]
+        lpt = torch.argsort(ncs.to(torch.int64) * 1024 + s.t["item_region"][phys].to(torch.int64) % 1024, stable=True)
+        unsort = torch.empty_like(lpt)
+        unsort[lpt] = torch.arange(lpt.numel(), device=dev)
+        ps = phys[lpt]
+        starts = s.t["best_theta"][ps].contiguous()
+        r = s._map(starts, s.t["item_region"][ps].contiguous(), s.t["item_ncomp"][ps].contiguous(),
                    int(max(models[m][1] for m in model_ids)), int(maxiter or iterations), 0, xtol, ftol, polish_dtype)
+        r = {k: v[unsort] for k, v in r.items()}
         logp = torch.nan_to_num(r["logp"].view(-1, K), nan=-float("inf"))
         win = logp.argmax(dim=1)
         pick = torch.arange(mg.numel(), device=dev) * K + win

@@ -321,8 +321,8 @@ k3_map_kernel(MapDev p, int kmax, int ncmax) {
         for (int i = threadIdx.x; i < p.rs.lsf_taps; i += blockDim.x) lsf_s[i] = RS<T>::lsf(p.rs)[i];
     }
     __syncthreads();
-    const int s = blockIdx.x;
-    if (s >= p.S) return;
+    const int s = p.S - 1 - (int)blockIdx.x;           // the host sorts starts by ascending cost: longest first
+    if (s < 0) return;
     unsigned char* base = smem_raw + head;
     double* sm = reinterpret_cast<double*>(base);
     base += k3_align16(sizeof(double) * ((size_t)(kmax + 1) * p.tstride + (kmax + 1) + 4 * p.tstride + 4 * K3_WARPS));
@@ -436,8 +436,8 @@ k3w_map_kernel(MapDev p, int kmax, int ncomp_max) {
     constexpr int NP = (KIND == VAMP_KIND_VOIGT) ? 4 : 3;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int s = blockIdx.x * K3W_WARPS + warp;
-    if (s >= p.S) return;
+    const int s = p.S - 1 - (blockIdx.x * K3W_WARPS + warp);      // starts sorted by ascending cost: longest first
+    if (s < 0) return;
     const int ts = p.tstride;
     unsigned char* wbase = smem_raw + (size_t)warp * k3w_warp_bytes(kmax, ts, ncomp_max);
     const RegionSetDev& rs = p.rs;
