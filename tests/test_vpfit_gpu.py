@@ -142,3 +142,14 @@ def test_fit_regions_polish_schedules_agree(ctx):
         assert rb.lnL == pytest.approx(ra.lnL, abs=2e-2)
         np.testing.assert_allclose(rb.theta, ra.theta, rtol=2e-3)
         assert rb.chi2 == pytest.approx(ra.chi2, rel=1e-3)
+
+
+def test_gelman_rubin_from_device_accumulators(ctx):
+    """R-hat over the ~100 chains of a well-determined one-line fit is close to 1 for every sampled variable."""
+    reg = synth.make_region(120, 1, 60.0, 515, voigt=False)
+    fit = VPfit(seed=3, n_chains=96)
+    fit.initialise_model(reg["nu"], reg["flux"], 1, voigt=False)
+    fit.mcmc_fit(iterations=6000, burnin=3000, thinning=5)
+    r = fit.gelman_rubin()
+    assert set(r) == {"xexp_0", "est_centroid_0", "est_sigma_0", "sd"}
+    assert all(0.98 < v < 1.2 for v in r.values()), r

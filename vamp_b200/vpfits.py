@@ -358,6 +358,26 @@ class VPfit():
             out[name] = {"n": n, "mean": mean[idx] * f + o, "standard deviation": np.sqrt(var) * f}
         return out
 
+    def gelman_rubin(self, good_only=True):
+        """New: multi-chain R-hat per variable (PyMC 2 names) over the chains of this fit, straight from the
+        device accumulators (``vamp_b200.diagnostics.rhat``).  ``good_only``: chains within 30 log-posterior units
+        of the best one (chains that never left a noise mode would dominate the between-chain variance)."""
+        from . import diagnostics
+        s = self._sampler
+        mean, m2, nt, blp = s.get("mean"), s.get("m2"), s.get("ntally"), s.get("best_logp")
+        keep = np.isfinite(blp)
+        if good_only:
+            keep &= blp > np.nanmax(blp) - 30.0
+        r = diagnostics.rhat(mean[keep], m2[keep], nt[keep])
+        out = {}
+        for name, (c, i) in self._param_index.items():
+            if c == "sd":
+                if self._sd_free:
+                    out[name] = float(r[4 * s.cmax])
+            else:
+                out[name] = float(r[4 * c + i])
+        return out
+
     def _dic(self):
         """PyMC 2: ``DIC = 2 E[D] - D(E[theta])``, ``BPIC = 3 E[D] - 2 D(E[theta])``, D = -2 lnL."""
         s = self._sampler
