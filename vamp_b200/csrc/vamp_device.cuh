@@ -155,6 +155,19 @@ template <> struct Fad<double> {
     static __device__ __forceinline__ double BIG() { return 1.0e150; }
 };
 
+// Mid-fidelity float64 set: Weideman N = 20 (|dH| <= 2.5e-10) and 6 continued-fraction levels beyond |z|^2 = 48
+// (<= 4.5e-11).  Rounding-noise free (float64 arithmetic) at 60 % of the cost of the N = 32 set: the second
+// stage of K3w's simplex search, whose stopping tolerance (1e-3 in logp) is five orders above its error.
+struct FadMid {
+    static constexpr int N = WEID_N_MID;
+    static constexpr int CFN = 4, CFD = 4;
+    static __device__ __forceinline__ double L() { return WEID_L_MID; }
+    static __device__ __forceinline__ constexpr double ac(int i) { return WEID_A_MID_c(i); }
+    static __device__ __forceinline__ constexpr double cfnc(int i) { return CF_NUM_MID_c(i); }
+    static __device__ __forceinline__ constexpr double cfdc(int i) { return CF_DEN_MID_c(i); }
+    static __device__ __forceinline__ double R2() { return 48.0; }
+};
+
 // H for |z|^2 < R2 (valid over the whole upper half plane): Weideman.  s = x^2 + y^2.
 // p(Z) has REAL coefficients, so it is evaluated with the real second-order recurrence
 //   b_k = c_k + t b_{k+1} - n b_{k+2},  t = 2 Re Z, n = |Z|^2,   p(Z) = b_1 Z + c_0 - n b_2
@@ -352,9 +365,9 @@ template <typename T> __device__ __forceinline__ P2<T> p2_exp_scaled(P2<T> a) { 
 // Z = (L + iz)/(L - iz):  with R = 1/|L - iz|^2 = 1/(s + 2Ly + L^2),
 //   Re Z = (L^2 - s) R,  Im Z = 2 L x R,  |Z|^2 = (s - 2Ly + L^2) R   (no dependence on Re/Im Z).
 // 40 packed operations + 2 MUFU per pixel pair.
-template <typename T>
+template <typename T, typename F = Fad<T>>
 __device__ __forceinline__ P2<T> fad_core2(P2<T> X, T y, P2<T> S) {
-    const T L = Fad<T>::L();
+    const T L = F::L();
     const T L2 = L * L, twoLy = (T(2) * L) * y;
     const P2<T> R = p2_rcp<T>(p2_add(S, p2_bc<T>(twoLy + L2)));
     const P2<T> Zr = p2_mul(p2_sub(p2_bc<T>(L2), S), R);
@@ -362,14 +375,14 @@ __device__ __forceinline__ P2<T> fad_core2(P2<T> X, T y, P2<T> S) {
     const P2<T> Zi = p2_mul(XR, p2_bc<T>(T(2) * L));
     const P2<T> t = p2_add(Zr, Zr);
     const P2<T> nn = p2_mul(p2_sub(p2_bc<T>(twoLy - L2), S), R);        // -|Z|^2
-    P2<T> b1 = p2_fma(t, p2_bc<T>(Fad<T>::ac(0)), p2_bc<T>(Fad<T>::ac(1))), b2 = p2_bc<T>(Fad<T>::ac(0));
+    P2<T> b1 = p2_fma(t, p2_bc<T>(F::ac(0)), p2_bc<T>(F::ac(1))), b2 = p2_bc<T>(F::ac(0));
 #pragma unroll
-    for (int j = 2; j < Fad<T>::N - 1; ++j) {
-        const P2<T> nb = p2_fma(t, b1, p2_fma(nn, b2, p2_bc<T>(Fad<T>::ac(j))));
+    for (int j = 2; j < F::N - 1; ++j) {
+        const P2<T> nb = p2_fma(t, b1, p2_fma(nn, b2, p2_bc<T>(F::ac(j))));
         b2 = b1;
         b1 = nb;
     }
-    const P2<T> pr = p2_fma(b1, Zr, p2_fma(nn, b2, p2_bc<T>(Fad<T>::ac(Fad<T>::N - 1))));
+    const P2<T> pr = p2_fma(b1, Zr, p2_fma(nn, b2, p2_bc<T>(F::ac(F::N - 1))));
     const P2<T> pi = p2_mul(b1, Zi);
     const P2<T> ir = p2_mul(p2_bc<T>(L + y), R);                        // Re 1/(L - iz)
     const P2<T> i2r = p2_sub(p2_mul(ir, ir), p2_mul(XR, XR));
@@ -379,7 +392,7 @@ __device__ __forceinline__ P2<T> fad_core2(P2<T> X, T y, P2<T> S) {
 }
 
 // fad_far for two rows: 28 (fp32) packed operations + 4 MUFU per pixel pair
-template <typename T>
+template <typename T, typename F = Fad<T>>
 __device__ __forceinline__ P2<T> fad_far2(P2<T> X, T y, P2<T> S) {
     const P2<T> RS_ = p2_rcp<T>(S);
     const P2<T> tr = p2_mul(X, RS_), ti = p2_mul(p2_bc<T>(-y), RS_);
@@ -387,19 +400,19 @@ __device__ __forceinline__ P2<T> fad_far2(P2<T> X, T y, P2<T> S) {
     const P2<T> vi = p2_mul(p2_add(tr, tr), ti);
     const P2<T> nvi = p2_neg(vi);
     // Horner in v with real coefficients; the first step has a real accumulator
-    P2<T> nr = p2_fma(p2_bc<T>(Fad<T>::cfnc(Fad<T>::CFN - 1)), vr, p2_bc<T>(Fad<T>::cfnc(Fad<T>::CFN - 2)));
-    P2<T> ni = p2_mul(p2_bc<T>(Fad<T>::cfnc(Fad<T>::CFN - 1)), vi);
+    P2<T> nr = p2_fma(p2_bc<T>(F::cfnc(F::CFN - 1)), vr, p2_bc<T>(F::cfnc(F::CFN - 2)));
+    P2<T> ni = p2_mul(p2_bc<T>(F::cfnc(F::CFN - 1)), vi);
 #pragma unroll
-    for (int k = Fad<T>::CFN - 3; k >= 0; --k) {
-        const P2<T> a = p2_fma(nr, vr, p2_fma(ni, nvi, p2_bc<T>(Fad<T>::cfnc(k))));
+    for (int k = F::CFN - 3; k >= 0; --k) {
+        const P2<T> a = p2_fma(nr, vr, p2_fma(ni, nvi, p2_bc<T>(F::cfnc(k))));
         ni = p2_fma(nr, vi, p2_mul(ni, vr));
         nr = a;
     }
-    P2<T> dr = p2_fma(p2_bc<T>(Fad<T>::cfdc(Fad<T>::CFD - 1)), vr, p2_bc<T>(Fad<T>::cfdc(Fad<T>::CFD - 2)));
-    P2<T> di = p2_mul(p2_bc<T>(Fad<T>::cfdc(Fad<T>::CFD - 1)), vi);
+    P2<T> dr = p2_fma(p2_bc<T>(F::cfdc(F::CFD - 1)), vr, p2_bc<T>(F::cfdc(F::CFD - 2)));
+    P2<T> di = p2_mul(p2_bc<T>(F::cfdc(F::CFD - 1)), vi);
 #pragma unroll
-    for (int k = Fad<T>::CFD - 3; k >= 0; --k) {
-        const P2<T> a = p2_fma(dr, vr, p2_fma(di, nvi, p2_bc<T>(Fad<T>::cfdc(k))));
+    for (int k = F::CFD - 3; k >= 0; --k) {
+        const P2<T> a = p2_fma(dr, vr, p2_fma(di, nvi, p2_bc<T>(F::cfdc(k))));
         di = p2_fma(dr, vi, p2_mul(di, vr));
         dr = a;
     }
@@ -565,7 +578,7 @@ __device__ __forceinline__ T row_shape(const CompC<T>& cc, T du, unsigned& nfar)
 // guard: make_comp_fast clamps g and y, so padding pixels give H ~ 1e-18 (exp(-tau) = 1 exactly).
 // Split in two so the chain kernel can classify pair j + 1 (load, 3 packed operations, vote)
 // under the arithmetic of pair j.
-template <typename T, int KIND>
+template <typename T, int KIND, typename F = Fad<T>>
 __device__ __forceinline__ void pair_classify(const CompC<T>& cc, P2<T> DU, P2<T>& X, P2<T>& S, bool& far) {
     X = p2_mul(p2_sub(DU, p2_bc<T>(cc.cb)), p2_bc<T>(cc.g));
     if (KIND == VAMP_KIND_GAUSS) {
@@ -573,17 +586,17 @@ __device__ __forceinline__ void pair_classify(const CompC<T>& cc, P2<T> DU, P2<T
         far = false;
     } else {
         S = p2_fma(X, X, p2_bc<T>(cc.y2));
-        far = __all_sync(VAMP_FULL_MASK, !(fmin(p2_lo(S), p2_hi(S)) < Fad<T>::R2()));
+        far = __all_sync(VAMP_FULL_MASK, !(fmin(p2_lo(S), p2_hi(S)) < F::R2()));
     }
 }
-template <typename T, int KIND>
+template <typename T, int KIND, typename F = Fad<T>>
 __device__ __forceinline__ P2<T> pair_eval(const CompC<T>& cc, P2<T> X, P2<T> S, bool far, unsigned& nfar) {
     if (KIND == VAMP_KIND_GAUSS) return p2_make(Real<T>::exp2_neg(p2_lo(S)), Real<T>::exp2_neg(p2_hi(S)));
     if (far) {
         nfar += 64u;
-        return fad_far2<T>(X, cc.y, S);
+        return fad_far2<T, F>(X, cc.y, S);
     }
-    return fad_core2<T>(X, cc.y, S);
+    return fad_core2<T, F>(X, cc.y, S);
 }
 template <typename T, int KIND>
 __device__ __forceinline__ P2<T> pair_shape(const CompC<T>& cc, P2<T> DU, bool& far) {

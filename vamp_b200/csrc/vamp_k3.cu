@@ -360,7 +360,7 @@ __host__ __device__ inline size_t k3w_warp_bytes(int kmax, int ts, int ncomp_max
 
 // -logp of `th` (full layout, shared memory); +inf outside the prior support.  All lanes get the
 // same value.  T = float: search precision; T = double: reporting precision.
-template <typename T, int KIND>
+template <typename T, int KIND, typename F = Fad<T>>
 __device__ __noinline__ double k3w_objective(const MapDev& p, const double* th, int r, int P, int n, int lane, void* ccbuf,
                                              double c_hi, double w_hi, double ubase, double& lnL, double& chi2) {
     constexpr int NP = (KIND == VAMP_KIND_VOIGT) ? 4 : 3;
@@ -414,8 +414,8 @@ __device__ __noinline__ double k3w_objective(const MapDev& p, const double* th, 
             cc.L2 = T(0);
             P2<T> X, S;
             bool far;
-            pair_classify<T, KIND>(cc, DU, X, S, far);
-            tau = p2_fma(p2_bc<T>(cc.A), pair_eval<T, KIND>(cc, X, S, far, nfar), tau);
+            pair_classify<T, KIND, F>(cc, DU, X, S, far);
+            tau = p2_fma(p2_bc<T>(cc.A), pair_eval<T, KIND, F>(cc, X, S, far, nfar), tau);
         }
         // padding pixels: du = 1e12 gives tau = 0 exactly, flux 1, weight 0 (vamp_regions_create)
         const P2<T> R = p2_sub(p2_from(__ldg(gf + e)), p2_exp_scaled<T>(tau));
@@ -467,9 +467,12 @@ k3w_map_kernel(MapDev p, int kmax, int ncomp_max) {
     // to 2e-3 (measured, tools/noise_scan.py) - the size of the stopping tolerance - so once the simplex's
     // function spread is within K3W_SWITCH the search continues on the float64 objective (all vertices
     // re-evaluated).  Before that every comparison is far above the noise and the two objectives decide alike.
-    bool fine = false;
+    // The float64 stage of the SEARCH uses the mid-fidelity set (FadMid: |dH| <= 2.5e-10, no rounding noise); what is
+    // reported at the end is evaluated with the full float64 set.
+    bool fine = false, report = false;
     auto F = [&](const double* th) -> double {
-        return fine ? k3w_objective<double, KIND>(p, th, r, P, n, lane, ccbuf, c_hi, w_hi, ubase, lnL, chi2)
+        if (report) return k3w_objective<double, KIND>(p, th, r, P, n, lane, ccbuf, c_hi, w_hi, ubase, lnL, chi2);
+        return fine ? k3w_objective<double, KIND, FadMid>(p, th, r, P, n, lane, ccbuf, c_hi, w_hi, ubase, lnL, chi2)
                     : k3w_objective<float, KIND>(p, th, r, P, n, lane, ccbuf, c_hi, w_hi, ubase, lnL, chi2);
     };
 
@@ -586,7 +589,7 @@ k3w_map_kernel(MapDev p, int kmax, int ncomp_max) {
         ++iters;
     }
     // ---- report in float64 at the best vertex
-    fine = true;
+    report = true;
     const double fbest = F(sim + (size_t)ib * ts);
     for (int i = lane; i < ts; i += 32) p.theta[(size_t)s * ts + i] = sim[(size_t)ib * ts + i];
     if (lane == 0) {
