@@ -121,3 +121,21 @@ def test_empty_inputs_need_no_device():
     assert FR.fit_regions([], distributed=False) == []
     out = FR.fit_local([], [], cmax_rec=5, nmax=4, restarts=3)
     assert out.shape == (0, FR._record_len(4, 3, 5))
+
+
+def test_chunked_batches_equal_single_batch():
+    """A shard above ``max_batch_regions`` is fitted in consecutive device batches; the records are the same."""
+    regs = _regions(11)
+    n0 = [1 + (i % 3) for i in range(11)]
+    calls = []
+
+    def counting(regions_host, uids, **kw):
+        calls.append(len(regions_host))
+        return _fake_fit(regions_host, uids, **kw)
+
+    one = FR.fit_regions(regs, uids=list(range(100, 111)), fit_fn=_fake_fit, n0=n0, distributed=False)
+    many = FR.fit_regions(regs, uids=list(range(100, 111)), fit_fn=counting, n0=n0, distributed=False, max_batch_regions=4)
+    assert calls == [4, 4, 3]
+    for a, b in zip(one, many):
+        assert a.uid == b.uid and a.n == b.n
+        np.testing.assert_array_equal(a.theta, b.theta)

@@ -43,6 +43,19 @@ def lpt_partition(costs, world_size):
 
 
 MIXED_POLISH_STARTS = 2048
+MAX_BATCH_REGIONS = 16384      # regions per device batch: ~1.2e6 chains, ~5 GB of chain state at the C4 settings
+
+
+def fit_chunked(fit_fn, regions_host, uids, n0, max_batch_regions=MAX_BATCH_REGIONS, **kw):
+    """A shard larger than ``max_batch_regions`` is fitted in consecutive device batches (bounded chain state in
+    HBM whatever the shard size - 10^5 regions on one GPU are seven batches); Philox streams are keyed by region
+    uid, so the batching does not change any result."""
+    R = len(regions_host)
+    step = max(1, int(max_batch_regions))
+    if R <= step:
+        return fit_fn(regions_host, uids, n0=n0, **kw)
+    out = [fit_fn(regions_host[a: a + step], uids[a: a + step], n0=n0[a: a + step], **kw) for a in range(0, R, step)]
+    return np.concatenate(out, axis=0)
 
 
 def default_polish_top(chains_per_restart):
@@ -186,6 +199,7 @@ def fit_local(regions_host, uids, voigt=False, sd_free=True, iterations=3000, bu
                              mb.std[m, g, :kept], None if mb.sd_mean is None else mb.sd_mean[m, g],
                              None if mb.sd_std is None else mb.sd_std[m, g], mb.lnL[m, g], chi2=mb.chi2[m, g],
                              cov_aw=cov_aw)
+    regs.close()                                  # the next device batch (fit_chunked) starts from free memory
     return out
 
 
@@ -235,14 +249,15 @@ def fit_regions(regions_host, uids=None, distributed=None, fit_fn=None, **kw):
         starts = R * window * G * (kw.get("polish_top") or default_polish_top(kw.get("chains_per_restart", 32)))
         kw["polish_dtype"] = "mixed" if (starts >= MIXED_POLISH_STARTS and kw.get("lsf") is None) else "f64"
     fit_fn = fit_fn or fit_local
+    chunk = kw.pop("max_batch_regions", MAX_BATCH_REGIONS)
     if not use_dist:
-        recs = fit_fn(regions_host, uids, n0=n0, cmax_rec=cmax_rec, **kw)
+        recs = fit_chunked(fit_fn, regions_host, uids, n0, chunk, cmax_rec=cmax_rec, **kw)
     else:
         world, rank = dist.get_world_size(), dist.get_rank()
         costs = [region_cost(len(regions_host[i][1]), n0[i], window, voigt) for i in range(R)]
         mine = lpt_partition(costs, world)[rank]
-        local = fit_fn([regions_host[i] for i in mine], [uids[i] for i in mine], n0=[n0[i] for i in mine],
-                       cmax_rec=cmax_rec, **kw)        # same record geometry on every rank
+        local = fit_chunked(fit_fn, [regions_host[i] for i in mine], [uids[i] for i in mine], [n0[i] for i in mine],
+                            chunk, cmax_rec=cmax_rec, **kw)        # same record geometry on every rank
         assert local.shape[1] == rec_len
         device = None
         if dist.get_backend() == "nccl":
