@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define VAMP_ABI_VERSION 2   /* 2: vamp_detect_*, VAMP_MIXED for vamp_map_dev */
+#define VAMP_ABI_VERSION 3   /* 2: vamp_detect_*, VAMP_MIXED for vamp_map_dev; 3: vamp_regions_set_multiplet */
 
 enum { VAMP_F32 = 0, VAMP_F64 = 1,            /* arithmetic of the pixel math */
        VAMP_MIXED = 2 };                       /* vamp_map_dev only: fp32 objective during the simplex search,
@@ -60,6 +60,19 @@ int vamp_regions_create(vamp_ctx* ctx, int R, const int* npix, const double* nu,
 int vamp_regions_destroy(vamp_regions* regions);
 int vamp_regions_info(const vamp_regions* regions, int* R, int* max_npix, long long* total_pix);
 int vamp_regions_scale(const vamp_regions* regions, double* nu0 /*[R]*/, double* scale /*[R]*/);
+
+/* Multiplets (doublets with tied v / b: BASELINE config C3 - CIV 1548/1550, MgII 2796/2803; the reference has
+ * only single lines, VPfit.VoigtFunction vpfits.py:58-76 once per component).  In region r every component
+ * (amplitude A, centroid c, L_fwhm, G_fwhm | sigma) carries a second line with
+ *     amplitude amp_ratio[r] A,  centroid freq_ratio[r] c,  G_fwhm freq_ratio[r] G_fwhm  (sigma likewise),
+ *     L_fwhm lorentz_ratio[r] L_fwhm
+ * i.e. for lines of rest frequencies nu_1, nu_2 at one velocity and one Doppler width: freq_ratio = nu_2 / nu_1,
+ * amp_ratio = (f_2 lambda_2)/(f_1 lambda_1), lorentz_ratio = Gamma_2 / Gamma_1 (NULL = 1).  The free parameters,
+ * their priors, BIC's k and every buffer layout are unchanged; K1 / K2 / K3 evaluate both lines.
+ * amp_ratio[r] = 0: region r keeps single lines.  HOST arrays [R]; NULL, NULL, NULL clears the table.
+ * Synchronises the context's stream. */
+int vamp_regions_set_multiplet(vamp_regions* regions, const double* freq_ratio, const double* amp_ratio,
+                               const double* lorentz_ratio);
 
 /* K1 - fused model + likelihood.  Replaces, per item:
  *   VPfit.VoigtFunction / GaussFunction (vpfits.py:44-76), total = Tau2flux(sum(profiles))

@@ -94,7 +94,7 @@ def _tune_factor(rate):
 
 
 def replay_chain(u, flux, noise, theta0, n, voigt, sd_free, uid, seed, iters, burn, thin, tune_interval,
-                 tune_throughout, cmax, lsf=None, record_every_step=False):
+                 tune_throughout, cmax, lsf=None, record_every_step=False, multiplet=None):
     """Run one chain exactly as ``mcmc_chain`` does.  ``u``: scaled pixel grid (0..P-1 for a
     uniform grid).  Returns dict(theta, trace, best_theta, best_logp, mean, m2, ntally, steps)."""
     NP = 4 if voigt else 3
@@ -114,7 +114,7 @@ def replay_chain(u, flux, noise, theta0, n, voigt, sd_free, uid, seed, iters, bu
 
     def S_of(theta):
         comps = theta[: 4 * n].reshape(n, 4)
-        m = D.model_flux(u, comps, voigt, lsf)
+        m = D.model_flux(u, comps, voigt, lsf, multiplet)      # multiplet in scaled units: (fr, ar, lr, shift)
         r = flux - m
         return float(np.sum((r * w) ** 2)) if not sd_free else float(np.sum(r * r))
 

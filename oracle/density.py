@@ -61,13 +61,32 @@ def tau2flux(tau):
     return np.exp(-tau)
 
 
-def component_taus(x, comps, voigt):
+def second_line(comp, voigt, multiplet):
+    """Tied second line of a component (doublets of BASELINE config C3; NOT IN THE REFERENCE, which
+    evaluates ``VoigtFunction`` once per component - parity-unpinned convention of this repo, stated in
+    include/vamp_b200.h ``vamp_regions_set_multiplet``): with ``multiplet = (freq_ratio, amp_ratio,
+    lorentz_ratio[, shift])`` the line has amplitude ``amp_ratio A``, centroid ``freq_ratio c + shift``
+    (``shift`` = 0 in Hz; non-zero only in the kernels' scaled coordinates), Gaussian width
+    ``freq_ratio G`` (sigma likewise) and Lorentzian width ``lorentz_ratio L``."""
+    fr, ar, lr = multiplet[0], multiplet[1], multiplet[2]
+    sh = multiplet[3] if len(multiplet) > 3 else 0.0
+    a, c, w1, w2 = comp
+    return (ar * a, fr * c + sh, lr * w1, fr * w2) if voigt else (ar * a, fr * c + sh, fr * w1, w2)
+
+
+def component_taus(x, comps, voigt, multiplet=None):
     """Per-component optical depths = the ``component_i`` deterministics
-    (vamp_1.0/vpfits.py:254-262, 299-307).  Returns ``[n, P]``."""
+    (vamp_1.0/vpfits.py:254-262, 299-307).  Returns ``[n, P]``.  ``multiplet``: every component is the
+    sum of its line and the tied :func:`second_line`, each evaluated by the reference's profile function."""
     comps = np.atleast_2d(np.asarray(comps, dtype=np.float64))
     out = np.empty((comps.shape[0], len(x)), dtype=np.float64)
     for k, (a, c, w1, w2) in enumerate(comps):
         out[k] = voigt_tau(x, c, a, w1, w2) if voigt else gauss_tau(x, a, c, w1)
+        if multiplet is not None and multiplet[1] != 0.0:
+            a2, c2, v1, v2 = second_line((a, c, w1, w2), voigt, multiplet)
+            with np.errstate(all="ignore"):
+                t2 = voigt_tau(x, c2, a2, v1, v2) if voigt else gauss_tau(x, a2, c2, v1)
+            out[k] += t2
     return out
 
 
@@ -92,10 +111,10 @@ def lsf_convolve(flux, lsf):
     return 1.0 + np.convolve(padded, lsf, "valid")
 
 
-def model_flux(x, comps, voigt, lsf=None):
+def model_flux(x, comps, voigt, lsf=None, multiplet=None):
     """The ``total`` deterministic: ``Tau2flux(sum(profile_sum))`` -
-    vamp_1.0/vpfits.py:334-338 (+ this repo's LSF)."""
-    taus = component_taus(x, comps, voigt)
+    vamp_1.0/vpfits.py:334-338 (+ this repo's LSF and multiplets)."""
+    taus = component_taus(x, comps, voigt, multiplet)
     return lsf_convolve(tau2flux(taus.sum(axis=0)), lsf)
 
 
@@ -175,13 +194,13 @@ def log_prior(comps, x, voigt, sd=None):
     return float(lp)
 
 
-def log_posterior(comps, x, flux, voigt, sd=None, noise=None, lsf=None):
+def log_posterior(comps, x, flux, voigt, sd=None, noise=None, lsf=None, multiplet=None):
     """``model.logp`` = priors + observed Normal (what MCMC and MAP see)."""
     lp = log_prior(comps, x, voigt, sd=sd)
     if not np.isfinite(lp):
         return -np.inf
     with np.errstate(all="ignore"):
-        ll = normal_loglike(flux, model_flux(x, comps, voigt, lsf), sd=sd, noise=noise)
+        ll = normal_loglike(flux, model_flux(x, comps, voigt, lsf, multiplet), sd=sd, noise=noise)
     return lp + ll if np.isfinite(ll) else -np.inf
 
 

@@ -14,6 +14,8 @@ Outputs (committed, small):
 * ``tests/golden/physics.npz``    - outputs of every ``physics.py`` function.
 * ``tests/golden/wofz_mp.npz``    - w(z) from mpmath at 40 digits (independent of
   scipy) on a z-plane sample covering every branch of the device Faddeeva.
+* ``tests/golden/doublet.npz``    - doublet regions (tied second line per component): sums of the reference's
+  own profile-function calls, one per line.
 * ``tests/golden/simba.npz``      - the two simba fixtures' regions (pixel bounds
   from simba_spec_demo.ipynb) with the reference
   ``VPregion.estimate_n`` / ``set_freedom`` results.
@@ -219,9 +221,49 @@ def make_detect(ref):
     return {n: [out["%s/s%d/region_pixels" % (n, j)].tolist() for j in range(len(settings))] for n in out["names"]}
 
 
+def make_doublets(ref):
+    """Doublet regions (BASELINE config C3; a tied second line per component - this repo's extension): the optical
+    depths are sums of the REFERENCE'S OWN ``VoigtFunction`` / ``GaussFunction`` calls (vpfits.py:44-76), one per
+    line, with the second line's arguments formed as include/vamp_b200.h ``vamp_regions_set_multiplet`` states."""
+    out, names = {}, []
+    lsf = synth.gaussian_lsf(2.0, 7)
+    cases = [("civ_voigt_n2", synth.make_doublet_region(256, 2, 50.0, 501, "CIV", True)),
+             ("civ_voigt_n3_lsf", synth.make_doublet_region(256, 3, 80.0, 502, "CIV", True, lsf=lsf)),
+             ("mgii_voigt_n1", synth.make_doublet_region(250, 1, 30.0, 503, "MgII", True)),
+             ("civ_gauss_n2", synth.make_doublet_region(200, 2, 50.0, 504, "CIV", False)),
+             ("mgii_gauss_n2_lsf", synth.make_doublet_region(256, 2, 40.0, 505, "MgII", False, lsf=lsf))]
+    rng = np.random.default_rng(77)
+    for name, reg in cases:
+        voigt, (fr, ar, lr) = reg["voigt"], reg["multiplet"]
+        comps = reg["truth"] * (1.0 + rng.uniform(-0.03, 0.03, reg["truth"].shape))
+        comps[:, 1] = reg["truth"][:, 1] + rng.uniform(-1, 1, len(comps)) * reg["dnu"]
+        nu = reg["nu"]
+        taus = []
+        for a, c, w1, w2 in comps:
+            if voigt:
+                t = ref.VPfit.VoigtFunction(nu, c, a, w1, w2) + ref.VPfit.VoigtFunction(nu, fr * c, ar * a, lr * w1, fr * w2)
+            else:
+                t = ref.VPfit.GaussFunction(nu, a, c, w1) + ref.VPfit.GaussFunction(nu, ar * a, fr * c, fr * w1)
+            taus.append(t)
+        total = ref.physics.Tau2flux(sum(taus))
+        names.append(name)
+        for k, v in (("nu", nu), ("flux", reg["flux"]), ("noise", reg["noise"]), ("voigt", np.array(voigt)),
+                     ("comps", comps), ("multiplet", np.array([fr, ar, lr])), ("taus", np.array(taus)), ("total", total),
+                     ("lsf", lsf if name.endswith("lsf") else np.array([1.0])),
+                     ("chi2", np.array(float(ref.VPfit.Chisquared(reg["flux"], total, reg["noise"]))))):
+            out[name + "/" + k] = v
+    out["names"] = np.array(names)
+    np.savez_compressed(os.path.join(OUT, "doublet.npz"), **out)
+    return len(names)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = LR.load()
+    if "--doublets-only" in __import__("sys").argv:
+        print("wrote %d doublet cases" % make_doublets(ref))
+        return
+    make_doublets(ref)
     n = make_profiles(ref)
     make_physics(ref)
     make_wofz_mp()

@@ -144,3 +144,29 @@ def test_region_ladder_rule():
     table[2] = ([-50, -52, -54], [1, 1, 1])
     kept, n_exit, _ = OR.region_fit_ladder(1, lambda n: table[n], chi_limit=1.5)
     assert kept == 2 and n_exit == 2
+
+
+def test_doublets_match_reference_lines():
+    """Doublet regions (a tied second line per component, BASELINE config C3): the oracle's ``multiplet`` form
+    equals the sum of the reference's own profile-function calls, one per line (tests/golden/doublet.npz)."""
+    g = np.load(os.path.join(GOLDEN, "doublet.npz"))
+    for name in _cases(g):
+        nu, comps, voigt = g[name + "/nu"], g[name + "/comps"], bool(g[name + "/voigt"])
+        mult = tuple(g[name + "/multiplet"])
+        taus = D.component_taus(nu, comps, voigt, multiplet=mult)
+        np.testing.assert_allclose(taus, g[name + "/taus"], rtol=1e-13, atol=1e-300, err_msg=name)
+        total = D.model_flux(nu, comps, voigt, multiplet=mult)
+        np.testing.assert_allclose(total, g[name + "/total"], rtol=1e-13, atol=1e-300, err_msg=name)
+        assert D.chisquared(g[name + "/flux"], total, g[name + "/noise"]) == pytest.approx(float(g[name + "/chi2"]), rel=1e-12)
+        # a zero amplitude ratio is the single-line model
+        np.testing.assert_array_equal(D.component_taus(nu, comps, voigt, multiplet=(mult[0], 0.0, mult[2])),
+                                      D.component_taus(nu, comps, voigt))
+        # the second line really is there: a doublet differs from its first line alone
+        assert np.max(np.abs(taus - D.component_taus(nu, comps, voigt))) > 1e-2
+
+
+def test_doublet_ratios():
+    fr, ar, lr = P.doublet_ratios("CIV")
+    assert fr == pytest.approx(1548.204 / 1550.781) and ar == pytest.approx(0.09475 * 1550.781 / (0.1899 * 1548.204))
+    assert lr == pytest.approx(2.628 / 2.643)
+    assert P.doublet_ratios((1000.0, 0.2, 1e8), (1010.0, 0.1, 2e8)) == pytest.approx((1000.0 / 1010.0, 0.505, 2.0))

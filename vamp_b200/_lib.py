@@ -56,6 +56,7 @@ SIGNATURES = {
     "vamp_regions_destroy": (C.c_int, [C.c_void_p]),
     "vamp_regions_info": (C.c_int, [C.c_void_p, c_int_p, c_int_p, C.POINTER(C.c_longlong)]),
     "vamp_regions_scale": (C.c_int, [C.c_void_p, c_dbl_p, c_dbl_p]),
+    "vamp_regions_set_multiplet": (C.c_int, [C.c_void_p, c_dbl_p, c_dbl_p, c_dbl_p]),
     "vamp_detect_dev": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_int, C.c_int, C.c_void_p]),
     "vamp_detect_host": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_int_p, c_dbl_p, c_dbl_p, c_dbl_p, C.c_int, C.c_int, c_dbl_p]),
@@ -96,7 +97,7 @@ def load():
         fn = getattr(lib, name)      # AttributeError if the symbol is missing
         fn.restype = res
         fn.argtypes = args
-    if lib.vamp_abi_version() != 2:
+    if lib.vamp_abi_version() != 3:
         raise VampError("libvamp_b200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -1,7 +1,7 @@
 """Build libvamp_b200.so in-tree with nvcc for sm_100a (no torch dependency in the library).
 
 Each kernel file is compiled once per (precision, profile kind) so the objects build in
-parallel; `python -m vamp_b200.build` or `__graft_entry__.build()` runs this.
+parallel (the sampler once more for its multiplet instantiations); `python -m vamp_b200.build` or `__graft_entry__.build()` runs this.
 """
 import hashlib
 import os
@@ -45,6 +45,8 @@ def _jobs():
                 obj = os.path.join(OBJ, "%s_%s_%s.o" % (base, "f64" if f64 else "f32", "voigt" if voigt else "gauss"))
                 defs = ["-DVAMP_INST_F64=%d" % f64, "-DVAMP_INST_VOIGT=%d" % voigt]
                 jobs.append((src, obj, defs, hdr))
+                if base == "vamp_k2":       # the sampler's multiplet instantiations (two tied lines per component)
+                    jobs.append((src, obj[:-2] + "_mult.o", defs + ["-DVAMP_INST_MULT=1"], hdr))
     jobs.append((os.path.join(CSRC, "vamp_k4.cu"), os.path.join(OBJ, "vamp_k4.o"), [], hdr))
     jobs.append((os.path.join(CSRC, "vamp_cabi.cu"), os.path.join(OBJ, "vamp_cabi.o"), [], hdr))
     return jobs

@@ -68,6 +68,7 @@ struct vamp_regions {
     std::vector<int> npix, pix_off, tile_off;
     std::vector<double> nu0, scale;
     void* blob = nullptr;      // one device allocation for everything
+    void* mult = nullptr;      // [R][4] multiplet table (vamp_regions_set_multiplet) or nullptr
     RegionSetDev dev{};
 };
 
@@ -393,7 +394,42 @@ int vamp_regions_destroy(vamp_regions* rg) {
     if (!rg) return 0;
     cudaSetDevice(rg->ctx->device);
     if (rg->blob) cudaFree(rg->blob);
+    if (rg->mult) cudaFree(rg->mult);
     delete rg;
+    return 0;
+}
+
+int vamp_regions_set_multiplet(vamp_regions* rg, const double* freq_ratio, const double* amp_ratio, const double* lorentz_ratio) {
+    if (!rg) return fail(-1, "null regions");
+    VAMP_CUDA(cudaSetDevice(rg->ctx->device));
+    VAMP_CUDA(cudaStreamSynchronize(rg->ctx->stream));       // kernels in flight may still read the old table
+    if (rg->mult) cudaFree(rg->mult);
+    rg->mult = nullptr;
+    rg->dev.mult = nullptr;
+    if (!freq_ratio && !amp_ratio) return 0;                  // cleared: single lines everywhere
+    if (!freq_ratio || !amp_ratio) return fail(-1, "freq_ratio and amp_ratio must be given together");
+    std::vector<double> t(4 * (size_t)rg->R);
+    bool any = false;
+    for (int r = 0; r < rg->R; ++r) {
+        const double fr = freq_ratio[r], ar = amp_ratio[r], lr = lorentz_ratio ? lorentz_ratio[r] : 1.0;
+        if (!(fr > 0.0) || !(ar >= 0.0) || !(lr >= 0.0) || fr != fr || ar != ar || lr != lr || fr > 1e300 || ar > 1e300 || lr > 1e300)
+            return fail(-2, "region %d: multiplet ratios must be finite, freq_ratio > 0, amp_ratio >= 0, lorentz_ratio >= 0", r);
+        // centroid of line 2 in Hz is fr * c; in the region's scaled units u = (nu - nu0)/s that is fr * u + nu0 (fr - 1)/s
+        t[4 * r + 0] = fr;
+        t[4 * r + 1] = rg->nu0[r] * (fr - 1.0) / rg->scale[r];
+        t[4 * r + 2] = ar;
+        t[4 * r + 3] = lr;
+        any = any || ar != 0.0;
+    }
+    if (!any) return 0;
+    VAMP_CUDA(cudaMalloc(&rg->mult, sizeof(double) * t.size()));
+    cudaError_t e = cudaMemcpy(rg->mult, t.data(), sizeof(double) * t.size(), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        cudaFree(rg->mult);
+        rg->mult = nullptr;
+        return fail(-100, "H2D: %s", cudaGetErrorString(e));
+    }
+    rg->dev.mult = static_cast<const double*>(rg->mult);
     return 0;
 }
 
@@ -516,7 +552,8 @@ int vamp_mcmc_run_dev(vamp_ctx* ctx, const vamp_regions* rg, int dtype, int kind
     if (a->it1 < a->it0 || a->it0 < 0) return fail(-2, "bad iteration range [%d, %d)", a->it0, a->it1);
     VAMP_CUDA(cudaSetDevice(ctx->device));
     const McmcDev p = to_dev(rg, a);
-    VAMP_CUDA(VAMP_DISPATCH4(vamp_launch_k2, dtype, kind, p, rg->max_npix, a->max_ncomp, ctx->stream));
+    if (rg->dev.mult) VAMP_CUDA(VAMP_DISPATCH4(vamp_launch_k2m, dtype, kind, p, rg->max_npix, a->max_ncomp, ctx->stream));
+    else VAMP_CUDA(VAMP_DISPATCH4(vamp_launch_k2, dtype, kind, p, rg->max_npix, a->max_ncomp, ctx->stream));
     return 0;
 }
 

@@ -52,7 +52,50 @@ struct RegionSetDev {
     const float* lsf32;     // [taps] or nullptr
     const double* lsf64;
     int lsf_taps;           // odd, 0/1 = identity
+    // Multiplets (vamp_regions_set_multiplet): every component of region r carries a SECOND line with tied
+    // parameters - in scaled units  amplitude ar A, centroid fr c + sh, Gaussian width fr G (sigma fr s),
+    // Lorentzian width lr L.  [R][4] = (fr, sh, ar, lr); ar = 0: the region has single lines; nullptr: none has.
+    const double* mult;
 };
+
+struct MultD { double fr, sh, ar, lr; };
+// The region's multiplet descriptor; false when its components are single lines.
+__device__ __forceinline__ bool region_mult(const RegionSetDev& rs, int r, MultD& m) {
+    if (!rs.mult) return false;
+    m.fr = rs.mult[4 * r + 0];
+    m.sh = rs.mult[4 * r + 1];
+    m.ar = rs.mult[4 * r + 2];
+    m.lr = rs.mult[4 * r + 3];
+    return m.ar != 0.0;
+}
+// The same from the table row (nullptr: single lines) - for callers that must not keep the descriptor live.
+__device__ __forceinline__ const double* region_mult_row(const RegionSetDev& rs, int r) {
+    if (!rs.mult) return nullptr;
+    const double* row = rs.mult + 4 * r;
+    return (row[2] != 0.0) ? row : nullptr;
+}
+// Parameters of line l of an item with n components (l < n: the component itself; n <= l < 2n: the second
+// line of component l - n), read from the flat layout theta[4c + i].  K1 / K3 loop over LINES, so a
+// multiplet costs them nothing but the longer loop; K2 keeps the sum of both lines in a component's cache slot.
+template <int KIND>
+__device__ __forceinline__ void line_params(const double* th, int l, int n, const MultD& m, double& a, double& ce,
+                                            double& w1, double& w2) {
+    const int c = (l < n) ? l : l - n;
+    a = th[4 * c + 0];
+    ce = th[4 * c + 1];
+    w1 = th[4 * c + 2];
+    w2 = th[4 * c + 3];
+    if (l >= n) {
+        a *= m.ar;
+        ce = m.fr * ce + m.sh;
+        if (KIND == VAMP_KIND_VOIGT) {
+            w1 *= m.lr;
+            w2 *= m.fr;
+        } else {
+            w1 *= m.fr;
+        }
+    }
+}
 
 template <typename T> struct RS;
 template <> struct RS<float> {
@@ -699,16 +742,25 @@ constexpr int InstKind = VAMP_INST_VOIGT ? VAMP_KIND_VOIGT : VAMP_KIND_GAUSS;
 // Rows are processed two at a time in the packed two-row form (pair_classify / pair_eval: one
 // FFMA2 per step for both rows, path chosen per 64-pixel pair); a single-row tile (<= 32 px)
 // takes the scalar form.
-template <typename T, int KIND, int PPL>
+// MULT (a separate kernel instantiation, launched for region sets with a multiplet table - the single-line
+// kernel keeps its registers): md != nullptr marks a multiplet region.
+template <typename T, int KIND, int PPL, bool MULT = false>
 __device__ __forceinline__ void eval_model(const LaneTile<T, PPL>& t, const double* __restrict__ theta, int ncomp,
-                                           double ubase, T (&m)[PPL], T* lsf_buf, const T* lsf_s, int taps, int lane) {
+                                           double ubase, T (&m)[PPL], T* lsf_buf, const T* lsf_s, int taps, int lane,
+                                           const MultD* md = nullptr) {
+    // lines to evaluate: the components, then (multiplet regions) their second lines
+    const int nlines = (MULT && md) ? 2 * ncomp : ncomp;
+    MultD mz;
+    mz.fr = mz.sh = mz.ar = mz.lr = 0.0;
+    const MultD& mm = (MULT && md) ? *md : mz;
     if (PPL == 1) {
         T tau[PPL];
 #pragma unroll
         for (int j = 0; j < PPL; ++j) tau[j] = T(0);
-        for (int c = 0; c < ncomp; ++c) {
-            const CompC<T> cc = make_comp<T, KIND>(theta[VAMP_TH(c, 0)], theta[VAMP_TH(c, 1)], theta[VAMP_TH(c, 2)],
-                                                   theta[VAMP_TH(c, 3)], ubase);
+        for (int c = 0; c < nlines; ++c) {
+            double pa, pce, pw1, pw2;
+            line_params<KIND>(theta, c, ncomp, mm, pa, pce, pw1, pw2);
+            const CompC<T> cc = make_comp<T, KIND>(pa, pce, pw1, pw2, ubase);
             T H[PPL];
             comp_shape<T, KIND, PPL>(cc, t.du, H);
 #pragma unroll
@@ -722,17 +774,17 @@ __device__ __forceinline__ void eval_model(const LaneTile<T, PPL>& t, const doub
 #pragma unroll
         for (int jj = 0; jj < NPR; ++jj) tau2[jj] = p2_bc<T>(T(0));
         unsigned nfar = 0u;
-        for (int c0 = 0; c0 < ncomp; c0 += 32) {
-            // lane l forms the constants of component c0 + l (the float64 divisions run once per component, in
-            // parallel, instead of ncomp times per lane) and they are handed out with shuffles
+        for (int c0 = 0; c0 < nlines; c0 += 32) {
+            // lane l forms the constants of line c0 + l (the float64 divisions run once per line, in
+            // parallel, instead of nlines times per lane) and they are handed out with shuffles
             CompC<T> mine;
             mine.A = mine.cb = mine.g = mine.y = mine.y2 = mine.L2 = T(0);
-            if (c0 + lane < ncomp) {
-                const int c = c0 + lane;
-                mine = make_comp_k1<T, KIND>(theta[VAMP_TH(c, 0)], theta[VAMP_TH(c, 1)], theta[VAMP_TH(c, 2)],
-                                             theta[VAMP_TH(c, 3)], ubase);
+            if (c0 + lane < nlines) {
+                double pa, pce, pw1, pw2;
+                line_params<KIND>(theta, c0 + lane, ncomp, mm, pa, pce, pw1, pw2);
+                mine = make_comp_k1<T, KIND>(pa, pce, pw1, pw2, ubase);
             }
-            const int cend = (ncomp - c0 < 32) ? ncomp - c0 : 32;
+            const int cend = (nlines - c0 < 32) ? nlines - c0 : 32;
             for (int l = 0; l < cend; ++l) {
             CompC<T> cc;
             cc.A = __shfl_sync(VAMP_FULL_MASK, mine.A, l);

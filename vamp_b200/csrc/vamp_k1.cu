@@ -21,7 +21,7 @@ namespace {
 constexpr int K1_WARPS = 8;
 constexpr int K1_CHUNK = 2048;   // pixels per CTA in k1_cta
 
-template <typename T, int KIND, int PPL>
+template <typename T, int KIND, int PPL, bool MULT>
 __device__ __forceinline__ void k1_warp_run(const RegionSetDev& rs, int item, int r, int P, int ncomp,
                                             const double* __restrict__ th, const double* __restrict__ sd,
                                             double* __restrict__ out_lnL, double* __restrict__ out_chi2,
@@ -32,7 +32,9 @@ __device__ __forceinline__ void k1_warp_run(const RegionSetDev& rs, int item, in
     load_tile<T, PPL>(t, rs, off, P, lane);
     const double ubase = rs.ubase[rs.tile_off[r]];
     T m[PPL];
-    eval_model<T, KIND, PPL>(t, th, ncomp, ubase, m, lsf_buf, lsf_s, rs.lsf_taps, lane);
+    MultD md;
+    const bool mult = MULT && region_mult(rs, r, md);
+    eval_model<T, KIND, PPL, MULT>(t, th, ncomp, ubase, m, lsf_buf, lsf_s, rs.lsf_taps, lane, mult ? &md : nullptr);
     if (out_flux) {
 #pragma unroll
         for (int j = 0; j < PPL; ++j)
@@ -48,7 +50,7 @@ __device__ __forceinline__ void k1_warp_run(const RegionSetDev& rs, int item, in
     }
 }
 
-template <typename T, int KIND>
+template <typename T, int KIND, bool MULT>
 __global__ void __launch_bounds__(K1_WARPS * 32)
 k1_warp_kernel(RegionSetDev rs, int B, const int* __restrict__ item_region, const int* __restrict__ item_ncomp,
                const double* __restrict__ theta, int tstride, const double* __restrict__ sd,
@@ -73,7 +75,7 @@ k1_warp_kernel(RegionSetDev rs, int B, const int* __restrict__ item_region, cons
     const double* th = theta + (size_t)item * tstride;
     const int ppl = (P + 31) >> 5;
 #define VAMP_K1_RUN(PPL_)                                                                                     \
-    k1_warp_run<T, KIND, PPL_>(rs, item, r, P, ncomp, th, sd, out_lnL, out_chi2, out_flux, fstride, \
+    k1_warp_run<T, KIND, PPL_, MULT>(rs, item, r, P, ncomp, th, sd, out_lnL, out_chi2, out_flux, fstride, \
                                           lsf_buf, lsf_s, lane)
     if (ppl <= 1) VAMP_K1_RUN(1);
     else if (ppl <= 2) VAMP_K1_RUN(2);
@@ -103,7 +105,7 @@ k1_cta_kernel(RegionSetDev rs, int B, int nchunk_max, const int* __restrict__ it
     if (P <= VAMP_TILE_PIX) return;        // k1_warp's job
     const int g0 = chunk * K1_CHUNK;
     if (g0 >= P) return;
-    const int ncomp = item_ncomp[item];
+    const int ncomp0 = item_ncomp[item];
     const double* th = theta + (size_t)item * tstride;
     const bool LSF = rs.lsf_taps > 1;
     const bool FLUX = out_flux != nullptr;
@@ -115,24 +117,33 @@ k1_cta_kernel(RegionSetDev rs, int B, int nchunk_max, const int* __restrict__ it
     double* red = reinterpret_cast<double*>(smem_raw);                  // [16]
     T* lsf_s = reinterpret_cast<T*>(red + 16);                          // [MAX_TAPS]
     T* mbuf = lsf_s + VAMP_MAX_LSF_TAPS;                                // [CHUNK + MAX_TAPS]
-    CompS<T>* cs = reinterpret_cast<CompS<T>*>(mbuf + K1_CHUNK + VAMP_MAX_LSF_TAPS + 1);  // [ncomp]
-    T* cb = reinterpret_cast<T*>(cs + ncomp);                           // [ROWS][ncomp]
+    // lines to evaluate: the components, then (multiplet regions) their second lines; from here on `ncomp`
+    // counts lines
+    MultD md;
+    md.fr = md.sh = md.ar = md.lr = 0.0;
+    const int nlines = region_mult(rs, r, md) ? 2 * ncomp0 : ncomp0;
+    const int ncomp = nlines;
+    CompS<T>* cs = reinterpret_cast<CompS<T>*>(mbuf + K1_CHUNK + VAMP_MAX_LSF_TAPS + 1);  // [nlines]
+    T* cb = reinterpret_cast<T*>(cs + nlines);                          // [ROWS][nlines]
 
     const int off = rs.pix_off[r];
     const int tile0 = rs.tile_off[r] + chunk * PPL;
     const int ntile = (P + VAMP_TILE_PIX - 1) / VAMP_TILE_PIX;
     for (int i = tid; i < taps; i += 256) lsf_s[i] = RS<T>::lsf(rs)[i];
-    for (int c = tid; c < ncomp; c += 256) {
-        const CompC<T> cc = make_comp_k1<T, KIND>(th[VAMP_TH(c, 0)], th[VAMP_TH(c, 1)], th[VAMP_TH(c, 2)],
-                                                  th[VAMP_TH(c, 3)], 0.0);
+    for (int c = tid; c < nlines; c += 256) {
+        double pa, pce, pw1, pw2;
+        line_params<KIND>(th, c, ncomp0, md, pa, pce, pw1, pw2);
+        const CompC<T> cc = make_comp_k1<T, KIND>(pa, pce, pw1, pw2, 0.0);
         cs[c].A = cc.A; cs[c].g = cc.g; cs[c].y = cc.y; cs[c].y2 = cc.y2; cs[c].L2 = cc.L2;
     }
-    for (int i = tid; i < ROWS * ncomp; i += 256) {
-        const int row = i / ncomp, c = i - row * ncomp;
+    for (int i = tid; i < ROWS * nlines; i += 256) {
+        const int row = i / nlines, c = i - row * nlines;
         // rows 0..7: tiles of this chunk; row 8: tile left of the chunk; row 9: tile right of it
         int tl = (row < PPL) ? chunk * PPL + row : (row == PPL ? chunk * PPL - 1 : chunk * PPL + PPL);
         tl = min(max(tl, 0), ntile - 1);
-        cb[i] = T(th[VAMP_TH(c, 1)] - rs.ubase[rs.tile_off[r] + tl]);
+        double pa, pce, pw1, pw2;
+        line_params<KIND>(th, c, ncomp0, md, pa, pce, pw1, pw2);
+        cb[i] = T(pce - rs.ubase[rs.tile_off[r] + tl]);
     }
     __syncthreads();
     (void)tile0;
@@ -261,13 +272,18 @@ cudaError_t launch_k1_t(const RegionSetDev& rs, int B, int max_npix, int max_nco
     {   // small regions
         const size_t smem = sizeof(T) * (VAMP_MAX_LSF_TAPS + K1_WARPS * (VAMP_TILE_PIX + VAMP_MAX_LSF_TAPS));
         const int grid = (B + K1_WARPS - 1) / K1_WARPS;
-        k1_warp_kernel<T, KIND><<<grid, K1_WARPS * 32, LSF ? smem : 0, st>>>(
-            rs, B, item_region, item_ncomp, theta, tstride, sd, out_lnL, out_chi2, (T*)out_flux, fstride);
+        if (rs.mult)      // region set with a multiplet table: the two-lines-per-component instantiation
+            k1_warp_kernel<T, KIND, true><<<grid, K1_WARPS * 32, LSF ? smem : 0, st>>>(
+                rs, B, item_region, item_ncomp, theta, tstride, sd, out_lnL, out_chi2, (T*)out_flux, fstride);
+        else
+            k1_warp_kernel<T, KIND, false><<<grid, K1_WARPS * 32, LSF ? smem : 0, st>>>(
+                rs, B, item_region, item_ncomp, theta, tstride, sd, out_lnL, out_chi2, (T*)out_flux, fstride);
     }
     if (max_npix > VAMP_TILE_PIX) {
         const int nchunk_max = (max_npix + K1_CHUNK - 1) / K1_CHUNK;
+        const size_t nl_max = (size_t)max_ncomp * (rs.mult ? 2 : 1);          // multiplet regions: two lines per component
         const size_t smem = 16 * sizeof(double) + sizeof(T) * (VAMP_MAX_LSF_TAPS + K1_CHUNK + VAMP_MAX_LSF_TAPS + 1) +
-                            sizeof(CompS<T>) * max_ncomp + sizeof(T) * (K1_CHUNK / 256 + 2) * max_ncomp + 16;
+                            sizeof(CompS<T>) * nl_max + sizeof(T) * (K1_CHUNK / 256 + 2) * nl_max + 16;
         auto kern = k1_cta_kernel<T, KIND>;
         if (smem > 48 * 1024) {
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

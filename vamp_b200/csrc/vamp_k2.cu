@@ -27,6 +27,9 @@
 namespace {
 
 constexpr int K2_WARPS = 4;
+#ifndef VAMP_INST_MULT
+#define VAMP_INST_MULT 0          // 1: this object holds the multiplet (two tied lines per component) instantiations
+#endif
 #ifndef VAMP_K2_MINBLOCKS
 #define VAMP_K2_MINBLOCKS 5
 #endif
@@ -231,16 +234,23 @@ __device__ __forceinline__ void sm_st4(unsigned a, unsigned x, unsigned y, unsig
 // pixels (mcmc_chain).  ar / aw: shared addresses of this lane's element 0 in the region slice and in
 // the chain slice.  `nfar` counts pixels that took the continued-fraction path (padding included; the
 // caller corrects with `last_far`).
-template <typename T, int KIND, bool WT, bool LSF, bool FRESH>
+// MULT (multiplet regions, vamp_regions_set_multiplet): the component's shape is the sum of its two tied lines,
+// H(u; c, g, y) + ar H(u; fr c + dsh, g / fr, y lr / fr) - a second evaluation per fresh quad, everything
+// else (cache slots, base, accept) unchanged.  `last_far` then counts the lines of the last quad that took
+// the continued fraction (0..2).
+template <typename T>
+struct Mult2 { T fr, dsh, ar, ginv, yfac; };
+
+template <typename T, int KIND, bool WT, bool LSF, bool FRESH, bool MULT = false>
 __device__ __forceinline__ T chain_pass(const CompC<T>& cc, T An, unsigned ahc, unsigned ahs, unsigned ar, unsigned aw,
                                         const unsigned char* rb, int npairs, int lane, const LsfCtx<T>& lc, unsigned& nfar,
-                                        bool& last_far) {
+                                        unsigned& last_far, const Mult2<T>* ml = nullptr) {
     typedef K2Lay<T, WT> Lay;
     constexpr int SZ = (int)sizeof(P2<T>);
     constexpr int ROW = 32 * SZ;                       // bytes between the two pairs of a quad
     const P2<T> A2 = p2_bc<T>(An);
     P2<T> S2 = p2_bc<T>(T(0)), S2b = p2_bc<T>(T(0));
-    bool far = false;
+    bool far = false, farb = false;
     const unsigned end = ar + (unsigned)(npairs * ROW);
 #pragma unroll 1
     for (; ar < end; ar += 2 * ROW, aw += 2 * ROW, ahc += 2 * ROW, ahs += 2 * ROW) {
@@ -267,6 +277,35 @@ __device__ __forceinline__ T chain_pass(const CompC<T>& cc, T An, unsigned ahc, 
                     H1 = fad_core2<T>(X1, cc.y, S1);
                 }
             }
+            if (MULT) {
+                // the second line of the component, same two forms
+                const T cbb = Real<T>::fma_(ml->fr, cc.cb, ml->dsh), gb = cc.g * ml->ginv, yb = cc.y * ml->yfac;
+                const P2<T> cbb2 = p2_bc<T>(cbb), gb2 = p2_bc<T>(gb);
+                const P2<T> X0b = p2_mul(p2_sub(SM<T>::template ld<Lay::DU>(ar), cbb2), gb2);
+                const P2<T> X1b = p2_mul(p2_sub(SM<T>::template ld<Lay::DU + ROW>(ar), cbb2), gb2);
+                P2<T> H0b, H1b;
+                if (KIND == VAMP_KIND_GAUSS) {
+                    const P2<T> Q0 = p2_mul(X0b, X0b), Q1 = p2_mul(X1b, X1b);
+                    H0b = p2_make(Real<T>::exp2_neg(p2_lo(Q0)), Real<T>::exp2_neg(p2_hi(Q0)));
+                    H1b = p2_make(Real<T>::exp2_neg(p2_lo(Q1)), Real<T>::exp2_neg(p2_hi(Q1)));
+                } else {
+                    const P2<T> y22 = p2_bc<T>(yb * yb);
+                    const P2<T> S0 = p2_fma(X0b, X0b, y22), S1 = p2_fma(X1b, X1b, y22);
+                    const T smin = fmin(fmin(p2_lo(S0), p2_hi(S0)), fmin(p2_lo(S1), p2_hi(S1)));
+                    farb = __all_sync(VAMP_FULL_MASK, !(smin < Fad<T>::R2()));
+                    if (farb) {
+                        nfar += 128u;
+                        H0b = fad_far2<T>(X0b, yb, S0);
+                        H1b = fad_far2<T>(X1b, yb, S1);
+                    } else {
+                        H0b = fad_core2<T>(X0b, yb, S0);
+                        H1b = fad_core2<T>(X1b, yb, S1);
+                    }
+                }
+                const P2<T> ar2 = p2_bc<T>(ml->ar);
+                H0 = p2_fma(ar2, H0b, H0);
+                H1 = p2_fma(ar2, H1b, H1);
+            }
             SM<T>::template st<0>(ahs, H0);
             SM<T>::template st<ROW>(ahs, H1);
         } else {
@@ -292,7 +331,7 @@ __device__ __forceinline__ T chain_pass(const CompC<T>& cc, T An, unsigned ahc, 
         }
     }
     S2 = p2_add(S2, S2b);
-    last_far = far;
+    last_far = (far ? 1u : 0u) + ((MULT && farb) ? 1u : 0u);
     T S = p2_lo(S2) + p2_hi(S2);
     if (LSF) S = lsf_residuals<T, WT>(lc, rb, npairs, lane);
     return warp_sum(S);
@@ -309,7 +348,7 @@ __device__ __forceinline__ T chain_pass(const CompC<T>& cc, T An, unsigned ahc, 
 // vector load at the start, one read-modify-write at the end of the component), rejections are
 // derived (every parameter is proposed exactly once per iteration) and the post-burn acceptance
 // total is settled at tune / burn / exit events.
-template <typename T, int KIND, bool WT, bool LSF>
+template <typename T, int KIND, bool WT, bool LSF, bool MULT>
 __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, const unsigned char* rb, unsigned char* wb, int ncomp_max,
                            const T* lsf_s) {
     typedef K2Lay<T, WT> Lay;
@@ -380,6 +419,21 @@ __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, const unsigned
     const double ubase = rs.ubase[rs.tile_off[r]];
     const T ub_hi = T(ubase), ub_lo = T(ubase - (double)ub_hi);
     auto cbase = [&](T c) -> T { return (c - ub_hi) - ub_lo; };
+    // multiplet descriptor of the region, relative to the tile base: cb2 = fr cb + [(fr - 1) ubase + sh]
+    Mult2<T> ml;
+    ml.fr = T(1);
+    ml.dsh = ml.ar = T(0);
+    ml.ginv = ml.yfac = T(1);
+    if (MULT) {
+        MultD md;
+        if (region_mult(rs, r, md)) {
+            ml.fr = T(md.fr);
+            ml.dsh = T((md.fr - 1.0) * ubase + md.sh);
+            ml.ar = T(md.ar);
+            ml.ginv = T(1.0 / md.fr);
+            ml.yfac = T(md.lr / md.fr);
+        }
+    }
 
     // ---- build the shape cache; base holds the FULL tau here, one cached pass with A = 0 gives S
     {
@@ -391,8 +445,14 @@ __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, const unsigned
             rc.y = (float)cc.y;
             const P2<T> A2 = p2_bc<T>(NK * cc.A);
             bool far;
+            CompC<T> cb_ = cc;                   // second line (MULT)
+            cb_.cb = Real<T>::fma_(ml.fr, cc.cb, ml.dsh);
+            cb_.g = cc.g * ml.ginv;
+            cb_.y = cc.y * ml.yfac;
+            cb_.y2 = cb_.y * cb_.y;
             for (int e = 0; e < 32 * npairs; e += 32) {
-                const P2<T> H = pair_shape<T, KIND>(cc, sd_[e], far);
+                P2<T> H = pair_shape<T, KIND>(cc, sd_[e], far);
+                if (MULT) H = p2_fma(p2_bc<T>(ml.ar), pair_shape<T, KIND>(cb_, sd_[e], far), H);
                 Hbuf[c * Lay::NE + e] = H;
                 pbase[e] = p2_fma(A2, H, pbase[e]);
             }
@@ -401,7 +461,7 @@ __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, const unsigned
     CompC<T> cz;
     cz.A = cz.cb = cz.g = cz.y = cz.y2 = cz.L2 = T(0);
     unsigned dummy = 0u;
-    bool dummy_far;
+    unsigned dummy_far;
     T Scur = chain_pass<T, KIND, WT, LSF, false>(cz, T(0), slot_addr(n), 0u, ar0, aw0, rb, npairs, lane, lc, dummy, dummy_far);
     T sd = WT ? T(1) : sdrec->th;
     T logsd = WT ? T(0) : StepMath<T>::log_(sd);
@@ -583,11 +643,11 @@ __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, const unsigned
 #endif
                         cc = make_comp_fast<T, KIND>(pA, cbase(qc), q1, q2);
                     unsigned nf = 0u;
-                    bool last_far;
-                    const T Snew = chain_pass<T, KIND, WT, LSF, true>(cc, NK * pA, 0u, slot_addr(hs), ar0, aw0, rb, npairs, lane, lc,
-                                                                      nf, last_far);
-                    n_far += nf - (last_far ? (unsigned)npad : 0u);
-                    ++n_shape;
+                    unsigned last_far;
+                    const T Snew = chain_pass<T, KIND, WT, LSF, true, MULT>(cc, NK * pA, 0u, slot_addr(hs), ar0, aw0, rb, npairs,
+                                                                            lane, lc, nf, last_far, &ml);
+                    n_far += nf - last_far * (unsigned)npad;
+                    n_shape += MULT ? 2u : 1u;            // line evaluations over the region
                     ++n_like;
                     if (lu < (Scur - Snew) * hiv) {
                         Scur = Snew;
@@ -729,7 +789,7 @@ __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, const unsigned
 // (du, flux, 1/noise) are staged ONCE per CTA and shared, which is what lets a sixth CTA fit on an
 // SM.  A CTA whose warps belong to different regions (group boundaries) processes its distinct
 // regions one after the other - rare, and always correct.
-template <typename T, int KIND, bool WT, bool LSF>
+template <typename T, int KIND, bool WT, bool LSF, bool MULT>
 __global__ void __launch_bounds__(K2_WARPS * 32, (sizeof(T) == 4) ? VAMP_K2_MINBLOCKS : 2)
 k2_mcmc_kernel(McmcDev p, int ncomp_max) {
     typedef K2Lay<T, WT> Lay;
@@ -770,7 +830,7 @@ k2_mcmc_kernel(McmcDev p, int ncomp_max) {
             }
         }
         __syncthreads();
-        if (my_region == rr) mcmc_chain<T, KIND, WT, LSF>(p, chain, lane, rb, wb, ncomp_max, lsf_s);
+        if (my_region == rr) mcmc_chain<T, KIND, WT, LSF, MULT>(p, chain, lane, rb, wb, ncomp_max, lsf_s);
     }
 }
 
@@ -832,7 +892,7 @@ template <typename T, int KIND, bool WT, bool LSF>
 cudaError_t launch_k2_t(const McmcDev& p, int max_ncomp, cudaStream_t st) {
     const size_t smem = (LSF ? align16(sizeof(T) * VAMP_MAX_LSF_TAPS) : 0) + K2Lay<T, WT>::REGION +
                         K2_WARPS * K2Lay<T, WT>::bytes(max_ncomp, LSF);
-    auto kern = k2_mcmc_kernel<T, KIND, WT, LSF>;
+    auto kern = k2_mcmc_kernel<T, KIND, WT, LSF, VAMP_INST_MULT != 0>;
     if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -843,7 +903,7 @@ cudaError_t launch_k2_t(const McmcDev& p, int max_ncomp, cudaStream_t st) {
 
 }  // namespace
 
-#if VAMP_INST_F64 == 0
+#if VAMP_INST_F64 == 0 && VAMP_INST_MULT == 0
 // precision-independent helpers live in the f32 objects only
 cudaError_t VAMP_CAT3(vamp_launch_init_prior, any, VAMP_KN)(const McmcDev& p, cudaStream_t st) {
     if (p.B <= 0) return cudaSuccess;
@@ -859,7 +919,13 @@ cudaError_t vamp_launch_init_state(const McmcDev& p, cudaStream_t st) {
 #endif
 #endif
 
+// -DVAMP_INST_MULT=1 objects hold the multiplet instantiations (vamp_launch_k2m_*), chosen by the C ABI when the
+// region set carries a multiplet table
+#if VAMP_INST_MULT
+cudaError_t VAMP_INST_NAME(vamp_launch_k2m)(const McmcDev& p, int max_npix, int max_ncomp, cudaStream_t st) {
+#else
 cudaError_t VAMP_INST_NAME(vamp_launch_k2)(const McmcDev& p, int max_npix, int max_ncomp, cudaStream_t st) {
+#endif
     if (p.B <= 0 || p.it1 <= p.it0) return cudaSuccess;
     if (max_npix > VAMP_TILE_PIX) return cudaErrorInvalidValue;
     const bool lsf = p.rs.lsf_taps > 1;

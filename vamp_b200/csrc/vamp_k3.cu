@@ -37,6 +37,8 @@ struct Objective {
     const MapDev& p;
     const RegionSetDev& rs;
     int P, n, sdi, taps, lane, warp, nrows;
+    int nl;                // lines per evaluation: n, or 2 n in a multiplet region
+    const double* mrow;    // the region's row of the multiplet table, or nullptr
     double ubase, lognorm, c_hi, w_hi;
     const T* gdu;
     const T* gf;
@@ -65,6 +67,13 @@ struct Objective {
             else ok = ok && (w1 > 0.0) && (w1 <= w_hi);
             lp += log(a) - a;
             ccs[c] = make_comp_k1<T, KIND, true>(a, ce, w1, w2, ubase);      // clamped 1/G: the padding coordinate stays finite
+            if (nl > n) {                                                    // multiplet region: the component's second line
+                double a2, ce2, w12, w22;
+                MultD md;
+                md.fr = mrow[0]; md.sh = mrow[1]; md.ar = mrow[2]; md.lr = mrow[3];
+                line_params<KIND>(th, n + c, n, md, a2, ce2, w12, w22);
+                ccs[n + c] = make_comp_k1<T, KIND, true>(a2, ce2, w12, w22, ubase);
+            }
         }
         double sd = 1.0;
         if (p.sd_free) {
@@ -84,11 +93,11 @@ struct Objective {
             T tau = T(0);
             // two components at a time as the halves of a two-wide value (two independent dependency chains: this
             // kernel is bound by the latency of one evaluation); one path per component pair and row
-            for (int c = 0; c < n; c += 2) {
+            for (int c = 0; c < nl; c += 2) {
                 const CompC<T> c0 = ccs[c];
                 CompC<T> c1 = c0;
                 c1.A = T(0);
-                if (c + 1 < n) c1 = ccs[c + 1];
+                if (c + 1 < nl) c1 = ccs[c + 1];
                 const P2<T> X = p2_mul(p2_sub(p2_bc<T>(du), p2_make(c0.cb, c1.cb)), p2_make(c0.g, c1.g));
                 P2<T> H;
                 if (KIND == VAMP_KIND_GAUSS) {
@@ -150,6 +159,8 @@ __device__ void nm_run(const MapDev& p, int s, double* sm, CompC<T>* ccw, int nc
     Objective<T, KIND> f{p, rs};
     f.P = rs.npix[r];
     f.n = p.item_ncomp[s];
+    f.mrow = region_mult_row(rs, r);
+    f.nl = f.mrow ? 2 * f.n : f.n;
     f.sdi = 4 * p.cmax;
     f.taps = rs.lsf_taps;
     f.lane = tid & 31;
@@ -368,6 +379,8 @@ __device__ __noinline__ double k3w_objective(const MapDev& p, const double* th, 
     const RegionSetDev& rs = p.rs;
     const int sdi = 4 * p.cmax;
     CompK<T>* ccs = reinterpret_cast<CompK<T>*>(ccbuf);
+    const double* mrow = region_mult_row(rs, r);              // the region's row of the multiplet table, or nullptr
+    const int nl = mrow ? 2 * n : n;                          // lines per evaluation
     // ---- bounds, prior and component constants: lane c handles component c (c + 32, ...)
     bool ok = true;
     double lp = 0.0;
@@ -382,6 +395,17 @@ __device__ __noinline__ double k3w_objective(const MapDev& p, const double* th, 
         ccs[c].cb = cc.cb;
         ccs[c].g = cc.g;
         ccs[c].y = cc.y;
+        if (nl > n) {                          // multiplet region: the component's second line
+            double a2, ce2, w12, w22;
+            MultD md;
+            md.fr = mrow[0]; md.sh = mrow[1]; md.ar = mrow[2]; md.lr = mrow[3];
+            line_params<KIND>(th, n + c, n, md, a2, ce2, w12, w22);
+            const CompC<T> c2 = make_comp_k1<T, KIND, true>(a2, ce2, w12, w22, ubase);
+            ccs[n + c].A = Real<T>::NEGK() * c2.A;
+            ccs[n + c].cb = c2.cb;
+            ccs[n + c].g = c2.g;
+            ccs[n + c].y = c2.y;
+        }
     }
     double sd = 1.0;
     if (p.sd_free) {
@@ -404,7 +428,7 @@ __device__ __noinline__ double k3w_objective(const MapDev& p, const double* th, 
         const P2<T> DU = p2_from(__ldg(gdu + e));
         P2<T> tau = p2_bc<T>(T(0));
 #pragma unroll 1
-        for (int c = 0; c < n; ++c) {
+        for (int c = 0; c < nl; ++c) {
             CompC<T> cc;
             cc.A = ccs[c].A;
             cc.cb = ccs[c].cb;
@@ -612,12 +636,13 @@ cudaError_t VAMP_INST_NAME(vamp_launch_k3)(const MapDev& p, int max_npix, int ma
     const bool LSF = p.rs.lsf_taps > 1;
     const int NP = (InstKind == VAMP_KIND_VOIGT) ? 4 : 3;
     const int kmax = NP * max_ncomp + 1;
-    const size_t smem = k3_align16(sizeof(T) * VAMP_MAX_LSF_TAPS) + k3_smem_bytes<T>(kmax, p.tstride, LSF, max_ncomp);
+    const int nl_max = max_ncomp * (p.rs.mult ? 2 : 1);                 // multiplet regions: two lines per component
+    const size_t smem = k3_align16(sizeof(T) * VAMP_MAX_LSF_TAPS) + k3_smem_bytes<T>(kmax, p.tstride, LSF, nl_max);
     if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
     auto kern = k3_map_kernel<T, InstKind>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    kern<<<p.S, K3_THREADS, smem, st>>>(p, kmax, max_ncomp);
+    kern<<<p.S, K3_THREADS, smem, st>>>(p, kmax, nl_max);
     return cudaGetLastError();
 }
 
@@ -628,12 +653,13 @@ cudaError_t VAMP_CAT3(vamp_launch_k3w, mixed, VAMP_KN)(const MapDev& p, int max_
     if (max_npix > VAMP_TILE_PIX || p.rs.lsf_taps > 1) return cudaErrorInvalidValue;
     const int NP = (InstKind == VAMP_KIND_VOIGT) ? 4 : 3;
     const int kmax = NP * max_ncomp + 1;
-    const size_t smem = K3W_WARPS * k3w_warp_bytes(kmax, p.tstride, max_ncomp);
+    const int nl_max = max_ncomp * (p.rs.mult ? 2 : 1);
+    const size_t smem = K3W_WARPS * k3w_warp_bytes(kmax, p.tstride, nl_max);
     if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
     auto kern = k3w_map_kernel<InstKind>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    kern<<<(p.S + K3W_WARPS - 1) / K3W_WARPS, K3W_WARPS * 32, smem, st>>>(p, kmax, max_ncomp);
+    kern<<<(p.S + K3W_WARPS - 1) / K3W_WARPS, K3W_WARPS * 32, smem, st>>>(p, kmax, nl_max);
     return cudaGetLastError();
 }
 #endif

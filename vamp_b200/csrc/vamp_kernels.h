@@ -58,6 +58,8 @@ cudaError_t vamp_launch_init_prior_any_gauss(const McmcDev& p, cudaStream_t st);
 cudaError_t vamp_launch_init_prior_any_voigt(const McmcDev& p, cudaStream_t st);
 cudaError_t vamp_launch_init_state(const McmcDev& p, cudaStream_t st);
 VAMP_DECL4(cudaError_t, vamp_launch_k2, const McmcDev& p, int max_npix, int max_ncomp, cudaStream_t st)
+// multiplet instantiations (region sets with a multiplet table: two tied lines per component)
+VAMP_DECL4(cudaError_t, vamp_launch_k2m, const McmcDev& p, int max_npix, int max_ncomp, cudaStream_t st)
 
 // ---- K3 (vamp_k3.cu)
 struct MapDev {

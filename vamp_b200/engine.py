@@ -88,9 +88,14 @@ class Regions:
     """A set of absorption regions resident on the device (``vamp_regions``).
 
     ``regions``: sequence of ``(nu, flux, noise)`` float64 arrays, ``nu`` ascending (what
-    ``VPregion.__init__`` receives, vamp_1.0/vpregion.py:10-19)."""
+    ``VPregion.__init__`` receives, vamp_1.0/vpregion.py:10-19).
 
-    def __init__(self, ctx, regions, lsf=None):
+    ``multiplet``: ``None`` (single lines, the reference), one ``(freq_ratio, amp_ratio[, lorentz_ratio])``
+    tuple for every region, or a per-region list of such tuples / ``None`` - every component of the region then
+    carries a second line with tied parameters (``vamp_regions_set_multiplet``, include/vamp_b200.h;
+    :func:`vamp_b200.physics.doublet_ratios` gives the ratios of a doublet)."""
+
+    def __init__(self, ctx, regions, lsf=None, multiplet=None):
         self.ctx = ctx
         self.lib = ctx.lib
         regions = list(regions)
@@ -114,6 +119,30 @@ class Regions:
         check(self.lib.vamp_regions_scale(h, _lib.as_dbl_p(self.nu0), _lib.as_dbl_p(self.scale)))
         self.max_npix = int(self.npix.max())
         self.h2d_bytes = int(nu.nbytes + flux.nbytes + noise.nbytes + self.npix.nbytes)
+        self.multiplet = None
+        if multiplet is not None:
+            self.set_multiplet(multiplet)
+
+    def set_multiplet(self, multiplet):
+        """Install (or, with ``None``, clear) the regions' multiplet table."""
+        if multiplet is None:
+            check(self.lib.vamp_regions_set_multiplet(self.handle, None, None, None))
+            self.multiplet = None
+            return
+        if len(multiplet) in (2, 3) and np.isscalar(multiplet[0]):
+            multiplet = [tuple(multiplet)] * self.R
+        if len(multiplet) != self.R:
+            raise ValueError("multiplet: one (freq_ratio, amp_ratio[, lorentz_ratio]) per region expected")
+        tab = np.zeros((self.R, 3))
+        tab[:, 0] = 1.0
+        tab[:, 2] = 1.0
+        for r, m in enumerate(multiplet):
+            if m is not None:
+                tab[r, : len(m)] = m
+        cols = [np.ascontiguousarray(tab[:, i]) for i in range(3)]
+        check(self.lib.vamp_regions_set_multiplet(self.handle, _lib.as_dbl_p(cols[0]), _lib.as_dbl_p(cols[1]),
+                                                  _lib.as_dbl_p(cols[2])))
+        self.multiplet = tab if np.any(tab[:, 1] != 0.0) else None
 
     # -- unit conversion ------------------------------------------------------------------
     def to_scaled(self, theta, item_region):

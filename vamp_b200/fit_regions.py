@@ -46,6 +46,17 @@ MIXED_POLISH_STARTS = 2048
 MAX_BATCH_REGIONS = 16384      # regions per device batch: ~1.2e6 chains, ~5 GB of chain state at the C4 settings
 
 
+def per_region_multiplet(multiplet, R):
+    """``multiplet`` (None, one tuple for every region, or a per-region list) -> per-region list or None."""
+    if multiplet is None:
+        return None
+    if len(multiplet) in (2, 3) and np.isscalar(multiplet[0]):
+        return [tuple(multiplet)] * R
+    if len(multiplet) != R:
+        raise ValueError("multiplet: one (freq_ratio, amp_ratio[, lorentz_ratio]) tuple, or one per region")
+    return list(multiplet)
+
+
 def fit_chunked(fit_fn, regions_host, uids, n0, max_batch_regions=MAX_BATCH_REGIONS, **kw):
     """A shard larger than ``max_batch_regions`` is fitted in consecutive device batches (bounded chain state in
     HBM whatever the shard size - 10^5 regions on one GPU are seven batches); Philox streams are keyed by region
@@ -54,7 +65,12 @@ def fit_chunked(fit_fn, regions_host, uids, n0, max_batch_regions=MAX_BATCH_REGI
     step = max(1, int(max_batch_regions))
     if R <= step:
         return fit_fn(regions_host, uids, n0=n0, **kw)
-    out = [fit_fn(regions_host[a: a + step], uids[a: a + step], n0=n0[a: a + step], **kw) for a in range(0, R, step)]
+    mult = kw.pop("multiplet", None)
+    out = []
+    for a in range(0, R, step):
+        if mult is not None:
+            kw["multiplet"] = mult[a: a + step]
+        out.append(fit_fn(regions_host[a: a + step], uids[a: a + step], n0=n0[a: a + step], **kw))
     return np.concatenate(out, axis=0)
 
 
@@ -127,8 +143,10 @@ def unpack_record(rec, nmax, G, cmax):
 
 def fit_local(regions_host, uids, voigt=False, sd_free=True, iterations=3000, burn=300, thin=15, restarts=3,
               chains_per_restart=32, window=3, max_rounds=4, chi_limit=1.5, dtype="f32", seed=0, lsf=None,
-              n0=None, nmax=12, ctx=None, polish_top=None, tune_interval=50, stats=None, cmax_rec=None, polish_dtype="f64"):
-    """Fit the given regions on this process's GPU.  Returns ``[R, record_len]`` float64."""
+              n0=None, nmax=12, ctx=None, polish_top=None, tune_interval=50, stats=None, cmax_rec=None, polish_dtype="f64",
+              multiplet=None):
+    """Fit the given regions on this process's GPU.  Returns ``[R, record_len]`` float64.
+    ``multiplet``: per-region ``(freq_ratio, amp_ratio[, lorentz_ratio])`` or None (``engine.Regions``)."""
     R = len(regions_host)
     G = int(restarts)
     if R == 0:                                   # nothing to fit (an empty shard): no device work, no context
@@ -143,7 +161,7 @@ def fit_local(regions_host, uids, voigt=False, sd_free=True, iterations=3000, bu
     cmax_rec = int(cmax_rec or (max(n0) + nmax if R else 1 + nmax))
     if R == 0:
         return np.zeros((0, _record_len(nmax, G, cmax_rec)))
-    regs = engine.Regions(ctx, regions_host, lsf=lsf)
+    regs = engine.Regions(ctx, regions_host, lsf=lsf, multiplet=multiplet)
     if stats is not None:
         stats["h2d_bytes"] = stats.get("h2d_bytes", 0) + regs.h2d_bytes
     tables = [dict() for _ in range(R)]
@@ -238,7 +256,13 @@ def fit_regions(regions_host, uids=None, distributed=None, fit_fn=None, **kw):
     nmax = kw.get("nmax", 12)
     G = kw.get("restarts", 3)
     n0 = kw.pop("n0", None)
-    n0 = [estimate_n(r[1]) for r in regions_host] if n0 is None else [int(v) for v in n0]
+    if n0 is None:
+        n0 = [estimate_n(r[1]) for r in regions_host]
+        if kw.get("multiplet") is not None:          # a doublet shows two minima per absorber
+            mult = per_region_multiplet(kw["multiplet"], R)
+            n0 = [max(1, n // 2) if (mult[i] is not None and mult[i][1] != 0.0) else n for i, n in enumerate(n0)]
+    else:
+        n0 = [int(v) for v in n0]
     cmax_rec = (max(n0) if n0 else 1) + nmax
     rec_len = _record_len(nmax, G, cmax_rec)
     use_dist = dist.is_available() and dist.is_initialized() if distributed is None else bool(distributed)
@@ -250,12 +274,18 @@ def fit_regions(regions_host, uids=None, distributed=None, fit_fn=None, **kw):
         kw["polish_dtype"] = "mixed" if (starts >= MIXED_POLISH_STARTS and kw.get("lsf") is None) else "f64"
     fit_fn = fit_fn or fit_local
     chunk = kw.pop("max_batch_regions", MAX_BATCH_REGIONS)
+    if kw.get("multiplet") is not None:
+        kw["multiplet"] = per_region_multiplet(kw["multiplet"], R)
+    else:
+        kw.pop("multiplet", None)
     if not use_dist:
         recs = fit_chunked(fit_fn, regions_host, uids, n0, chunk, cmax_rec=cmax_rec, **kw)
     else:
         world, rank = dist.get_world_size(), dist.get_rank()
         costs = [region_cost(len(regions_host[i][1]), n0[i], window, voigt) for i in range(R)]
         mine = lpt_partition(costs, world)[rank]
+        if "multiplet" in kw:
+            kw["multiplet"] = [kw["multiplet"][i] for i in mine]
         local = fit_chunked(fit_fn, [regions_host[i] for i in mine], [uids[i] for i in mine], [n0[i] for i in mine],
                             chunk, cmax_rec=cmax_rec, **kw)        # same record geometry on every rank
         assert local.shape[1] == rec_len

@@ -73,3 +73,23 @@ def Wave2freq(wavelength):
 def Wave2red(wave, rest_wave):
     """physics.py:128-134."""
     return (wave - rest_wave) / rest_wave
+
+
+# Doublets of BASELINE config C3 (rest wavelength in Angstrom, oscillator strength f, damping Gamma in 1/s; Morton
+# 2003 values).  NOT IN THE REFERENCE, which fits single lines only.
+DOUBLETS = {
+    "CIV": ((1548.204, 0.1899, 2.643e8), (1550.781, 0.09475, 2.628e8)),
+    "MgII": ((2796.354, 0.6155, 2.625e8), (2803.531, 0.3058, 2.595e8)),
+}
+
+
+def doublet_ratios(line1, line2=None):
+    """``(freq_ratio, amp_ratio, lorentz_ratio)`` of a doublet for ``Regions(multiplet=...)`` /
+    ``fit_regions(multiplet=...)``: the second line sits at ``nu_2/nu_1`` times the first line's frequency (same
+    velocity), its Doppler width scales likewise (same b), its optical depth by ``(f_2 lambda_2)/(f_1 lambda_1)``
+    (same column density) and its Lorentzian width by ``Gamma_2/Gamma_1``.  ``line1`` / ``line2`` are
+    ``(wavelength, f, Gamma)`` tuples, or ``line1`` names an entry of :data:`DOUBLETS`."""
+    if line2 is None:
+        line1, line2 = DOUBLETS[line1]
+    (l1, f1, g1), (l2, f2, g2) = line1, line2
+    return l1 / l2, (f2 * l2) / (f1 * l1), g2 / g1

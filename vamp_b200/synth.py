@@ -89,6 +89,61 @@ def make_region(P, n_true, snr, region_id, voigt=True, lsf=None, ratio_range=(0.
             "voigt": bool(voigt), "region_id": int(region_id), "snr": float(snr), "tau0": amp}
 
 
+def make_doublet_region(P, n_true, snr, region_id, doublet="CIV", voigt=True, lsf=None, dv_kms=5.0):
+    """One synthetic region holding BOTH lines of a doublet (BASELINE config C3: CIV 1548/1550, MgII 2796/2803;
+    tied velocity, Doppler width and column density): ``n_true`` absorbers, each the sum of its line and the tied
+    second line (``vamp_b200.physics.doublet_ratios``).  The grid has ``dv_kms`` pixels around the doublet; ``truth
+    [n_true, 4]`` holds the FIRST line's ``(amplitude, centroid, L_fwhm | sigma, G_fwhm | 0)`` in Hz, ``multiplet``
+    the ratios to pass to ``Regions(multiplet=...)`` / ``fit_regions(multiplet=...)``."""
+    from . import physics
+    fr, ar, lr = physics.doublet_ratios(doublet)
+    rng = rng_for(region_id, stream=2)
+    nu1 = C_REF / (physics.DOUBLETS[doublet][0][0] * 1e-10)
+    dnu = nu1 * dv_kms * 1e3 / C_REF
+    sep = nu1 * (1.0 - fr) / dnu                                # separation of the two lines in pixels
+    if sep + 60 > P - 1:
+        raise ValueError("region of %d px cannot hold a doublet %.0f px apart" % (P, sep))
+    p2 = 0.5 * (P - 1 - sep)                                    # rest position of line 2; line 1 at p2 + sep
+    nu = nu1 + (np.arange(P, dtype=np.float64) - (p2 + sep)) * dnu
+    half = min(p2 - 12.0, 0.45 * sep)                           # absorbers within +- half px of the rest position
+    sig_px = rng.uniform(2.5, 6.0, n_true)
+    tau0 = rng.uniform(0.4, 2.5, n_true)
+    off = np.empty(n_true)
+    for k in range(n_true):
+        for _ in range(200):
+            o = rng.uniform(-half, half)
+            if all(abs(o - off[j]) >= 2.0 * max(sig_px[k], sig_px[j]) for j in range(k)):
+                break
+        off[k] = o
+    ratio = 10.0 ** rng.uniform(-2.0, np.log10(0.3), n_true)
+    truth = np.zeros((n_true, 4))
+    truth[:, 1] = nu1 + off * dnu
+    tau = np.zeros(P)
+    for k in range(n_true):
+        c = truth[k, 1]
+        if voigt:
+            G = FWHM_PER_SIGMA * sig_px[k] * dnu
+            truth[k, 2], truth[k, 3] = ratio[k] * G, G
+            truth[k, 0] = tau0[k] / voigt_peak_shape(truth[k, 2], truth[k, 3])
+            tau += voigt_tau(nu, truth[k, 0], c, truth[k, 2], G)
+            tau += voigt_tau(nu, ar * truth[k, 0], fr * c, lr * truth[k, 2], fr * G)
+        else:
+            truth[k, 0], truth[k, 2] = tau0[k], sig_px[k] * dnu
+            tau += gauss_tau(nu, tau0[k], c, truth[k, 2])
+            tau += gauss_tau(nu, ar * tau0[k], fr * c, fr * truth[k, 2])
+    clean = np.exp(-tau)
+    if lsf is not None:
+        lsf = np.asarray(lsf, dtype=np.float64)
+        h = lsf.size // 2
+        clean = 1.0 + np.convolve(np.concatenate([np.zeros(h), clean - 1.0, np.zeros(h)]), lsf, "valid")
+    sigma = 1.0 / float(snr)
+    flux = clean + rng.normal(0.0, sigma, P)
+    flux[flux < 0.0] = 0.0
+    return {"nu": nu, "flux": flux, "noise": np.full(P, sigma), "truth": truth, "clean": clean, "voigt": bool(voigt),
+            "region_id": int(region_id), "snr": float(snr), "tau0": tau0, "multiplet": (fr, ar, lr), "dnu": dnu,
+            "sep_px": sep}
+
+
 def gaussian_lsf(fwhm_px=2.0, taps=7):
     """Normalised Gaussian LSF (config C3: FWHM 2 px, 7 taps)."""
     s = fwhm_px / FWHM_PER_SIGMA

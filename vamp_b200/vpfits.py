@@ -100,9 +100,12 @@ class _MCMC:
 class VPfit():
 
     def __init__(self, noise=None, n_chains=96, dtype="f32", seed=None, lsf=None, tune_interval=50,
-                 tune_throughout=True, polish_top=4, ctx=None):
+                 tune_throughout=True, polish_top=4, ctx=None, multiplet=None):
         """``noise=None``: the noise level ``sd ~ U(0,1)`` is a free parameter (vpfits.py:35-39);
-        otherwise the per-pixel noise array.  The keyword arguments are new (GPU controls)."""
+        otherwise the per-pixel noise array.  The keyword arguments are new (GPU controls).
+        ``multiplet = (freq_ratio, amp_ratio[, lorentz_ratio])`` (``physics.doublet_ratios``): every component
+        is a doublet with tied velocity / width / column density - new, the reference fits single lines."""
+        self.multiplet = None if multiplet is None else tuple(float(v) for v in multiplet)
         self.noise = None if noise is None else np.asarray(noise, dtype=np.float64)
         self.verbose = False
         self.n_chains = max(3, int(n_chains) // 3 * 3)
@@ -195,7 +198,7 @@ class VPfit():
             np.ones_like(flux) if noise_array is None else np.asarray(noise_array, dtype=np.float64))
         self._chi_noise = chi_noise
         ctx = self._context()
-        self._regions = engine.Regions(ctx, [(frequency, flux, chi_noise)], lsf=self.lsf)
+        self._regions = engine.Regions(ctx, [(frequency, flux, chi_noise)], lsf=self.lsf, multiplet=self.multiplet)
         B = self.n_chains
         fit_id = next(_fit_counter)
         uid = (np.uint64(fit_id) << np.uint64(24)) + np.arange(B, dtype=np.uint64)
@@ -220,7 +223,13 @@ class VPfit():
         self._sd = float(theta_row_scaled[4 * cm]) if self._sd_free else None
 
     def _component_tau(self, row):
-        return engine.profile_tau(self._x, row[1], row[0], row[2], row[3], voigt=self._voigt, ctx=self._context())
+        tau = engine.profile_tau(self._x, row[1], row[0], row[2], row[3], voigt=self._voigt, ctx=self._context())
+        if self.multiplet is not None and self.multiplet[1] != 0.0:      # the tied second line of the doublet
+            fr, ar = self.multiplet[0], self.multiplet[1]
+            lr = self.multiplet[2] if len(self.multiplet) > 2 else 1.0
+            w1, w2 = (lr * row[2], fr * row[3]) if self._voigt else (fr * row[2], row[3])
+            tau = tau + engine.profile_tau(self._x, fr * row[1], ar * row[0], w1, w2, voigt=self._voigt, ctx=self._context())
+        return tau
 
     def _total_flux(self):
         _, _, flux = engine.loglike(self._regions, self._theta[None], [self._ridx], sd=None, voigt=self._voigt,
@@ -404,7 +413,8 @@ class VPfit():
         flux_array = np.asarray(flux_array, dtype=np.float64)
         chi_noise = self.noise if self.noise is not None else np.asarray(noise_array, dtype=np.float64)
         starttime = datetime.datetime.now()
-        regions = engine.Regions(self._context(), [(frequency_array, flux_array, chi_noise)], lsf=self.lsf)
+        regions = engine.Regions(self._context(), [(frequency_array, flux_array, chi_noise)], lsf=self.lsf,
+                                 multiplet=self.multiplet)
         mb = batch.fit_models(regions, [(0, int(n))], voigt=voigt, sd_free=self.noise is None,
                               iterations=int(iterations) * (2 if thorough else 1), burn=burn, thin=thin, restarts=3,
                               chains_per_restart=self.n_chains // 3, polish_top=self.polish_top, dtype=self.dtype,

@@ -51,7 +51,7 @@ class VPregion():
         compared through its last restart's BIC."""
         proto = VPfit(**self.fit_kwargs)
         regions = engine.Regions(proto._context(), [(self.frequency_array, self.flux_array, self.noise_array)],
-                                 lsf=proto.lsf)
+                                 lsf=proto.lsf, multiplet=proto.multiplet)
         uid = next(_fit_counter)
         n0 = self.n
         if verbose:
