@@ -172,3 +172,56 @@ def test_fit_regions_recovers_civ_doublet(ctx):
     res1 = fit_regions(host[:1], voigt=True, iterations=3000, burn=300, thin=15, restarts=3, chains_per_restart=32, window=3,
                        n0=[1], nmax=4, lsf=lsf, seed=4, distributed=False)
     assert res1[0].n == 2
+
+
+def _civ_sightline(P=1000, seed=5, snr=70.0, systems=((200.0, 1.6, 5.0), (600.0, 1.1, 7.0)), lsf=None):
+    """A CIV sightline: ~5 km/s pixels around 1548 A, each system = (pixel of line 1, tau0, sigma in px)."""
+    rng = np.random.default_rng(seed)
+    (l1, f1, g1), (l2, f2, g2) = physics.DOUBLETS["CIV"]
+    wave = l1 * (1.0 - 0.004) + (l1 * 5.0e3 / 2.98e8) * np.arange(P)
+    nu = physics.Wave2freq(wave)
+    fr, ar, lr = physics.doublet_ratios("CIV")
+    truth, tau = [], np.zeros(P)
+    for px, tau0, sig_px in systems:
+        c = nu[int(px)]
+        G = 2.3548200450309493 * sig_px * abs(nu[int(px)] - nu[int(px) + 1])
+        L = 0.05 * G
+        A = tau0 / synth.voigt_peak_shape(L, G)
+        tau += D.voigt_tau(nu, c, A, L, G) + D.voigt_tau(nu, fr * c, ar * A, lr * L, fr * G)
+        truth.append((A, c, L, G))
+    clean = np.exp(-tau)
+    if lsf is not None:
+        h = lsf.size // 2
+        clean = 1.0 + np.convolve(np.concatenate([np.zeros(h), clean - 1.0, np.zeros(h)]), lsf, "valid")
+    return wave, clean + rng.normal(0, 1.0 / snr, P), np.full(P, 1.0 / snr), np.array(truth), clean
+
+
+def test_fit_spectrum_civ_doublet_sightline(ctx):
+    """BASELINE config C3: an LSF-convolved sightline with CIV doublets - detection, pairing of the two lines' regions,
+    the tied fit and the harvest of the first line's parameters."""
+    from vamp_b200 import vpspectrum as VS
+    lsf = synth.gaussian_lsf(2.0, 7)
+    wave, flux, noise, truth, clean = _civ_sightline(lsf=lsf)
+    sp = VS.VPspectrum(1548.204, voigt=True, doublet="CIV", chi_limit=1.5, convergence_attempts=2, iterations=2000, burn=300,
+                       thin=5, restarts=3, chains_per_restart=32, window=2, nmax=3, seed=3, lsf=lsf).set_spectrum(wave, flux, noise)
+    sp.compute_detection_regions(min_region_width=2)
+    assert len(sp.region_pixels) == 4                       # two lines x two systems
+    params = sp.fit_spectrum()
+    assert len(sp.region_pixels) == 2                       # paired: one joint region per system
+    for (s, e), px in zip(sp.region_pixels, (200, 600)):
+        assert s < px < px + 99 < e and e - s <= 256
+    assert [r.n for r in sp.regions] == [1, 1]
+    assert np.all(sp.flux_model["chi_squared"] < 1.5)
+    # the model (both lines of both systems, before the LSF) follows the unconvolved truth within the LSF's smoothing
+    assert np.max(np.abs(sp.flux_model["total"] - clean)) < 0.1
+    cen_true = physics.Freq2wave(truth[:, 1])
+    sig_true = truth[:, 3] / 2.3548200450309493
+    for k in range(2):
+        j = int(np.argmin(np.abs(params["centers"] - cen_true[k])))
+        assert abs(params["centers"][j] - cen_true[k]) < 0.5 * (wave[1] - wave[0])
+        assert params["b"][j] == pytest.approx(physics.DopplerParameter(sig_true[k], 1548.204), rel=0.15)
+        # central optical depth of the first line (amplitude_L alone is degenerate with the poorly constrained L / G)
+        th = sp.regions[k].theta[0]
+        assert th[0] * synth.voigt_peak_shape(th[2], th[3]) == pytest.approx(
+            truth[k, 0] * synth.voigt_peak_shape(truth[k, 2], truth[k, 3]), rel=0.15)
+        assert params["N"][j] > 0 and params["N_std"][j] > 0 and params["EW"][j] > 0

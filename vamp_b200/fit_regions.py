@@ -23,6 +23,20 @@ def estimate_n(flux_array):
     return int(k) if k >= 4 else 1
 
 
+def estimate_n_doublet(flux_array, noise_array, n_sigma=3.0):
+    """Initial absorber count of a DOUBLET region (new; the reference has single lines only).  A region holding both
+    lines of a doublet is mostly continuum, where ``estimate_n``'s count of every local minimum of the smoothed flux
+    counts noise; here only minima ``n_sigma`` smoothed-noise deviations below the continuum count, and two of them
+    make one absorber."""
+    from scipy.ndimage import gaussian_filter
+    from scipy.signal import argrelextrema
+    f = gaussian_filter(np.asarray(flux_array, dtype=np.float64), 3)
+    idx = argrelextrema(f, np.less)[0]
+    sm_noise = float(np.median(np.abs(noise_array))) / np.sqrt(2.0 * np.sqrt(np.pi) * 3.0)   # noise after the sigma = 3 filter
+    k = int(np.sum(1.0 - f[idx] > n_sigma * sm_noise))
+    return max(1, (k + 1) // 2)
+
+
 def region_cost(npix, n0, window, voigt):
     """Relative cost of fitting a region: pixels x sum over candidates of free parameters."""
     per = 4 if voigt else 3
@@ -260,7 +274,8 @@ def fit_regions(regions_host, uids=None, distributed=None, fit_fn=None, **kw):
         n0 = [estimate_n(r[1]) for r in regions_host]
         if kw.get("multiplet") is not None:          # a doublet shows two minima per absorber
             mult = per_region_multiplet(kw["multiplet"], R)
-            n0 = [max(1, n // 2) if (mult[i] is not None and mult[i][1] != 0.0) else n for i, n in enumerate(n0)]
+            n0 = [estimate_n_doublet(regions_host[i][1], regions_host[i][2]) if (mult[i] is not None and mult[i][1] != 0.0)
+                  else n for i, n in enumerate(n0)]
     else:
         n0 = [int(v) for v in n0]
     cmax_rec = (max(n0) if n0 else 1) + nmax

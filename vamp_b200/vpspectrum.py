@@ -24,7 +24,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib, engine
-from .fit_regions import estimate_n, fit_regions
+from .fit_regions import estimate_n, estimate_n_doublet, fit_regions
 from .physics import (ColumnDensity, DopplerParameter, EquivalentWidthFlux, EquivalentWidthTau, ErrorB, ErrorN,
                       Freq2wave, Tau2flux, Wave2freq)
 from .vpfits import VPfit
@@ -94,10 +94,21 @@ class VPspectrum():
 
     def __init__(self, line, spectrum_file=None, out_folder=None, voigt=False, chi_limit=1.5, mcmc_cov=False,
                  get_mcmc_err=True, convergence_attempts=10, chi_sq_maximum=10., max_single_region_components=15,
-                 ideal_single_region_components=5, min_region_percentage=2., **fit_kwargs):
+                 ideal_single_region_components=5, min_region_percentage=2., doublet=None, **fit_kwargs):
         """vpspectrum.py:23-55.  ``fit_kwargs`` (new): GPU controls forwarded to ``fit_regions``
-        (iterations, burn, thin, restarts, chains_per_restart, window, nmax, dtype, seed, lsf ...)."""
+        (iterations, burn, thin, restarts, chains_per_restart, window, nmax, dtype, seed, lsf ...).
+        ``doublet`` (new; BASELINE config C3): a name in ``physics.DOUBLETS`` ("CIV", "MgII") or a pair of
+        ``(wavelength, f, Gamma)`` lines, ``line`` being the first: the detection regions of the two lines are
+        paired (``pair_doublet_regions``) and every absorber is fitted as a doublet with tied velocity, Doppler
+        width and column density; the reported parameters are those of the first line."""
         self.line = line
+        self.doublet = doublet
+        self.multiplet = None
+        if doublet is not None:
+            from .physics import DOUBLETS, doublet_ratios
+            l1, l2 = DOUBLETS[doublet] if isinstance(doublet, str) else doublet
+            self.multiplet = doublet_ratios(l1, l2)
+            self.doublet_wave_ratio = l2[0] / l1[0]
         self.spectrum_file = spectrum_file
         self.out_folder = out_folder
         self.voigt = voigt
@@ -198,6 +209,50 @@ class VPspectrum():
             self.region_waves = [[self.wavelength_array[s], self.wavelength_array[min(e, len(self.wavelength_array) - 1)]]
                                  for s, e in out]
 
+    def pair_doublet_regions(self, max_pixels=256):
+        """New (doublets): a detection region of the first line and the region holding its second line - the one
+        that contains the first region's centre moved to ``wavelength x lambda_2/lambda_1`` - are fitted as ONE
+        region, from the start of the first to the end of the second (both lines of an absorber must be under the
+        same model).  Chains of overlapping pairs merge; a joint region longer than ``max_pixels`` (one coordinate
+        tile of the sampler kernels) is left unpaired."""
+        if self.multiplet is None or not self.region_pixels:
+            return
+        regs = sorted([list(r) for r in self.region_pixels])
+        wave = self.wavelength_array
+        P = len(wave)
+        group = list(range(len(regs)))
+
+        def find(i):
+            while group[i] != i:
+                group[i] = group[group[i]]
+                i = group[i]
+            return i
+
+        for i, (s, e) in enumerate(regs):
+            target = 0.5 * (wave[s] + wave[min(e, P - 1)]) * self.doublet_wave_ratio
+            for j, (s2, e2) in enumerate(regs):
+                if j != i and wave[s2] <= target <= wave[min(e2, P - 1)]:
+                    a, b = find(i), find(j)
+                    lo = min(regs[k][0] for k in range(len(regs)) if find(k) in (a, b))
+                    hi = max(regs[k][1] for k in range(len(regs)) if find(k) in (a, b))
+                    if hi - lo <= max_pixels:
+                        group[b] = a
+        merged = {}
+        for k, (s, e) in enumerate(regs):
+            g = find(k)
+            lo, hi = merged.get(g, (s, e))
+            merged[g] = (min(lo, s), max(hi, e))
+        out = sorted([list(v) for v in merged.values()])
+        # regions swallowed by a joint region (between the two lines) join it
+        final = []
+        for s, e in out:
+            if final and s < final[-1][1] and max(e, final[-1][1]) - final[-1][0] <= max_pixels:
+                final[-1][1] = max(final[-1][1], e)
+            else:
+                final.append([s, e])
+        self.region_pixels = final
+        self.region_waves = [[wave[s], wave[min(e, P - 1)]] for s, e in final]
+
     # ------------------------------------------------------------------ fit
     def _region_arrays(self, start, end):
         """vpspectrum.py:274-279: flipped so that frequency ascends."""
@@ -210,6 +265,7 @@ class VPspectrum():
         if not hasattr(self, "region_pixels"):
             self.compute_detection_regions(min_region_width=2)
             self.split_difficult_region()
+        self.pair_doublet_regions()
         self.split_long_regions()
         R = len(self.region_pixels)
         self.params = {'b': np.array([]), 'b_std': np.array([]), 'N': np.array([]), 'N_std': np.array([]),
@@ -225,6 +281,8 @@ class VPspectrum():
         arrays = [self._region_arrays(s, e) for s, e in self.region_pixels]
         host = [(a[0], a[1], a[2]) for a in arrays]
         n_est = [estimate_n(a[1]) for a in arrays]
+        if self.multiplet is not None:                                    # two significant minima per absorber
+            n_est = [estimate_n_doublet(a[1], a[2]) for a in arrays]
         # ---- rounds over the regions that have not converged (the reference's per-region attempt loop)
         attempts_left = []
         for n in n_est:
@@ -238,6 +296,8 @@ class VPspectrum():
         history = [[] for _ in range(R)]                                  # (n fitted, reduced chi^2) per attempt
         n0 = list(n_est)
         kw = dict(self.fit_kwargs)
+        if self.multiplet is not None:
+            kw["multiplet"] = self.multiplet
         base_seed = int(kw.pop("seed", 0))
         rnd = 0
         while True:
@@ -273,6 +333,13 @@ class VPspectrum():
                     profiles.append(VPfit.VoigtFunction(nu, th[k, 1], th[k, 0], th[k, 2], th[k, 3]))
                 else:
                     profiles.append(VPfit.GaussFunction(nu, th[k, 0], th[k, 1], th[k, 2]))
+                if self.multiplet is not None:                            # the absorber's tied second line
+                    fr, ar, lr = self.multiplet
+                    if self.voigt:
+                        profiles[-1] = profiles[-1] + VPfit.VoigtFunction(nu, fr * th[k, 1], ar * th[k, 0], lr * th[k, 2],
+                                                                          fr * th[k, 3])
+                    else:
+                        profiles[-1] = profiles[-1] + VPfit.GaussFunction(nu, ar * th[k, 0], fr * th[k, 1], fr * th[k, 2])
             total = Tau2flux(np.sum(profiles, axis=0))
             self.flux_model['chi_squared'][j] = best_chi[j]
             self.flux_model['total'][start:end] = np.flip(total, 0)
