@@ -42,6 +42,10 @@ for rep in range(int(os.environ.get("REPS", 3))):
     dt = time.perf_counter() - t0
     k2 = sum(a.elapsed_time(b) for n, a, b in evs if n == "k2"); k3 = sum(a.elapsed_time(b) for n, a, b in evs if n == "k3")
     if rank == 0:
+        tm = st.get("timing", {})
+        print("   fit_models: K2 %.0f ms, polish %.0f ms (device); host set-up %.3f s, launch %.3f s, wait %.3f s, post %.3f s" % (
+            tm.get("k2_ms", 0), tm.get("polish_ms", 0), tm.get("host_setup_s", 0), tm.get("host_launch_s", 0),
+            tm.get("host_wait_s", 0), tm.get("host_post_s", 0)), flush=True)
         nfit = np.array([r.n for r in res])
         print("rep %d: %d regions on %d GPU(s): %.2f s -> %.1f regions/s | rank0 K2 %.0f ms K3 %.0f ms rounds %d chains %d | "
               "n == truth %.2f, |n - truth| <= 1 %.2f, status0 %.2f" % (

@@ -21,6 +21,23 @@ def chain_uids(region_uid, n, restarts, chains_per_restart):
     return (np.uint64(int(region_uid) & 0xFFFFFFFFFF) << np.uint64(24)) | (np.uint64(int(n) & 0xFF) << np.uint64(16)) | c
 
 
+# component-count edges of the polish launch groups (<= 4, 5..8, 9..12, more): see ``fit_models.polish``
+POLISH_GROUP_EDGES = (4, 8, 12)
+POLISH_STREAMS = __import__("os").environ.get("VAMP_POLISH_STREAMS", "1") != "0"
+
+
+_streams = {}
+
+
+def _polish_streams(dev, n):
+    """``n`` side streams of the device (created once)."""
+    torch = engine._torch()
+    pool = _streams.setdefault(str(dev), [])
+    while len(pool) < n:
+        pool.append(torch.cuda.Stream(dev))
+    return pool[:n]
+
+
 class ModelBatch:
     """Result tables of one batched fit (numpy, host).  Shapes: M models, G restarts."""
 
@@ -35,14 +52,16 @@ class ModelBatch:
 def fit_models(regions, models, voigt=False, sd_free=True, iterations=3000, burn=300, thin=15, restarts=3,
                chains_per_restart=32, polish_top=4, dtype="f32", seed=0, region_uids=None, tune_interval=50,
                tune_throughout=True, keep_sampler=False, trace=False, maxiter=None, xtol=1e-4, ftol=1e-3,
-               polish_dtype="f64", overlap=False):
+               polish_dtype="f64", overlap=False, timing=None):
     """Fit ``models = [(region_index, n), ...]`` on the device-resident ``regions``.
 
     Per model and restart group: prior-drawn starts -> ``iterations`` of K2 Metropolis ->
     Nelder-Mead polish (K3) of the group's ``polish_top`` best chains -> the group's MAP,
     ``BIC = k ln P - 2 lnL`` and noise-weighted chi^2 (the quantities ``find_bic`` appends,
     vpfits.py:427-428).  Returns a :class:`ModelBatch`."""
+    import time as _time
     torch = engine._torch()
+    _t0 = _time.perf_counter()
     models = [(int(r), int(n)) for r, n in models]
     M, G, Cn = len(models), int(restarts), int(chains_per_restart)
     if M == 0:
@@ -94,8 +113,48 @@ def fit_models(regions, models, voigt=False, sd_free=True, iterations=3000, burn
         unsort[lpt] = torch.arange(lpt.numel(), device=dev)
         ps = phys[lpt]
         starts = s.t["best_theta"][ps].contiguous()
-        r = s._map(starts, s.t["item_region"][ps].contiguous(), s.t["item_ncomp"][ps].contiguous(),
-                   int(max(models[m][1] for m in model_ids)), int(maxiter or iterations), 0, xtol, ftol, polish_dtype)
+        p_reg, p_nc = s.t["item_region"][ps].contiguous(), s.t["item_ncomp"][ps].contiguous()
+        # The warp-per-start schedule keeps a (k + 1) x (4 n_max + 1) simplex per warp in shared memory, n_max being
+        # the LAUNCH's largest component count, and that footprint decides how many warps an SM holds: the starts
+        # (sorted by component count) go out in groups of similar size, largest first, so that the many small
+        # simplexes do not pay for the few large ones.  Group sizes follow from the model list (no device read).
+        ncount = np.bincount(np.array([models[m][1] for m in model_ids]), minlength=2) * (G * K)
+        groups, a = [], 0
+        if polish_dtype == "mixed":
+            for hi in POLISH_GROUP_EDGES + (len(ncount) - 1,):
+                b = int(ncount[: hi + 1].sum())
+                if b > a:
+                    groups.append((a, b, int(np.nonzero(ncount[: hi + 1])[0].max())))
+                a = max(a, b)
+        else:
+            groups.append((0, int(ncount.sum()), int(max(models[m][1] for m in model_ids))))
+        parts = []
+        if len(groups) == 1:
+            a, b, nmax_g = groups[0]
+            parts.append(s._map(starts, p_reg, p_nc, nmax_g, int(maxiter or iterations), 0, xtol, ftol, polish_dtype))
+        elif not POLISH_STREAMS:
+            for a, b, nmax_g in reversed(groups):
+                parts.append(s._map(starts[a:b], p_reg[a:b], p_nc[a:b], nmax_g, int(maxiter or iterations), 0, xtol, ftol,
+                                    polish_dtype))
+            parts.reverse()
+        else:
+            # one stream per group, largest simplexes first: the groups' tails (a launch lasts as long as its longest
+            # simplex) overlap instead of adding up
+            cur = torch.cuda.current_stream(dev)
+            side = _polish_streams(dev, len(groups))
+            for st, (a, b, nmax_g) in zip(side, reversed(groups)):
+                st.wait_stream(cur)
+                with torch.cuda.stream(st):
+                    q = s._map(starts[a:b], p_reg[a:b], p_nc[a:b], nmax_g, int(maxiter or iterations), 0, xtol, ftol,
+                               polish_dtype)
+                for v in q.values():
+                    v.record_stream(cur)             # allocated on the side stream, consumed on the current one
+                parts.append(q)
+            for st in side[: len(groups)]:
+                cur.wait_stream(st)
+            s.ctx.use_current_stream()
+            parts.reverse()
+        r = {k: torch.cat([q[k] for q in parts]) for k in parts[0]} if len(parts) > 1 else parts[0]
         r = {k: v[unsort] for k, v in r.items()}
         logp = torch.nan_to_num(r["logp"].view(-1, K), nan=-float("inf"))
         win = logp.argmax(dim=1)
@@ -131,9 +190,24 @@ def fit_models(regions, models, voigt=False, sd_free=True, iterations=3000, burn
             main.wait_stream(hp)
         s.iteration += int(iterations)
     else:
+        _t1 = _time.perf_counter()
+        if timing is not None:
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            ev[0].record()
         s.run(iterations)
+        if timing is not None:
+            ev[1].record()
         polish(list(range(M)))
+        if timing is not None:
+            ev[2].record()
+    _t2 = _time.perf_counter()
     out = {k: res[k].view(M, G).cpu().numpy() for k in ("logp", "lnL", "chi2", "bic", "iters")}
+    _t3 = _time.perf_counter()
+    if timing is not None and not (overlap and len(counts) > 1):
+        # host seconds: set-up before the launches, launching, waiting for the device; device ms of K2 and the polish
+        for key, v in (("host_setup_s", _t1 - _t0), ("host_launch_s", _t2 - _t1), ("host_wait_s", _t3 - _t2),
+                       ("k2_ms", ev[0].elapsed_time(ev[1])), ("polish_ms", ev[1].elapsed_time(ev[2]))):
+            timing[key] = timing.get(key, 0.0) + v
     theta_map = res["theta"].cpu().numpy()                                    # [M*G, ts] scaled
     prow = primary_rows.cpu().numpy()                                         # sampler row of the winning chain
     ts = s.ts
@@ -163,6 +237,8 @@ def fit_models(regions, models, voigt=False, sd_free=True, iterations=3000, burn
                     voigt_evals=s.voigt_evals(iterations), work=s.work(), n_chains=M * per,
                     scale=regions.scale[[r for r, _ in models]], iterations=int(iterations),
                     host_regions=getattr(regions, "host_regions", None))
+    if timing is not None:
+        timing["host_post_s"] = timing.get("host_post_s", 0.0) + (_time.perf_counter() - _t3)
     if keep_sampler:
         mb.sampler = s
         mb.inv = inv

@@ -369,15 +369,14 @@ __host__ __device__ inline size_t k3w_warp_bytes(int kmax, int ts, int ncomp_max
            k3_align16(sizeof(CompK<double>) * ncomp_max);
 }
 
-// -logp of `th` (full layout, shared memory); +inf outside the prior support.  All lanes get the
-// same value.  T = float: search precision; T = double: reporting precision.
+// -logp of `th` (component slots + sd at index `sdi`, shared memory); +inf outside the prior support.  All lanes
+// get the same value.  T = float: search precision; T = double: reporting precision.
 template <typename T, int KIND, typename F = Fad<T>>
-__device__ __noinline__ double k3w_objective(const MapDev& p, const double* th, int r, int P, int n, int lane, void* ccbuf,
-                                             double c_hi, double w_hi, double ubase, double& lnL, double& chi2) {
+__device__ __noinline__ double k3w_objective(const MapDev& p, const double* th, int sdi, int r, int P, int n, int lane,
+                                             void* ccbuf, double c_hi, double w_hi, double ubase, double& lnL, double& chi2) {
     constexpr int NP = (KIND == VAMP_KIND_VOIGT) ? 4 : 3;
     typedef typename RS<T>::Pair Pair;
     const RegionSetDev& rs = p.rs;
-    const int sdi = 4 * p.cmax;
     CompK<T>* ccs = reinterpret_cast<CompK<T>*>(ccbuf);
     const double* mrow = region_mult_row(rs, r);              // the region's row of the multiplet table, or nullptr
     const int nl = mrow ? 2 * n : n;                          // lines per evaluation
@@ -462,13 +461,20 @@ k3w_map_kernel(MapDev p, int kmax, int ncomp_max) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int s = p.S - 1 - (blockIdx.x * K3W_WARPS + warp);      // starts sorted by ascending cost: longest first
     if (s < 0) return;
-    const int ts = p.tstride;
+    // A vertex in shared memory holds the component slots of THIS LAUNCH (4 * mc values, mc = the launch's largest
+    // component count) and sd - not the batch-wide stride of the global parameter vectors: the simplex is
+    // (k + 1) x vs doubles per warp, and its size decides how many warps an SM holds (the host launches the starts
+    // in groups of similar component count for that reason, vamp_b200/batch.py).
+    const int gts = p.tstride;                        // stride and sd index of the global parameter vectors
+    const int gsd = 4 * p.cmax;
+    const int mc = (kmax - 1) / NP;
+    const int ts = 4 * mc + 1;                        // vertex stride in shared memory
     unsigned char* wbase = smem_raw + (size_t)warp * k3w_warp_bytes(kmax, ts, ncomp_max);
     const RegionSetDev& rs = p.rs;
     const int r = p.item_region[s];
     const int P = rs.npix[r];
     const int n = p.item_ncomp[s];
-    const int sdi = 4 * p.cmax;
+    const int sdi = 4 * mc;                           // sd inside a shared-memory vertex
     const double ubase = rs.ubase[rs.tile_off[r]];
     const double c_hi = (double)(P - 1);
     const double w_hi = 0.5 * (double)(P - 1) * (KIND == VAMP_KIND_VOIGT ? FWHM_PER_SIGMA : 1.0);
@@ -495,16 +501,16 @@ k3w_map_kernel(MapDev p, int kmax, int ncomp_max) {
     // reported at the end is evaluated with the full float64 set.
     bool fine = false, report = false;
     auto F = [&](const double* th) -> double {
-        if (report) return k3w_objective<double, KIND>(p, th, r, P, n, lane, ccbuf, c_hi, w_hi, ubase, lnL, chi2);
-        return fine ? k3w_objective<double, KIND, FadMid>(p, th, r, P, n, lane, ccbuf, c_hi, w_hi, ubase, lnL, chi2)
-                    : k3w_objective<float, KIND>(p, th, r, P, n, lane, ccbuf, c_hi, w_hi, ubase, lnL, chi2);
+        if (report) return k3w_objective<double, KIND>(p, th, sdi, r, P, n, lane, ccbuf, c_hi, w_hi, ubase, lnL, chi2);
+        return fine ? k3w_objective<double, KIND, FadMid>(p, th, sdi, r, P, n, lane, ccbuf, c_hi, w_hi, ubase, lnL, chi2)
+                    : k3w_objective<float, KIND>(p, th, sdi, r, P, n, lane, ccbuf, c_hi, w_hi, ubase, lnL, chi2);
     };
 
     // ---- initial simplex (scipy: vertex j+1 perturbs coordinate j by 5 %, or 0.00025 if zero)
     for (int v = 0; v < nv; ++v) {
         const int pj = v > 0 ? free_pos(v - 1) : -1;
         for (int i = lane; i < ts; i += 32) {
-            double x = p.theta[(size_t)s * ts + i];
+            double x = p.theta[(size_t)s * gts + ((i == sdi) ? gsd : i)];
             if (i == pj) x = (x != 0.0) ? 1.05 * x : 0.00025;
             sim[(size_t)v * ts + i] = x;
         }
@@ -615,7 +621,7 @@ k3w_map_kernel(MapDev p, int kmax, int ncomp_max) {
     // ---- report in float64 at the best vertex
     report = true;
     const double fbest = F(sim + (size_t)ib * ts);
-    for (int i = lane; i < ts; i += 32) p.theta[(size_t)s * ts + i] = sim[(size_t)ib * ts + i];
+    for (int i = lane; i < ts; i += 32) p.theta[(size_t)s * gts + ((i == sdi) ? gsd : i)] = sim[(size_t)ib * ts + i];
     if (lane == 0) {
         p.out_logp[s] = -fbest;
         p.out_lnL[s] = lnL;
@@ -654,7 +660,7 @@ cudaError_t VAMP_CAT3(vamp_launch_k3w, mixed, VAMP_KN)(const MapDev& p, int max_
     const int NP = (InstKind == VAMP_KIND_VOIGT) ? 4 : 3;
     const int kmax = NP * max_ncomp + 1;
     const int nl_max = max_ncomp * (p.rs.mult ? 2 : 1);
-    const size_t smem = K3W_WARPS * k3w_warp_bytes(kmax, p.tstride, nl_max);
+    const size_t smem = K3W_WARPS * k3w_warp_bytes(kmax, 4 * max_ncomp + 1, nl_max);     // vertex stride 4 mc + 1
     if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
     auto kern = k3w_map_kernel<InstKind>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

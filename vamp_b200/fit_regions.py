@@ -194,7 +194,8 @@ def fit_local(regions_host, uids, voigt=False, sd_free=True, iterations=3000, bu
                     owner.append(i)
         mb = batch.fit_models(regs, models, voigt=voigt, sd_free=sd_free, iterations=iterations, burn=burn, thin=thin,
                               restarts=G, chains_per_restart=chains_per_restart, polish_top=polish_top, dtype=dtype,
-                              seed=seed, region_uids=uids, tune_interval=tune_interval, polish_dtype=polish_dtype)
+                              seed=seed, region_uids=uids, tune_interval=tune_interval, polish_dtype=polish_dtype,
+                              timing=None if stats is None else stats.setdefault("timing", {}))
         if stats is not None:
             stats["voigt_evals"] = stats.get("voigt_evals", 0) + mb.voigt_evals
             stats["voigt_evals_actual"] = stats.get("voigt_evals_actual", 0) + mb.work["shape_pix"]
