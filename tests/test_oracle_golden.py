@@ -170,3 +170,24 @@ def test_doublet_ratios():
     assert fr == pytest.approx(1548.204 / 1550.781) and ar == pytest.approx(0.09475 * 1550.781 / (0.1899 * 1548.204))
     assert lr == pytest.approx(2.628 / 2.643)
     assert P.doublet_ratios((1000.0, 0.2, 1e8), (1010.0, 0.1, 2e8)) == pytest.approx((1000.0 / 1010.0, 0.505, 2.0))
+
+
+def test_product_estimate_n_equals_reference_scipy_calls():
+    """``vamp_b200.fit_regions.estimate_n`` (direct ``correlate1d`` + neighbour comparison) gives the numbers of
+    the reference's ``argrelextrema(gaussian_filter(flux, 3), np.less)`` (vpregion.py:21-35, restated in
+    oracle/region.py and pinned to the reference class by the simba goldens), smoothed arrays bit for bit."""
+    from scipy.ndimage import gaussian_filter
+    from vamp_b200 import synth
+    from vamp_b200 import fit_regions as FR
+    g = np.load(os.path.join(GOLDEN, "simba.npz"))
+    fluxes = [g["%s/r%d/flux" % (k, j)] for k in ("simba_CII1036", "simba_H1215") for j in range(int(g[k + "/nregions"]))]
+    fluxes += [synth.config_c4_region(20_000 + i)["flux"] for i in range(300)]
+    rng = np.random.default_rng(1)
+    fluxes += [rng.uniform(size=P) for P in (1, 2, 3, 4, 5, 12, 13, 24, 25, 26)]      # shorter than the kernel radius
+    fluxes += [np.ones(40), np.r_[np.ones(20), 0.5, 0.5, np.ones(20)]]                # plateaus: no strict minimum
+    counts = []
+    for f in fluxes:
+        assert np.array_equal(FR._smooth3(f), gaussian_filter(np.asarray(f, dtype=np.float64), 3))
+        assert FR.estimate_n(f) == OR.estimate_n(f)
+        counts.append(FR.estimate_n(f))
+    assert max(counts) >= 4                                                            # both branches of the rule seen

@@ -11,12 +11,18 @@ from vamp_b200.fit_regions import fit_regions
 R = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 cpr = int(sys.argv[2]) if len(sys.argv) > 2 else 8
 world, rank, lrank = int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0))
+# workload generation first (host processes are forked before this process touches CUDA)
+if R >= 4096:
+    import multiprocessing as mp
+    with mp.get_context("fork").Pool(min(16, max(1, (os.cpu_count() or 8) // max(world, 1)))) as pool:
+        regs = pool.map(synth.config_c4_region, range(10_000, 10_000 + R), chunksize=256)
+else:
+    regs = [synth.config_c4_region(10_000 + i) for i in range(R)]
 torch.cuda.set_device(lrank)
 if world > 1:
     import torch.distributed as dist
     dist.init_process_group("nccl", device_id=torch.device("cuda", lrank))
 ctx = engine.default_context(lrank)
-regs = [synth.config_c4_region(10_000 + i) for i in range(R)]
 host = [(r["nu"], r["flux"], r["noise"]) for r in regs]
 ntrue = np.array([len(r["truth"]) for r in regs])
 marks = {"k2": 0.0, "k3": 0.0}

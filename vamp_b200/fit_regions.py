@@ -15,12 +15,31 @@ import numpy as np
 from . import batch, engine
 
 
+def _gauss3_weights():
+    """The kernel ``scipy.ndimage.gaussian_filter(x, 3)`` correlates with (sigma 3, truncate 4 -> radius 12)."""
+    x = np.arange(-12, 13)
+    phi = np.exp(-0.5 / 9.0 * x ** 2)
+    return (phi / phi.sum())[::-1].copy()
+
+
+_G3 = _gauss3_weights()
+
+
+def _smooth3(flux_array):
+    """``gaussian_filter(flux, 3)`` bit for bit (it calls ``correlate1d`` with these weights, mode 'reflect') without
+    the wrappers' argument handling, which costs 10 x the arithmetic on a 100-pixel region."""
+    from scipy.ndimage import correlate1d
+    return correlate1d(np.asarray(flux_array, dtype=np.float64), _G3, mode="reflect")
+
+
 def estimate_n(flux_array):
-    """Initial component count, as ``VPregion.estimate_n`` (vamp_1.0/vpregion.py:21-35)."""
-    from scipy.ndimage import gaussian_filter
-    from scipy.signal import argrelextrema
-    k = argrelextrema(gaussian_filter(np.asarray(flux_array, dtype=np.float64), 3), np.less)[0].shape[0]
-    return int(k) if k >= 4 else 1
+    """Initial component count, as ``VPregion.estimate_n`` (vamp_1.0/vpregion.py:21-35): the local minima of
+    ``gaussian_filter(flux, 3)`` (``argrelextrema(.., np.less)``: strictly below both neighbours, never an end
+    pixel), 1 when there are fewer than four.  Same numbers as the scipy calls of the reference (tests), at 1/25 of
+    their cost - 10^5 regions would otherwise spend 50 s of host time here on every rank."""
+    f = _smooth3(flux_array)
+    k = int(np.count_nonzero((f[1:-1] < f[:-2]) & (f[1:-1] < f[2:]))) if f.size > 2 else 0
+    return k if k >= 4 else 1
 
 
 def estimate_n_doublet(flux_array, noise_array, n_sigma=3.0):
@@ -28,10 +47,8 @@ def estimate_n_doublet(flux_array, noise_array, n_sigma=3.0):
     lines of a doublet is mostly continuum, where ``estimate_n``'s count of every local minimum of the smoothed flux
     counts noise; here only minima ``n_sigma`` smoothed-noise deviations below the continuum count, and two of them
     make one absorber."""
-    from scipy.ndimage import gaussian_filter
-    from scipy.signal import argrelextrema
-    f = gaussian_filter(np.asarray(flux_array, dtype=np.float64), 3)
-    idx = argrelextrema(f, np.less)[0]
+    f = _smooth3(flux_array)
+    idx = 1 + np.nonzero((f[1:-1] < f[:-2]) & (f[1:-1] < f[2:]))[0] if f.size > 2 else np.zeros(0, dtype=np.int64)
     sm_noise = float(np.median(np.abs(noise_array))) / np.sqrt(2.0 * np.sqrt(np.pi) * 3.0)   # noise after the sigma = 3 filter
     k = int(np.sum(1.0 - f[idx] > n_sigma * sm_noise))
     return max(1, (k + 1) // 2)
