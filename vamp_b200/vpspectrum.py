@@ -16,8 +16,9 @@ Same constructor arguments, attribute names (``region_pixels``, ``region_waves``
 The reference file has undefined names on some paths (``attempt_n``, ``n``, ``min_region_size``,
 ``forced_number_regions`` at vpspectrum.py:203,216,308,317) and asks the MCMC statistics for
 ``est_sigma_i`` in Voigt mode (KeyError, :401-410); the intended behaviour is implemented here
-(Voigt widths are ``GaussianWidth(G_fwhm)``, vpspectrum.py:376-377).  HDF5 I/O needs ``h5py``
-(not a dependency): ``set_spectrum`` takes arrays, ``write_file`` falls back to ``.npz``.
+(Voigt widths are ``GaussianWidth(G_fwhm)``, vpspectrum.py:376-377).  HDF5 I/O goes through ``h5py`` when it is
+installed and through ``vamp_b200.h5lite`` (the subset of the format the reference's files use) otherwise;
+``set_spectrum`` takes arrays.
 """
 import ctypes as C
 
@@ -141,8 +142,11 @@ class VPspectrum():
         """vpspectrum.py:58-64: HDF5 with ``wavelength``, ``noise``, ``flux`` datasets."""
         try:
             import h5py
-        except ImportError as e:
-            raise ImportError("reading %r needs h5py; use set_spectrum(wavelength, flux, noise)" % self.spectrum_file) from e
+        except ImportError:                                # no h5py: the built-in reader of the same file subset
+            from .h5lite import read_h5
+            data = read_h5(self.spectrum_file)
+            self.set_spectrum(data['wavelength'], data['flux'], data['noise'])
+            return
         with h5py.File(self.spectrum_file, 'r') as data:
             self.set_spectrum(np.array(data['wavelength'][:]), np.array(data['flux'][:]), np.array(data['noise'][:]))
 
@@ -387,12 +391,18 @@ class VPspectrum():
 
     # ------------------------------------------------------------------ output
     def write_file(self):
-        """vpspectrum.py:528-538: ``*params.h5`` and ``*flux_model.h5`` (``.npz`` without h5py)."""
+        """vpspectrum.py:528-538: ``*params.h5`` and ``*flux_model.h5`` with one dataset per key - through h5py when
+        it is installed, otherwise through the built-in writer of the same file subset (``h5lite``)."""
         try:
             import h5py
         except ImportError:
-            np.savez(self.output_filename + 'params.npz', **{k: np.array(v) for k, v in self.params.items()})
-            np.savez(self.output_filename + 'flux_model.npz', **{k: np.array(v) for k, v in self.flux_model.items()})
+            import os
+            from .h5lite import read_h5, write_h5
+            for suffix, table in (('params.h5', self.params), ('flux_model.h5', self.flux_model)):
+                name = self.output_filename + suffix
+                merged = read_h5(name) if os.path.exists(name) else {}      # the reference opens in append mode
+                merged.update({k: np.array(v) for k, v in table.items()})
+                write_h5(name, merged)
             return
         with h5py.File(self.output_filename + 'params.h5', 'a') as f:
             for p in self.params.keys():
