@@ -198,3 +198,39 @@ def test_profile_tau_matches_reference_voigt(ctx, golden_profiles):
         for k, (a, c, w1, w2) in enumerate(comps):
             tau = engine.profile_tau(nu, c, a, w1, w2, voigt=voigt, ctx=ctx)
             np.testing.assert_allclose(tau, g[name + "/taus"][k], rtol=1e-9, atol=1e-13 * max(a, 1.0), err_msg=name)
+
+
+def test_c5_largest_corner(ctx):
+    """BASELINE config C5's largest shapes - 65 536-pixel regions x 32 components - through the chunked CTA schedule:
+    oracle comparison on a few items, then size-independent properties on a batch (multiplicativity of the flux in
+    disjoint component sets, permutation invariance, lnL from the returned flux)."""
+    P, C = 65536, 32
+    rng = np.random.default_rng(65536)
+    nu = synth.NU_LYA + (np.arange(P) - P / 2.0) * synth.DNU
+    cen = rng.uniform(nu[200], nu[-200], C)
+    G = rng.uniform(4.0, 40.0, C) * synth.DNU
+    comps = np.stack([rng.uniform(0.2, 5.0, C), cen, G * 10 ** rng.uniform(-2, -0.3, C), G], axis=1)
+    clean = D.model_flux(nu, comps, True)
+    flux = clean + rng.normal(0, 0.02, P)
+    regs = engine.Regions(ctx, [(nu, flux, np.full(P, 0.02))])
+    for dtype in ("f64", "f32"):
+        lnL, chi2, m = engine.loglike(regs, comps[None], [0], sd=[0.02], dtype=dtype, want_flux=True)
+        np.testing.assert_allclose(m[0], clean, rtol=FLUX_RTOL[dtype], atol=FLUX_ATOL[dtype])
+        if dtype == "f64":
+            assert lnL[0] == pytest.approx(D.normal_loglike(flux, clean, sd=0.02), rel=LNL_RTOL[dtype])
+            assert chi2[0] == pytest.approx(D.chisquared(flux, clean, np.full(P, 0.02)), rel=CHI_RTOL[dtype])
+    # a batch of 48 parameter vectors (fp64): flux(all 32) = flux(first 16) x flux(last 16); order does not matter
+    B = 16
+    th = np.repeat(comps[None], B, axis=0) * (1.0 + rng.uniform(-0.2, 0.2, (B, C, 4)))
+    th[:, :, 1] = comps[None, :, 1] + rng.uniform(-20, 20, (B, C)) * synth.DNU
+    halves = np.zeros((2 * B, C, 4))
+    halves[:B, :16], halves[B:, :16] = th[:, :16], th[:, 16:]
+    ir = np.zeros(B, np.int32)
+    lnL_a, _, m_all = engine.loglike(regs, th, ir, sd=np.full(B, 0.05), dtype="f64", want_flux=True)
+    _, _, m_half = engine.loglike(regs, halves, np.zeros(2 * B, np.int32), np.full(2 * B, 16, np.int32), sd=np.full(2 * B, 0.05),
+                                  dtype="f64", want_flux=True)
+    np.testing.assert_allclose(m_half[:B] * m_half[B:], m_all, rtol=1e-12, atol=1e-300)
+    lnL_p, _ = engine.loglike(regs, th[:, ::-1].copy(), ir, sd=np.full(B, 0.05), dtype="f64")
+    np.testing.assert_allclose(lnL_p, lnL_a, rtol=1e-11)
+    want = [D.normal_loglike(flux, m_all[b], sd=0.05) for b in range(B)]
+    np.testing.assert_allclose(lnL_a, want, rtol=1e-9)
