@@ -35,7 +35,10 @@ def _map(self, *a_, **k):
     a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
     a.record(); r = orig_map(self, *a_, **k); b.record(); evs.append(("k3", a, b)); return r
 engine.Sampler.run, engine.Sampler._map = run, _map
+import gc
 for rep in range(int(os.environ.get("REPS", 3))):
+    if os.environ.get("GCOFF"):
+        gc.collect(); gc.disable()
     evs.clear()
     st = {}
     torch.cuda.synchronize()
@@ -52,6 +55,8 @@ for rep in range(int(os.environ.get("REPS", 3))):
         print("   fit_models: K2 %.0f ms, polish %.0f ms (device); host set-up %.3f s, launch %.3f s, wait %.3f s, post %.3f s" % (
             tm.get("k2_ms", 0), tm.get("polish_ms", 0), tm.get("host_setup_s", 0), tm.get("host_launch_s", 0),
             tm.get("host_wait_s", 0), tm.get("host_post_s", 0)), flush=True)
+        print("   fit_local: upload %.3f s, ladder %.3f s, records %.3f s, close %.3f s" % (
+            tm.get("upload_s", 0), tm.get("ladder_s", 0), tm.get("records_s", 0), tm.get("close_s", 0)), flush=True)
         nfit = np.array([r.n for r in res])
         print("rep %d: %d regions on %d GPU(s): %.2f s -> %.1f regions/s | rank0 K2 %.0f ms K3 %.0f ms rounds %d chains %d | "
               "n == truth %.2f, |n - truth| <= 1 %.2f, status0 %.2f" % (

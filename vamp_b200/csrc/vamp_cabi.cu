@@ -57,6 +57,36 @@ struct vamp_ctx {
     cudaStream_t stream = nullptr;
     DevBuf partial;     // k1_cta per-chunk partial sums
     DevBuf scratch[8];  // staging for the *_host entry points
+    // Region blobs of destroyed region sets, kept for the next upload: cudaFree is a device-wide synchronisation and
+    // was measured at 0.4 - 0.8 s on some calls (tools/bench_regions.py: a third of a 512-region fit), so a batched
+    // fitter that uploads a region set per batch must not pay it per batch.
+    DevBuf region_pool[4];
+    void* take_blob(size_t bytes, size_t* cap) {
+        int best = -1;
+        for (int i = 0; i < 4; ++i)
+            if (region_pool[i].p && region_pool[i].cap >= bytes && (best < 0 || region_pool[i].cap < region_pool[best].cap)) best = i;
+        if (best < 0) return nullptr;
+        void* p = region_pool[best].p;
+        *cap = region_pool[best].cap;
+        region_pool[best].p = nullptr;
+        region_pool[best].cap = 0;
+        return p;
+    }
+    void give_blob(void* p, size_t cap) {
+        int slot = -1;
+        for (int i = 0; i < 4; ++i)
+            if (!region_pool[i].p) { slot = i; break; }
+        if (slot < 0) {                       // full: keep the larger blobs
+            int smallest = 0;
+            for (int i = 1; i < 4; ++i)
+                if (region_pool[i].cap < region_pool[smallest].cap) smallest = i;
+            if (region_pool[smallest].cap >= cap) { cudaFree(p); return; }
+            cudaFree(region_pool[smallest].p);
+            slot = smallest;
+        }
+        region_pool[slot].p = p;
+        region_pool[slot].cap = cap;
+    }
 };
 
 struct vamp_regions {
@@ -67,8 +97,9 @@ struct vamp_regions {
     long long padded_pix = 0;
     std::vector<int> npix, pix_off, tile_off;
     std::vector<double> nu0, scale;
-    void* blob = nullptr;      // one device allocation for everything
-    void* mult = nullptr;      // [R][4] multiplet table (vamp_regions_set_multiplet) or nullptr
+    void* blob = nullptr;      // one device allocation for everything (from / back to the context's pool)
+    size_t blob_cap = 0;
+    void* mult = nullptr;      // [R][4] multiplet table inside the blob (vamp_regions_set_multiplet)
     RegionSetDev dev{};
 };
 
@@ -205,6 +236,7 @@ int vamp_ctx_destroy(vamp_ctx* ctx) {
     cudaSetDevice(ctx->device);
     ctx->partial.release();
     for (auto& b : ctx->scratch) b.release();
+    for (auto& b : ctx->region_pool) b.release();
     delete ctx;
     return 0;
 }
@@ -333,14 +365,23 @@ int vamp_regions_create(vamp_ctx* ctx, int R, const int* npix, const double* nu,
     const size_t o_ln = o; o += al(sizeof(double) * R);
     const size_t o_l32 = o; o += al(sizeof(float) * l32.size());
     const size_t o_l64 = o; o += al(sizeof(double) * l64.size());
-    cudaError_t e = cudaMalloc(&rg->blob, o);
-    if (e != cudaSuccess) { delete rg; return fail(-100, "cudaMalloc(%zu): %s", o, cudaGetErrorString(e)); }
+    const size_t o_mult = o; o += al(sizeof(double) * 4 * (size_t)R);     // room for the multiplet table
+    cudaError_t e = cudaSuccess;
+    rg->blob = ctx->take_blob(o, &rg->blob_cap);          // a pooled blob of a destroyed region set, if one is large enough
+    if (!rg->blob) {
+        // a little headroom, so that the next batch of about the same size finds this blob large enough
+        const size_t want = o + o / 8;
+        e = cudaMalloc(&rg->blob, want);
+        if (e != cudaSuccess) { delete rg; return fail(-100, "cudaMalloc(%zu): %s", want, cudaGetErrorString(e)); }
+        rg->blob_cap = want;
+    }
     char* base = static_cast<char*>(rg->blob);
+    rg->mult = base + o_mult;
     cudaStream_t st = ctx->stream;
 #define VAMP_UP(off, vec, bytes)                                                                         \
     do {                                                                                                 \
         e = cudaMemcpyAsync(base + (off), (vec), (bytes), cudaMemcpyHostToDevice, st);                   \
-        if (e != cudaSuccess) { cudaFree(rg->blob); delete rg; return fail(-100, "H2D: %s", cudaGetErrorString(e)); } \
+        if (e != cudaSuccess) { ctx->give_blob(rg->blob, rg->blob_cap); delete rg; return fail(-100, "H2D: %s", cudaGetErrorString(e)); } \
     } while (0)
     VAMP_UP(o_npix, rg->npix.data(), sizeof(int) * R);
     VAMP_UP(o_poff, rg->pix_off.data(), sizeof(int) * R);
@@ -363,7 +404,7 @@ int vamp_regions_create(vamp_ctx* ctx, int R, const int* npix, const double* nu,
     VAMP_UP(o_l64, l64.data(), sizeof(double) * l64.size());
 #undef VAMP_UP
     e = cudaStreamSynchronize(st);   // host vectors go out of scope
-    if (e != cudaSuccess) { cudaFree(rg->blob); delete rg; return fail(-100, "sync: %s", cudaGetErrorString(e)); }
+    if (e != cudaSuccess) { ctx->give_blob(rg->blob, rg->blob_cap); delete rg; return fail(-100, "sync: %s", cudaGetErrorString(e)); }
     RegionSetDev& d = rg->dev;
     d.R = R;
     d.npix = reinterpret_cast<int*>(base + o_npix);
@@ -393,8 +434,10 @@ int vamp_regions_create(vamp_ctx* ctx, int R, const int* npix, const double* nu,
 int vamp_regions_destroy(vamp_regions* rg) {
     if (!rg) return 0;
     cudaSetDevice(rg->ctx->device);
-    if (rg->blob) cudaFree(rg->blob);
-    if (rg->mult) cudaFree(rg->mult);
+    // kernels of this region set may still be in flight (on the context's stream or on the caller's side streams):
+    // the blob goes back to the pool only after they are done
+    cudaDeviceSynchronize();
+    if (rg->blob) rg->ctx->give_blob(rg->blob, rg->blob_cap);
     delete rg;
     return 0;
 }
@@ -403,8 +446,6 @@ int vamp_regions_set_multiplet(vamp_regions* rg, const double* freq_ratio, const
     if (!rg) return fail(-1, "null regions");
     VAMP_CUDA(cudaSetDevice(rg->ctx->device));
     VAMP_CUDA(cudaStreamSynchronize(rg->ctx->stream));       // kernels in flight may still read the old table
-    if (rg->mult) cudaFree(rg->mult);
-    rg->mult = nullptr;
     rg->dev.mult = nullptr;
     if (!freq_ratio && !amp_ratio) return 0;                  // cleared: single lines everywhere
     if (!freq_ratio || !amp_ratio) return fail(-1, "freq_ratio and amp_ratio must be given together");
@@ -422,13 +463,7 @@ int vamp_regions_set_multiplet(vamp_regions* rg, const double* freq_ratio, const
         any = any || ar != 0.0;
     }
     if (!any) return 0;
-    VAMP_CUDA(cudaMalloc(&rg->mult, sizeof(double) * t.size()));
-    cudaError_t e = cudaMemcpy(rg->mult, t.data(), sizeof(double) * t.size(), cudaMemcpyHostToDevice);
-    if (e != cudaSuccess) {
-        cudaFree(rg->mult);
-        rg->mult = nullptr;
-        return fail(-100, "H2D: %s", cudaGetErrorString(e));
-    }
+    VAMP_CUDA(cudaMemcpy(rg->mult, t.data(), sizeof(double) * t.size(), cudaMemcpyHostToDevice));   // room inside the blob
     rg->dev.mult = static_cast<const double*>(rg->mult);
     return 0;
 }

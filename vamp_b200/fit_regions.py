@@ -192,9 +192,13 @@ def fit_local(regions_host, uids, voigt=False, sd_free=True, iterations=3000, bu
     cmax_rec = int(cmax_rec or (max(n0) + nmax if R else 1 + nmax))
     if R == 0:
         return np.zeros((0, _record_len(nmax, G, cmax_rec)))
+    import time as _time
+    _t = _time.perf_counter()
     regs = engine.Regions(ctx, regions_host, lsf=lsf, multiplet=multiplet)
     if stats is not None:
         stats["h2d_bytes"] = stats.get("h2d_bytes", 0) + regs.h2d_bytes
+        tm = stats.setdefault("timing", {})
+        tm["upload_s"] = tm.get("upload_s", 0.0) + (_time.perf_counter() - _t)
     tables = [dict() for _ in range(R)]
     fits = [dict() for _ in range(R)]
     nxt = list(n0)
@@ -218,6 +222,7 @@ def fit_local(regions_host, uids, voigt=False, sd_free=True, iterations=3000, bu
             stats["voigt_evals_actual"] = stats.get("voigt_evals_actual", 0) + mb.work["shape_pix"]
             stats["launches"] = stats.get("launches", 0) + 4
             stats["chains"] = stats.get("chains", 0) + mb.n_chains
+        _t = _time.perf_counter()
         for m, (i, n) in enumerate(models):
             tables[i][n] = (mb.bic[m].copy(), mb.chi2[m] / freedom[i])
             fits[i][n] = (mb, m)
@@ -231,6 +236,9 @@ def fit_local(regions_host, uids, voigt=False, sd_free=True, iterations=3000, bu
                 nxt[i] = last + 1
                 still.append(i)
         active = still
+        if stats is not None:
+            tm["ladder_s"] = tm.get("ladder_s", 0.0) + (_time.perf_counter() - _t)
+    _t = _time.perf_counter()
     for i in active:      # rounds exhausted: keep the best so far
         kept, exit_n, _ = batch.ladder_replay(n0[i], tables[i], chi_limit)
         outcome[i] = (kept, kept, 2)
@@ -249,7 +257,11 @@ def fit_local(regions_host, uids, voigt=False, sd_free=True, iterations=3000, bu
                              mb.std[m, g, :kept], None if mb.sd_mean is None else mb.sd_mean[m, g],
                              None if mb.sd_std is None else mb.sd_std[m, g], mb.lnL[m, g], chi2=mb.chi2[m, g],
                              cov_aw=cov_aw)
+    _t2 = _time.perf_counter()
     regs.close()                                  # the next device batch (fit_chunked) starts from free memory
+    if stats is not None:
+        tm["records_s"] = tm.get("records_s", 0.0) + (_t2 - _t)
+        tm["close_s"] = tm.get("close_s", 0.0) + (_time.perf_counter() - _t2)
     return out
 
 
