@@ -24,6 +24,9 @@ def chain_uids(region_uid, n, restarts, chains_per_restart):
 # component-count edges of the polish launch groups (<= 4, 5..8, 9..12, more): see ``fit_models.polish``
 POLISH_GROUP_EDGES = (4, 8, 12)
 POLISH_STREAMS = __import__("os").environ.get("VAMP_POLISH_STREAMS", "1") != "0"
+# component-count edges of the sampler launch groups, by CTAs per SM (<= 8: 5, 9..10: 4, 11..15: 3, more: 2); VAMP_K2_GROUPS=0: one launch
+K2_GROUP_EDGES = (8, 10, 15)
+K2_GROUPS = __import__("os").environ.get("VAMP_K2_GROUPS", "1") != "0"
 
 
 _streams = {}
@@ -194,7 +197,28 @@ def fit_models(regions, models, voigt=False, sd_free=True, iterations=3000, burn
         if timing is not None:
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
             ev[0].record()
-        s.run(iterations)
+        # K2's shared memory per chain grows with the LAUNCH's largest component count (base + n_max + 1 cache slots of
+        # 1 KB): a batch holding a few 17-component chains would run everybody at 2 CTAs per SM instead of 5.  The
+        # rows are sorted by component count, so they go out in groups (<= 8, 9..10, 11..15, more), largest first on side
+        # streams; a batch whose counts fit one group (BASELINE C2: n <= 6) is the single launch it always was.
+        bounds, a0 = [], 0
+        for hi in K2_GROUP_EDGES + (int(sorted_nc[-1]),):
+            b0 = int(np.searchsorted(sorted_nc, hi, "right"))
+            if b0 > a0:
+                bounds.append((a0, b0, int(sorted_nc[b0 - 1])))
+            a0 = max(a0, b0)
+        if len(bounds) == 1 or not K2_GROUPS:
+            s.run(iterations)
+        else:
+            side = _polish_streams(dev, len(bounds))
+            for st, (a0, b0, nmax_g) in zip(side, reversed(bounds)):
+                st.wait_stream(main)
+                with torch.cuda.stream(st):
+                    s.run(iterations, rows=(a0, b0), max_ncomp=nmax_g, advance=False)
+            for st in side:
+                main.wait_stream(st)
+            s.ctx.use_current_stream()
+            s.iteration += int(iterations)
         if timing is not None:
             ev[1].record()
         polish(list(range(M)))
