@@ -53,16 +53,19 @@ def test_ladder_replay_matches_oracle_rule():
             assert (k2, e2) == (kept_o, exit_o)
 
 
-def _fake_fit(regions_host, uids, n0=None, cmax_rec=None, nmax=12, restarts=3, **kw):
-    """Stand-in for the GPU fit: a deterministic function of (uid, data) only."""
+def _fake_fit(regions_host, uids, n0=None, cmax_rec=None, nmax=12, restarts=3, multiplet=None, **kw):
+    """Stand-in for the GPU fit: a deterministic function of (uid, data) only (and of the region's multiplet
+    entry, which must arrive sliced like the regions: it is written to ``sd_mean``)."""
     out = np.empty((len(uids), FR._record_len(nmax, restarts, cmax_rec)))
+    assert multiplet is None or len(multiplet) == len(uids)
     for i, uid in enumerate(uids):
         nu, flux, noise = regions_host[i]
         kept = n0[i] + (uid % 2)
         tables = {n0[i] + j: (np.full(restarts, -10.0 * j - uid), np.full(restarts, 2.0 / (j + 1))) for j in range(2)}
         th = np.tile(np.array([flux.mean(), nu[0], noise[0], float(uid)]), (kept, 1))
+        ar = 0.0 if (multiplet is None or multiplet[i] is None) else float(multiplet[i][1])
         out[i] = FR.pack_record(uid, 0, n0[i], kept, kept, tables, nmax, restarts, cmax_rec, th, 0.05, th, th * 0.1,
-                                0.05, 0.001, -float(uid))
+                                0.05 if multiplet is None else ar, 0.001, -float(uid))
     return out
 
 
@@ -82,6 +85,11 @@ def _worker(rank, world, port, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     regs = _regions(11)
     res = FR.fit_regions(regs, uids=list(range(100, 111)), fit_fn=_fake_fit, n0=[1 + (i % 3) for i in range(11)])
+    # per-region multiplet table: every rank's shard (and every device batch of it) gets ITS regions' entries
+    mult = [None if i % 4 == 0 else (0.998, 0.1 * i, 1.0) for i in range(11)]
+    resm = FR.fit_regions(regs, uids=list(range(100, 111)), fit_fn=_fake_fit, n0=[1 + (i % 3) for i in range(11)],
+                          multiplet=mult, max_batch_regions=2)
+    assert [r.sd_mean for r in resm] == [0.0 if m is None else m[1] for m in mult]
     q.put((rank, [(r.uid, r.n, float(r.theta[0, 0]), float(r.lnL), sorted(r.bic)) for r in res]))
     dist.destroy_process_group()
 
@@ -139,3 +147,27 @@ def test_chunked_batches_equal_single_batch():
     for a, b in zip(one, many):
         assert a.uid == b.uid and a.n == b.n
         np.testing.assert_array_equal(a.theta, b.theta)
+
+
+def test_multiplet_table_follows_the_regions():
+    """One tuple for all regions or one per region; sliced with the regions into device batches."""
+    regs = _regions(7)
+    n0 = [1] * 7
+    one = FR.fit_regions(regs, fit_fn=_fake_fit, n0=n0, distributed=False, multiplet=(0.998, 0.5, 1.0), max_batch_regions=3)
+    assert [r.sd_mean for r in one] == [0.5] * 7
+    per = [(0.998, 0.1 * (i + 1)) if i % 2 else None for i in range(7)]
+    res = FR.fit_regions(regs, fit_fn=_fake_fit, n0=n0, distributed=False, multiplet=per, max_batch_regions=3)
+    assert [r.sd_mean for r in res] == [0.0 if m is None else m[1] for m in per]
+    with pytest.raises(ValueError):
+        FR.fit_regions(regs, fit_fn=_fake_fit, n0=n0, distributed=False, multiplet=[(0.9, 0.5)] * 3)
+    # without n0 the absorber count of a doublet region comes from the significant minima
+    from vamp_b200 import synth
+    d = synth.make_doublet_region(256, 2, 60.0, 901)
+    got = {}
+
+    def spy(regions_host, uids, n0=None, **kw):
+        got["n0"] = list(n0)
+        return _fake_fit(regions_host, uids, n0=n0, **kw)
+
+    FR.fit_regions([(d["nu"], d["flux"], d["noise"])] * 2, fit_fn=spy, distributed=False, multiplet=[d["multiplet"], None])
+    assert got["n0"][0] == 2 and got["n0"][1] == FR.estimate_n(d["flux"]) >= 4
