@@ -90,7 +90,7 @@ struct CompS {          // component constants in shared memory (centroid kept i
     T A, g, y, y2, L2;
 };
 
-template <typename T, int KIND>
+template <typename T, int KIND, bool MULT>
 __global__ void __launch_bounds__(256)
 k1_cta_kernel(RegionSetDev rs, int B, int nchunk_max, const int* __restrict__ item_region,
               const int* __restrict__ item_ncomp, const double* __restrict__ theta, int tstride,
@@ -121,7 +121,7 @@ k1_cta_kernel(RegionSetDev rs, int B, int nchunk_max, const int* __restrict__ it
     // counts lines
     MultD md;
     md.fr = md.sh = md.ar = md.lr = 0.0;
-    const int nlines = region_mult(rs, r, md) ? 2 * ncomp0 : ncomp0;
+    const int nlines = (MULT && region_mult(rs, r, md)) ? 2 * ncomp0 : ncomp0;     // MULT: a separate instantiation
     const int ncomp = nlines;
     CompS<T>* cs = reinterpret_cast<CompS<T>*>(mbuf + K1_CHUNK + VAMP_MAX_LSF_TAPS + 1);  // [nlines]
     T* cb = reinterpret_cast<T*>(cs + nlines);                          // [ROWS][nlines]
@@ -131,8 +131,8 @@ k1_cta_kernel(RegionSetDev rs, int B, int nchunk_max, const int* __restrict__ it
     const int ntile = (P + VAMP_TILE_PIX - 1) / VAMP_TILE_PIX;
     for (int i = tid; i < taps; i += 256) lsf_s[i] = RS<T>::lsf(rs)[i];
     for (int c = tid; c < nlines; c += 256) {
-        double pa, pce, pw1, pw2;
-        line_params<KIND>(th, c, ncomp0, md, pa, pce, pw1, pw2);
+        double pa = th[VAMP_TH(c, 0)], pce = th[VAMP_TH(c, 1)], pw1 = th[VAMP_TH(c, 2)], pw2 = th[VAMP_TH(c, 3)];
+        if (MULT) line_params<KIND>(th, c, ncomp0, md, pa, pce, pw1, pw2);
         const CompC<T> cc = make_comp_k1<T, KIND>(pa, pce, pw1, pw2, 0.0);
         cs[c].A = cc.A; cs[c].g = cc.g; cs[c].y = cc.y; cs[c].y2 = cc.y2; cs[c].L2 = cc.L2;
     }
@@ -141,8 +141,8 @@ k1_cta_kernel(RegionSetDev rs, int B, int nchunk_max, const int* __restrict__ it
         // rows 0..7: tiles of this chunk; row 8: tile left of the chunk; row 9: tile right of it
         int tl = (row < PPL) ? chunk * PPL + row : (row == PPL ? chunk * PPL - 1 : chunk * PPL + PPL);
         tl = min(max(tl, 0), ntile - 1);
-        double pa, pce, pw1, pw2;
-        line_params<KIND>(th, c, ncomp0, md, pa, pce, pw1, pw2);
+        double pa, pce = th[VAMP_TH(c, 1)], pw1, pw2;
+        if (MULT) line_params<KIND>(th, c, ncomp0, md, pa, pce, pw1, pw2);
         cb[i] = T(pce - rs.ubase[rs.tile_off[r] + tl]);
     }
     __syncthreads();
@@ -284,7 +284,7 @@ cudaError_t launch_k1_t(const RegionSetDev& rs, int B, int max_npix, int max_nco
         const size_t nl_max = (size_t)max_ncomp * (rs.mult ? 2 : 1);          // multiplet regions: two lines per component
         const size_t smem = 16 * sizeof(double) + sizeof(T) * (VAMP_MAX_LSF_TAPS + K1_CHUNK + VAMP_MAX_LSF_TAPS + 1) +
                             sizeof(CompS<T>) * nl_max + sizeof(T) * (K1_CHUNK / 256 + 2) * nl_max + 16;
-        auto kern = k1_cta_kernel<T, KIND>;
+        auto kern = rs.mult ? k1_cta_kernel<T, KIND, true> : k1_cta_kernel<T, KIND, false>;
         if (smem > 48 * 1024) {
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
