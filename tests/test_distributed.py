@@ -124,6 +124,15 @@ def test_chain_uids_unique_and_world_independent():
     assert len(np.unique(allu)) == allu.size
 
 
+def test_model_chain_uids_equal_the_per_model_definition():
+    rng = np.random.default_rng(0)
+    region_uids = rng.integers(0, 2 ** 39, 50)
+    models = [(int(rng.integers(0, 50)), int(rng.integers(1, 18))) for _ in range(400)]
+    want = np.concatenate([batch.chain_uids(region_uids[r], n, 3, 8) for r, n in models])
+    got = batch.model_chain_uids(region_uids, models, 3, 8)
+    assert got.dtype == np.uint64 and np.array_equal(got, want)
+
+
 def test_empty_inputs_need_no_device():
     """No regions (an empty catalogue, or a rank whose shard is empty): an empty result, no GPU touched."""
     assert FR.fit_regions([], distributed=False) == []

@@ -41,6 +41,15 @@ def _polish_streams(dev, n):
     return pool[:n]
 
 
+def model_chain_uids(region_uids, models, restarts, chains_per_restart):
+    """``chain_uids`` of every model ``(region index, n)``, concatenated in model order, without the per-model loop
+    (0.3 s of host time at 4 x 10^4 models)."""
+    m_reg = np.asarray(region_uids)[[r for r, _ in models]].astype(np.int64).astype(np.uint64) & np.uint64(0xFFFFFFFFFF)
+    m_n = np.array([n for _, n in models], dtype=np.uint64) & np.uint64(0xFF)
+    c = np.arange(int(restarts) * int(chains_per_restart), dtype=np.uint64)
+    return (((m_reg << np.uint64(24)) | (m_n << np.uint64(16)))[:, None] | c[None, :]).reshape(-1)
+
+
 class ModelBatch:
     """Result tables of one batched fit (numpy, host).  Shapes: M models, G restarts."""
 
@@ -74,7 +83,7 @@ def fit_models(regions, models, voigt=False, sd_free=True, iterations=3000, burn
     per = G * Cn
     item_region = np.repeat(np.array([r for r, _ in models], dtype=np.int32), per)
     item_ncomp = np.repeat(np.array([n for _, n in models], dtype=np.int32), per)
-    uid = np.concatenate([chain_uids(region_uids[r], n, G, Cn) for r, n in models])
+    uid = model_chain_uids(region_uids, models, G, Cn)
     # sampler rows sorted by (component count, pixel class, model): CTAs are homogeneous, a kernel launches its
     # rows from the end (most expensive chains first), and the chains of one component count are contiguous,
     # so every count can run as its own launch on its own stream (below)
