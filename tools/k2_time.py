@@ -1,12 +1,14 @@
-"""Time the K2 launch of the bench workload (C2) with CUDA events:  python tools/k2_time.py [iters]"""
+"""Time the K2 launch of the bench workload (C2) with CUDA events:  python tools/k2_time.py [iters] [doublet]
+(``doublet``: the same chain set on a CIV doublet region - evals are then LINE evaluations, two per component)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from vamp_b200 import batch, engine, synth
 iters = int(sys.argv[1]) if len(sys.argv) > 1 else 1000
+doublet = len(sys.argv) > 2 and sys.argv[2] == "doublet"       # a CIV doublet region: two tied lines per component
 ctx = engine.default_context(0)
-reg = synth.config_c2(region_id=2)
-regs = engine.Regions(ctx, [(reg["nu"], reg["flux"], reg["noise"])])
+reg = synth.make_doublet_region(256, 3, 50.0, 2, "CIV", True) if doublet else synth.config_c2(region_id=2)
+regs = engine.Regions(ctx, [(reg["nu"], reg["flux"], reg["noise"])], multiplet=reg["multiplet"] if doublet else None)
 mb = batch.fit_models(regs, [(0, n) for n in range(1, 7)], voigt=True, iterations=50, burn=5, thin=15, restarts=4,
                       chains_per_restart=1024, dtype="f32", seed=1, region_uids=[2], keep_sampler=True)
 s = mb.sampler
