@@ -26,10 +26,11 @@ class Model:
     Flat vector layout: per component ``[amplitude, centroid, w1(, w2)]`` then
     ``sd`` when ``noise is None`` (``VPfit(noise=None)``, vpfits.py:35-39)."""
 
-    def __init__(self, x, flux, n, voigt, noise=None, lsf=None):
+    def __init__(self, x, flux, n, voigt, noise=None, lsf=None, multiplet=None):
         self.x = np.asarray(x, dtype=np.float64)
         self.flux = np.asarray(flux, dtype=np.float64)
         self.n, self.voigt, self.noise, self.lsf = int(n), bool(voigt), noise, lsf
+        self.multiplet = multiplet            # (freq_ratio, amp_ratio, lorentz_ratio): density.second_line
         self.per = 4 if voigt else 3
         self.sd_free = noise is None
         self.k = self.per * self.n + (1 if self.sd_free else 0)
@@ -56,16 +57,16 @@ class Model:
     def logp(self, theta):
         comps, sd = self.unpack(theta)
         return D.log_posterior(comps, self.x, self.flux, self.voigt, sd=sd,
-                               noise=None if self.sd_free else self.noise, lsf=self.lsf)
+                               noise=None if self.sd_free else self.noise, lsf=self.lsf, multiplet=self.multiplet)
 
     def loglike(self, theta):
         comps, sd = self.unpack(theta)
-        return D.normal_loglike(self.flux, D.model_flux(self.x, comps, self.voigt, self.lsf), sd=sd,
+        return D.normal_loglike(self.flux, D.model_flux(self.x, comps, self.voigt, self.lsf, self.multiplet), sd=sd,
                                 noise=None if self.sd_free else self.noise)
 
     def total(self, theta):
         comps, _ = self.unpack(theta)
-        return D.model_flux(self.x, comps, self.voigt, self.lsf)
+        return D.model_flux(self.x, comps, self.voigt, self.lsf, self.multiplet)
 
 
 def pymc2_tune(asf, acc_rate):

@@ -191,3 +191,18 @@ def test_product_estimate_n_equals_reference_scipy_calls():
         assert FR.estimate_n(f) == OR.estimate_n(f)
         counts.append(FR.estimate_n(f))
     assert max(counts) >= 4                                                            # both branches of the rule seen
+
+
+def test_restated_sampler_model_with_doublet():
+    """The restated PyMC 2 model (oracle/sampler.py) with a multiplet: its density is the doublet density, and the
+    truth of a synthetic CIV doublet region scores far above the same parameters read as single lines."""
+    from oracle import sampler as OS
+    from vamp_b200 import synth
+    reg = synth.make_doublet_region(256, 2, 50.0, 77, "CIV", True)
+    m2 = OS.Model(reg["nu"], reg["flux"], 2, True, multiplet=reg["multiplet"])
+    m1 = OS.Model(reg["nu"], reg["flux"], 2, True)
+    theta = np.concatenate([reg["truth"].reshape(-1), [0.02]])
+    np.testing.assert_allclose(m2.total(theta), reg["clean"], rtol=1e-12)
+    assert m2.logp(theta) == pytest.approx(D.log_posterior(reg["truth"], reg["nu"], reg["flux"], True, sd=0.02,
+                                                           multiplet=reg["multiplet"]), rel=1e-14)
+    assert m2.loglike(theta) - m1.loglike(theta) > 100.0
