@@ -170,7 +170,7 @@ def replay_chain(u, flux, noise, theta0, n, voigt, sd_free, uid, seed, iters, bu
                 else:
                     rej[idx] += 1
                 if record_every_step:
-                    steps.append((idx, prop, accept))
+                    steps.append((idx, prop, accept, ok))
         if sd_free:
             z, lu = rng.get(q)
             q += 1
@@ -186,7 +186,7 @@ def replay_chain(u, flux, noise, theta0, n, voigt, sd_free, uid, seed, iters, bu
             else:
                 rej[sdi] += 1
             if record_every_step:
-                steps.append((sdi, prop, accept))
+                steps.append((sdi, prop, accept, 0.0 < prop <= 1.0))
         lnL = lnL_of(Scur, sd)
         logp = lnL + sum(math.log(th[4 * c]) - th[4 * c] for c in range(n))
         if logp > best_logp:

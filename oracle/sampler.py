@@ -123,6 +123,35 @@ def metropolis_sample(model, theta0, iters, burn, thin, rng, tune_interval=1000,
     return np.array(trace), theta, logp
 
 
+class CachedModel(Model):
+    """``Model`` whose ``logp`` re-evaluates only the component that changed since the last call - the economy PyMC 2's
+    LazyFunction cache gives the reference (a step on a parameter of component c recomputes only
+    profile c, then ``total`` and the Normal logp).  Same floats as ``Model.logp`` (the per-component rows are summed in
+    the same order); it only makes the restated sampler fast enough to run ladders of many-component regions."""
+
+    def __init__(self, *a, **kw):
+        Model.__init__(self, *a, **kw)
+        self._comps = None
+        self._taus = None
+
+    def logp(self, theta):
+        comps, sd = self.unpack(theta)
+        lp = D.log_prior(comps, self.x, self.voigt, sd=sd)
+        if not np.isfinite(lp):
+            return -np.inf
+        if self._comps is None:
+            self._comps = np.full_like(comps, np.nan)
+            self._taus = np.zeros((self.n, len(self.x)))
+        for c in range(self.n):
+            if not np.array_equal(comps[c], self._comps[c]):
+                self._taus[c] = D.component_taus(self.x, comps[c: c + 1], self.voigt, self.multiplet)[0]
+                self._comps[c] = comps[c]
+        with np.errstate(all="ignore"):
+            m = D.lsf_convolve(D.tau2flux(self._taus.sum(axis=0)), self.lsf)
+            ll = D.normal_loglike(self.flux, m, sd=sd, noise=None if self.sd_free else self.noise)
+        return lp + ll if np.isfinite(ll) else -np.inf
+
+
 def map_fit(model, theta0, iterlim=3000, tol=1e-3):
     """``mc.MAP(model).fit(iterlim=..., tol=1e-3)`` (vpfits.py:358, 422-426):
     ``scipy.optimize.fmin`` (Nelder-Mead) on ``-logp`` with ``ftol=tol``,
@@ -136,15 +165,16 @@ def map_fit(model, theta0, iterlim=3000, tol=1e-3):
 
 
 def find_bic(x, flux, n, noise_array, freedom, voigt=False, iterations=3000, thin=15, burn=300,
-             rng=None, restarts=3):
+             rng=None, restarts=3, tune_interval=1000):
     """``VPfit.find_bic`` - vpfits.py:398-429 (non-``thorough`` branch):
     3 x (fresh model, MCMC, MAP from the last MCMC state) -> ``bic_array``,
     ``red_chi_array``; returns also the last restart's MAP vector."""
     rng = rng or np.random.default_rng(0)
-    model = Model(x, flux, n, voigt)
+    model = CachedModel(x, flux, n, voigt)
     bics, reds, theta = [], [], None
     for _ in range(restarts):
-        _, last, _ = metropolis_sample(model, model.initial(rng), iterations, burn, thin, rng)
+        _, last, _ = metropolis_sample(model, model.initial(rng), iterations, burn, thin, rng,
+                                       tune_interval=tune_interval)
         theta, _, b, _ = map_fit(model, last, iterlim=iterations)
         bics.append(b)
         reds.append(D.reduced_chisquared(flux, model.total(theta), noise_array, freedom))

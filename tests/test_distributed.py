@@ -90,7 +90,10 @@ def _worker(rank, world, port, q):
     resm = FR.fit_regions(regs, uids=list(range(100, 111)), fit_fn=_fake_fit, n0=[1 + (i % 3) for i in range(11)],
                           multiplet=mult, max_batch_regions=2)
     assert [r.sd_mean for r in resm] == [0.0 if m is None else m[1] for m in mult]
-    q.put((rank, [(r.uid, r.n, float(r.theta[0, 0]), float(r.lnL), sorted(r.bic)) for r in res]))
+    # no n0 given: every rank counts the minima of its slice, one all-gather makes the counts global
+    auto = FR.fit_regions(regs, uids=list(range(100, 111)), fit_fn=_fake_fit)
+    q.put((rank, [(r.uid, r.n, float(r.theta[0, 0]), float(r.lnL), sorted(r.bic)) for r in res], auto.checksum(),
+           [int(v) for v in auto.records[:, 2]]))
     dist.destroy_process_group()
 
 
@@ -109,11 +112,37 @@ def test_fit_regions_gloo_world2_equals_single_process():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    got = dict(q.get(timeout=120) for _ in range(2))
+    rows = [q.get(timeout=120) for _ in range(2)]
+    got = {r[0]: r[1] for r in rows}
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
     assert got[0] == ref and got[1] == ref
+    # the sliced estimate_n + gather gives the single-process counts, and the records' checksum is world-size independent
+    auto1 = FR.fit_regions(regs, uids=list(range(100, 111)), fit_fn=_fake_fit, distributed=False)
+    assert [r[3] for r in rows] == [[FR.estimate_n(r[1]) for r in regs]] * 2
+    assert {r[2] for r in rows} == {auto1.checksum()}
+
+
+def test_emulated_ranks_reassemble_the_single_process_result():
+    """``emulate=(rank, world)``: the records a rank of a W-rank run computes; their union is the 1-rank result."""
+    regs = _regions(23)
+    uids = list(range(500, 523))
+    one = FR.fit_regions(regs, uids=uids, fit_fn=_fake_fit, distributed=False)
+    for world in (2, 3, 8):
+        parts = [FR.fit_regions(regs, uids=uids, fit_fn=_fake_fit, emulate=(r, world)).records for r in range(world)]
+        assert sum(len(p) for p in parts) == 23
+        allr = np.concatenate(parts)
+        allr = allr[np.argsort(allr[:, 0])]
+        assert FR.RegionResults(allr, one.nmax, one.G, one.cmax).checksum() == one.checksum()
+
+
+def test_region_costs_vectorised_equals_scalar():
+    rng = np.random.default_rng(1)
+    P, n0 = rng.integers(17, 257, 50), rng.integers(1, 9, 50)
+    for voigt in (False, True):
+        for w in (1, 3, 4):
+            np.testing.assert_allclose(FR.region_costs(P, n0, w, voigt), [FR.region_cost(p, n, w, voigt) for p, n in zip(P, n0)])
 
 
 def test_chain_uids_unique_and_world_independent():

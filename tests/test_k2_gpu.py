@@ -80,6 +80,7 @@ def test_chain_replay_mixed_regions_per_cta(ctx):
     s.run(25)
     s.run(iters - 25)
     th, ntal, tr, acc, rej, acct = s.get("theta"), s.get("ntally"), s.get("trace"), s.get("acc"), s.get("rej"), s.get("acc_total")
+    work = s.get("work")
     for b in range(B):
         r = int(item_region[b])
         u = _scaled_grid(regs, r)
@@ -90,12 +91,19 @@ def test_chain_replay_mixed_regions_per_cta(ctx):
         np.testing.assert_allclose(tr[b, : ntal[b]], ref["trace"], rtol=1e-8, atol=1e-10)
         # counters: acc + rej = proposals since the last tune; acc_total = accepted steps of iterations >= burn
         k = 4 * ns[r] + 1
-        steps = np.array([(i, a) for i, _, a in ref["steps"]]).reshape(iters, k, 2)
+        steps = np.array([(i, a) for i, _, a, _ in ref["steps"]]).reshape(iters, k, 2)
         free = steps[0, :, 0]
         np.testing.assert_array_equal(acct[b][free], steps[burn:, :, 1].sum(axis=0))
         last_tune = (iters - 1) // tune * tune
         np.testing.assert_array_equal(acc[b][free], steps[last_tune:, :, 1].sum(axis=0))
         np.testing.assert_array_equal((acc[b] + rej[b])[free], np.full(k, iters - last_tune))
+        # work counters (the numerator of bench.py's ``value``): shape evaluations = in-bounds centroid / width
+        # proposals, likelihood passes = in-bounds amplitude, centroid and width proposals (sd steps evaluate nothing)
+        inb = np.array([(i, ok) for i, _, _, ok in ref["steps"]])
+        comp = inb[:, 0] < 4 * ns[r]
+        assert work[b, 0] == int(np.sum(inb[comp & (inb[:, 0] % 4 != 0), 1]))
+        assert work[b, 2] == int(np.sum(inb[comp, 1]))
+        assert 0 <= work[b, 1] <= work[b, 0] * sizes[r]
 
 
 def test_chain_fp32_tracks_fp64_initially(ctx):

@@ -1,0 +1,80 @@
+"""GPU: the BENCHMARKED sampler (fp32, Voigt, multi-component) against reference-style chains and the truth.
+
+north_star: "Sampler output is validated statistically against the reference's PyMC chains (posterior means and
+credible intervals of N, b and v within Monte Carlo error on synthetic absorbers with known truth)".  The chains of
+``tests/golden/posterior_c2.json`` come from the oracle's restated PyMC 2 scalar Metropolis sampler over the reference
+density (oracle/make_posterior_golden.py; PyMC 2 itself is not installable: parity unpinned, statistical) on the
+3-component 256-px C2 region; N, b, v are derived per sample with the reference's physics.py formulas
+(vamp_1.0/vpspectrum.py:377, 421-422).  The device chains (fp32 K2, the kernel ``bench.py`` times) start at the
+truth like the oracle's, are pooled over all chains, and must give the same posterior.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle.make_posterior_golden import nbv
+from vamp_b200 import engine, synth
+
+pytestmark = pytest.mark.gpu
+
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "posterior_c2.json")))
+
+
+def _device_chains(ctx, dtype, B=256, iters=24000, seed=31):
+    reg = synth.config_c2()
+    regs = engine.Regions(ctx, [(reg["nu"], reg["flux"], reg["noise"])])
+    burn, thin = GOLD["burn"], GOLD["thin"]
+    cap = (iters - burn) // thin + 2
+    s = engine.Sampler(regs, np.zeros(B, np.int32), np.full(B, 3, np.int32), np.arange(B, dtype=np.uint64) + 7000,
+                       voigt=True, sd_free=True, dtype=dtype, seed=seed, burn=burn, thin=thin, tune_interval=200,
+                       tune_throughout=True, trace_cap=cap)
+    start = np.zeros((B, s.ts))
+    start[:, :12] = regs.to_scaled(reg["truth"][None], [0])[0].reshape(-1)
+    start[:, 12] = 1.0 / reg["snr"]
+    s.init(start)
+    s.run(iters)
+    nt = s.get("ntally")
+    tr = s.get("trace")
+    assert nt.min() == nt.max() <= cap
+    T = int(nt[0])
+    comps = regs.to_physical(tr[:, :T, :12].reshape(B * T, 3, 4), np.zeros(B * T, np.int32))
+    q = nbv(comps).reshape(B, T, 3, 3)                    # [chain, sample, component (by centroid), (N, b, v)]
+    return q, tr[:, :T, 12], reg
+
+
+@pytest.mark.parametrize("dtype", ["f32", "f64"])
+def test_voigt_posterior_nbv_matches_reference_style_chains_and_truth(ctx, dtype):
+    q, sd, reg = _device_chains(ctx, dtype)
+    B = q.shape[0]
+    pooled = q.reshape(-1, 3, 3)
+    mean, std = pooled.mean(axis=0), pooled.std(axis=0)
+    mc_gpu = q.mean(axis=1).std(axis=0, ddof=1) / np.sqrt(B)
+    g_mean, g_std, g_mc = np.array(GOLD["mean"]), np.array(GOLD["std"]), np.array(GOLD["mc_error"])
+    truth = np.array(GOLD["truth"])
+    out = {"dtype": dtype, "mean": mean.tolist(), "std": std.tolist(), "oracle_mean": g_mean.tolist(),
+           "oracle_std": g_std.tolist(), "truth": truth.tolist(), "mc_gpu": mc_gpu.tolist(), "mc_oracle": g_mc.tolist()}
+    try:
+        d = os.path.join(os.path.dirname(os.path.dirname(__file__)), "gpurun_out")
+        os.makedirs(d, exist_ok=True)
+        json.dump(out, open(os.path.join(d, "posterior_c2_%s.json" % dtype), "w"), indent=1)
+    except OSError:
+        pass
+    # posterior means of N, b, v of every component: equal within the Monte-Carlo error of the two estimates
+    # (5 sigma of their combined error + 3 % of the posterior width for the finite burn-in of both)
+    tol = 5.0 * np.sqrt(g_mc ** 2 + mc_gpu ** 2) + 0.03 * g_std
+    assert np.all(np.abs(mean - g_mean) <= tol), (np.abs(mean - g_mean) / tol)
+    # credible intervals: 16 / 50 / 84 % quantiles within the same error + 10 % of the posterior width
+    for name, p in (("q16", 16), ("q50", 50), ("q84", 84)):
+        qq = np.percentile(pooled, p, axis=0)
+        assert np.all(np.abs(qq - np.array(GOLD[name])) <= tol + 0.10 * g_std), (name, (qq - np.array(GOLD[name])) / g_std)
+    # posterior widths agree within 15 %
+    np.testing.assert_allclose(std, g_std, rtol=0.15)
+    # known truth: b and v (well constrained) inside the central 99.7 % of the posterior; N (the reference's
+    # amplitude_L x sigma, degenerate with the poorly constrained L / G) inside its sampled range
+    assert np.all(np.abs(mean[:, 1:] - truth[:, 1:]) <= 4.0 * std[:, 1:]), (mean - truth) / std
+    assert np.all((pooled[:, :, 0].min(axis=0) <= truth[:, 0]) & (truth[:, 0] <= pooled[:, :, 0].max(axis=0)))
+    # the free noise parameter sd ~ 1 / SNR
+    assert sd.mean() == pytest.approx(GOLD["sd_mean"], abs=5 * GOLD["sd_std"] / np.sqrt(50.0))
+    assert sd.mean() == pytest.approx(1.0 / reg["snr"], rel=0.15)

@@ -64,13 +64,15 @@ class ModelBatch:
 def fit_models(regions, models, voigt=False, sd_free=True, iterations=3000, burn=300, thin=15, restarts=3,
                chains_per_restart=32, polish_top=4, dtype="f32", seed=0, region_uids=None, tune_interval=50,
                tune_throughout=True, keep_sampler=False, trace=False, maxiter=None, xtol=1e-4, ftol=1e-3,
-               polish_dtype="f64", overlap=False, timing=None):
+               polish_dtype="f64", overlap=False, timing=None, polish_from="best"):
     """Fit ``models = [(region_index, n), ...]`` on the device-resident ``regions``.
 
     Per model and restart group: prior-drawn starts -> ``iterations`` of K2 Metropolis ->
     Nelder-Mead polish (K3) of the group's ``polish_top`` best chains -> the group's MAP,
     ``BIC = k ln P - 2 lnL`` and noise-weighted chi^2 (the quantities ``find_bic`` appends,
-    vpfits.py:427-428).  Returns a :class:`ModelBatch`."""
+    vpfits.py:427-428).  ``polish_from``: "best" - the polish starts from each chain's best visited state (default);
+    "last" - from its LAST state, which is what the reference does (``map.fit`` after ``mcmc.sample`` starts from the
+    sampler's final values, vpfits.py:425-426).  Returns a :class:`ModelBatch`."""
     import time as _time
     torch = engine._torch()
     _t0 = _time.perf_counter()
@@ -100,6 +102,9 @@ def fit_models(regions, models, voigt=False, sd_free=True, iterations=3000, burn
     d_inv = torch.from_numpy(inv).to(dev)
     K = max(1, min(int(polish_top), Cn))
     MG = M * G
+    if polish_from not in ("best", "last"):
+        raise ValueError("polish_from must be 'best' or 'last'")
+    rank_key, start_key = ("best_logp", "best_theta") if polish_from == "best" else ("logp", "theta")
     f64 = torch.float64
     res = {k: torch.empty(MG, dtype=f64, device=dev) for k in ("logp", "lnL", "chi2", "bic")}
     res["iters"] = torch.empty(MG, dtype=torch.int32, device=dev)
@@ -113,7 +118,7 @@ def fit_models(regions, models, voigt=False, sd_free=True, iterations=3000, burn
         mg = (mid[:, None] * G + torch.arange(G, device=dev)[None, :]).reshape(-1)        # (model, restart) ids
         chains = (mg[:, None] * Cn + torch.arange(Cn, device=dev)[None, :])               # logical chain ids [mg, Cn]
         rows = d_inv[chains]                                                             # sampler rows
-        blp = torch.nan_to_num(s.t["best_logp"][rows], nan=-float("inf"))
+        blp = torch.nan_to_num(s.t[rank_key][rows], nan=-float("inf"))
         top = blp.topk(K, dim=1).indices
         phys = torch.gather(rows, 1, top).reshape(-1)
         # launch order of the polish: cheapest starts first in memory, the kernels take their work from the END of
@@ -124,7 +129,7 @@ def fit_models(regions, models, voigt=False, sd_free=True, iterations=3000, burn
         unsort = torch.empty_like(lpt)
         unsort[lpt] = torch.arange(lpt.numel(), device=dev)
         ps = phys[lpt]
-        starts = s.t["best_theta"][ps].contiguous()
+        starts = s.t[start_key][ps].contiguous()
         p_reg, p_nc = s.t["item_region"][ps].contiguous(), s.t["item_ncomp"][ps].contiguous()
         # The warp-per-start schedule keeps a (k + 1) x (4 n_max + 1) simplex per warp in shared memory, n_max being
         # the LAUNCH's largest component count, and that footprint decides how many warps an SM holds: the starts

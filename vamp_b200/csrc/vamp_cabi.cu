@@ -317,6 +317,13 @@ int vamp_regions_create(vamp_ctx* ctx, int R, const int* npix, const double* nu,
                 du32[o] = (float)(u - ub);
                 f64[o] = flux[src + i];
                 f32[o] = (float)flux[src + i];
+                // a zero / NaN / inf noise or a non-finite flux would give an inf or NaN weight: chains would freeze
+                // (every accept test compares false) and BIC / chi^2 turn NaN without any error raised
+                if (!std::isfinite(flux[src + i]) || !std::isfinite(noise[src + i]) || noise[src + i] == 0.0) {
+                    delete rg;
+                    return fail(-4, "region %d, pixel %d: flux must be finite and noise finite and non-zero (flux %g, noise %g)",
+                                r, i, flux[src + i], noise[src + i]);
+                }
                 const double w = 1.0 / noise[src + i];
                 w64[o] = w;
                 w32[o] = (float)w;

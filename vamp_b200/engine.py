@@ -107,6 +107,12 @@ class Regions:
         noise = np.ascontiguousarray(np.concatenate([np.asarray(r[2], dtype=np.float64) for r in regions]))
         if not (len(nu) == len(flux) == len(noise) == int(self.npix.sum())):
             raise ValueError("nu / flux / noise lengths differ")
+        bad = ~(np.isfinite(flux) & np.isfinite(noise) & (noise != 0.0))
+        if bad.any():            # mirrored in vamp_regions_create (error -4): fail before anything is uploaded
+            i = int(np.argmax(bad))
+            r = int(np.searchsorted(np.cumsum(self.npix), i, side="right"))
+            raise ValueError("region %d: flux must be finite and noise finite and non-zero (flux %r, noise %r at pixel %d)"
+                             % (r, flux[i], noise[i], i - int(self.npix[:r].sum())))
         self.lsf = None if lsf is None else np.ascontiguousarray(np.asarray(lsf, dtype=np.float64))
         h = C.c_void_p()
         check(self.lib.vamp_regions_create(

@@ -60,18 +60,34 @@ def region_cost(npix, n0, window, voigt):
     return float(npix) * sum(per * n + 1 for n in range(n0, n0 + window))
 
 
+def region_costs(npix, n0, window, voigt):
+    """``region_cost`` of many regions at once (numpy)."""
+    per = 4 if voigt else 3
+    n0 = np.asarray(n0, dtype=np.float64)
+    w = float(window)
+    return np.asarray(npix, dtype=np.float64) * (per * (w * n0 + 0.5 * w * (w - 1.0)) + w)
+
+
 def lpt_partition(costs, world_size):
     """Longest-processing-time-first static partition.  Returns a list of index lists
-    (deterministic: ties broken by index)."""
-    order = sorted(range(len(costs)), key=lambda i: (-costs[i], i))
-    loads = [0.0] * world_size
+    (deterministic: ties broken by index).  Heap-based: O(R log W), 10^5 regions in ~0.1 s."""
+    import heapq
+    costs = np.asarray(costs, dtype=np.float64)
+    order = np.lexsort((np.arange(costs.size), -costs))
+    heap = [(0.0, k) for k in range(world_size)]
     parts = [[] for _ in range(world_size)]
     for i in order:
-        r = min(range(world_size), key=lambda k: (loads[k], k))
-        parts[r].append(i)
-        loads[r] += costs[i]
+        load, r = heapq.heappop(heap)
+        parts[r].append(int(i))
+        heapq.heappush(heap, (load + float(costs[i]), r))
     return [sorted(p) for p in parts]
 
+
+# ``fit_regions(..., **REFERENCE_DEFAULTS)``: the reference's own sampling settings - ONE chain per restart
+# (vpfits.py:417-425), PyMC 2's tuning interval of 1000 iterations, Nelder-Mead from the chain's LAST state
+# (vpfits.py:426).  The many-chain defaults explore better (lower BIC per candidate); this mode exists so that the
+# ladder's outcome can be compared with the reference's like for like (tests/test_ladder_gpu.py).
+REFERENCE_DEFAULTS = dict(chains_per_restart=1, tune_interval=1000, polish_from="last", polish_top=1)
 
 MIXED_POLISH_STARTS = 2048
 MAX_BATCH_REGIONS = 16384      # regions per device batch: ~1.2e6 chains, ~5 GB of chain state at the C4 settings
@@ -119,23 +135,26 @@ class RegionResult:
         self.__dict__.update(kw)
 
 
+_HEAD = 7       # uid, status, n0, kept n, exit n, candidates fitted, tallied samples of the winning chain
+
+
 def _record_len(nmax, G, cmax):
-    return 6 + 2 * nmax * G + 1 + 3 * cmax * 4 + 3 + 1 + cmax
+    return _HEAD + 2 * nmax * G + 1 + 3 * cmax * 4 + 3 + 1 + cmax
 
 
 def pack_record(uid, status, n0, kept, exit_n, tables, nmax, G, cmax, theta, sd, mean, std, sd_mean, sd_std, lnL,
-                chi2=np.nan, cov_aw=None):
+                chi2=np.nan, cov_aw=None, ntally=0):
     """Fixed-geometry float64 record of one region (the unit of the result all-gather).  ``chi2``:
     noise-weighted chi^2 of the kept fit; ``cov_aw``: posterior covariance of (amplitude, Gaussian
     width) per component (physical units) - what ``chain_covariance`` / ``ErrorN`` consume."""
     rec = np.full(_record_len(nmax, G, cmax), np.nan)
-    rec[0:6] = [uid, status, n0, kept, exit_n, len(tables)]
+    rec[0:_HEAD] = [uid, status, n0, kept, exit_n, len(tables), ntally]
     bic = np.full((nmax, G), np.nan)
     red = np.full((nmax, G), np.nan)
     for n, (b, r) in tables.items():
         if n - n0 < nmax:
             bic[n - n0], red[n - n0] = b, r
-    o = 6
+    o = _HEAD
     rec[o: o + nmax * G] = bic.reshape(-1); o += nmax * G
     rec[o: o + nmax * G] = red.reshape(-1); o += nmax * G
     rec[o] = lnL; o += 1
@@ -154,8 +173,8 @@ def pack_record(uid, status, n0, kept, exit_n, tables, nmax, G, cmax, theta, sd,
 
 
 def unpack_record(rec, nmax, G, cmax):
-    uid, status, n0, kept, exit_n, ncand = (int(v) for v in rec[0:6])
-    o = 6
+    uid, status, n0, kept, exit_n, ncand, ntally = (int(v) for v in rec[0:_HEAD])
+    o = _HEAD
     bic = rec[o: o + nmax * G].reshape(nmax, G); o += nmax * G
     red = rec[o: o + nmax * G].reshape(nmax, G); o += nmax * G
     lnL = rec[o]; o += 1
@@ -166,7 +185,7 @@ def unpack_record(rec, nmax, G, cmax):
     o += 3
     chi2 = rec[o]
     cov_aw = rec[o + 1: o + 1 + cmax][:kept].copy()
-    return RegionResult(uid=uid, status=status, n0=n0, n=kept, exit_n=exit_n, chi2=chi2, cov_aw=cov_aw,
+    return RegionResult(uid=uid, status=status, n0=n0, n=kept, exit_n=exit_n, chi2=chi2, cov_aw=cov_aw, ntally=ntally,
                         bic={n0 + i: bic[i].copy() for i in range(min(ncand, nmax))},
                         red_chi={n0 + i: red[i].copy() for i in range(min(ncand, nmax))},
                         lnL=lnL, theta=arrs[0], mean=arrs[1], std=arrs[2], sd=sd, sd_mean=sd_mean, sd_std=sd_std)
@@ -175,9 +194,10 @@ def unpack_record(rec, nmax, G, cmax):
 def fit_local(regions_host, uids, voigt=False, sd_free=True, iterations=3000, burn=300, thin=15, restarts=3,
               chains_per_restart=32, window=3, max_rounds=4, chi_limit=1.5, dtype="f32", seed=0, lsf=None,
               n0=None, nmax=12, ctx=None, polish_top=None, tune_interval=50, stats=None, cmax_rec=None, polish_dtype="f64",
-              multiplet=None):
+              multiplet=None, polish_from="best"):
     """Fit the given regions on this process's GPU.  Returns ``[R, record_len]`` float64.
-    ``multiplet``: per-region ``(freq_ratio, amp_ratio[, lorentz_ratio])`` or None (``engine.Regions``)."""
+    ``multiplet``: per-region ``(freq_ratio, amp_ratio[, lorentz_ratio])`` or None (``engine.Regions``);
+    ``polish_from``: see ``batch.fit_models``."""
     R = len(regions_host)
     G = int(restarts)
     if R == 0:                                   # nothing to fit (an empty shard): no device work, no context
@@ -216,6 +236,7 @@ def fit_local(regions_host, uids, voigt=False, sd_free=True, iterations=3000, bu
         mb = batch.fit_models(regs, models, voigt=voigt, sd_free=sd_free, iterations=iterations, burn=burn, thin=thin,
                               restarts=G, chains_per_restart=chains_per_restart, polish_top=polish_top, dtype=dtype,
                               seed=seed, region_uids=uids, tune_interval=tune_interval, polish_dtype=polish_dtype,
+                              polish_from=polish_from,
                               timing=None if stats is None else stats.setdefault("timing", {}))
         if stats is not None:
             stats["voigt_evals"] = stats.get("voigt_evals", 0) + mb.voigt_evals
@@ -256,7 +277,7 @@ def fit_local(regions_host, uids, voigt=False, sd_free=True, iterations=3000, bu
                              mb.theta[m, g, :kept], None if mb.sd is None else mb.sd[m, g], mb.mean[m, g, :kept],
                              mb.std[m, g, :kept], None if mb.sd_mean is None else mb.sd_mean[m, g],
                              None if mb.sd_std is None else mb.sd_std[m, g], mb.lnL[m, g], chi2=mb.chi2[m, g],
-                             cov_aw=cov_aw)
+                             cov_aw=cov_aw, ntally=int(mb.ntally[m, g]))
     _t2 = _time.perf_counter()
     regs.close()                                  # the next device batch (fit_chunked) starts from free memory
     if stats is not None:
@@ -285,13 +306,91 @@ def gather_records(local, world_size, rec_len, device=None):
     return np.concatenate([allbuf[r, : cnt[r]] for r in range(world_size)], axis=0)
 
 
-def fit_regions(regions_host, uids=None, distributed=None, fit_fn=None, **kw):
+class RegionResults:
+    """The uid-ordered result of ``fit_regions``: a read-only sequence of :class:`RegionResult` that unpacks a region's
+    fixed-geometry record on access (10^5 regions cost nothing until they are looked at; every rank of a
+    distributed fit holds the same records).  ``records`` is the ``[R, record_len]`` float64 array itself."""
+
+    def __init__(self, records, nmax, G, cmax):
+        self.records, self.nmax, self.G, self.cmax = records, int(nmax), int(G), int(cmax)
+
+    def __len__(self):
+        return int(self.records.shape[0])
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[j] for j in range(*i.indices(len(self)))]
+        return unpack_record(self.records[i], self.nmax, self.G, self.cmax)
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
+
+    def __eq__(self, other):
+        return list(self) == other if isinstance(other, list) else NotImplemented
+
+    @property
+    def n(self):
+        """Chosen component count of every region (int array) without unpacking anything."""
+        return self.records[:, 3].astype(np.int64)
+
+    @property
+    def uid(self):
+        return self.records[:, 0].astype(np.int64)
+
+    @property
+    def status(self):
+        return self.records[:, 1].astype(np.int64)
+
+    def checksum(self):
+        """SHA-256 of the records (NaN padding included: it is produced by the same code on every rank).  Philox
+        streams are keyed by region uid and every kernel schedule is chosen from GLOBAL quantities, so this value is
+        the same for every world size and batching of the same call."""
+        import hashlib
+        return hashlib.sha256(np.ascontiguousarray(self.records, dtype=np.float64).tobytes()).hexdigest()
+
+
+def _gather_int(local, counts_total, world, device):
+    """All-gather of per-rank int64 blocks of known (rank-dependent) lengths ``counts_total[rank]``."""
+    import torch
+    import torch.distributed as dist
+    dev = device or "cpu"
+    m = int(max(counts_total)) if len(counts_total) else 0
+    buf = torch.zeros(max(m, 1), dtype=torch.int64, device=dev)
+    if len(local):
+        buf[: len(local)] = torch.as_tensor(np.asarray(local, dtype=np.int64), device=dev)
+    allb = torch.empty(world * max(m, 1), dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(allb, buf)
+    allb = allb.cpu().numpy().reshape(world, max(m, 1))
+    return np.concatenate([allb[r, : counts_total[r]] for r in range(world)]) if world else np.zeros(0, np.int64)
+
+
+def initial_counts(regions_host, multiplet, lo=0, hi=None):
+    """``estimate_n`` (doublet regions: ``estimate_n_doublet``) of regions ``[lo, hi)``."""
+    hi = len(regions_host) if hi is None else hi
+    out = []
+    for i in range(lo, hi):
+        m = None if multiplet is None else multiplet[i]
+        if m is not None and m[1] != 0.0:           # a doublet shows two minima per absorber
+            out.append(estimate_n_doublet(regions_host[i][1], regions_host[i][2]))
+        else:
+            out.append(estimate_n(regions_host[i][1]))
+    return out
+
+
+def shard_plan(npix, n0, window, voigt, world):
+    """The static partition of the regions over ``world`` ranks (LPT on ``region_costs``): list of index lists."""
+    return lpt_partition(region_costs(npix, n0, window, voigt), world)
+
+
+def fit_regions(regions_host, uids=None, distributed=None, fit_fn=None, emulate=None, **kw):
     """Fit ``regions_host = [(nu, flux, noise), ...]`` (host float64 arrays, nu ascending).
 
-    With an initialised ``torch.distributed`` process group (or ``distributed=True``) the
-    regions are LPT-partitioned over the ranks, each rank fits its share on its own GPU and
-    the records are all-gathered; every rank returns the full, uid-ordered result list.
-    ``fit_fn`` (tests only) replaces the GPU fit of a shard."""
+    With an initialised ``torch.distributed`` process group (or ``distributed=True``) every rank estimates the
+    initial component count of a 1/W slice of the regions (one small all-gather makes the counts global), the
+    regions are LPT-partitioned over the ranks, each rank fits its share on its own GPU and the fixed-size records
+    are all-gathered; every rank returns the full, uid-ordered :class:`RegionResults`.
+    ``fit_fn`` (tests only) replaces the GPU fit of a shard.  ``emulate=(rank, world)`` (tests): no process group -
+    compute exactly the records rank ``rank`` of a ``world``-rank run would compute, and return only those."""
     import torch.distributed as dist
     R = len(regions_host)
     uids = list(range(R)) if uids is None else [int(u) for u in uids]
@@ -300,17 +399,28 @@ def fit_regions(regions_host, uids=None, distributed=None, fit_fn=None, **kw):
     nmax = kw.get("nmax", 12)
     G = kw.get("restarts", 3)
     n0 = kw.pop("n0", None)
+    use_dist = dist.is_available() and dist.is_initialized() if distributed is None else bool(distributed)
+    if emulate is not None:
+        use_dist = False
+    mult = per_region_multiplet(kw["multiplet"], R) if kw.get("multiplet") is not None else None
+    device = None
+    if use_dist:
+        world, rank = dist.get_world_size(), dist.get_rank()
+        if dist.get_backend() == "nccl":
+            import torch
+            device = torch.device("cuda", torch.cuda.current_device())
     if n0 is None:
-        n0 = [estimate_n(r[1]) for r in regions_host]
-        if kw.get("multiplet") is not None:          # a doublet shows two minima per absorber
-            mult = per_region_multiplet(kw["multiplet"], R)
-            n0 = [estimate_n_doublet(regions_host[i][1], regions_host[i][2]) if (mult[i] is not None and mult[i][1] != 0.0)
-                  else n for i, n in enumerate(n0)]
+        if use_dist and R >= 4 * world:
+            # every rank counts the minima of its slice only; the counts travel, not the work
+            bounds = [(r * R) // world for r in range(world + 1)]
+            mine = initial_counts(regions_host, mult, bounds[rank], bounds[rank + 1])
+            n0 = [int(v) for v in _gather_int(mine, [bounds[r + 1] - bounds[r] for r in range(world)], world, device)]
+        else:
+            n0 = initial_counts(regions_host, mult)
     else:
         n0 = [int(v) for v in n0]
     cmax_rec = (max(n0) if n0 else 1) + nmax
     rec_len = _record_len(nmax, G, cmax_rec)
-    use_dist = dist.is_available() and dist.is_initialized() if distributed is None else bool(distributed)
     if kw.get("polish_dtype", "auto") == "auto" and fit_fn is None:
         # K3 schedule from the GLOBAL number of starts (the same on every rank and for every world size):
         # thousands of starts -> one warp per start, fp32 search stage + float64 finish ("mixed");
@@ -319,25 +429,22 @@ def fit_regions(regions_host, uids=None, distributed=None, fit_fn=None, **kw):
         kw["polish_dtype"] = "mixed" if (starts >= MIXED_POLISH_STARTS and kw.get("lsf") is None) else "f64"
     fit_fn = fit_fn or fit_local
     chunk = kw.pop("max_batch_regions", MAX_BATCH_REGIONS)
-    if kw.get("multiplet") is not None:
-        kw["multiplet"] = per_region_multiplet(kw["multiplet"], R)
+    if mult is not None:
+        kw["multiplet"] = mult
     else:
         kw.pop("multiplet", None)
-    if not use_dist:
+    if not use_dist and emulate is None:
         recs = fit_chunked(fit_fn, regions_host, uids, n0, chunk, cmax_rec=cmax_rec, **kw)
     else:
-        world, rank = dist.get_world_size(), dist.get_rank()
-        costs = [region_cost(len(regions_host[i][1]), n0[i], window, voigt) for i in range(R)]
-        mine = lpt_partition(costs, world)[rank]
+        if emulate is not None:
+            rank, world = int(emulate[0]), int(emulate[1])
+        npix = np.fromiter((len(r[1]) for r in regions_host), dtype=np.int64, count=R)
+        mine = shard_plan(npix, n0, window, voigt, world)[rank]
         if "multiplet" in kw:
             kw["multiplet"] = [kw["multiplet"][i] for i in mine]
         local = fit_chunked(fit_fn, [regions_host[i] for i in mine], [uids[i] for i in mine], [n0[i] for i in mine],
                             chunk, cmax_rec=cmax_rec, **kw)        # same record geometry on every rank
         assert local.shape[1] == rec_len
-        device = None
-        if dist.get_backend() == "nccl":
-            import torch
-            device = torch.device("cuda", torch.cuda.current_device())
-        recs = gather_records(local, world, rec_len, device)
-    order = np.argsort([int(r[0]) for r in recs], kind="stable")
-    return [unpack_record(recs[i], nmax, G, cmax_rec) for i in order]
+        recs = local if emulate is not None else gather_records(local, world, rec_len, device)
+    order = np.argsort(recs[:, 0].astype(np.int64), kind="stable") if len(recs) else np.zeros(0, np.int64)
+    return RegionResults(np.ascontiguousarray(recs[order]) if len(recs) else np.zeros((0, rec_len)), nmax, G, cmax_rec)

@@ -144,6 +144,64 @@ def make_doublet_region(P, n_true, snr, region_id, doublet="CIV", voigt=True, ls
             "sep_px": sep}
 
 
+def make_sightline(ion="HI", P=1000, snr=70.0, systems=((200.0, 1.6, 5.0), (450.0, 0.9, 6.5), (700.0, 1.3, 4.0)), lsf=None,
+                   seed=5, dv_kms=5.0, lorentz_over_gauss=0.05):
+    """One SIMBA-like sightline of ``P`` velocity pixels around one ion's line (BASELINE config C3; the reference's
+    fixtures ``simba_H1215.h5`` / ``simba_CII1036.h5`` are such per-ion 1000-pixel spectra at 5 km/s).  ``ion``: "HI"
+    (Ly-alpha 1215.67, single line) or a doublet of ``physics.DOUBLETS`` ("CIV", "MgII": both lines of every absorber,
+    tied velocity / Doppler width / column density).  ``systems``: ``(pixel of the first line, tau_0, sigma in
+    pixels)`` per absorber.  Returns a dict: ``wave`` (Angstrom, ascending), ``flux``, ``noise``, ``clean`` (noiseless,
+    LSF-convolved), ``clean_intrinsic``, ``truth [n, 4]`` = the first line's (amplitude_L, centroid, L_fwhm, G_fwhm) in Hz,
+    ``line``, ``doublet`` (None for HI), ``multiplet``."""
+    from . import physics
+    rng = np.random.Generator(np.random.Philox(key=[SEED_BASE ^ 0xC3, int(seed)]))
+    if ion == "HI":
+        l1, doublet, mult = 1215.67, None, None
+    else:
+        l1, doublet, mult = physics.DOUBLETS[ion][0][0], ion, physics.doublet_ratios(ion)
+    wave = l1 * (1.0 - 0.004) + (l1 * dv_kms * 1.0e3 / C_REF) * np.arange(P)
+    nu = C_REF / (wave * 1e-10)
+    truth, tau = [], np.zeros(P)
+    for px, tau0, sig_px in systems:
+        i = int(px)
+        c = nu[i]
+        G = FWHM_PER_SIGMA * sig_px * abs(nu[i] - nu[i + 1])
+        L = lorentz_over_gauss * G
+        A = tau0 / voigt_peak_shape(L, G)
+        tau += voigt_tau(nu, A, c, L, G)
+        if mult is not None:
+            fr, ar, lr = mult
+            tau += voigt_tau(nu, ar * A, fr * c, lr * L, fr * G)
+        truth.append((A, c, L, G))
+    intrinsic = np.exp(-tau)
+    clean = intrinsic
+    if lsf is not None:
+        lsf = np.asarray(lsf, dtype=np.float64)
+        h = lsf.size // 2
+        clean = 1.0 + np.convolve(np.concatenate([np.zeros(h), intrinsic - 1.0, np.zeros(h)]), lsf, "valid")
+    sigma = 1.0 / float(snr)
+    flux = clean + rng.normal(0.0, sigma, P)
+    return {"ion": ion, "line": l1, "doublet": doublet, "multiplet": mult, "wave": wave, "flux": flux,
+            "noise": np.full(P, sigma), "clean": clean, "clean_intrinsic": intrinsic, "truth": np.array(truth),
+            "systems": [tuple(s_) for s_ in systems], "dv_kms": dv_kms, "snr": float(snr)}
+
+
+def config_c3(lsf=True):
+    """C3: one synthetic SIMBA-like sightline seen in three ions - HI 1215 (single line), CIV 1548/1550 and MgII
+    2796/2803 (doublets with tied v / b / N) - each a 1000-pixel spectrum at 5 km/s, convolved with the Gaussian LSF
+    (FWHM 2 px, 7 taps), S/N 70.  The same three absorbers (same velocities) in every ion, with
+    ion-dependent central depths."""
+    taps = gaussian_lsf(2.0, 7) if lsf else None
+    base = ((200.0, 5.0), (450.0, 6.5), (700.0, 4.0))
+    depth = {"HI": (2.2, 1.4, 1.8), "CIV": (1.6, 0.9, 1.3), "MgII": (1.2, 1.5, 0.8)}
+    out = []
+    for k, ion in enumerate(("HI", "CIV", "MgII")):
+        systems = tuple((px, depth[ion][i], sig) for i, (px, sig) in enumerate(base))
+        out.append(make_sightline(ion, 1000, 70.0, systems, lsf=taps, seed=30 + k))
+        out[-1]["lsf"] = taps
+    return out
+
+
 def gaussian_lsf(fwhm_px=2.0, taps=7):
     """Normalised Gaussian LSF (config C3: FWHM 2 px, 7 taps)."""
     s = fwhm_px / FWHM_PER_SIGMA

@@ -315,6 +315,11 @@ class VPfit():
         for k in ("mean", "m2", "comom", "sum_lnL", "sum_lnL2"):
             s.t[k].zero_()
         s.t["ntally"].zero_()
+        # burn / thin are counted from the start of THIS run, so the iteration counter restarts; the Philox stream must
+        # not: every further run of the same sampler gets its own key (the first keeps the fit's seed)
+        run = getattr(s, "_runs", 0)
+        s.seed = (self._seed + run * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+        s._runs = run + 1
         s.iteration = 0
         s.run(int(iters))
         self._mcmc_done = True
@@ -488,38 +493,3 @@ class VPfit():
             c_sc = com[i, pair[(1, wi)]] * fw * sc / d
             cov[i] = [[va, c_as, c_ac], [c_as, vs, c_sc], [c_ac, c_sc, vc]]
         return cov
-
-    # ------------------------------------------------------------------ plotting (optional dependency)
-    def plot(self, wavelength_array, flux_array, clouds=None, n=1, onesigmaerror=0.02,
-             start_pix=None, end_pix=None, filename=None):
-        """vpfits.py:134-199 (residuals / components / total); needs matplotlib."""
-        import matplotlib.pyplot as plt
-        f, (ax1, ax2, ax3) = plt.subplots(3, sharex=True, sharey=False, figsize=(10, 10))
-        total = self.total.value
-        ax1.plot(wavelength_array, (flux_array - total) / onesigmaerror)
-        for lvl, ls in ((1, '-'), (-1, '-'), (3, '--'), (-3, '--')):
-            ax1.hlines(lvl, wavelength_array[0], wavelength_array[-1], color='red', linestyles=ls)
-        ax2.plot(wavelength_array, flux_array, color='black', linewidth=1.0)
-        for c in range(n):
-            ax2.plot(wavelength_array, Tau2flux(self.estimated_profiles[c].value), color="green",
-                     label="Fit" if c == 0 else None)
-        ax2.legend()
-        ax3.plot(wavelength_array, flux_array, label="Measured")
-        ax3.plot(wavelength_array, total, color='green', label="Fit", linewidth=2.0)
-        ax3.legend()
-        f.subplots_adjust(hspace=0)
-        if hasattr(self, 'fit_time'):
-            ax1.set_title("Fit time: " + self.fit_time)
-        ax1.set_ylabel("Residuals")
-        ax2.set_ylabel("Normalised Flux")
-        ax3.set_ylabel("Normalised Flux")
-        if filename:
-            plt.savefig(filename)
-        else:
-            plt.show()
-
-    def find_local_minima(self, f_array, window=101):
-        """vpfits.py:202-216."""
-        from scipy.signal import find_peaks_cwt, savgol_filter
-        smoothed_flux = savgol_filter(f_array, window, 1)
-        return find_peaks_cwt(smoothed_flux * -1, np.array([window / 3]))

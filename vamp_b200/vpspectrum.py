@@ -362,6 +362,10 @@ class VPspectrum():
                              ('sigmas', sigmas)):
                 self.flux_model[key] = np.append(self.flux_model[key], val)
             if self.mcmc_cov:                                             # vpspectrum.py:384-397
+                # the reference takes sqrt(diag(np.cov(...))) here (chain_covariance, N - 1 normalised), while the
+                # record's ``std`` is PyMC's trace.std() (population): rescale so std_* agree with cov_as
+                f = np.sqrt(r.ntally / (r.ntally - 1.0)) if r.ntally > 1 else 1.0
+                std_a, std_s, std_c = std_a * f, std_s * f, std_c * f
                 for key, val in (('std_a', std_a), ('std_s', std_s), ('std_c', std_c), ('cov_as', r.cov_aw)):
                     self.flux_model[key] = np.append(self.flux_model[key], val)
                 self.params['N_std'] = np.append(self.params['N_std'], ErrorN(heights, sigmas, std_a, std_s, r.cov_aw))
