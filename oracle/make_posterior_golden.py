@@ -29,7 +29,7 @@ from oracle import sampler as OS          # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden", "posterior_c2.json")
 LINE = 1215.67
-BURN, THIN = 4000, 10
+BURN, THIN = 20000, 10       # the chains start at the truth, 5 sigma from the bulk of the amplitude_L posterior: long burn-in
 
 
 def nbv(comps):
@@ -63,7 +63,7 @@ def _chain(job):
 
 def main():
     chains = int(sys.argv[1]) if len(sys.argv) > 1 else 8
-    iters = int(sys.argv[2]) if len(sys.argv) > 2 else 24000
+    iters = int(sys.argv[2]) if len(sys.argv) > 2 else 60000
     t0 = time.time()
     with Pool(min(chains, os.cpu_count() or 4)) as pool:
         res = pool.map(_chain, [(s, iters) for s in range(chains)])

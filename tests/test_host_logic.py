@@ -1,0 +1,51 @@
+"""CPU: host-side guards of the product (no GPU needed: every check fires before the device is touched)."""
+import types
+import warnings
+
+import numpy as np
+import pytest
+
+from vamp_b200 import _lib, engine
+from vamp_b200 import vpspectrum as VS
+
+
+def _fake_ctx():
+    return types.SimpleNamespace(lib=None, handle=None, torch_device="cpu")
+
+
+def test_regions_reject_bad_noise_and_flux_before_upload():
+    """a zero / NaN / inf noise pixel (weight inf or NaN) used to freeze chains silently and turn BIC / chi^2
+    into NaN; it is refused at upload, by ``engine.Regions`` and again by ``vamp_regions_create`` (code -4)."""
+    nu = 1e15 + 4e10 * np.arange(40)
+    good = (nu, np.ones(40), np.full(40, 0.02))
+    for k, bad in ((2, 0.0), (2, np.nan), (2, np.inf), (1, np.nan), (1, np.inf)):
+        arrs = [a.copy() for a in good]
+        arrs[k][17] = bad
+        with pytest.raises(ValueError, match="region 1.*pixel 17"):
+            engine.Regions(_fake_ctx(), [good, tuple(arrs)])
+
+
+def test_sampler_refuses_regions_longer_than_a_tile_with_guidance():
+    regs = types.SimpleNamespace(ctx=_fake_ctx(), npix=np.array([200, 300], dtype=np.int32))
+    with pytest.raises(_lib.VampError, match="300 pixels.*split_long_regions"):
+        engine.Sampler(regs, np.array([0, 1], np.int32), np.array([1, 1], np.int32), np.arange(2, dtype=np.uint64))
+
+
+def test_split_long_regions_flags_cuts_through_absorption():
+    P = 900
+    wave = 1215.0 + 0.02 * np.arange(P)
+    flux = np.ones(P)
+    flux[100:330] = 0.4                       # region A: 300 px, continuum only at its far end
+    flux[450:800] = 0.4                       # region B: saturated trough all the way - no continuum to cut at
+    flux[620] = 1.0                           # ... except one pixel in its middle half
+    sp = VS.VPspectrum(1215.0).set_spectrum(wave, flux, np.full(P, 0.01))
+    sp.region_pixels = [[60, 360], [440, 810]]
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        sp.split_long_regions()
+    assert all(e - s <= 256 for s, e in sp.region_pixels)
+    assert [s for s, _ in sp.region_pixels][0] == 60 and sp.region_pixels[-1][1] == 810
+    assert 620 in [s for s, _ in sp.region_pixels]            # the continuum pixel is where region B is cut
+    assert len(sp.cuts_through_absorption) == len(w) >= 1     # region A had to be cut through absorption
+    assert all(flux[c] < 1.0 - 4.0 * 0.01 for c in sp.cuts_through_absorption)
+    assert 620 not in sp.cuts_through_absorption

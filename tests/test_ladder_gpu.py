@@ -114,3 +114,24 @@ def test_simba_fixtures_reach_the_notebook_outcome(ctx, spec, voigt, iters):
         for n, ref in zip(range(1, 6), NOTEBOOK_LADDER_R0):
             if n in res[0].bic:
                 assert float(np.min(res[0].bic[n])) <= ref + 1.0, (n, res[0].bic[n], ref)
+
+
+def test_records_do_not_depend_on_world_size_or_batching(ctx):
+    """The records of a W-rank run (``emulate=(rank, W)``: exactly what rank ``rank`` would compute on its LPT shard),
+    put together, are BIT-identical to the single-process records, for W = 2, 4, and for a run cut into small device
+    batches: Philox streams are keyed by region uid and every schedule is chosen from global quantities."""
+    uids = list(range(300, 324))
+    regs = [synth.config_c4_region(u) for u in uids]
+    host = [(r["nu"], r["flux"], r["noise"]) for r in regs]
+    kw = dict(C4_KW)
+    kw.update(iterations=900, burn=150)
+    one = fit_regions(host, uids=uids, seed=3, distributed=False, **kw)
+    for world in (2, 4):
+        parts = [fit_regions(host, uids=uids, seed=3, emulate=(r, world), **kw).records for r in range(world)]
+        assert sum(len(p) for p in parts) == len(uids) and all(len(p) for p in parts)
+        allr = np.concatenate(parts)
+        allr = allr[np.argsort(allr[:, 0].astype(np.int64), kind="stable")]
+        np.testing.assert_array_equal(allr, one.records)
+    many = fit_regions(host, uids=uids, seed=3, distributed=False, max_batch_regions=5, **kw)
+    assert many.checksum() == one.checksum()
+    assert fit_regions(host, uids=uids, seed=4, distributed=False, **kw).checksum() != one.checksum()

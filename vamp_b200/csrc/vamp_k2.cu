@@ -26,7 +26,10 @@
 
 namespace {
 
-constexpr int K2_WARPS = 4;
+#ifndef VAMP_K2_WARPS
+#define VAMP_K2_WARPS 4           // chains (warps) per CTA; with VAMP_K2_MINBLOCKS CTAs per SM (96 registers: 4 x 5 = 20 warps)
+#endif
+constexpr int K2_WARPS = VAMP_K2_WARPS;
 #ifndef VAMP_INST_MULT
 #define VAMP_INST_MULT 0          // 1: this object holds the multiplet (two tied lines per component) instantiations
 #endif
@@ -35,6 +38,9 @@ constexpr int K2_WARPS = 4;
 #endif
 #ifndef VAMP_K2_STEPUNROLL
 #define VAMP_K2_STEPUNROLL 1      // 1: the centroid / width steps of a component are unrolled (no selects)
+#endif
+#ifndef VAMP_K2_FUSEBASE
+#define VAMP_K2_FUSEBASE 1        // 1: the move of `base` to a component runs inside its amplitude pass (FuseArgs)
 #endif
 constexpr double FWHM_PER_SIGMA = 2.35482004503094938202;
 
@@ -241,10 +247,17 @@ __device__ __forceinline__ void sm_st4(unsigned a, unsigned x, unsigned y, unsig
 template <typename T>
 struct Mult2 { T fr, dsh, ar, ginv, yfac; };
 
-template <typename T, int KIND, bool WT, bool LSF, bool FRESH, bool MULT = false>
+// FUSE (cached passes only - the amplitude step, which is the first pass of a component): the move of `base` to this
+// component, base += Ap H_prev + Ac H_c (the tau of the previous component comes in, this one's goes out), is done
+// inside the pass - one loop, one load of base and H_c instead of two.  Same arithmetic in the same order as the
+// separate update loop of mcmc_chain, so the chain is bit-identical.
+template <typename T>
+struct FuseArgs { T Ap, Ac; unsigned ahp; };
+
+template <typename T, int KIND, bool WT, bool LSF, bool FRESH, bool MULT = false, bool FUSE = false>
 __device__ __forceinline__ T chain_pass(const CompC<T>& cc, T An, unsigned ahc, unsigned ahs, unsigned ar, unsigned aw,
                                         const unsigned char* rb, int npairs, int lane, const LsfCtx<T>& lc, unsigned& nfar,
-                                        unsigned& last_far, const Mult2<T>* ml = nullptr) {
+                                        unsigned& last_far, const Mult2<T>* ml = nullptr, const FuseArgs<T>* fz = nullptr) {
     typedef K2Lay<T, WT> Lay;
     constexpr int SZ = (int)sizeof(P2<T>);
     constexpr int ROW = 32 * SZ;                       // bytes between the two pairs of a quad
@@ -252,6 +265,8 @@ __device__ __forceinline__ T chain_pass(const CompC<T>& cc, T An, unsigned ahc, 
     P2<T> S2 = p2_bc<T>(T(0)), S2b = p2_bc<T>(T(0));
     bool far = false, farb = false;
     const unsigned end = ar + (unsigned)(npairs * ROW);
+    unsigned ahp = FUSE ? fz->ahp : 0u;
+    const P2<T> Ap2 = p2_bc<T>(FUSE ? fz->Ap : T(0)), Ac2 = p2_bc<T>(FUSE ? fz->Ac : T(0));
 #pragma unroll 1
     for (; ar < end; ar += 2 * ROW, aw += 2 * ROW, ahc += 2 * ROW, ahs += 2 * ROW) {
         P2<T> H0, H1;
@@ -312,8 +327,16 @@ __device__ __forceinline__ T chain_pass(const CompC<T>& cc, T An, unsigned ahc, 
             H0 = SM<T>::template ld<0>(ahc);
             H1 = SM<T>::template ld<ROW>(ahc);
         }
-        const P2<T> M0 = p2_exp_scaled<T>(p2_fma(A2, H0, SM<T>::template ld<Lay::BASE>(aw)));
-        const P2<T> M1 = p2_exp_scaled<T>(p2_fma(A2, H1, SM<T>::template ld<Lay::BASE + ROW>(aw)));
+        P2<T> B0 = SM<T>::template ld<Lay::BASE>(aw), B1 = SM<T>::template ld<Lay::BASE + ROW>(aw);
+        if (FUSE) {
+            B0 = p2_fma(Ac2, H0, p2_fma(Ap2, SM<T>::template ld<0>(ahp), B0));
+            B1 = p2_fma(Ac2, H1, p2_fma(Ap2, SM<T>::template ld<ROW>(ahp), B1));
+            SM<T>::template st<Lay::BASE>(aw, B0);
+            SM<T>::template st<Lay::BASE + ROW>(aw, B1);
+            ahp += 2 * ROW;
+        }
+        const P2<T> M0 = p2_exp_scaled<T>(p2_fma(A2, H0, B0));
+        const P2<T> M1 = p2_exp_scaled<T>(p2_fma(A2, H1, B1));
         if (LSF) {
             const int e = (int)(npairs * ROW - (end - ar)) / SZ;          // pair-layout element of this quad
             lc.buf[(lc.taps >> 1) + lane + 2 * e] = p2_lo(M0) - T(1);
@@ -561,49 +584,69 @@ __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, const unsigned
             sm_ld4<O_SLOT>(arec, v0, v1, v2, v3);
             const T sA = T(__uint_as_float(u0)), sC = T(__uint_as_float(u1)), sW1 = T(__uint_as_float(u2)), sW2 = T(__uint_as_float(u3));
             int hc = (int)v0;
-            // ---- base = tau of the other components (shared-address form, see SM<T>)
+            // ---- base = tau of the other components (shared-address form, see SM<T>), then the amplitude step on the
+            //      cached shape.  VAMP_K2_FUSEBASE: when base only has to MOVE from the previous component to this one
+            //      and the amplitude proposal is in bounds, the move is done inside the amplitude pass (FuseArgs).
+            unsigned am = 0u;                 // accept bits of this component's steps
             {
                 constexpr int ROW = 32 * (int)sizeof(P2<T>);
                 const unsigned endw = aw0 + (unsigned)(npairs * ROW);
+                T z, lu;
+                draw(z, lu);
+                const T prop = pA + z * sA;
+                // how base gets to this component: 0 nothing to do (n == 1), 1 rebuild from the cache, 2 move
+                int mode = 2;
+                T Ap_ = NK * Aprev;
+                unsigned ap_ = slot_addr(hprev);
                 if (c == 0) {
                     if (rebuild == 0) {
-                        // rebuilt from the cache (first iteration, then every 8th) so that rounding never accumulates
+                        mode = 1;
                         rebuild = 8;
-                        for (unsigned a = aw0; a < endw; a += ROW) SM<T>::template st<Lay::BASE>(a, p2_bc<T>(T(0)));
-                        for (int c2 = 1; c2 < n; ++c2) {
-                            const P2<T> A2 = p2_bc<T>(NK * recs[c2].th[0]);
-                            unsigned ah = slot_addr(recs[c2].slot);
-                            for (unsigned a = aw0; a < endw; a += ROW, ah += ROW)
-                                SM<T>::template st<Lay::BASE>(a, p2_fma(A2, SM<T>::template ld<0>(ah), SM<T>::template ld<Lay::BASE>(a)));
-                        }
                     } else if (n > 1) {
                         // from the last component of the previous iteration back to the first
-                        const P2<T> Ap = p2_bc<T>(NK * recs[n - 1].th[0]), Ac = p2_bc<T>(-NK * pA);
-                        unsigned ap = slot_addr(recs[n - 1].slot), an = slot_addr(hc);
-                        for (unsigned a = aw0; a < endw; a += ROW, ap += ROW, an += ROW)
-                            SM<T>::template st<Lay::BASE>(a, p2_fma(Ac, SM<T>::template ld<0>(an),
-                                                                   p2_fma(Ap, SM<T>::template ld<0>(ap), SM<T>::template ld<Lay::BASE>(a))));
+                        Ap_ = NK * recs[n - 1].th[0];
+                        ap_ = slot_addr(recs[n - 1].slot);
+                    } else {
+                        mode = 0;
                     }
                     --rebuild;
-                } else {
-                    // next component: base += tau_{c-1} - tau_c  (two FMAs per pixel instead of n - 1)
-                    const P2<T> Ap = p2_bc<T>(NK * Aprev), Ac = p2_bc<T>(-NK * pA);
-                    unsigned ap = slot_addr(hprev), an = slot_addr(hc);
+                }
+                bool fused = false;
+#if VAMP_K2_FUSEBASE
+                fused = (mode == 2) && (prop > T(0));
+#endif
+                if (mode == 1) {
+                    // rebuilt from the cache (first iteration, then every 8th) so that rounding never accumulates
+                    for (unsigned a = aw0; a < endw; a += ROW) SM<T>::template st<Lay::BASE>(a, p2_bc<T>(T(0)));
+                    for (int c2 = 1; c2 < n; ++c2) {
+                        const P2<T> A2 = p2_bc<T>(NK * recs[c2].th[0]);
+                        unsigned ah = slot_addr(recs[c2].slot);
+                        for (unsigned a = aw0; a < endw; a += ROW, ah += ROW)
+                            SM<T>::template st<Lay::BASE>(a, p2_fma(A2, SM<T>::template ld<0>(ah), SM<T>::template ld<Lay::BASE>(a)));
+                    }
+                } else if (mode == 2 && !fused) {
+                    // base += tau_prev - tau_c  (two FMAs per pixel instead of n - 1)
+                    const P2<T> Ap = p2_bc<T>(Ap_), Ac = p2_bc<T>(-NK * pA);
+                    unsigned ap = ap_, an = slot_addr(hc);
                     for (unsigned a = aw0; a < endw; a += ROW, ap += ROW, an += ROW)
                         SM<T>::template st<Lay::BASE>(a, p2_fma(Ac, SM<T>::template ld<0>(an),
                                                                p2_fma(Ap, SM<T>::template ld<0>(ap), SM<T>::template ld<Lay::BASE>(a))));
                 }
-            }
-            unsigned am = 0u;                 // accept bits of this component's steps
-
-            // ---- amplitude: cached shape
-            {
-                T z, lu;
-                draw(z, lu);
-                const T prop = pA + z * sA;
+                // ---- amplitude: cached shape
                 if (prop > T(0)) {
-                    const T Snew = chain_pass<T, KIND, WT, LSF, false>(cz, NK * prop, slot_addr(hc), 0u, ar0, aw0, rb, npairs, lane,
-                                                                       lc, dummy, dummy_far);
+                    T Snew;
+#if VAMP_K2_FUSEBASE
+                    if (fused) {
+                        FuseArgs<T> fz;
+                        fz.Ap = Ap_;
+                        fz.Ac = -NK * pA;
+                        fz.ahp = ap_;
+                        Snew = chain_pass<T, KIND, WT, LSF, false, false, true>(cz, NK * prop, slot_addr(hc), 0u, ar0, aw0, rb, npairs,
+                                                                                lane, lc, dummy, dummy_far, nullptr, &fz);
+                    } else
+#endif
+                        Snew = chain_pass<T, KIND, WT, LSF, false>(cz, NK * prop, slot_addr(hc), 0u, ar0, aw0, rb, npairs, lane,
+                                                                   lc, dummy, dummy_far);
                     const T dprior = StepMath<T>::log_(prop * Real<T>::rcp(pA)) - (prop - pA);
                     ++n_like;
                     if (lu < (Scur - Snew) * hiv + dprior) {          // false for NaN
@@ -789,8 +832,13 @@ __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, const unsigned
 // (du, flux, 1/noise) are staged ONCE per CTA and shared, which is what lets a sixth CTA fit on an
 // SM.  A CTA whose warps belong to different regions (group boundaries) processes its distinct
 // regions one after the other - rare, and always correct.
+#ifdef VAMP_K2_MAXNREG              // experiments with other CTA sizes: a plain register cap instead of launch bounds
+#define VAMP_K2_BOUNDS __maxnreg__(VAMP_K2_MAXNREG)
+#else
+#define VAMP_K2_BOUNDS __launch_bounds__(K2_WARPS * 32, (sizeof(T) == 4) ? VAMP_K2_MINBLOCKS : 2)
+#endif
 template <typename T, int KIND, bool WT, bool LSF, bool MULT>
-__global__ void __launch_bounds__(K2_WARPS * 32, (sizeof(T) == 4) ? VAMP_K2_MINBLOCKS : 2)
+__global__ void VAMP_K2_BOUNDS
 k2_mcmc_kernel(McmcDev p, int ncomp_max) {
     typedef K2Lay<T, WT> Lay;
     extern __shared__ __align__(16) unsigned char smem_raw[];

@@ -16,6 +16,7 @@ from . import _lib
 from ._lib import VAMP_F32, VAMP_F64, VAMP_MIXED, VAMP_GAUSS, VAMP_VOIGT, McmcArgs, MapArgs, check
 
 FWHM_PER_SIGMA = 2.0 * np.sqrt(2.0 * np.log(2.0))
+MAX_SAMPLER_PIXELS = 256      # VAMP_TILE_PIX of the sampler / MAP kernels (include/vamp_b200.h)
 _DTYPES = {"f32": VAMP_F32, "f64": VAMP_F64, "float32": VAMP_F32, "float64": VAMP_F64, VAMP_F32: VAMP_F32,
            VAMP_F64: VAMP_F64}
 
@@ -297,6 +298,14 @@ class Sampler:
         self.item_region_h = np.asarray(item_region, dtype=np.int32)
         self.item_ncomp_h = np.asarray(item_ncomp, dtype=np.int32)
         self.max_ncomp = int(self.item_ncomp_h.max())
+        longest = int(regions.npix[self.item_region_h].max()) if self.B else 0
+        if longest > MAX_SAMPLER_PIXELS:
+            # the C ABI answers -3 at launch; say it here, before any state is allocated, with the way out
+            raise _lib.VampError(
+                "the MCMC / MAP kernels hold one region per %d-pixel coordinate tile; a region of %d pixels was given. "
+                "Fit it as several regions (VPspectrum.split_long_regions cuts where the flux is closest to the "
+                "continuum and flags cuts through absorption), or evaluate likelihoods of long arrays with "
+                "engine.loglike (K1 takes any length)" % (MAX_SAMPLER_PIXELS, longest))
         self.cmax = int(cmax or self.max_ncomp)
         self.ts = 4 * self.cmax + 1
         self.np_per = 4 if self.voigt else 3

@@ -191,13 +191,14 @@ class VPspectrum():
         self.region_pixels = [[points[i], points[i + 1]] for i in range(len(points) - 1)]
         self.region_waves = [[self.wavelength_array[s], self.wavelength_array[e]] for s, e in self.region_pixels]
 
-    def split_long_regions(self, max_pixels=256):
+    def split_long_regions(self, max_pixels=256, n_sigma=4.0):
         """New (GPU constraint): the sampler kernels hold one region per 256-pixel coordinate tile.  A longer
         detection region is cut where the flux comes closest to the continuum (the same choice
         ``split_difficult_region`` makes, vpspectrum.py:200-232): recursively at the highest-flux pixel of the
         middle half, so both parts keep at least a quarter of the pixels.  Absorbers separated by continuum are
         independent, which is what makes regions the unit of the fit in the first place."""
         out = []
+        self.cuts_through_absorption = []       # cut pixels whose flux is NOT continuum (a blended / saturated absorber)
         stack = [list(r) for r in reversed(self.region_pixels)]
         while stack:
             s, e = stack.pop()
@@ -206,6 +207,14 @@ class VPspectrum():
                 continue
             lo, hi = s + (e - s) // 4, e - (e - s) // 4
             cut = lo + int(np.argmax(self.flux_array[lo:hi]))
+            if self.flux_array[cut] < 1.0 - n_sigma * self.noise_array[cut]:
+                # no continuum pixel in the middle half: the cut goes through absorption, lines straddling it are
+                # fitted in both halves and the per-region n / EW / chi^2 differ from an unsplit fit - say so
+                import warnings
+                self.cuts_through_absorption.append(int(cut))
+                warnings.warn("split_long_regions: region [%d, %d) of %d pixels is cut at pixel %d where the flux (%.3f) is "
+                              "more than %.1f sigma below the continuum; the two parts are not independent"
+                              % (s, e, e - s, cut, self.flux_array[cut], n_sigma))
             stack.append([cut, e])
             stack.append([s, cut])
         if len(out) != len(self.region_pixels):
@@ -279,6 +288,8 @@ class VPspectrum():
                            'centers': np.array([]), 'region_numbers': np.array([]), 'EW': np.zeros(R),
                            'std_a': np.array([]), 'std_s': np.array([]), 'std_c': np.array([]), 'cov_as': np.array([]),
                            'difficult_fit': self.difficult_fit}
+        if getattr(self, "cuts_through_absorption", None):               # new key: only present when it applies
+            self.flux_model['cuts_through_absorption'] = np.array(self.cuts_through_absorption)
         self.regions = []
         if R == 0:
             return self.params
