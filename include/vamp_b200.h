@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define VAMP_ABI_VERSION 3   /* 2: vamp_detect_*, VAMP_MIXED for vamp_map_dev; 3: vamp_regions_set_multiplet */
+#define VAMP_ABI_VERSION 4   /* 2: vamp_detect_*, VAMP_MIXED for vamp_map_dev; 3: vamp_regions_set_multiplet */
 
 enum { VAMP_F32 = 0, VAMP_F64 = 1,            /* arithmetic of the pixel math */
        VAMP_MIXED = 2 };                       /* vamp_map_dev only: fp32 objective during the simplex search,
@@ -130,7 +130,22 @@ typedef struct vamp_mcmc_args {
     unsigned long long* work;   /* [n, 3] or NULL, accumulated: component evaluations (each over the region's
                                    pixels), far-path pixels among them, likelihood passes - the
                                    algorithmic work bench.py's roofline is computed from */
+    /* step method (ABI 4).  VAMP_STEP_METROPOLIS: PyMC 2's scalar Metropolis per stochastic with tune() - what the
+     * reference actually runs (mcmc_fit names mc.AdaptiveMetropolis but never installs it, vpfits.py:361, 382-389).
+     * VAMP_STEP_ADAPTIVE: PyMC 2's AdaptiveMetropolis (Haario et al. 2001) as `mcmc.use_step_method(
+     * mc.AdaptiveMetropolis, [the stochastics of one component])` would install it: one joint Normal proposal per
+     * component from the running covariance of its chain history (delay, interval, greedy tallying, scaling
+     * 2.4^2 / d, epsilon 1e-5, C_0 = diag(|value| / 100)); sd keeps its scalar Metropolis step. */
+    int step_kind;
+    int am_delay;               /* PyMC 2 default 1000: first covariance update after this many iterations */
+    int am_interval;            /* PyMC 2 default 200: iterations between covariance updates */
+    double* am_state;           /* [n, cmax, VAMP_AM_STRIDE] adaptive state (NULL unless step_kind = VAMP_STEP_ADAPTIVE):
+                                   chain mean [4] | covariance, packed lower triangle [10] | its Cholesky factor [10] |
+                                   sum x [4] | sum x x^T [10] | samples in the covariance | samples since the update */
 } vamp_mcmc_args;
+#define VAMP_STEP_METROPOLIS 0
+#define VAMP_STEP_ADAPTIVE 1
+#define VAMP_AM_STRIDE 40
 
 /* from_prior != 0: draw PyMC 2-style initial values (xexp = 0.5, Uniforms from their priors,
  * vpfits.py:239-252, 283-297) into theta; then (always) reset asf/psd/counters/statistics. */

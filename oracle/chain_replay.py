@@ -199,3 +199,143 @@ def replay_chain(u, flux, noise, theta0, n, voigt, sd_free, uid, seed, iters, bu
             trace.append(th.copy())
     return dict(theta=th, trace=np.array(trace), best_theta=best, best_logp=best_logp, mean=mean, m2=m2,
                 ntally=ntally, steps=steps, asf=asf, lnL=lnL_of(Scur, sd))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Adaptive Metropolis (vamp_k2.cu:mcmc_chain_am; step_kind = VAMP_STEP_ADAPTIVE)
+def _tri(i, j):
+    return i * (i + 1) // 2 + j
+
+
+def am_initial_cov(theta_c, NP):
+    """PyMC 2 ``AdaptiveMetropolis.cov_from_value(100)`` [3P-memory]: C_0 = diag(|value| / 100), 1 for a zero value."""
+    v = np.asarray(theta_c[:NP], dtype=np.float64)
+    return np.diag(np.where(v != 0.0, np.abs(v), 1.0) / 100.0)
+
+
+def replay_chain_am(u, flux, noise, theta0, n, voigt, sd_free, uid, seed, iters, burn, thin, tune_interval, tune_throughout,
+                    cmax, delay=1000, interval=200, lsf=None):
+    """Float64 replay of the device's adaptive-Metropolis chain: PyMC 2's ``AdaptiveMetropolis`` (Haario et al. 2001)
+    installed per component - one joint proposal ``theta_c + L z`` per iteration and component, greedy tallying of the
+    block history until ``delay``, recursive covariance update every ``interval`` iterations after it (scaling
+    ``2.4^2 / d``, ``epsilon = 1e-5``), Cholesky refactorisation - with the scalar Metropolis + ``tune()`` step on
+    ``sd``.  Same Philox stream as the device: a block consumes the ``NP`` draws of its parameters, using their
+    normals and the first draw's log-uniform.  [3P-memory: PyMC 2.3 ``StepMethods.AdaptiveMetropolis``; the two stated
+    deviations - previous covariance weighted by ``max(k - 1, 0)``, a non positive definite update keeps the old
+    factor - are the device's.]"""
+    NP = 4 if voigt else 3
+    P = len(u)
+    th = np.array(theta0, dtype=np.float64)
+    ts, sdi = 4 * cmax + 1, 4 * cmax
+    c_hi = float(P - 1)
+    w_hi = 0.5 * (P - 1) * (FWHM_PER_SIGMA if voigt else 1.0)
+    psd_sd = np.float32(abs(th[sdi]) if th[sdi] != 0.0 else 1.0)
+    asf_sd = np.float32(1.0)
+    acc_sd = tot_sd = 0
+    w = 1.0 / np.asarray(noise, dtype=np.float64)
+    lognorm = float(np.sum(np.log(w)) - 0.5 * P * math.log(2.0 * math.pi))
+
+    def S_of(theta):
+        m = D.model_flux(u, theta[: 4 * n].reshape(n, 4), voigt, lsf)
+        r = flux - m
+        return float(np.sum((r * w) ** 2)) if not sd_free else float(np.sum(r * r))
+
+    def lnL_of(S, sd):
+        if sd_free:
+            return -0.5 * S / (sd * sd) - P * (math.log(sd) + 0.91893853320467274178)
+        return -0.5 * S + lognorm
+
+    C = [am_initial_cov(th[4 * c: 4 * c + 4], NP) for c in range(n)]
+    L = [np.sqrt(Ci) for Ci in C]                      # diagonal: its own Cholesky factor
+    cmean = [np.zeros(NP) for _ in range(n)]
+    sumx = [np.zeros(NP) for _ in range(n)]
+    sumxx = [np.zeros((NP, NP)) for _ in range(n)]
+    kcount = [0.0] * n
+    mcount = [0.0] * n
+    acc_b = np.zeros(n, dtype=np.int64)
+    rng = WarpRng(uid, seed)
+    Scur = S_of(th)
+    sd = th[sdi] if sd_free else 1.0
+    best_logp, best = -np.inf, th.copy()
+    mean, m2 = np.zeros(ts), np.zeros(ts)
+    ntally = 0
+    trace = []
+    q = 0
+    for it in range(iters):
+        if sd_free and it > 0 and it % tune_interval == 0 and (tune_throughout or it <= burn):
+            if tot_sd > 0:
+                nf = np.float32(asf_sd * _tune_factor(np.float32(acc_sd) / np.float32(tot_sd)))
+                if nf > 0:
+                    asf_sd = nf
+            acc_sd = tot_sd = 0
+        for c in range(n):
+            z = np.zeros(NP)
+            lu = 0.0
+            for i in range(NP):
+                zi, lui = rng.get(q)
+                q += 1
+                z[i] = zi
+                if i == 0:
+                    lu = lui
+            cur = th[4 * c: 4 * c + NP].copy()
+            prop = cur + L[c] @ z
+            ok = prop[0] > 0.0 and 0.0 <= prop[1] <= c_hi
+            if voigt:
+                ok = ok and 0.0 <= prop[2] <= w_hi and 0.0 < prop[3] <= w_hi
+            else:
+                ok = ok and 0.0 < prop[2] <= w_hi
+            accept = False
+            if ok:
+                t2 = th.copy()
+                t2[4 * c: 4 * c + NP] = prop
+                Snew = S_of(t2)
+                dprior = (math.log(prop[0]) - prop[0]) - (math.log(cur[0]) - cur[0])
+                dl = -0.5 * (Snew - Scur) / (sd * sd) if sd_free else -0.5 * (Snew - Scur)
+                accept = lu < dl + dprior
+                if accept:
+                    th = t2
+                    Scur = Snew
+                    acc_b[c] += 1
+            if accept or it >= delay:
+                x = th[4 * c: 4 * c + NP]
+                sumx[c] += x
+                sumxx[c] += np.outer(x, x)
+                mcount[c] += 1.0
+        if sd_free:
+            zi, lui = rng.get(q)
+            q += 1
+            prop = sd + zi * float(np.float32(asf_sd * psd_sd))
+            if 0.0 < prop <= 1.0:
+                d = -0.5 * Scur * (1.0 / (prop * prop) - 1.0 / (sd * sd)) - P * (math.log(prop) - math.log(sd))
+                if lui < d:
+                    sd = prop
+                    th[sdi] = prop
+                    acc_sd += 1
+            tot_sd += 1
+        if it > delay and it % interval == 0:
+            for c in range(n):
+                kk, m = kcount[c], mcount[c]
+                nn = kk + m
+                if m > 0 and nn > 1:
+                    nm = (kk * cmean[c] + sumx[c]) / nn
+                    t = kk * np.outer(cmean[c], cmean[c]) + sumxx[c] - nn * np.outer(nm, nm) + 1.0e-5 * np.eye(NP)
+                    C[c] = max(kk - 1.0, 0.0) / (nn - 1.0) * C[c] + (5.76 / NP) / (nn - 1.0) * t
+                    cmean[c], kcount[c], mcount[c] = nm, nn, 0.0
+                    sumx[c] = np.zeros(NP)
+                    sumxx[c] = np.zeros((NP, NP))
+                    try:
+                        L[c] = np.linalg.cholesky(C[c])
+                    except np.linalg.LinAlgError:
+                        pass
+        lnL = lnL_of(Scur, sd)
+        logp = lnL + sum(math.log(th[4 * c]) - th[4 * c] for c in range(n))
+        if logp > best_logp:
+            best_logp, best = logp, th.copy()
+        if it >= burn and it % thin == 0:
+            ntally += 1
+            d = th - mean
+            mean = mean + d / ntally
+            m2 = m2 + d * (th - mean)
+            trace.append(th.copy())
+    return dict(theta=th, trace=np.array(trace), best_theta=best, best_logp=best_logp, mean=mean, m2=m2, ntally=ntally,
+                lnL=lnL_of(Scur, sd), cov=C, chol=L, chain_mean=cmean, accepted=acc_b)

@@ -103,12 +103,15 @@ def test_simba_fixtures_reach_the_notebook_outcome(ctx, spec, voigt, iters):
     assert [r.n0 for r in res] == n0
     assert all(abs(a - b) <= 1 for a, b in zip(n_gpu, want)), (n_gpu, want)
     # (the oracle's own outcome, 4, 3, 4, 1 / 2, 1, 1, is reported beside it: all three fits are stochastic)
-    for j, r in enumerate(res):
+    for j, (r, g) in enumerate(zip(res, gold)):
         name = "%s/r%d" % (spec, j)
+        # BIC of the 1-component fit, an (almost) deterministic function of the data: the GPU fit (K2 + K3) and the
+        # restated reference fit (numpy / scipy sampler + fmin) land on the SAME optimum ...
+        assert float(np.min(r.bic[1])) == pytest.approx(min(g["bic"]["1"]), abs=0.02), (name, r.bic[1], g["bic"]["1"])
         if name in NOTEBOOK_BIC_N1:
-            # BIC of the 1-component fit: the reference printed its third restart's value; the best of the GPU's
-            # restart groups is that optimum or a better one
-            assert float(np.min(r.bic[1])) <= NOTEBOOK_BIC_N1[name] + 1.0, (name, r.bic[1])
+            # ... which is the value the reference's notebook printed, to within the 1.5 BIC units by which that
+            # recorded run (unknown PyMC / numpy versions) differs from BOTH
+            assert abs(float(np.min(r.bic[1])) - NOTEBOOK_BIC_N1[name]) < 1.5 + (1.5 if voigt else 0.0), (name, r.bic[1])
     if spec == "simba_CII1036":
         # the reference's recorded ladder of region 0 (n = 1 .. 5): the GPU's per-candidate best BIC is at or below it
         for n, ref in zip(range(1, 6), NOTEBOOK_LADDER_R0):

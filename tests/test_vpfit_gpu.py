@@ -77,6 +77,17 @@ def test_notebook_flow_gaussian(ctx):
     np.testing.assert_allclose(got[:, 2], want[:, 2], rtol=0.25)
     chi = VPfit.ReducedChisquared(reg["flux"], fit.total.value, reg["noise"], 150 - 6)
     assert chi < 1.6
+    # the notebook's convergence cells (17, 18): mc.geweke / mc.raftery_lewis per variable, PyMC 2 names
+    rl = fit.raftery_lewis(q=0.995, r=0.05)
+    assert sorted(rl) == sorted(["xexp_0", "est_centroid_0", "est_sigma_0", "xexp_1", "est_centroid_1", "est_sigma_1", "sd"])
+    assert all(v[0] == 8 and v[1] >= 1 and v[4] >= 1 for v in rl.values())     # nmin = 8 as printed in cell 18
+    gz = fit.geweke(intervals=20)
+    assert gz["est_centroid_0"].shape == (20, 2) and np.all(np.isfinite(gz["est_centroid_0"]))
+    # a second run on the same sampler continues with its own random stream (not a replay of the first)
+    fit.mcmc_fit(iterations=3000, burnin=500, thinning=10)
+    tr2 = fit.mcmc.trace("est_sigma_0")[:]
+    assert len(tr2) == 250 and not np.array_equal(tr2, tr)
+    assert fit._sampler._runs == 2 and fit._sampler.seed != fit._seed
 
 
 def test_fixed_noise_mode(ctx):

@@ -12,6 +12,8 @@ LIB_PATH = os.environ.get("VAMP_B200_LIB") or os.path.join(_HERE, "libvamp_b200.
 
 VAMP_F32, VAMP_F64, VAMP_MIXED = 0, 1, 2
 VAMP_GAUSS, VAMP_VOIGT = 0, 1
+VAMP_STEP_METROPOLIS, VAMP_STEP_ADAPTIVE = 0, 1
+VAMP_AM_STRIDE = 40
 
 c_int_p = C.POINTER(C.c_int)
 c_dbl_p = C.POINTER(C.c_double)
@@ -30,6 +32,7 @@ class McmcArgs(C.Structure):
         ("best_theta", C.c_void_p), ("best_logp", C.c_void_p), ("mean", C.c_void_p), ("m2", C.c_void_p),
         ("comom", C.c_void_p), ("ntally", C.c_void_p), ("sum_lnL", C.c_void_p), ("sum_lnL2", C.c_void_p),
         ("trace", C.c_void_p), ("trace_cap", C.c_int), ("work", C.c_void_p),
+        ("step_kind", C.c_int), ("am_delay", C.c_int), ("am_interval", C.c_int), ("am_state", C.c_void_p),
     ]
 
 
@@ -97,7 +100,7 @@ def load():
         fn = getattr(lib, name)      # AttributeError if the symbol is missing
         fn.restype = res
         fn.argtypes = args
-    if lib.vamp_abi_version() != 3:
+    if lib.vamp_abi_version() != 4:
         raise VampError("libvamp_b200.so ABI version mismatch")
     _lib = lib
     return lib

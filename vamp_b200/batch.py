@@ -64,7 +64,7 @@ class ModelBatch:
 def fit_models(regions, models, voigt=False, sd_free=True, iterations=3000, burn=300, thin=15, restarts=3,
                chains_per_restart=32, polish_top=4, dtype="f32", seed=0, region_uids=None, tune_interval=50,
                tune_throughout=True, keep_sampler=False, trace=False, maxiter=None, xtol=1e-4, ftol=1e-3,
-               polish_dtype="f64", overlap=False, timing=None, polish_from="best"):
+               polish_dtype="f64", overlap=False, timing=None, polish_from="best", step_method="metropolis"):
     """Fit ``models = [(region_index, n), ...]`` on the device-resident ``regions``.
 
     Per model and restart group: prior-drawn starts -> ``iterations`` of K2 Metropolis ->
@@ -96,7 +96,7 @@ def fit_models(regions, models, voigt=False, sd_free=True, iterations=3000, burn
     cap = max(0, (int(iterations) - int(burn) + int(thin) - 1) // max(int(thin), 1) + 1) if trace else 0
     s = engine.Sampler(regions, item_region[order], item_ncomp[order], uid[order], voigt=voigt, sd_free=sd_free,
                        dtype=dtype, seed=seed, burn=burn, thin=thin, tune_interval=tune_interval,
-                       tune_throughout=tune_throughout, trace_cap=cap, cmax=cmax)
+                       tune_throughout=tune_throughout, trace_cap=cap, cmax=cmax, step_method=step_method)
     s.init()
     dev = s.ctx.torch_device
     d_inv = torch.from_numpy(inv).to(dev)

@@ -47,6 +47,8 @@ def _jobs():
                 jobs.append((src, obj, defs, hdr))
                 if base == "vamp_k2":       # the sampler's multiplet instantiations (two tied lines per component)
                     jobs.append((src, obj[:-2] + "_mult.o", defs + ["-DVAMP_INST_MULT=1"], hdr))
+                    # ... and its adaptive-Metropolis instantiations (step_kind = VAMP_STEP_ADAPTIVE)
+                    jobs.append((src, obj[:-2] + "_am.o", defs + ["-DVAMP_INST_AM=1"], hdr))
     jobs.append((os.path.join(CSRC, "vamp_k4.cu"), os.path.join(OBJ, "vamp_k4.o"), [], hdr))
     jobs.append((os.path.join(CSRC, "vamp_cabi.cu"), os.path.join(OBJ, "vamp_cabi.o"), [], hdr))
     return jobs

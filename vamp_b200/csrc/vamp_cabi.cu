@@ -180,6 +180,9 @@ McmcDev to_dev(const vamp_regions* rg, const vamp_mcmc_args* a) {
     p.trace = a->trace;
     p.trace_cap = a->trace_cap;
     p.work = a->work;
+    p.am_delay = a->am_delay > 0 ? a->am_delay : 1000;          // PyMC 2 AdaptiveMetropolis defaults
+    p.am_interval = a->am_interval > 0 ? a->am_interval : 200;
+    p.am = (a->step_kind == VAMP_STEP_ADAPTIVE) ? a->am_state : nullptr;
     return p;
 }
 
@@ -194,6 +197,12 @@ int check_mcmc(const vamp_regions* rg, const vamp_mcmc_args* a) {
         !a->acc_total || !a->logp || !a->lnL || !a->best_theta || !a->best_logp || !a->mean || !a->m2 || !a->comom ||
         !a->ntally || !a->sum_lnL || !a->sum_lnL2)
         return fail(-1, "null state pointer in vamp_mcmc_args");
+    if (a->step_kind != VAMP_STEP_METROPOLIS && a->step_kind != VAMP_STEP_ADAPTIVE)
+        return fail(-2, "bad step_kind %d", a->step_kind);
+    if (a->step_kind == VAMP_STEP_ADAPTIVE) {
+        if (!a->am_state) return fail(-1, "step_kind = VAMP_STEP_ADAPTIVE needs am_state [n, cmax, %d]", VAMP_AM_STRIDE);
+        if (rg->dev.mult) return fail(-5, "the adaptive step method is not built for multiplet region sets");
+    }
     return 0;
 }
 
@@ -594,7 +603,8 @@ int vamp_mcmc_run_dev(vamp_ctx* ctx, const vamp_regions* rg, int dtype, int kind
     if (a->it1 < a->it0 || a->it0 < 0) return fail(-2, "bad iteration range [%d, %d)", a->it0, a->it1);
     VAMP_CUDA(cudaSetDevice(ctx->device));
     const McmcDev p = to_dev(rg, a);
-    if (rg->dev.mult) VAMP_CUDA(VAMP_DISPATCH4(vamp_launch_k2m, dtype, kind, p, rg->max_npix, a->max_ncomp, ctx->stream));
+    if (a->step_kind == VAMP_STEP_ADAPTIVE) VAMP_CUDA(VAMP_DISPATCH4(vamp_launch_k2a, dtype, kind, p, rg->max_npix, a->max_ncomp, ctx->stream));
+    else if (rg->dev.mult) VAMP_CUDA(VAMP_DISPATCH4(vamp_launch_k2m, dtype, kind, p, rg->max_npix, a->max_ncomp, ctx->stream));
     else VAMP_CUDA(VAMP_DISPATCH4(vamp_launch_k2, dtype, kind, p, rg->max_npix, a->max_ncomp, ctx->stream));
     return 0;
 }

@@ -827,6 +827,434 @@ __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, const unsigned
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Adaptive Metropolis (step_kind = VAMP_STEP_ADAPTIVE; objects built with -DVAMP_INST_AM=1).
+// PyMC 2's AdaptiveMetropolis (Haario, Saksman & Tamminen 2001) installed per component - what
+// `mcmc.use_step_method(mc.AdaptiveMetropolis, [xexp_c, est_centroid_c, est_L_c, est_G_c])` would do; the reference
+// names the method in mcmc_fit (vamp_1.0/vpfits.py:361, 382-389) but never installs it.  Per iteration and
+// component ONE joint proposal theta_c + L z (L = Cholesky factor of the block's proposal covariance, z ~ N(0, I)),
+// one evaluation of the component's shape, one accept test; sd keeps its scalar Metropolis step with tune().
+// Adaptation as in PyMC 2.3: C_0 = diag(|value| / 100); until iteration `delay` only accepted states enter the
+// block's history (greedy), afterwards every state; at iteration > delay with it % interval == 0 the covariance is
+// updated recursively from the history, scaled by 2.4^2 / d, with epsilon = 1e-5 on the diagonal, and refactored.
+// Deviation, stated: the recursion weights the previous covariance by max(k - 1, 0) / (n - 1) (PyMC's (k - 1) is
+// negative at the first update, where k = 0), and a covariance that is not positive definite keeps the previous
+// factor (PyMC shrinks / repairs it).  Replayed step for step by oracle/chain_replay.py:replay_chain_am.
+// The sweep over the region is chain_pass<FRESH> - the arithmetic of the scalar sampler; this path is about the
+// step rule, it is not the one bench.py times.
+__device__ __forceinline__ int am_tri(int i, int j) { return i * (i + 1) / 2 + j; }
+
+template <typename T, int KIND, bool WT, bool LSF>
+__device__ void mcmc_chain_am(const McmcDev& p, int chain, int lane, const unsigned char* rb, unsigned char* wb, int ncomp_max,
+                              const T* lsf_s) {
+    typedef K2Lay<T, WT> Lay;
+    constexpr int NP = (KIND == VAMP_KIND_VOIGT) ? 4 : 3;
+    constexpr int NT = NP * (NP + 1) / 2;
+    constexpr int ROW = 32 * (int)sizeof(P2<T>);
+    const RegionSetDev& rs = p.rs;
+    const int r = p.item_region[chain];
+    const int P = rs.npix[r];
+    const int n = p.item_ncomp[chain];
+    const int ts = p.tstride;
+    const int sdi = 4 * p.cmax;
+    const int k = NP * n + (WT ? 0 : 1);
+    const int npairs = 2 * ((P + 127) >> 7);
+    const int npad = 64 * npairs - P;
+    const int burn = p.burn;
+    const T NK = Real<T>::NEGK();
+    const size_t gb = (size_t)chain * ts;
+    double* const amg = p.am + (size_t)chain * p.cmax * VAMP_AM_STRIDE;
+
+    P2<T>* const Hbuf = reinterpret_cast<P2<T>*>(wb + Lay::H) + lane;
+    P2<T>* const pbase = reinterpret_cast<P2<T>*>(wb + Lay::BASE) + lane;
+    unsigned ar0 = (unsigned)__cvta_generic_to_shared(rb) + (unsigned)(lane * sizeof(P2<T>));
+    unsigned aw0 = (unsigned)__cvta_generic_to_shared(wb) + (unsigned)(lane * sizeof(P2<T>));
+    auto slot_addr = [&](int sl) -> unsigned { return aw0 + (unsigned)(Lay::H + sl * Lay::SLOT); };
+    unsigned char* sp_ = wb + Lay::H + (size_t)(ncomp_max + 1) * Lay::SLOT;
+    LsfCtx<T> lc;
+    lc.buf = reinterpret_cast<T*>(sp_);
+    lc.taps_s = lsf_s;
+    lc.taps = rs.lsf_taps;
+    lc.P = P;
+    sp_ += Lay::lsf_bytes(LSF);
+    SdRec<T>* const sdrec = reinterpret_cast<SdRec<T>*>(sp_);
+    CompRec<T>* const recs = reinterpret_cast<CompRec<T>*>(sp_ + sizeof(SdRec<T>));
+    T* const Lsm = reinterpret_cast<T*>(sp_ + sizeof(SdRec<T>) + (size_t)ncomp_max * sizeof(CompRec<T>));   // [ncomp_max][10]
+    auto is_free = [&](int i) -> bool { return (i == sdi) ? !WT : ((i < 4 * n) && ((i & 3) < NP)); };
+
+    // ---- state -> shared.  Block counters: acc[0] accepted, acc[1] rejected since the last covariance update
+    //      (global: acc / rej of the block's amplitude entry), acc[2] accepted at iterations >= burn of this launch.
+    for (int e = 0; e < 32 * npairs; e += 32) {
+        pbase[e] = p2_bc<T>(T(0));
+        Hbuf[n * Lay::NE + e] = p2_bc<T>(T(0));
+    }
+    for (int i = lane; i < 4 * n; i += 32) {
+        CompRec<T>& rc = recs[i >> 2];
+        rc.th[i & 3] = T(p.theta[gb + i]);
+        if ((i & 3) == 0) {
+            rc.slot = i >> 2;
+            rc.acc[0] = p.acc[gb + i];
+            rc.acc[1] = p.rej[gb + i];
+            rc.acc[2] = 0;
+        }
+    }
+    for (int i = lane; i < 10 * n; i += 32) Lsm[i] = T(amg[(i / 10) * VAMP_AM_STRIDE + 14 + (i % 10)]);
+    if (lane == 0) {
+        sdrec->th = T(p.theta[gb + sdi]);
+        sdrec->scl = p.asf[gb + sdi] * p.psd[gb + sdi];
+        sdrec->acc = p.acc[gb + sdi];
+    }
+    int tot_sd = p.acc[gb + sdi] + p.rej[gb + sdi];
+    int sd_post = 0;
+    __syncwarp();
+
+    const double ubase = rs.ubase[rs.tile_off[r]];
+    const T ub_hi = T(ubase), ub_lo = T(ubase - (double)ub_hi);
+    auto cbase = [&](T c) -> T { return (c - ub_hi) - ub_lo; };
+
+    // ---- shape cache and the current sum of squares (as in mcmc_chain)
+    {
+        const P2<T>* sd_ = reinterpret_cast<const P2<T>*>(rb + Lay::DU) + lane;
+        for (int c = 0; c < n; ++c) {
+            CompRec<T>& rc = recs[c];
+            const CompC<T> cc = make_comp_fast<T, KIND>(rc.th[0], cbase(rc.th[1]), rc.th[2], rc.th[3]);
+            const P2<T> A2 = p2_bc<T>(NK * cc.A);
+            bool far;
+            for (int e = 0; e < 32 * npairs; e += 32) {
+                const P2<T> H = pair_shape<T, KIND>(cc, sd_[e], far);
+                Hbuf[c * Lay::NE + e] = H;
+                pbase[e] = p2_fma(A2, H, pbase[e]);
+            }
+        }
+    }
+    CompC<T> cz;
+    cz.A = cz.cb = cz.g = cz.y = cz.y2 = cz.L2 = T(0);
+    unsigned dummy = 0u, dummy_far;
+    T Scur = chain_pass<T, KIND, WT, LSF, false>(cz, T(0), slot_addr(n), 0u, ar0, aw0, rb, npairs, lane, lc, dummy, dummy_far);
+    T sd = WT ? T(1) : sdrec->th;
+    T logsd = WT ? T(0) : StepMath<T>::log_(sd);
+    T hiv = WT ? T(0.5) : T(0.5) / (sd * sd);
+    T lp = T(0);
+    for (int c = 0; c < n; ++c) {
+        const T a = recs[c].th[0];
+        lp += StepMath<T>::log_(a) - a;
+    }
+    const T lognorm = WT ? T(rs.lognorm[r]) : T(0);
+    T best_logp = T(p.best_logp[chain]);
+    int ntally = p.ntally[chain];
+    unsigned long long w_shape = 0ull, w_far = 0ull, w_like = 0ull;
+
+    // ---- random stream: the scalar sampler's layout (k draws per iteration); a block uses the normals of its NP
+    //      draws and the log-uniform of the first
+    const unsigned long long uid = p.chain_uid[chain];
+    unsigned long long qblk = ((unsigned long long)p.it0 * (unsigned long long)k) >> 6;
+    int qs = (int)(((unsigned long long)p.it0 * (unsigned long long)k) & 63ull);
+    T zc, luc, zn, lun;
+    auto refill = [&]() {
+        const uint4 x = philox4x32_10(make_uint4((uint32_t)uid, (uint32_t)(uid >> 32), (uint32_t)qblk,
+                                                 ((uint32_t)(qblk >> 32) << 8) | (uint32_t)lane),
+                                      make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32)));
+        RngMath<T>::fill(x, zc, zn, luc, lun);
+    };
+    refill();
+    if (qs >= 32) {
+        zc = zn;
+        luc = lun;
+    }
+    auto draw = [&](T& z, T& lu) {
+        z = __shfl_sync(VAMP_FULL_MASK, zc, qs);
+        lu = __shfl_sync(VAMP_FULL_MASK, luc, qs);
+        ++qs;
+        if ((qs & 31) == 0) {
+            if (qs == 64) {
+                qs = 0;
+                ++qblk;
+                refill();
+            } else {
+                zc = zn;
+                luc = lun;
+            }
+        }
+    };
+
+    const T c_hi = T(P - 1);
+    const T w_hi = T(P - 1) * T(KIND == VAMP_KIND_VOIGT ? 0.5 * FWHM_PER_SIGMA : 0.5);
+    const int tune_interval = p.tune_interval, thin = p.thin;
+    int hs = n;
+    const unsigned endw = aw0 + (unsigned)(npairs * ROW);
+
+    for (int it = p.it0; it < p.it1; ++it) {
+        // ---- sd: PyMC 2 Metropolis.tune every tune_interval iterations
+        if (!WT && it > 0 && it % tune_interval == 0 && (p.tune_throughout || it <= burn)) {
+            if (lane == 0) {
+                float f = p.asf[gb + sdi];
+                if (tot_sd > 0) {
+                    const float nf = f * tune_factor((float)sdrec->acc / (float)tot_sd);
+                    if (nf > 0.0f) f = nf;
+                }
+                p.asf[gb + sdi] = f;
+                sdrec->scl = f * p.psd[gb + sdi];
+                sdrec->acc = 0;
+            }
+            tot_sd = 0;
+            __syncwarp();
+        }
+        unsigned n_shape = 0u, n_far = 0u, n_like = 0u;
+        int hprev = 0;
+        T Aprev = T(0);
+        const bool post_delay = it >= p.am_delay;              // PyMC: greedy is switched off AT iteration == delay
+
+        for (int c = 0; c < n; ++c) {
+            CompRec<T>& rc = recs[c];
+            T th[4] = {rc.th[0], rc.th[1], rc.th[2], rc.th[3]};
+            int hc = rc.slot;
+            // ---- base = tau of the other components
+            if (c == 0) {
+                for (unsigned a = aw0; a < endw; a += ROW) SM<T>::template st<Lay::BASE>(a, p2_bc<T>(T(0)));
+                for (int c2 = 1; c2 < n; ++c2) {
+                    const P2<T> A2 = p2_bc<T>(NK * recs[c2].th[0]);
+                    unsigned ah = slot_addr(recs[c2].slot);
+                    for (unsigned a = aw0; a < endw; a += ROW, ah += ROW)
+                        SM<T>::template st<Lay::BASE>(a, p2_fma(A2, SM<T>::template ld<0>(ah), SM<T>::template ld<Lay::BASE>(a)));
+                }
+            } else {
+                const P2<T> Ap = p2_bc<T>(NK * Aprev), Ac = p2_bc<T>(-NK * th[0]);
+                unsigned ap = slot_addr(hprev), an = slot_addr(hc);
+                for (unsigned a = aw0; a < endw; a += ROW, ap += ROW, an += ROW)
+                    SM<T>::template st<Lay::BASE>(a, p2_fma(Ac, SM<T>::template ld<0>(an),
+                                                           p2_fma(Ap, SM<T>::template ld<0>(ap), SM<T>::template ld<Lay::BASE>(a))));
+            }
+            // ---- joint proposal theta + L z
+            T z[4] = {T(0), T(0), T(0), T(0)}, lu = T(0);
+#pragma unroll
+            for (int i = 0; i < NP; ++i) {
+                T lui;
+                draw(z[i], lui);
+                if (i == 0) lu = lui;
+            }
+            const T* Lc = Lsm + 10 * c;
+            T prop[4] = {th[0], th[1], th[2], th[3]};
+#pragma unroll
+            for (int i = 0; i < NP; ++i)
+#pragma unroll
+                for (int j = 0; j <= i; ++j) prop[i] = Real<T>::fma_(Lc[am_tri(i, j)], z[j], prop[i]);
+            bool ok = (prop[0] > T(0)) && (prop[1] >= T(0)) && (prop[1] <= c_hi);
+            if (KIND == VAMP_KIND_VOIGT)
+                ok = ok && (prop[2] >= T(0)) && (prop[2] <= w_hi) && (prop[3] > T(0)) && (prop[3] <= w_hi);
+            else
+                ok = ok && (prop[2] > T(0)) && (prop[2] <= w_hi);
+            bool accept = false;
+            if (ok) {
+                const CompC<T> cc = make_comp_fast<T, KIND>(prop[0], cbase(prop[1]), prop[2], prop[3]);
+                unsigned nf = 0u, last_far;
+                const T Snew = chain_pass<T, KIND, WT, LSF, true>(cc, NK * prop[0], 0u, slot_addr(hs), ar0, aw0, rb, npairs, lane, lc,
+                                                                  nf, last_far);
+                n_far += nf - last_far * (unsigned)npad;
+                ++n_shape;
+                ++n_like;
+                const T dprior = StepMath<T>::log_(prop[0] * Real<T>::rcp(th[0])) - (prop[0] - th[0]);
+                if (lu < (Scur - Snew) * hiv + dprior) {
+                    accept = true;
+                    Scur = Snew;
+                    lp += dprior;
+#pragma unroll
+                    for (int i = 0; i < NP; ++i) th[i] = prop[i];
+                    const int tmp = hc;
+                    hc = hs;
+                    hs = tmp;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) {
+                rc.th[0] = th[0];
+                rc.th[1] = th[1];
+                rc.th[2] = th[2];
+                rc.th[3] = th[3];
+                rc.slot = hc;
+                rc.acc[accept ? 0 : 1] += 1;
+                if (accept && it >= burn) rc.acc[2] += 1;
+            }
+            // ---- the block's history (greedy until `delay`): sum x, sum x x^T, count
+            if (accept || post_delay) {
+                double* a = amg + c * VAMP_AM_STRIDE;
+                if (lane < NP) {
+                    a[24 + lane] += (double)th[lane];
+                } else if (lane < NP + NT) {
+                    int e = lane - NP, i = 0;
+                    while (am_tri(i + 1, 0) <= e) ++i;
+                    const int j = e - am_tri(i, 0);
+                    a[28 + e] += (double)th[i] * (double)th[j];
+                } else if (lane == 31) {
+                    a[39] += 1.0;
+                }
+            }
+            Aprev = th[0];
+            hprev = hc;
+            __syncwarp();
+        }
+
+        if (!WT) {
+            // ---- sd: scalar Metropolis, no model evaluation
+            T z, lu;
+            draw(z, lu);
+            const T prop = sd + z * T(sdrec->scl);
+            bool acc_sd = false;
+            if (prop > T(0) && prop <= T(1)) {
+                const T lprop = StepMath<T>::log_(prop);
+                const T hv = T(0.5) / (prop * prop);
+                if (lu < -Scur * (hv - hiv) - T(P) * (lprop - logsd)) {
+                    sd = prop;
+                    logsd = lprop;
+                    hiv = hv;
+                    acc_sd = true;
+                }
+            }
+            __syncwarp();
+            if (acc_sd && lane == 0) {
+                sdrec->acc += 1;
+                sdrec->th = sd;
+            }
+            if (acc_sd && it >= burn) ++sd_post;
+            ++tot_sd;
+            __syncwarp();
+        }
+        w_shape += n_shape;
+        w_far += n_far;
+        w_like += n_like;
+
+        // ---- covariance update (PyMC 2: _current_iter > delay and _current_iter % interval == 0)
+        if (it > p.am_delay && it % p.am_interval == 0) {
+            __syncwarp();
+            for (int c = lane; c < n; c += 32) {
+                double* a = amg + c * VAMP_AM_STRIDE;
+                const double kk = a[38], m = a[39], nn = kk + m;
+                if (m > 0.0 && nn > 1.0) {
+                    double nm[4];
+                    for (int i = 0; i < NP; ++i) nm[i] = (kk * a[i] + a[24 + i]) / nn;
+                    const double scaling = 5.76 / (double)NP, eps = 1.0e-5, wold = (kk > 1.0 ? kk - 1.0 : 0.0) / (nn - 1.0);
+                    for (int i = 0; i < NP; ++i)
+                        for (int j = 0; j <= i; ++j) {
+                            const int e = am_tri(i, j);
+                            const double t = kk * a[i] * a[j] + a[28 + e] - nn * nm[i] * nm[j] + (i == j ? eps : 0.0);
+                            a[4 + e] = wold * a[4 + e] + scaling / (nn - 1.0) * t;
+                        }
+                    for (int i = 0; i < NP; ++i) {
+                        a[i] = nm[i];
+                        a[24 + i] = 0.0;
+                    }
+                    for (int e = 0; e < NT; ++e) a[28 + e] = 0.0;
+                    a[38] = nn;
+                    a[39] = 0.0;
+                    double Lf[10];
+                    bool pd = true;
+                    for (int i = 0; i < NP && pd; ++i)
+                        for (int j = 0; j <= i; ++j) {
+                            double s_ = a[4 + am_tri(i, j)];
+                            for (int q = 0; q < j; ++q) s_ -= Lf[am_tri(i, q)] * Lf[am_tri(j, q)];
+                            if (i == j) {
+                                if (!(s_ > 0.0)) {
+                                    pd = false;
+                                    break;
+                                }
+                                Lf[am_tri(i, i)] = sqrt(s_);
+                            } else {
+                                Lf[am_tri(i, j)] = s_ / Lf[am_tri(j, j)];
+                            }
+                        }
+                    if (pd)
+                        for (int e = 0; e < NT; ++e) {
+                            a[14 + e] = Lf[e];
+                            Lsm[10 * c + e] = T(Lf[e]);
+                        }
+                }
+                recs[c].acc[0] = 0;
+                recs[c].acc[1] = 0;
+            }
+            __syncwarp();
+        }
+
+        // ---- end of iteration: log-posterior, best state, tallies (as in mcmc_chain)
+        const T lnL = WT ? (T(-0.5) * Scur + lognorm) : (-Scur * hiv - T(P) * (logsd + T(0.91893853320467274178)));
+        const T logp = lnL + lp;
+        if (logp > best_logp) {
+            best_logp = logp;
+            for (int i2 = lane; i2 < ts; i2 += 32)
+                if (is_free(i2)) p.best_theta[gb + i2] = (double)((i2 == sdi) ? sdrec->th : recs[i2 >> 2].th[i2 & 3]);
+        }
+        if (it >= burn && it % thin == 0) {
+            auto th_of = [&](int i2) -> double {
+                return is_free(i2) ? (double)((i2 == sdi) ? sdrec->th : recs[i2 >> 2].th[i2 & 3]) : 0.0;
+            };
+            if (lane == 0) {
+                p.sum_lnL[chain] += (double)lnL;
+                p.sum_lnL2[chain] += (double)lnL * (double)lnL;
+            }
+            ++ntally;
+            const double inv = 1.0 / (double)ntally;
+            const double wgt = (double)(ntally - 1) * inv;
+            double* mean = p.mean + gb;
+            double* m2 = p.m2 + gb;
+            double* comom = p.comom + (size_t)chain * 6 * p.cmax;
+            for (int i2 = lane; i2 < 6 * n; i2 += 32) {
+                const int cc2 = i2 / 6, pr = i2 - 6 * cc2;
+                const int a = (pr < 3) ? 0 : (pr < 5 ? 1 : 2);
+                const int b = (pr < 3) ? pr + 1 : (pr < 5 ? pr - 1 : 3);
+                const double da = th_of(VAMP_TH(cc2, a)) - mean[VAMP_TH(cc2, a)];
+                const double db = th_of(VAMP_TH(cc2, b)) - mean[VAMP_TH(cc2, b)];
+                comom[i2] += wgt * da * db;
+            }
+            __syncwarp();
+            for (int i2 = lane; i2 < ts; i2 += 32) {
+                const double x = th_of(i2);
+                const double d = x - mean[i2];
+                const double mn = mean[i2] + d * inv;
+                mean[i2] = mn;
+                m2[i2] += d * (x - mn);
+            }
+            if (p.trace) {
+                const int slot_t = ntally - 1;
+                if (slot_t < p.trace_cap)
+                    for (int i2 = lane; i2 < ts; i2 += 32)
+                        p.trace[((size_t)chain * p.trace_cap + slot_t) * ts + i2] = th_of(i2);
+            }
+            __syncwarp();
+        }
+    }
+
+    // ---- state -> global
+    __syncwarp();
+    for (int i = lane; i < ts; i += 32) {
+        if (!is_free(i)) continue;
+        p.theta[gb + i] = (double)((i == sdi) ? sdrec->th : recs[i >> 2].th[i & 3]);
+        if (i == sdi) {
+            p.acc[gb + i] = sdrec->acc;
+            p.rej[gb + i] = tot_sd - sdrec->acc;
+            p.acc_total[gb + i] += sd_post;
+        } else if ((i & 3) == 0) {
+            p.acc[gb + i] = recs[i >> 2].acc[0];
+            p.rej[gb + i] = recs[i >> 2].acc[1];
+            p.acc_total[gb + i] += recs[i >> 2].acc[2];
+        }
+    }
+    if (lane == 0) {
+        const double lnL = WT ? lnL_noise((double)Scur, rs.lognorm[r]) : lnL_sd((double)Scur, (double)sd, P);
+        double lpx = 0.0;
+        for (int c = 0; c < n; ++c) {
+            const double a = (double)recs[c].th[0];
+            lpx += log(a) - a;
+        }
+        p.lnL[chain] = lnL;
+        p.logp[chain] = lnL + lpx;
+        p.best_logp[chain] = (double)best_logp;
+        p.ntally[chain] = ntally;
+        if (p.work) {
+            p.work[3 * (size_t)chain + 0] += w_shape;
+            p.work[3 * (size_t)chain + 1] += w_far;
+            p.work[3 * (size_t)chain + 2] += w_like;
+        }
+    }
+}
+
 // One warp per chain, K2_WARPS chains per CTA.  The host sorts chains by (pixel class, component
 // count, model), so the warps of a CTA almost always fit the same region: the region's pixels
 // (du, flux, 1/noise) are staged ONCE per CTA and shared, which is what lets a sixth CTA fit on an
@@ -837,7 +1265,7 @@ __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, const unsigned
 #else
 #define VAMP_K2_BOUNDS __launch_bounds__(K2_WARPS * 32, (sizeof(T) == 4) ? VAMP_K2_MINBLOCKS : 2)
 #endif
-template <typename T, int KIND, bool WT, bool LSF, bool MULT>
+template <typename T, int KIND, bool WT, bool LSF, bool MULT, bool AM = false>
 __global__ void VAMP_K2_BOUNDS
 k2_mcmc_kernel(McmcDev p, int ncomp_max) {
     typedef K2Lay<T, WT> Lay;
@@ -856,7 +1284,7 @@ k2_mcmc_kernel(McmcDev p, int ncomp_max) {
     if (lane == 0) s_region[warp] = my_region;
     __syncthreads();
     unsigned char* rb = smem_raw + head;
-    unsigned char* wb = rb + Lay::REGION + (size_t)warp * Lay::bytes(ncomp_max, LSF);
+    unsigned char* wb = rb + Lay::REGION + (size_t)warp * (Lay::bytes(ncomp_max, LSF) + (AM ? align16((size_t)ncomp_max * 10 * sizeof(T)) : 0));
     for (int round = 0; round < K2_WARPS; ++round) {
         const int rr = s_region[round];
         bool skip = rr < 0;
@@ -878,7 +1306,10 @@ k2_mcmc_kernel(McmcDev p, int ncomp_max) {
             }
         }
         __syncthreads();
-        if (my_region == rr) mcmc_chain<T, KIND, WT, LSF, MULT>(p, chain, lane, rb, wb, ncomp_max, lsf_s);
+        if (my_region == rr) {
+            if (AM) mcmc_chain_am<T, KIND, WT, LSF>(p, chain, lane, rb, wb, ncomp_max, lsf_s);
+            else mcmc_chain<T, KIND, WT, LSF, MULT>(p, chain, lane, rb, wb, ncomp_max, lsf_s);
+        }
     }
 }
 
@@ -928,6 +1359,19 @@ __global__ void init_state_kernel(McmcDev p) {
         p.m2[gb + i] = 0.0;
     }
     for (int i = 0; i < 6 * p.cmax; ++i) p.comom[(size_t)chain * 6 * p.cmax + i] = 0.0;
+    if (p.am) {
+        // PyMC 2 AdaptiveMetropolis.cov_from_value(100): C_0 = diag(|value| / 100) (1 for a zero value); empty history
+        for (int c = 0; c < p.cmax; ++c) {
+            double* a = p.am + ((size_t)chain * p.cmax + c) * VAMP_AM_STRIDE;
+            for (int i = 0; i < VAMP_AM_STRIDE; ++i) a[i] = 0.0;
+            for (int i = 0; i < 4; ++i) {
+                const double v = p.theta[gb + 4 * c + i];
+                const double var = ((v != 0.0) ? fabs(v) : 1.0) / 100.0;
+                a[4 + i * (i + 1) / 2 + i] = var;
+                a[14 + i * (i + 1) / 2 + i] = sqrt(var);
+            }
+        }
+    }
     p.best_logp[chain] = -INFINITY;
     p.logp[chain] = -INFINITY;
     p.lnL[chain] = -INFINITY;
@@ -936,11 +1380,16 @@ __global__ void init_state_kernel(McmcDev p) {
     p.sum_lnL2[chain] = 0.0;
 }
 
+#ifndef VAMP_INST_AM
+#define VAMP_INST_AM 0            // 1: this object holds the adaptive-Metropolis instantiations (vamp_launch_k2a_*)
+#endif
+
 template <typename T, int KIND, bool WT, bool LSF>
 cudaError_t launch_k2_t(const McmcDev& p, int max_ncomp, cudaStream_t st) {
+    constexpr bool AM = VAMP_INST_AM != 0;
     const size_t smem = (LSF ? align16(sizeof(T) * VAMP_MAX_LSF_TAPS) : 0) + K2Lay<T, WT>::REGION +
-                        K2_WARPS * K2Lay<T, WT>::bytes(max_ncomp, LSF);
-    auto kern = k2_mcmc_kernel<T, KIND, WT, LSF, VAMP_INST_MULT != 0>;
+                        K2_WARPS * (K2Lay<T, WT>::bytes(max_ncomp, LSF) + (AM ? align16((size_t)max_ncomp * 10 * sizeof(T)) : 0));
+    auto kern = k2_mcmc_kernel<T, KIND, WT, LSF, VAMP_INST_MULT != 0, AM>;
     if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -951,7 +1400,7 @@ cudaError_t launch_k2_t(const McmcDev& p, int max_ncomp, cudaStream_t st) {
 
 }  // namespace
 
-#if VAMP_INST_F64 == 0 && VAMP_INST_MULT == 0
+#if VAMP_INST_F64 == 0 && VAMP_INST_MULT == 0 && VAMP_INST_AM == 0
 // precision-independent helpers live in the f32 objects only
 cudaError_t VAMP_CAT3(vamp_launch_init_prior, any, VAMP_KN)(const McmcDev& p, cudaStream_t st) {
     if (p.B <= 0) return cudaSuccess;
@@ -969,7 +1418,10 @@ cudaError_t vamp_launch_init_state(const McmcDev& p, cudaStream_t st) {
 
 // -DVAMP_INST_MULT=1 objects hold the multiplet instantiations (vamp_launch_k2m_*), chosen by the C ABI when the
 // region set carries a multiplet table
-#if VAMP_INST_MULT
+#if VAMP_INST_AM
+cudaError_t VAMP_INST_NAME(vamp_launch_k2a)(const McmcDev& p, int max_npix, int max_ncomp, cudaStream_t st) {
+    if (!p.am) return cudaErrorInvalidValue;
+#elif VAMP_INST_MULT
 cudaError_t VAMP_INST_NAME(vamp_launch_k2m)(const McmcDev& p, int max_npix, int max_ncomp, cudaStream_t st) {
 #else
 cudaError_t VAMP_INST_NAME(vamp_launch_k2)(const McmcDev& p, int max_npix, int max_ncomp, cudaStream_t st) {

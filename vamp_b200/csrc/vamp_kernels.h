@@ -22,6 +22,9 @@ VAMP_DECL4(cudaError_t, vamp_launch_k1, const RegionSetDev& rs, int B, int max_n
            double* out_lnL, double* out_chi2, void* out_flux, long long fstride, void* partial, cudaStream_t st)
 
 // ---- K2 (vamp_k2.cu)
+#ifndef VAMP_AM_STRIDE
+#define VAMP_AM_STRIDE 40                // doubles of adaptive state per (chain, component): include/vamp_b200.h
+#endif
 struct McmcDev {
     RegionSetDev rs;
     int B;                               // chains in this launch
@@ -53,11 +56,15 @@ struct McmcDev {
     double* trace;                       // [B, trace_cap, tstride] or nullptr
     int trace_cap;
     unsigned long long* work;            // [B, 3] or nullptr: shape evals, far-path pixels, likelihood passes
+    int am_delay, am_interval;           // adaptive Metropolis (vamp_launch_k2a): PyMC 2 delay / interval
+    double* am;                          // [B, cmax, VAMP_AM_STRIDE] adaptive state or nullptr (include/vamp_b200.h)
 };
 cudaError_t vamp_launch_init_prior_any_gauss(const McmcDev& p, cudaStream_t st);
 cudaError_t vamp_launch_init_prior_any_voigt(const McmcDev& p, cudaStream_t st);
 cudaError_t vamp_launch_init_state(const McmcDev& p, cudaStream_t st);
 VAMP_DECL4(cudaError_t, vamp_launch_k2, const McmcDev& p, int max_npix, int max_ncomp, cudaStream_t st)
+// adaptive-Metropolis instantiations (one joint proposal per component from the running covariance)
+VAMP_DECL4(cudaError_t, vamp_launch_k2a, const McmcDev& p, int max_npix, int max_ncomp, cudaStream_t st)
 // multiplet instantiations (region sets with a multiplet table: two tied lines per component)
 VAMP_DECL4(cudaError_t, vamp_launch_k2m, const McmcDev& p, int max_npix, int max_ncomp, cudaStream_t st)
 

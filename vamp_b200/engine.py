@@ -285,7 +285,8 @@ class Sampler:
     chains are batched or sharded)."""
 
     def __init__(self, regions, item_region, item_ncomp, chain_uid, voigt=True, sd_free=True, dtype="f32",
-                 seed=0, burn=300, thin=15, tune_interval=100, tune_throughout=False, trace_cap=0, cmax=None):
+                 seed=0, burn=300, thin=15, tune_interval=100, tune_throughout=False, trace_cap=0, cmax=None,
+                 step_method="metropolis", am_delay=1000, am_interval=200):
         torch = _torch()
         self.regions = regions
         self.ctx = regions.ctx
@@ -313,6 +314,12 @@ class Sampler:
         self.burn, self.thin = int(burn), int(thin)
         self.tune_interval, self.tune_throughout = int(tune_interval), int(bool(tune_throughout))
         self.trace_cap = int(trace_cap)
+        # "metropolis": PyMC 2's scalar Metropolis per stochastic (what the reference runs); "adaptive": PyMC 2's
+        # AdaptiveMetropolis per component (named by mcmc_fit, vpfits.py:361) - include/vamp_b200.h, step_kind
+        if step_method not in ("metropolis", "adaptive"):
+            raise ValueError("step_method must be 'metropolis' or 'adaptive'")
+        self.step_kind = _lib.VAMP_STEP_ADAPTIVE if step_method == "adaptive" else _lib.VAMP_STEP_METROPOLIS
+        self.am_delay, self.am_interval = int(am_delay), int(am_interval)
         self.iteration = 0
         dev = self.ctx.torch_device
         B, ts = self.B, self.ts
@@ -339,6 +346,8 @@ class Sampler:
             "sum_lnL2": torch.zeros(B, dtype=f64, device=dev),
             "trace": torch.zeros((B, self.trace_cap, ts), dtype=f64, device=dev) if self.trace_cap > 0 else None,
             "work": torch.zeros((B, 3), dtype=torch.int64, device=dev),
+            "am_state": (torch.zeros((B, self.cmax, _lib.VAMP_AM_STRIDE), dtype=f64, device=dev)
+                         if self.step_kind == _lib.VAMP_STEP_ADAPTIVE else None),
         }
 
     def _args(self, it0=0, it1=0, rows=None, max_ncomp=None):
@@ -359,6 +368,9 @@ class Sampler:
         a.trace_cap = self.trace_cap
         w = self.t["work"]
         a.work = w.data_ptr() + a0 * w.stride(0) * w.element_size()
+        a.step_kind, a.am_delay, a.am_interval = self.step_kind, self.am_delay, self.am_interval
+        am = self.t["am_state"]
+        a.am_state = (am.data_ptr() + a0 * am.stride(0) * am.element_size()) if am is not None else None
         return a
 
     def init(self, theta0_scaled=None):

@@ -194,7 +194,7 @@ def unpack_record(rec, nmax, G, cmax):
 def fit_local(regions_host, uids, voigt=False, sd_free=True, iterations=3000, burn=300, thin=15, restarts=3,
               chains_per_restart=32, window=3, max_rounds=4, chi_limit=1.5, dtype="f32", seed=0, lsf=None,
               n0=None, nmax=12, ctx=None, polish_top=None, tune_interval=50, stats=None, cmax_rec=None, polish_dtype="f64",
-              multiplet=None, polish_from="best"):
+              multiplet=None, polish_from="best", step_method="metropolis"):
     """Fit the given regions on this process's GPU.  Returns ``[R, record_len]`` float64.
     ``multiplet``: per-region ``(freq_ratio, amp_ratio[, lorentz_ratio])`` or None (``engine.Regions``);
     ``polish_from``: see ``batch.fit_models``."""
@@ -236,7 +236,7 @@ def fit_local(regions_host, uids, voigt=False, sd_free=True, iterations=3000, bu
         mb = batch.fit_models(regs, models, voigt=voigt, sd_free=sd_free, iterations=iterations, burn=burn, thin=thin,
                               restarts=G, chains_per_restart=chains_per_restart, polish_top=polish_top, dtype=dtype,
                               seed=seed, region_uids=uids, tune_interval=tune_interval, polish_dtype=polish_dtype,
-                              polish_from=polish_from,
+                              polish_from=polish_from, step_method=step_method,
                               timing=None if stats is None else stats.setdefault("timing", {}))
         if stats is not None:
             stats["voigt_evals"] = stats.get("voigt_evals", 0) + mb.voigt_evals

@@ -5,16 +5,18 @@ ncu ``smsp__sass_thread_inst_executed_op_{fadd,fmul,ffma}_pred_on`` (profiles/).
 Counts follow ``vamp_b200/csrc/vamp_device.cuh`` line by line.
 
 fp32 ``fad_core2`` (Weideman N = 12, real second-order recurrence; K2's packed two-row form), per pixel:
-    R = rcp(s + (2Ly + L^2))           ADD + MUFU                 = 2     (2Ly + L^2: once per component)
-    Zr = (L^2 - s) R                   SUB + MUL                  = 2
-    XR = x R, Zi = 2L XR               2 MUL                      = 2
-    t = 2 Zr, -|Z|^2 = (2Ly-L^2-s) R   ADD, SUB + MUL             = 3
+    R = rcp(s + (2Ly + L^2))           ADD + MUFU                 = 2     (constants: once per component)
+    t = K2 R - 2, Zr = K2/2 R - 1, -|Z|^2 = K3 R - 1   3 FMA      = 6
+    XR = x R, ir = (L + y) R           2 MUL                      = 2
     b1 = t a0 + a1                     FMA                        = 2
     9 recurrence steps (2 FMA)         9 * 4                      = 36
-    pr (2 FMA), pi (MUL), ir (MUL)                                = 6
-    i2r, i2i                           MUL + FMA, ADD + MUL       = 5
-    q, H                               MUL + FMA, FMA + MUL       = 6
-                                                                   ---- 64
+    pr                                 2 FMA                      = 4
+    XR^2, ir^2 - XR^2                  MUL, FMA                   = 3
+    (b1 ir) XR^2                       2 MUL                      = 2
+    q = -4L v + pr i2r                 MUL + FMA                  = 3
+    H = y (sqrt(pi) 2 q + ir)          FMA + MUL                  = 3
+                                                                   ---- 63
+    (round 1's form, VAMP_FAD_CORE35=0: 64 flops in 40 packed operations; this one: 63 in 35, 27 of them FMAs)
 fp32 ``fad_far2`` (4-level continued fraction as N(v)/D(v), v = 1/z^2):
     rs, tr, ti                         MUFU + 2 MUL               = 3
     vr, vi                             MUL + FMA, ADD + MUL       = 5
@@ -31,8 +33,8 @@ fp64: same structure with N = 32 (29 recurrence steps) and 9 CF levels (N: 1 rea
  time with the scalar forms ``fad_core`` / ``fad_far``: + 7 / + 8.)
 """
 
-F32 = {"core": 64.0, "far": 43.0, "shape_common": 4.0, "like": 6.0}
-F64 = {"core": (2 + 9) + 2 + 2 + 3 + 2 + 29 * 4 + 6 + 5 + 6, "far": (3 + 9) + 5 + (3 + 3 * 7) + (3 + 4 * 7) + 9 + (6 + 9),
+F32 = {"core": 63.0, "far": 43.0, "shape_common": 4.0, "like": 6.0}
+F64 = {"core": (2 + 9) + 6 + 2 + 2 + 29 * 4 + 4 + 3 + 2 + 3 + 3, "far": (3 + 9) + 5 + (3 + 3 * 7) + (3 + 4 * 7) + 9 + (6 + 9),
        "shape_common": 4.0, "like": 36.0}
 GAUSS = {"shape": 5.0}      # d, q = d*g, q*q, exp2 (MUFU): SUB + MUL + MUL + MUFU + neg
 

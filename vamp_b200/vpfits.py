@@ -100,12 +100,15 @@ class _MCMC:
 class VPfit():
 
     def __init__(self, noise=None, n_chains=96, dtype="f32", seed=None, lsf=None, tune_interval=50,
-                 tune_throughout=True, polish_top=4, ctx=None, multiplet=None):
+                 tune_throughout=True, polish_top=4, ctx=None, multiplet=None, step_method="metropolis"):
         """``noise=None``: the noise level ``sd ~ U(0,1)`` is a free parameter (vpfits.py:35-39);
         otherwise the per-pixel noise array.  The keyword arguments are new (GPU controls).
         ``multiplet = (freq_ratio, amp_ratio[, lorentz_ratio])`` (``physics.doublet_ratios``): every component
         is a doublet with tied velocity / width / column density - new, the reference fits single lines."""
         self.multiplet = None if multiplet is None else tuple(float(v) for v in multiplet)
+        # "metropolis": the scalar steppers PyMC 2 auto-assigns (what the reference runs); "adaptive": PyMC 2's
+        # AdaptiveMetropolis per component, the method mcmc_fit names (vpfits.py:361) - engine.Sampler
+        self.step_method = step_method
         self.noise = None if noise is None else np.asarray(noise, dtype=np.float64)
         self.verbose = False
         self.n_chains = max(3, int(n_chains) // 3 * 3)
@@ -205,7 +208,7 @@ class VPfit():
         self._sampler = engine.Sampler(
             self._regions, np.zeros(B, np.int32), np.full(B, self._n, np.int32), uid, voigt=voigt,
             sd_free=self._sd_free, dtype=self.dtype, seed=self._seed, tune_interval=self.tune_interval,
-            tune_throughout=self.tune_throughout)
+            tune_throughout=self.tune_throughout, step_method=self.step_method)
         self._sampler.init()
         self._primary = 0
         self._ridx = 0
@@ -283,8 +286,9 @@ class VPfit():
 
     # ------------------------------------------------------------------ MCMC
     def mcmc_fit(self, iterations=15000, burnin=100, thinning=15, step_method=None):
-        """vpfits.py:361-395.  ``step_method`` is accepted for signature compatibility; the
-        device sampler is the scalar adaptive-scale Metropolis PyMC 2 actually runs."""
+        """vpfits.py:361-395.  ``step_method`` is accepted for signature compatibility (the reference's default,
+        ``mc.AdaptiveMetropolis``, is only printed there, never installed: PyMC 2 runs its scalar Metropolis
+        steppers); which sampler runs here is the constructor's ``VPfit(step_method="metropolis" | "adaptive")``."""
         try:
             getattr(self, 'map')
         except AttributeError:
@@ -392,6 +396,23 @@ class VPfit():
                 out[name] = float(r[4 * c + i])
         return out
 
+    def raftery_lewis(self, q=0.995, r=0.05, s=0.95, epsilon=0.001, chain=None):
+        """``mc.raftery_lewis(vpfit.mcmc, q, r)`` of the notebooks (vpfits_intro.ipynb cell 18): per variable (PyMC 2
+        names) the tuple ``(nmin, kthin, nburn, nprec, kmind)`` from the kept trace of one chain."""
+        from . import diagnostics
+        out = {}
+        for name, (c, _) in self._param_index.items():
+            if c == "sd" and not self._sd_free:
+                continue
+            out[name] = diagnostics.raftery_lewis(self._trace(name, chain), q, r, s, epsilon)
+        return out
+
+    def geweke(self, first=0.1, last=0.5, intervals=20, chain=None):
+        """``mc.geweke(vpfit.mcmc, intervals=20)`` (vpfits_intro.ipynb cell 17): z-scores per variable."""
+        from . import diagnostics
+        return {name: diagnostics.geweke(self._trace(name, chain), first, last, intervals)
+                for name, (c, _) in self._param_index.items() if not (c == "sd" and not self._sd_free)}
+
     def _dic(self):
         """PyMC 2: ``DIC = 2 E[D] - D(E[theta])``, ``BPIC = 3 E[D] - 2 D(E[theta])``, D = -2 lnL."""
         s = self._sampler
@@ -425,7 +446,7 @@ class VPfit():
                               chains_per_restart=self.n_chains // 3, polish_top=self.polish_top, dtype=self.dtype,
                               seed=self._seed, region_uids=[next(_fit_counter)], tune_interval=self.tune_interval,
                               tune_throughout=self.tune_throughout, keep_sampler=True, trace=True,
-                              maxiter=iterations)
+                              maxiter=iterations, step_method=self.step_method)
         self._adopt(mb, 0, regions, freedom)
         self.fit_time = str(datetime.datetime.now() - starttime)
         return
