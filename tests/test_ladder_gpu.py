@@ -86,32 +86,53 @@ def test_c4_ladder_outcome_vs_oracle(ctx, mode):
         assert np.mean(bic_gpu <= bic_orc + 3.0) >= 0.85, payload["min_bic_gpu_minus_oracle"]
 
 
+@pytest.mark.parametrize("mode", ["reference", "default"])
 @pytest.mark.parametrize("spec,voigt,iters", [("simba_CII1036", False, 5000), ("simba_H1215", True, 3000)])
-def test_simba_fixtures_reach_the_notebook_outcome(ctx, spec, voigt, iters):
+def test_simba_fixtures_reach_the_notebook_outcome(ctx, spec, voigt, iters, mode):
+    """The reference's own fixtures and recorded outcomes.  ``reference`` mode (1 chain per restart, PyMC 2's tune
+    interval, polish from the last state - what the notebook ran): final n within one of the notebook's.  ``default``
+    mode (32 chains per restart, polish from the best state): per candidate the BIC is at or below the restated
+    reference's, and - because the ladder's rule then sees lower BICs for the larger models (HI region 0, n = 3: -35
+    against the reference-style +6) - the chosen n is the notebook's or larger."""
     gold = _gold(spec)
     host, n0 = [], []
     for j in range(int(SIMBA[spec + "/nregions"])):
         k = "%s/r%d/" % (spec, j)
         host.append((SIMBA[k + "nu"], SIMBA[k + "flux"], SIMBA[k + "noise"]))
         n0.append(int(SIMBA[k + "n0"]))
-    res = fit_regions(host, voigt=voigt, iterations=iters, burn=300, thin=15, restarts=3, chains_per_restart=32, window=3,
-                      nmax=8, seed=5, distributed=False)
+    kw = dict(voigt=voigt, iterations=iters, burn=300, thin=15, restarts=3, chains_per_restart=32, window=3, nmax=8)
+    if mode == "reference":
+        kw.update(REFERENCE_DEFAULTS)
+    res = fit_regions(host, seed=5, distributed=False, **kw)
     n_gpu = [r.n for r in res]
     want = NOTEBOOK_N[spec]
-    _report(spec, {"n_gpu": n_gpu, "notebook": want, "oracle": [g["kept_n"] for g in gold],
-                   "bic": [{str(n): [float(v) for v in b] for n, b in r.bic.items()} for r in res]})
+    _report("%s_%s" % (spec, mode), {"n_gpu": n_gpu, "notebook": want, "oracle": [g["kept_n"] for g in gold],
+                                     "bic": [{str(n): [float(v) for v in b] for n, b in r.bic.items()} for r in res]})
     assert [r.n0 for r in res] == n0
-    assert all(abs(a - b) <= 1 for a, b in zip(n_gpu, want)), (n_gpu, want)
-    # (the oracle's own outcome, 4, 3, 4, 1 / 2, 1, 1, is reported beside it: all three fits are stochastic)
+    if mode == "reference":
+        assert all(abs(a - b) <= 1 for a, b in zip(n_gpu, want)), (n_gpu, want)
+        return
+    assert all(a >= b - 1 for a, b in zip(n_gpu, want)), (n_gpu, want)
+    pairs = []
     for j, (r, g) in enumerate(zip(res, gold)):
         name = "%s/r%d" % (spec, j)
         # BIC of the 1-component fit, an (almost) deterministic function of the data: the GPU fit (K2 + K3) and the
         # restated reference fit (numpy / scipy sampler + fmin) land on the SAME optimum ...
         assert float(np.min(r.bic[1])) == pytest.approx(min(g["bic"]["1"]), abs=0.02), (name, r.bic[1], g["bic"]["1"])
         if name in NOTEBOOK_BIC_N1:
-            # ... which is the value the reference's notebook printed, to within the 1.5 BIC units by which that
-            # recorded run (unknown PyMC / numpy versions) differs from BOTH
-            assert abs(float(np.min(r.bic[1])) - NOTEBOOK_BIC_N1[name]) < 1.5 + (1.5 if voigt else 0.0), (name, r.bic[1])
+            # ... which is the value the reference's notebook printed, to within the 1.5 (Gauss) / 3 (Voigt) BIC units by
+            # which that recorded run (unknown PyMC / numpy / astropy versions) differs from BOTH
+            assert abs(float(np.min(r.bic[1])) - NOTEBOOK_BIC_N1[name]) < (3.0 if voigt else 1.5), (name, r.bic[1])
+        # every candidate both fits tried: the GPU's best restart against the reference-style MEAN over restarts (the
+        # quantity the ladder compares) and against its best restart
+        for n_s, b_ref in g["bic"].items():
+            if int(n_s) in r.bic:
+                pairs.append((name, int(n_s), float(np.min(r.bic[int(n_s)])), float(np.mean(b_ref)), float(np.min(b_ref))))
+    # many chains + polish from the best state: never worse than the reference-style mean over restarts, and at or
+    # below even its best restart for most candidates (a single chain's last state occasionally falls into a deeper,
+    # narrower optimum than the mode the pooled chains sit on: CII region 2, n = 3: -83.2 against -80.7)
+    assert all(gpu <= ref_mean + 1.0 for _, _, gpu, ref_mean, _ in pairs), pairs
+    assert np.mean([gpu <= ref_min + 1.0 for _, _, gpu, _, ref_min in pairs]) >= 0.7, pairs
     if spec == "simba_CII1036":
         # the reference's recorded ladder of region 0 (n = 1 .. 5): the GPU's per-candidate best BIC is at or below it
         for n, ref in zip(range(1, 6), NOTEBOOK_LADDER_R0):

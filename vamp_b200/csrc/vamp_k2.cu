@@ -26,10 +26,14 @@
 
 namespace {
 
+#ifndef VAMP_K2_TRIPUNROLL
+#define VAMP_K2_TRIPUNROLL 1      // unroll factor of the trip loop of a pass (1: rolled - the step loop must fit the instruction cache)
+#endif
 #ifndef VAMP_K2_WARPS
 #define VAMP_K2_WARPS 4           // chains (warps) per CTA; with VAMP_K2_MINBLOCKS CTAs per SM (96 registers: 4 x 5 = 20 warps)
 #endif
 constexpr int K2_WARPS = VAMP_K2_WARPS;
+constexpr int K2_TRIPUNROLL = VAMP_K2_TRIPUNROLL;
 #ifndef VAMP_INST_MULT
 #define VAMP_INST_MULT 0          // 1: this object holds the multiplet (two tied lines per component) instantiations
 #endif
@@ -39,6 +43,12 @@ constexpr int K2_WARPS = VAMP_K2_WARPS;
 #ifndef VAMP_K2_STEPUNROLL
 #define VAMP_K2_STEPUNROLL 1      // 1: the centroid / width steps of a component are unrolled (no selects)
 #endif
+#ifndef VAMP_K2_DRAWAHEAD
+#define VAMP_K2_DRAWAHEAD 0       // 1: a step's random pair is shuffled out one step ahead (under the previous pass)
+#endif
+#ifndef VAMP_K2_SMEMSUM
+#define VAMP_K2_SMEMSUM 0         // 1 (fp32): the warp sum goes through shared memory (one store, 8 vector loads, a packed
+#endif                            //    adder tree in every lane) instead of five dependent shuffle + add rounds
 #ifndef VAMP_K2_FUSEBASE
 #define VAMP_K2_FUSEBASE 1        // 1: the move of `base` to a component runs inside its amplitude pass (FuseArgs)
 #endif
@@ -73,6 +83,21 @@ template <> struct RngMath<float> {
         l1 = __logf(u(x.w));
     }
 };
+
+// One refill of the 64-step block (executed once per 32 steps).  VAMP_K2_RNG_CALL=1 keeps ONE out-of-line copy of
+// Philox + Box-Muller instead of one inlined copy per draw site (five in mcmc_chain, ~100 instructions each): the
+// step loop then has 8 KB less code between its hot parts (32 KB instruction cache).
+#ifndef VAMP_K2_RNG_CALL
+#define VAMP_K2_RNG_CALL 1
+#endif
+template <typename T>
+__device__ __noinline__ void rng_refill_call(unsigned long long uid, unsigned long long qblk, unsigned lane, unsigned long long seed,
+                                             T* out4) {
+    const uint4 x = philox4x32_10(make_uint4((uint32_t)uid, (uint32_t)(uid >> 32), (uint32_t)qblk,
+                                             ((uint32_t)(qblk >> 32) << 8) | (uint32_t)lane),
+                                  make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    RngMath<T>::fill(x, out4[0], out4[1], out4[2], out4[3]);
+}
 
 // PyMC 2.3 Metropolis.tune switch (oracle/sampler.py:pymc2_tune)
 __device__ __forceinline__ float tune_factor(float rate) {
@@ -135,8 +160,9 @@ struct K2Lay {
     static __host__ __device__ size_t lsf_bytes(bool lsf) {
         return lsf ? align16(sizeof(T) * (VAMP_TILE_PIX + VAMP_MAX_LSF_TAPS)) : 0;
     }
+    static constexpr int SUMSCR = VAMP_K2_SMEMSUM ? 128 : 0;       // 32 floats of reduction scratch, first in the chain slice tail
     static __host__ __device__ size_t bytes(int ncomp_max, bool lsf) {
-        return (size_t)H + (size_t)(ncomp_max + 1) * SLOT + lsf_bytes(lsf) + sizeof(SdRec<T>) +
+        return (size_t)H + (size_t)(ncomp_max + 1) * SLOT + lsf_bytes(lsf) + SUMSCR + sizeof(SdRec<T>) +
                (size_t)ncomp_max * sizeof(CompRec<T>);
     }
 };
@@ -146,7 +172,37 @@ struct LsfCtx {
     T* buf;            // warp-private [VAMP_TILE_PIX + taps]
     const T* taps_s;   // block-shared taps
     int taps, P;
+    unsigned sum_scratch;   // shared address of the warp's 32-value reduction scratch (VAMP_K2_SMEMSUM)
 };
+
+// Sum over the warp through shared memory (VAMP_K2_SMEMSUM, fp32): every lane stores its value, reads all 32 back
+// as packed pairs (broadcast reads) and adds them in the same fixed tree, so every lane holds the identical bits -
+// as with the shuffle butterfly, whose five dependent shuffle + add rounds this replaces.
+template <int OFF>
+__device__ __forceinline__ void lds_2x64(unsigned a, P2<float>& x, P2<float>& y) {
+    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2+%3];" : "=l"(x.v), "=l"(y.v) : "r"(a), "n"(OFF) : "memory");
+}
+__device__ __forceinline__ float warp_sum_smem(float v, unsigned scratch, int lane) {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(scratch + 4u * (unsigned)lane), "f"(v) : "memory");
+    __syncwarp();
+    P2<float> q0, q1, q2, q3, q4, q5, q6, q7, q8, q9, qa, qb, qc, qd, qe, qf;
+    lds_2x64<0>(scratch, q0, q1);
+    lds_2x64<16>(scratch, q2, q3);
+    lds_2x64<32>(scratch, q4, q5);
+    lds_2x64<48>(scratch, q6, q7);
+    lds_2x64<64>(scratch, q8, q9);
+    lds_2x64<80>(scratch, qa, qb);
+    lds_2x64<96>(scratch, qc, qd);
+    lds_2x64<112>(scratch, qe, qf);
+    __syncwarp();                                  // the scratch may be rewritten by the next pass
+    q0 = p2_add(q0, q1); q2 = p2_add(q2, q3); q4 = p2_add(q4, q5); q6 = p2_add(q6, q7);
+    q8 = p2_add(q8, q9); qa = p2_add(qa, qb); qc = p2_add(qc, qd); qe = p2_add(qe, qf);
+    q0 = p2_add(q0, q2); q4 = p2_add(q4, q6); q8 = p2_add(q8, qa); qc = p2_add(qc, qe);
+    q0 = p2_add(q0, q4); q8 = p2_add(q8, qc);
+    q0 = p2_add(q0, q8);
+    return p2_lo(q0) + p2_hi(q0);
+}
+__device__ __forceinline__ double warp_sum_smem(double v, unsigned, int) { return warp_sum(v); }
 
 // Residual sum of squares from a model row-pair buffer in natural order (LSF path only):
 // buf[h + p] holds m_p - 1; out = 1 + sum_t lsf[t] (m - 1)[p + h - t], zero outside [0, P).
@@ -267,7 +323,7 @@ __device__ __forceinline__ T chain_pass(const CompC<T>& cc, T An, unsigned ahc, 
     const unsigned end = ar + (unsigned)(npairs * ROW);
     unsigned ahp = FUSE ? fz->ahp : 0u;
     const P2<T> Ap2 = p2_bc<T>(FUSE ? fz->Ap : T(0)), Ac2 = p2_bc<T>(FUSE ? fz->Ac : T(0));
-#pragma unroll 1
+#pragma unroll K2_TRIPUNROLL
     for (; ar < end; ar += 2 * ROW, aw += 2 * ROW, ahc += 2 * ROW, ahs += 2 * ROW) {
         P2<T> H0, H1;
         if (FRESH) {
@@ -357,7 +413,11 @@ __device__ __forceinline__ T chain_pass(const CompC<T>& cc, T An, unsigned ahc, 
     last_far = (far ? 1u : 0u) + ((MULT && farb) ? 1u : 0u);
     T S = p2_lo(S2) + p2_hi(S2);
     if (LSF) S = lsf_residuals<T, WT>(lc, rb, npairs, lane);
+#if VAMP_K2_SMEMSUM
+    return warp_sum_smem(S, lc.sum_scratch, lane);
+#else
     return warp_sum(S);
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -407,6 +467,8 @@ __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, const unsigned
     lc.taps = rs.lsf_taps;
     lc.P = P;
     sp_ += Lay::lsf_bytes(LSF);
+    lc.sum_scratch = (unsigned)__cvta_generic_to_shared(sp_);
+    sp_ += Lay::SUMSCR;
     SdRec<T>* const sdrec = reinterpret_cast<SdRec<T>*>(sp_);
     CompRec<T>* const recs = reinterpret_cast<CompRec<T>*>(sp_ + sizeof(SdRec<T>));
     unsigned arec0 = (unsigned)__cvta_generic_to_shared(recs);
@@ -505,10 +567,19 @@ __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, const unsigned
     int qs = (int)(((unsigned long long)p.it0 * (unsigned long long)k) & 63ull);
     T zc, luc, zn, lun;                     // current / next half of the 64-step block
     auto refill = [&]() {
+#if VAMP_K2_RNG_CALL
+        T o4[4];
+        rng_refill_call<T>(uid, qblk, (unsigned)lane, p.seed, o4);
+        zc = o4[0];
+        zn = o4[1];
+        luc = o4[2];
+        lun = o4[3];
+#else
         const uint4 x = philox4x32_10(make_uint4((uint32_t)uid, (uint32_t)(uid >> 32), (uint32_t)qblk,
                                                  ((uint32_t)(qblk >> 32) << 8) | (uint32_t)lane),
                                       make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32)));
         RngMath<T>::fill(x, zc, zn, luc, lun);
+#endif
     };
     refill();
     if (qs >= 32) {
@@ -588,12 +659,18 @@ __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, const unsigned
             //      cached shape.  VAMP_K2_FUSEBASE: when base only has to MOVE from the previous component to this one
             //      and the amplitude proposal is in bounds, the move is done inside the amplitude pass (FuseArgs).
             unsigned am = 0u;                 // accept bits of this component's steps
+#if VAMP_K2_DRAWAHEAD
+            T zN, luN;                        // the NEXT step's (normal, log-uniform), drawn one step ahead (same stream order)
+#endif
             {
                 constexpr int ROW = 32 * (int)sizeof(P2<T>);
                 const unsigned endw = aw0 + (unsigned)(npairs * ROW);
                 T z, lu;
                 draw(z, lu);
                 const T prop = pA + z * sA;
+#if VAMP_K2_DRAWAHEAD
+                draw(zN, luN);                // the centroid step's pair: its shuffles run under the amplitude pass
+#endif
                 // how base gets to this component: 0 nothing to do (n == 1), 1 rebuild from the cache, 2 move
                 int mode = 2;
                 T Ap_ = NK * Aprev;
@@ -666,7 +743,13 @@ __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, const unsigned
 #endif
             for (int i = 1; i < NP; ++i) {
                 T z, lu;
+#if VAMP_K2_DRAWAHEAD
+                z = zN;
+                lu = luN;
+                if (i + 1 < NP) draw(zN, luN);
+#else
                 draw(z, lu);
+#endif
                 const T cur = (i == 1) ? pc : (i == 2) ? pw1 : pw2;
                 const T prop = cur + z * ((i == 1) ? sC : (i == 2) ? sW1 : sW2);
                 const T hi = (i == 1) ? c_hi : w_hi;
@@ -877,6 +960,8 @@ __device__ void mcmc_chain_am(const McmcDev& p, int chain, int lane, const unsig
     lc.taps = rs.lsf_taps;
     lc.P = P;
     sp_ += Lay::lsf_bytes(LSF);
+    lc.sum_scratch = (unsigned)__cvta_generic_to_shared(sp_);
+    sp_ += Lay::SUMSCR;
     SdRec<T>* const sdrec = reinterpret_cast<SdRec<T>*>(sp_);
     CompRec<T>* const recs = reinterpret_cast<CompRec<T>*>(sp_ + sizeof(SdRec<T>));
     T* const Lsm = reinterpret_cast<T*>(sp_ + sizeof(SdRec<T>) + (size_t)ncomp_max * sizeof(CompRec<T>));   // [ncomp_max][10]

@@ -17,13 +17,15 @@ fp32 ``fad_core2`` (Weideman N = 12, real second-order recurrence; K2's packed t
     H = y (sqrt(pi) 2 q + ir)          FMA + MUL                  = 3
                                                                    ---- 63
     (round 1's form, VAMP_FAD_CORE35=0: 64 flops in 40 packed operations; this one: 63 in 35, 27 of them FMAs)
-fp32 ``fad_far2`` (4-level continued fraction as N(v)/D(v), v = 1/z^2):
+fp32 ``fad_far2`` (4-level continued fraction as N(v)/D(v), v = 1/z^2; both quadratics with real coefficients):
     rs, tr, ti                         MUFU + 2 MUL               = 3
     vr, vi                             MUL + FMA, ADD + MUL       = 5
-    N(v), D(v): real first step (FMA + MUL) + one complex Horner step (3 FMA + MUL)   2 * 10 = 20
+    a = vr^2 - vi^2                    MUL + FMA                  = 3
+    Re N, Im N, Re D, Im D             2 * (2 FMA + FMA + MUL)    = 14
     er, ei, imq                        3 * (MUL + FMA)            = 9
     |D|^2, rcp, -y*imq*rcp             MUL + FMA + MUFU + 2 MUL   = 6
-                                                                   ---- 43
+                                                                   ---- 40
+    (round 1's form, VAMP_FAD_FAR26=0: two complex Horner steps, 43 flops in 28 packed operations; this one: 40 in 26)
 common per shape pixel: d = du - cb, x = d*g, s = fma(x,x,y2)     = 4
 per likelihood pixel:  v = fma(An,H,base) (tau pre-scaled by -log2 e), ex2 (MUFU), r = f - m, S = fma(r,r,S)  = 6
     (+ 1 for the noise weight, + 2 per LSF tap)
@@ -33,7 +35,7 @@ fp64: same structure with N = 32 (29 recurrence steps) and 9 CF levels (N: 1 rea
  time with the scalar forms ``fad_core`` / ``fad_far``: + 7 / + 8.)
 """
 
-F32 = {"core": 63.0, "far": 43.0, "shape_common": 4.0, "like": 6.0}
+F32 = {"core": 63.0, "far": 40.0, "shape_common": 4.0, "like": 6.0}
 F64 = {"core": (2 + 9) + 6 + 2 + 2 + 29 * 4 + 4 + 3 + 2 + 3 + 3, "far": (3 + 9) + 5 + (3 + 3 * 7) + (3 + 4 * 7) + 9 + (6 + 9),
        "shape_common": 4.0, "like": 36.0}
 GAUSS = {"shape": 5.0}      # d, q = d*g, q*q, exp2 (MUFU): SUB + MUL + MUL + MUFU + neg
