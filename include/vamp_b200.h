@@ -139,6 +139,11 @@ typedef struct vamp_mcmc_args {
     int step_kind;
     int am_delay;               /* PyMC 2 default 1000: first covariance update after this many iterations */
     int am_interval;            /* PyMC 2 default 200: iterations between covariance updates */
+    int pair_tail;              /* 1: some chain of this launch fits a region with an odd number of 64-pixel row pairs
+                                   (<= 64 or 129..192 pixels): run the pair-tail kernel, which sweeps ceil(P / 64) pairs
+                                   instead of whole 128-pixel quads.  Chains with an even count compute the same
+                                   either way; a caller must set it whenever such a chain is present (always, for
+                                   results that do not depend on batching).  Ignored for multiplet / adaptive runs. */
     double* am_state;           /* [n, cmax, VAMP_AM_STRIDE] adaptive state (NULL unless step_kind = VAMP_STEP_ADAPTIVE):
                                    chain mean [4] | covariance, packed lower triangle [10] | its Cholesky factor [10] |
                                    sum x [4] | sum x x^T [10] | samples in the covariance | samples since the update */

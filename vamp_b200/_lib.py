@@ -32,7 +32,8 @@ class McmcArgs(C.Structure):
         ("best_theta", C.c_void_p), ("best_logp", C.c_void_p), ("mean", C.c_void_p), ("m2", C.c_void_p),
         ("comom", C.c_void_p), ("ntally", C.c_void_p), ("sum_lnL", C.c_void_p), ("sum_lnL2", C.c_void_p),
         ("trace", C.c_void_p), ("trace_cap", C.c_int), ("work", C.c_void_p),
-        ("step_kind", C.c_int), ("am_delay", C.c_int), ("am_interval", C.c_int), ("am_state", C.c_void_p),
+        ("step_kind", C.c_int), ("am_delay", C.c_int), ("am_interval", C.c_int), ("pair_tail", C.c_int),
+        ("am_state", C.c_void_p),
     ]
 
 

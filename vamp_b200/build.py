@@ -49,6 +49,8 @@ def _jobs():
                     jobs.append((src, obj[:-2] + "_mult.o", defs + ["-DVAMP_INST_MULT=1"], hdr))
                     # ... and its adaptive-Metropolis instantiations (step_kind = VAMP_STEP_ADAPTIVE)
                     jobs.append((src, obj[:-2] + "_am.o", defs + ["-DVAMP_INST_AM=1"], hdr))
+                    # ... and its pair-tail instantiations (regions with an odd number of 64-pixel row pairs)
+                    jobs.append((src, obj[:-2] + "_tail.o", defs + ["-DVAMP_INST_TAIL=1"], hdr))
     jobs.append((os.path.join(CSRC, "vamp_k4.cu"), os.path.join(OBJ, "vamp_k4.o"), [], hdr))
     jobs.append((os.path.join(CSRC, "vamp_cabi.cu"), os.path.join(OBJ, "vamp_cabi.o"), [], hdr))
     return jobs

@@ -604,6 +604,7 @@ int vamp_mcmc_run_dev(vamp_ctx* ctx, const vamp_regions* rg, int dtype, int kind
     VAMP_CUDA(cudaSetDevice(ctx->device));
     const McmcDev p = to_dev(rg, a);
     if (a->step_kind == VAMP_STEP_ADAPTIVE) VAMP_CUDA(VAMP_DISPATCH4(vamp_launch_k2a, dtype, kind, p, rg->max_npix, a->max_ncomp, ctx->stream));
+    else if (a->pair_tail && !rg->dev.mult) VAMP_CUDA(VAMP_DISPATCH4(vamp_launch_k2t, dtype, kind, p, rg->max_npix, a->max_ncomp, ctx->stream));
     else if (rg->dev.mult) VAMP_CUDA(VAMP_DISPATCH4(vamp_launch_k2m, dtype, kind, p, rg->max_npix, a->max_ncomp, ctx->stream));
     else VAMP_CUDA(VAMP_DISPATCH4(vamp_launch_k2, dtype, kind, p, rg->max_npix, a->max_ncomp, ctx->stream));
     return 0;

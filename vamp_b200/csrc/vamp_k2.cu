@@ -310,7 +310,12 @@ struct Mult2 { T fr, dsh, ar, ginv, yfac; };
 template <typename T>
 struct FuseArgs { T Ap, Ac; unsigned ahp; };
 
-template <typename T, int KIND, bool WT, bool LSF, bool FRESH, bool MULT = false, bool FUSE = false>
+// TAIL (objects built with -DVAMP_INST_TAIL=1; single lines only): `npairs` = ceil(P / 64) row pairs instead of whole
+// quads - floor(npairs / 2) quad trips, then ONE pair trip when npairs is odd.  Regions of <= 64 or 129..192 pixels
+// stop paying for 64 pixels of padding (BASELINE config C4: P ~ U{32..256}, 14 % of the sampler's lanes).  A chain whose
+// pair count is odd ALWAYS takes this path (engine.Sampler sets vamp_mcmc_args.pair_tail when its launch holds one),
+// a chain with an even count computes exactly what the quad kernel computes, so results do not depend on the launch.
+template <typename T, int KIND, bool WT, bool LSF, bool FRESH, bool MULT = false, bool FUSE = false, bool TAIL = false>
 __device__ __forceinline__ T chain_pass(const CompC<T>& cc, T An, unsigned ahc, unsigned ahs, unsigned ar, unsigned aw,
                                         const unsigned char* rb, int npairs, int lane, const LsfCtx<T>& lc, unsigned& nfar,
                                         unsigned& last_far, const Mult2<T>* ml = nullptr, const FuseArgs<T>* fz = nullptr) {
@@ -320,11 +325,14 @@ __device__ __forceinline__ T chain_pass(const CompC<T>& cc, T An, unsigned ahc, 
     const P2<T> A2 = p2_bc<T>(An);
     P2<T> S2 = p2_bc<T>(T(0)), S2b = p2_bc<T>(T(0));
     bool far = false, farb = false;
-    const unsigned end = ar + (unsigned)(npairs * ROW);
+    const unsigned ar_begin = ar;
+    const unsigned end = ar + (unsigned)((npairs >> 1) * 2 * ROW);      // end of the whole quads
     unsigned ahp = FUSE ? fz->ahp : 0u;
     const P2<T> Ap2 = p2_bc<T>(FUSE ? fz->Ap : T(0)), Ac2 = p2_bc<T>(FUSE ? fz->Ac : T(0));
+    // (without TAIL a region has at least one quad: the loop is bottom-tested, which spares every pass the empty-loop guard)
+    if (!TAIL || ar < end)
 #pragma unroll K2_TRIPUNROLL
-    for (; ar < end; ar += 2 * ROW, aw += 2 * ROW, ahc += 2 * ROW, ahs += 2 * ROW) {
+    do {
         P2<T> H0, H1;
         if (FRESH) {
             const P2<T> cb2 = p2_bc<T>(cc.cb), g2 = p2_bc<T>(cc.g);
@@ -394,7 +402,7 @@ __device__ __forceinline__ T chain_pass(const CompC<T>& cc, T An, unsigned ahc, 
         const P2<T> M0 = p2_exp_scaled<T>(p2_fma(A2, H0, B0));
         const P2<T> M1 = p2_exp_scaled<T>(p2_fma(A2, H1, B1));
         if (LSF) {
-            const int e = (int)(npairs * ROW - (end - ar)) / SZ;          // pair-layout element of this quad
+            const int e = (int)(ar - ar_begin) / SZ;                      // pair-layout element of this quad
             lc.buf[(lc.taps >> 1) + lane + 2 * e] = p2_lo(M0) - T(1);
             lc.buf[(lc.taps >> 1) + lane + 2 * e + 32] = p2_hi(M0) - T(1);
             lc.buf[(lc.taps >> 1) + lane + 2 * e + 64] = p2_lo(M1) - T(1);
@@ -407,6 +415,48 @@ __device__ __forceinline__ T chain_pass(const CompC<T>& cc, T An, unsigned ahc, 
             }
             S2 = p2_fma(R0, R0, S2);
             S2b = p2_fma(R1, R1, S2b);
+        }
+        ar += 2 * ROW;
+        aw += 2 * ROW;
+        ahc += 2 * ROW;
+        ahs += 2 * ROW;
+    } while (ar < end);
+    if (TAIL && (npairs & 1)) {
+        // ---- the odd row pair (64 pixels): the quad body for one pair
+        P2<T> H0;
+        if (FRESH) {
+            const P2<T> X0 = p2_mul(p2_sub(SM<T>::template ld<Lay::DU>(ar), p2_bc<T>(cc.cb)), p2_bc<T>(cc.g));
+            if (KIND == VAMP_KIND_GAUSS) {
+                const P2<T> Q0 = p2_mul(X0, X0);
+                H0 = p2_make(Real<T>::exp2_neg(p2_lo(Q0)), Real<T>::exp2_neg(p2_hi(Q0)));
+            } else {
+                const P2<T> S0 = p2_fma(X0, X0, p2_bc<T>(cc.y2));
+                far = __all_sync(VAMP_FULL_MASK, !(fmin(p2_lo(S0), p2_hi(S0)) < Fad<T>::R2()));
+                if (far) {
+                    nfar += 64u;
+                    H0 = fad_far2<T>(X0, cc.y, S0);
+                } else {
+                    H0 = fad_core2<T>(X0, cc.y, S0);
+                }
+            }
+            SM<T>::template st<0>(ahs, H0);
+        } else {
+            H0 = SM<T>::template ld<0>(ahc);
+        }
+        P2<T> B0 = SM<T>::template ld<Lay::BASE>(aw);
+        if (FUSE) {
+            B0 = p2_fma(Ac2, H0, p2_fma(Ap2, SM<T>::template ld<0>(ahp), B0));
+            SM<T>::template st<Lay::BASE>(aw, B0);
+        }
+        const P2<T> M0 = p2_exp_scaled<T>(p2_fma(A2, H0, B0));
+        if (LSF) {
+            const int e = (int)(ar - ar_begin) / SZ;
+            lc.buf[(lc.taps >> 1) + lane + 2 * e] = p2_lo(M0) - T(1);
+            lc.buf[(lc.taps >> 1) + lane + 2 * e + 32] = p2_hi(M0) - T(1);
+        } else {
+            P2<T> R0 = p2_sub(SM<T>::template ld<Lay::F>(ar), M0);
+            if (WT) R0 = p2_mul(R0, SM<T>::template ld<Lay::W>(ar));
+            S2 = p2_fma(R0, R0, S2);
         }
     }
     S2 = p2_add(S2, S2b);
@@ -431,7 +481,7 @@ __device__ __forceinline__ T chain_pass(const CompC<T>& cc, T An, unsigned ahc, 
 // vector load at the start, one read-modify-write at the end of the component), rejections are
 // derived (every parameter is proposed exactly once per iteration) and the post-burn acceptance
 // total is settled at tune / burn / exit events.
-template <typename T, int KIND, bool WT, bool LSF, bool MULT>
+template <typename T, int KIND, bool WT, bool LSF, bool MULT, bool TAIL = false>
 __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, const unsigned char* rb, unsigned char* wb, int ncomp_max,
                            const T* lsf_s) {
     typedef K2Lay<T, WT> Lay;
@@ -445,7 +495,7 @@ __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, const unsigned
     const int k = NP * n + (WT ? 0 : 1);
     // row pairs swept by every per-pixel loop: with quad trips the region is padded to whole quads (padding
     // pixels - du 1e12, flux 1, weight 0 - contribute exactly nothing)
-    const int npairs = 2 * ((P + 127) >> 7);
+    const int npairs = TAIL ? ((P + 63) >> 6) : 2 * ((P + 127) >> 7);
     const int npad = 64 * npairs - P;
     const int burn = p.burn;
     const T NK = Real<T>::NEGK();
@@ -547,7 +597,7 @@ __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, const unsigned
     cz.A = cz.cb = cz.g = cz.y = cz.y2 = cz.L2 = T(0);
     unsigned dummy = 0u;
     unsigned dummy_far;
-    T Scur = chain_pass<T, KIND, WT, LSF, false>(cz, T(0), slot_addr(n), 0u, ar0, aw0, rb, npairs, lane, lc, dummy, dummy_far);
+    T Scur = chain_pass<T, KIND, WT, LSF, false, false, false, TAIL>(cz, T(0), slot_addr(n), 0u, ar0, aw0, rb, npairs, lane, lc, dummy, dummy_far);
     T sd = WT ? T(1) : sdrec->th;
     T logsd = WT ? T(0) : StepMath<T>::log_(sd);
     T hiv = WT ? T(0.5) : T(0.5) / (sd * sd);                 // 1 / (2 sd^2)
@@ -640,7 +690,9 @@ __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, const unsigned
             for (int i = lane; i < ts; i += 32)
                 if (is_free(i)) p.acc_total[gb + i] -= (i == sdi) ? sdrec->acc : recs[i >> 2].acc[i & 3];
         }
-        unsigned n_shape = 0u, n_far = 0u, n_like = 0u;
+        // work of this iteration: shape evaluations, far-path quads' pixels, passes whose LAST quad (the one holding
+        // the padding pixels) went far, in-bounds amplitude passes; settled once per iteration below
+        unsigned n_shape = 0u, n_far = 0u, n_lastfar = 0u, n_amp = 0u;
         int hprev = 0;                        // slot of component c - 1
         T Aprev = T(0);                       // its amplitude
 
@@ -718,14 +770,14 @@ __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, const unsigned
                         fz.Ap = Ap_;
                         fz.Ac = -NK * pA;
                         fz.ahp = ap_;
-                        Snew = chain_pass<T, KIND, WT, LSF, false, false, true>(cz, NK * prop, slot_addr(hc), 0u, ar0, aw0, rb, npairs,
+                        Snew = chain_pass<T, KIND, WT, LSF, false, false, true, TAIL>(cz, NK * prop, slot_addr(hc), 0u, ar0, aw0, rb, npairs,
                                                                                 lane, lc, dummy, dummy_far, nullptr, &fz);
                     } else
 #endif
-                        Snew = chain_pass<T, KIND, WT, LSF, false>(cz, NK * prop, slot_addr(hc), 0u, ar0, aw0, rb, npairs, lane,
+                        Snew = chain_pass<T, KIND, WT, LSF, false, false, false, TAIL>(cz, NK * prop, slot_addr(hc), 0u, ar0, aw0, rb, npairs, lane,
                                                                    lc, dummy, dummy_far);
                     const T dprior = StepMath<T>::log_(prop * Real<T>::rcp(pA)) - (prop - pA);
-                    ++n_like;
+                    ++n_amp;
                     if (lu < (Scur - Snew) * hiv + dprior) {          // false for NaN
                         Scur = Snew;
                         pA = prop;
@@ -770,11 +822,11 @@ __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, const unsigned
                         cc = make_comp_fast<T, KIND>(pA, cbase(qc), q1, q2);
                     unsigned nf = 0u;
                     unsigned last_far;
-                    const T Snew = chain_pass<T, KIND, WT, LSF, true, MULT>(cc, NK * pA, 0u, slot_addr(hs), ar0, aw0, rb, npairs,
+                    const T Snew = chain_pass<T, KIND, WT, LSF, true, MULT, false, TAIL>(cc, NK * pA, 0u, slot_addr(hs), ar0, aw0, rb, npairs,
                                                                             lane, lc, nf, last_far, &ml);
-                    n_far += nf - last_far * (unsigned)npad;
-                    n_shape += MULT ? 2u : 1u;            // line evaluations over the region
-                    ++n_like;
+                    n_far += nf;
+                    n_lastfar += last_far;
+                    ++n_shape;
                     if (lu < (Scur - Snew) * hiv) {
                         Scur = Snew;
                         pc = qc;
@@ -825,9 +877,9 @@ __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, const unsigned
             }
             __syncwarp();
         }
-        w_shape += n_shape;
-        w_far += n_far;
-        w_like += n_like;
+        w_shape += (MULT ? 2u : 1u) * n_shape;            // line evaluations over the region
+        w_far += n_far - n_lastfar * (unsigned)npad;
+        w_like += n_shape + n_amp;
 
         // ---- end of iteration: log-posterior of the current state
         const T lnL = WT ? (T(-0.5) * Scur + lognorm) : (-Scur * hiv - T(P) * (logsd + T(0.91893853320467274178)));
@@ -1350,7 +1402,7 @@ __device__ void mcmc_chain_am(const McmcDev& p, int chain, int lane, const unsig
 #else
 #define VAMP_K2_BOUNDS __launch_bounds__(K2_WARPS * 32, (sizeof(T) == 4) ? VAMP_K2_MINBLOCKS : 2)
 #endif
-template <typename T, int KIND, bool WT, bool LSF, bool MULT, bool AM = false>
+template <typename T, int KIND, bool WT, bool LSF, bool MULT, bool AM = false, bool TAIL = false>
 __global__ void VAMP_K2_BOUNDS
 k2_mcmc_kernel(McmcDev p, int ncomp_max) {
     typedef K2Lay<T, WT> Lay;
@@ -1379,7 +1431,7 @@ k2_mcmc_kernel(McmcDev p, int ncomp_max) {
         {
             const RegionSetDev& rs = p.rs;
             const int off = rs.pix_off[rr] >> 1, ne = 32 * ((rs.npix[rr] + 63) >> 6);
-            const int nq = 64 * ((rs.npix[rr] + 127) >> 7);                           // whole quads: pad the rest
+            const int nq = TAIL ? ne : 64 * ((rs.npix[rr] + 127) >> 7);               // whole quads: pad the rest
             P2<T>* sd_ = reinterpret_cast<P2<T>*>(rb + Lay::DU);
             P2<T>* sf_ = reinterpret_cast<P2<T>*>(rb + Lay::F);
             P2<T>* sw_ = reinterpret_cast<P2<T>*>(rb + Lay::W);
@@ -1393,7 +1445,7 @@ k2_mcmc_kernel(McmcDev p, int ncomp_max) {
         __syncthreads();
         if (my_region == rr) {
             if (AM) mcmc_chain_am<T, KIND, WT, LSF>(p, chain, lane, rb, wb, ncomp_max, lsf_s);
-            else mcmc_chain<T, KIND, WT, LSF, MULT>(p, chain, lane, rb, wb, ncomp_max, lsf_s);
+            else mcmc_chain<T, KIND, WT, LSF, MULT, TAIL>(p, chain, lane, rb, wb, ncomp_max, lsf_s);
         }
     }
 }
@@ -1468,13 +1520,16 @@ __global__ void init_state_kernel(McmcDev p) {
 #ifndef VAMP_INST_AM
 #define VAMP_INST_AM 0            // 1: this object holds the adaptive-Metropolis instantiations (vamp_launch_k2a_*)
 #endif
+#ifndef VAMP_INST_TAIL
+#define VAMP_INST_TAIL 0          // 1: this object holds the pair-tail instantiations (vamp_launch_k2t_*)
+#endif
 
 template <typename T, int KIND, bool WT, bool LSF>
 cudaError_t launch_k2_t(const McmcDev& p, int max_ncomp, cudaStream_t st) {
     constexpr bool AM = VAMP_INST_AM != 0;
     const size_t smem = (LSF ? align16(sizeof(T) * VAMP_MAX_LSF_TAPS) : 0) + K2Lay<T, WT>::REGION +
                         K2_WARPS * (K2Lay<T, WT>::bytes(max_ncomp, LSF) + (AM ? align16((size_t)max_ncomp * 10 * sizeof(T)) : 0));
-    auto kern = k2_mcmc_kernel<T, KIND, WT, LSF, VAMP_INST_MULT != 0, AM>;
+    auto kern = k2_mcmc_kernel<T, KIND, WT, LSF, VAMP_INST_MULT != 0, AM, VAMP_INST_TAIL != 0>;
     if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -1485,7 +1540,7 @@ cudaError_t launch_k2_t(const McmcDev& p, int max_ncomp, cudaStream_t st) {
 
 }  // namespace
 
-#if VAMP_INST_F64 == 0 && VAMP_INST_MULT == 0 && VAMP_INST_AM == 0
+#if VAMP_INST_F64 == 0 && VAMP_INST_MULT == 0 && VAMP_INST_AM == 0 && VAMP_INST_TAIL == 0
 // precision-independent helpers live in the f32 objects only
 cudaError_t VAMP_CAT3(vamp_launch_init_prior, any, VAMP_KN)(const McmcDev& p, cudaStream_t st) {
     if (p.B <= 0) return cudaSuccess;
@@ -1506,6 +1561,8 @@ cudaError_t vamp_launch_init_state(const McmcDev& p, cudaStream_t st) {
 #if VAMP_INST_AM
 cudaError_t VAMP_INST_NAME(vamp_launch_k2a)(const McmcDev& p, int max_npix, int max_ncomp, cudaStream_t st) {
     if (!p.am) return cudaErrorInvalidValue;
+#elif VAMP_INST_TAIL
+cudaError_t VAMP_INST_NAME(vamp_launch_k2t)(const McmcDev& p, int max_npix, int max_ncomp, cudaStream_t st) {
 #elif VAMP_INST_MULT
 cudaError_t VAMP_INST_NAME(vamp_launch_k2m)(const McmcDev& p, int max_npix, int max_ncomp, cudaStream_t st) {
 #else

@@ -63,6 +63,8 @@ cudaError_t vamp_launch_init_prior_any_gauss(const McmcDev& p, cudaStream_t st);
 cudaError_t vamp_launch_init_prior_any_voigt(const McmcDev& p, cudaStream_t st);
 cudaError_t vamp_launch_init_state(const McmcDev& p, cudaStream_t st);
 VAMP_DECL4(cudaError_t, vamp_launch_k2, const McmcDev& p, int max_npix, int max_ncomp, cudaStream_t st)
+// pair-tail instantiations (regions whose ceil(P / 64) is odd run a final 64-pixel trip instead of padding to a quad)
+VAMP_DECL4(cudaError_t, vamp_launch_k2t, const McmcDev& p, int max_npix, int max_ncomp, cudaStream_t st)
 // adaptive-Metropolis instantiations (one joint proposal per component from the running covariance)
 VAMP_DECL4(cudaError_t, vamp_launch_k2a, const McmcDev& p, int max_npix, int max_ncomp, cudaStream_t st)
 // multiplet instantiations (region sets with a multiplet table: two tied lines per component)

@@ -369,6 +369,9 @@ class Sampler:
         w = self.t["work"]
         a.work = w.data_ptr() + a0 * w.stride(0) * w.element_size()
         a.step_kind, a.am_delay, a.am_interval = self.step_kind, self.am_delay, self.am_interval
+        # a chain whose region has an odd number of 64-pixel row pairs always runs the pair-tail kernel
+        pairs = (self.regions.npix[self.item_region_h[a0:b0]] + 63) // 64
+        a.pair_tail = int(self.regions.multiplet is None and bool(np.any(pairs & 1)))
         am = self.t["am_state"]
         a.am_state = (am.data_ptr() + a0 * am.stride(0) * am.element_size()) if am is not None else None
         return a
