@@ -25,31 +25,20 @@ if world > 1:
 ctx = engine.default_context(lrank)
 host = [(r["nu"], r["flux"], r["noise"]) for r in regs]
 ntrue = np.array([len(r["truth"]) for r in regs])
-marks = {"k2": 0.0, "k3": 0.0}
-orig_run, orig_map = engine.Sampler.run, engine.Sampler._map
-evs = []
-def run(self, iters, *a_, **k_):
-    a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
-    a.record(); orig_run(self, iters, *a_, **k_); b.record(); evs.append(("k2", a, b))
-def _map(self, *a_, **k):
-    a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
-    a.record(); r = orig_map(self, *a_, **k); b.record(); evs.append(("k3", a, b)); return r
-engine.Sampler.run, engine.Sampler._map = run, _map
 import gc
 for rep in range(int(os.environ.get("REPS", 3))):
     if os.environ.get("GCOFF"):
         gc.collect(); gc.disable()
-    evs.clear()
     st = {}
     torch.cuda.synchronize()
     if world > 1: dist.barrier()
     t0 = time.perf_counter()
     res = fit_regions(host, uids=[10_000 + i for i in range(R)], voigt=True, iterations=3000, burn=300, thin=15, restarts=3,
-                      chains_per_restart=cpr, window=3, nmax=8, seed=rep, stats=st, polish_dtype=os.environ.get("POLISH", "auto"))
+                      chains_per_restart=cpr, window=eval(os.environ.get("WINDOW", "3")), nmax=8, seed=rep, stats=st,
+                      polish_dtype=os.environ.get("POLISH", "auto"))
     torch.cuda.synchronize()
     if world > 1: dist.barrier()
     dt = time.perf_counter() - t0
-    k2 = sum(a.elapsed_time(b) for n, a, b in evs if n == "k2"); k3 = sum(a.elapsed_time(b) for n, a, b in evs if n == "k3")
     if rank == 0:
         tm = st.get("timing", {})
         print("   fit_models: K2 %.0f ms, polish %.0f ms (device); host set-up %.3f s, launch %.3f s, wait %.3f s, post %.3f s" % (
@@ -58,9 +47,9 @@ for rep in range(int(os.environ.get("REPS", 3))):
         print("   fit_local: upload %.3f s, ladder %.3f s, records %.3f s, close %.3f s" % (
             tm.get("upload_s", 0), tm.get("ladder_s", 0), tm.get("records_s", 0), tm.get("close_s", 0)), flush=True)
         nfit = np.array([r.n for r in res])
-        print("rep %d: %d regions on %d GPU(s): %.2f s -> %.1f regions/s | rank0 K2 %.0f ms K3 %.0f ms rounds %d chains %d | "
+        print("rep %d: %d regions on %d GPU(s): %.2f s -> %.1f regions/s | rounds %d chains %d | checksum %s | "
               "n == truth %.2f, |n - truth| <= 1 %.2f, status0 %.2f" % (
-                  rep, R, world, dt, R / dt, k2, k3, st.get("launches", 0) // 4, st.get("chains", 0),
+                  rep, R, world, dt, R / dt, st.get("launches", 0) // 4, st.get("chains", 0), res.checksum()[:12],
                   np.mean(nfit == ntrue), np.mean(np.abs(nfit - ntrue) <= 1), np.mean([r.status == 0 for r in res])), flush=True)
 if world > 1:
     dist.destroy_process_group()

@@ -192,12 +192,16 @@ def unpack_record(rec, nmax, G, cmax):
 
 
 def fit_local(regions_host, uids, voigt=False, sd_free=True, iterations=3000, burn=300, thin=15, restarts=3,
-              chains_per_restart=32, window=3, max_rounds=4, chi_limit=1.5, dtype="f32", seed=0, lsf=None,
+              chains_per_restart=32, window=3, max_rounds=None, chi_limit=1.5, dtype="f32", seed=0, lsf=None,
               n0=None, nmax=12, ctx=None, polish_top=None, tune_interval=50, stats=None, cmax_rec=None, polish_dtype="f64",
               multiplet=None, polish_from="best", step_method="metropolis"):
     """Fit the given regions on this process's GPU.  Returns ``[R, record_len]`` float64.
     ``multiplet``: per-region ``(freq_ratio, amp_ratio[, lorentz_ratio])`` or None (``engine.Regions``);
-    ``polish_from``: see ``batch.fit_models``."""
+    ``polish_from``: see ``batch.fit_models``.
+    ``window``: candidate counts fitted per ladder round for every region still undecided - an int, or
+    ``(first, later)`` (e.g. ``(2, 1)``: the two candidates the first comparison needs, then one more per round: no
+    speculative fits at all, as the reference's sequential ladder, at the price of more rounds).  The ladder's
+    decisions do not depend on it (chains are keyed by (region, n)); ``max_rounds`` defaults to what ``nmax`` needs."""
     R = len(regions_host)
     G = int(restarts)
     if R == 0:                                   # nothing to fit (an empty shard): no device work, no context
@@ -224,12 +228,16 @@ def fit_local(regions_host, uids, voigt=False, sd_free=True, iterations=3000, bu
     nxt = list(n0)
     active = list(range(R))
     outcome = [None] * R
-    for _ in range(max_rounds):
+    w_first, w_later = (int(window), int(window)) if np.isscalar(window) else (int(window[0]), int(window[1]))
+    if max_rounds is None:
+        max_rounds = 1 + max(0, -(-(nmax - w_first) // max(w_later, 1)))
+    for rnd in range(max_rounds):
         if not active:
             break
         models, owner = [], []
+        wnd = w_first if rnd == 0 else w_later
         for i in active:
-            for n in range(nxt[i], min(nxt[i] + window, n0[i] + nmax)):
+            for n in range(nxt[i], min(nxt[i] + wnd, n0[i] + nmax)):
                 if n <= cap[i] or n == nxt[i]:
                     models.append((i, n))
                     owner.append(i)
@@ -396,6 +404,7 @@ def fit_regions(regions_host, uids=None, distributed=None, fit_fn=None, emulate=
     uids = list(range(R)) if uids is None else [int(u) for u in uids]
     voigt = kw.get("voigt", False)
     window = kw.get("window", 3)
+    window = int(window) if np.isscalar(window) else int(window[0])      # first-round window: cost model, K3 schedule
     nmax = kw.get("nmax", 12)
     G = kw.get("restarts", 3)
     n0 = kw.pop("n0", None)
