@@ -21,4 +21,4 @@ for rep in range(3):
     w1 = s.work()
     ms = e0.elapsed_time(e1); best = min(best, ms)
 ev = w1["shape_pix"] - w0["shape_pix"]
-print("K2 %d iters: %.2f ms  %.4g evals/s  far %.3f  mean best_logp %.3f" % (iters, best, ev / best * 1e3, (w1["far_pix"] - w0["far_pix"]) / ev, float(s.t["best_logp"].mean())))
+print("K2 %d iters: %.2f ms  %.4g evals/s  far %.3f  mean best_logp %.3f" % (iters, best, ev / best * 1e3, (w1["far_pix"] - w0["far_pix"]) / max(ev, 1.0), float(s.t["best_logp"].mean())))

@@ -49,6 +49,12 @@ constexpr int K2_TRIPUNROLL = VAMP_K2_TRIPUNROLL;
 #ifndef VAMP_K2_SMEMSUM
 #define VAMP_K2_SMEMSUM 0         // 1 (fp32): the warp sum goes through shared memory (one store, 8 vector loads, a packed
 #endif                            //    adder tree in every lane) instead of five dependent shuffle + add rounds
+#ifndef VAMP_K2_NOCOUNT
+#define VAMP_K2_NOCOUNT 0         // 1 (experiment only): no work counters - what the accounting of bench.py's numerator costs
+#endif
+#ifndef VAMP_K2_SMEMRNG
+#define VAMP_K2_SMEMRNG 1         // 1: the 64 (normal, log-uniform) pairs of a Philox block are parked in shared memory; a step reads its
+#endif                            //    pair with one broadcast load instead of two shuffles (same stream, same values)
 #ifndef VAMP_K2_FUSEBASE
 #define VAMP_K2_FUSEBASE 1        // 1: the move of `base` to a component runs inside its amplitude pass (FuseArgs)
 #endif
@@ -161,8 +167,9 @@ struct K2Lay {
         return lsf ? align16(sizeof(T) * (VAMP_TILE_PIX + VAMP_MAX_LSF_TAPS)) : 0;
     }
     static constexpr int SUMSCR = VAMP_K2_SMEMSUM ? 128 : 0;       // 32 floats of reduction scratch, first in the chain slice tail
+    static constexpr int RNGSCR = VAMP_K2_SMEMRNG ? 64 * (int)sizeof(P2<T>) : 0;      // the 64 (z, lu) pairs of a Philox block
     static __host__ __device__ size_t bytes(int ncomp_max, bool lsf) {
-        return (size_t)H + (size_t)(ncomp_max + 1) * SLOT + lsf_bytes(lsf) + SUMSCR + sizeof(SdRec<T>) +
+        return (size_t)H + (size_t)(ncomp_max + 1) * SLOT + lsf_bytes(lsf) + SUMSCR + RNGSCR + sizeof(SdRec<T>) +
                (size_t)ncomp_max * sizeof(CompRec<T>);
     }
 };
@@ -519,6 +526,8 @@ __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, const unsigned
     sp_ += Lay::lsf_bytes(LSF);
     lc.sum_scratch = (unsigned)__cvta_generic_to_shared(sp_);
     sp_ += Lay::SUMSCR;
+    unsigned rq0 = (unsigned)__cvta_generic_to_shared(sp_);        // VAMP_K2_SMEMRNG: the block's 64 (z, lu) pairs
+    sp_ += Lay::RNGSCR;
     SdRec<T>* const sdrec = reinterpret_cast<SdRec<T>*>(sp_);
     CompRec<T>* const recs = reinterpret_cast<CompRec<T>*>(sp_ + sizeof(SdRec<T>));
     unsigned arec0 = (unsigned)__cvta_generic_to_shared(recs);
@@ -631,6 +640,29 @@ __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, const unsigned
         RngMath<T>::fill(x, zc, zn, luc, lun);
 #endif
     };
+#if VAMP_K2_SMEMRNG
+    asm volatile("" : "+r"(rq0));
+    auto park = [&]() {                     // lane l owns steps l (zc, luc) and 32 + l (zn, lun) of the block
+        __syncwarp();
+        SM<T>::template st<0>(rq0 + (unsigned)(lane * sizeof(P2<T>)), p2_make(zc, luc));
+        SM<T>::template st<0>(rq0 + (unsigned)((32 + lane) * sizeof(P2<T>)), p2_make(zn, lun));
+        __syncwarp();
+    };
+    refill();
+    park();
+    auto draw = [&](T& z, T& lu) {
+        const P2<T> v = SM<T>::template ld<0>(rq0 + (unsigned)(qs * sizeof(P2<T>)));     // broadcast: every lane reads the same pair
+        z = p2_lo(v);
+        lu = p2_hi(v);
+        ++qs;
+        if (qs == 64) {
+            qs = 0;
+            ++qblk;
+            refill();
+            park();
+        }
+    };
+#else
     refill();
     if (qs >= 32) {
         zc = zn;
@@ -651,6 +683,7 @@ __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, const unsigned
             }
         }
     };
+#endif
 
     const T c_hi = T(P - 1);
     const T w_hi = T(P - 1) * T(KIND == VAMP_KIND_VOIGT ? 0.5 * FWHM_PER_SIGMA : 0.5);
@@ -777,7 +810,9 @@ __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, const unsigned
                         Snew = chain_pass<T, KIND, WT, LSF, false, false, false, TAIL>(cz, NK * prop, slot_addr(hc), 0u, ar0, aw0, rb, npairs, lane,
                                                                    lc, dummy, dummy_far);
                     const T dprior = StepMath<T>::log_(prop * Real<T>::rcp(pA)) - (prop - pA);
+#if !VAMP_K2_NOCOUNT
                     ++n_amp;
+#endif
                     if (lu < (Scur - Snew) * hiv + dprior) {          // false for NaN
                         Scur = Snew;
                         pA = prop;
@@ -824,9 +859,11 @@ __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, const unsigned
                     unsigned last_far;
                     const T Snew = chain_pass<T, KIND, WT, LSF, true, MULT, false, TAIL>(cc, NK * pA, 0u, slot_addr(hs), ar0, aw0, rb, npairs,
                                                                             lane, lc, nf, last_far, &ml);
+#if !VAMP_K2_NOCOUNT
                     n_far += nf;
                     n_lastfar += last_far;
                     ++n_shape;
+#endif
                     if (lu < (Scur - Snew) * hiv) {
                         Scur = Snew;
                         pc = qc;
@@ -1014,6 +1051,8 @@ __device__ void mcmc_chain_am(const McmcDev& p, int chain, int lane, const unsig
     sp_ += Lay::lsf_bytes(LSF);
     lc.sum_scratch = (unsigned)__cvta_generic_to_shared(sp_);
     sp_ += Lay::SUMSCR;
+    unsigned rq0 = (unsigned)__cvta_generic_to_shared(sp_);        // VAMP_K2_SMEMRNG: the block's 64 (z, lu) pairs
+    sp_ += Lay::RNGSCR;
     SdRec<T>* const sdrec = reinterpret_cast<SdRec<T>*>(sp_);
     CompRec<T>* const recs = reinterpret_cast<CompRec<T>*>(sp_ + sizeof(SdRec<T>));
     T* const Lsm = reinterpret_cast<T*>(sp_ + sizeof(SdRec<T>) + (size_t)ncomp_max * sizeof(CompRec<T>));   // [ncomp_max][10]
