@@ -488,9 +488,11 @@ def run_gpu(args):
     try:
         cap = json.load(open(os.path.join(ROOT, "profiles", "r2_k2.json")))
         traffic, traffic_src = cap["traffic_bytes"], "profiles/r2_k2.json (ncu dram__bytes_read.sum + dram__bytes_write.sum)"
-        executed = {"thread_inst_ffma": cap.get("thread_inst_ffma"), "thread_inst_fmul": cap.get("thread_inst_fmul"),
-                    "thread_inst_fadd": cap.get("thread_inst_fadd"),
-                    "executed_fp32_flops_ncu_convention": cap.get("executed_fp32_flops_ncu_convention"),
+        executed = {"source": "profiles/r2_k2.json (ncu counters of the same 3000-iteration launch, tools/capture_k2.py)",
+                    "scalar_thread_inst_ffma_fmul_fadd": [cap.get("thread_inst_ffma"), cap.get("thread_inst_fmul"), cap.get("thread_inst_fadd")],
+                    "warp_instructions": (cap.get("metrics") or {}).get("smsp__inst_executed.sum"),
+                    "fp32_flops_per_warp_lane_instruction": (cap.get("mix") or {}).get("fp32_flops_per_warp_lane_instruction"),
+                    "executed_fp32_flops": cap.get("executed_fp32_flops"),
                     "algorithmic_flops_same_launch": cap.get("algorithmic_flops"),
                     "executed_over_algorithmic": cap.get("executed_over_algorithmic")}
     except Exception:

@@ -1,7 +1,13 @@
 """Reproducible roofline evidence for K2 (the kernel ``bench.py``'s roofline is quoted on).
 
     python tools/capture_k2.py run [iters] [dtype]        # ONE K2 launch of the bench's C2 chain set (24 576 chains)
-    python tools/capture_k2.py parse <ncu.csv> <out.json> # -> profiles/r2_k2.json (read by bench.py: roofline.traffic)
+    python tools/capture_k2.py parse <ncu.csv> <out.json> [mix.json]   # -> profiles/r2_k2.json (read by bench.py: roofline.traffic)
+    python tools/capture_k2.py mix <full.ncu-rep> <mix.json>           # dynamic packed-FP mix from the source page of a --set full capture
+
+ncu's ``smsp__sass_thread_inst_executed_op_{ffma,fmul,fadd}_pred_on`` count the SCALAR instructions only: the packed
+FFMA2 / FMUL2 / FADD2 this kernel is made of are not in them (measured: they give 6 % of the algorithmic flops).
+Executed flops are therefore formed from the launch's warp-instruction count and the executed-instruction mix of the
+source page of a ``--set full`` capture of the same kernel (``mix``): ``32 x inst_executed x sum(share x flops)``.
 
 On the GPU box (one gpurun call; the plain run first, as the profiling recipe demands):
 
@@ -67,7 +73,34 @@ def run(iters, dtype):
                       "evals_per_sec": w["shape_pix"] / ms * 1e3}))
 
 
-def parse(path, out):
+def mix(rep, out):
+    """Executed-instruction mix of the kernel in a ``--set full --import-source on`` capture (no GPU needed)."""
+    import collections
+    import io
+    import subprocess
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr = rows[1]
+    isrc, iex = hdr.index("Source"), hdr.index("Instructions Executed")
+    h = collections.Counter()
+    for r in rows[2:]:
+        op = r[isrc].strip().split()
+        if not op:
+            continue
+        o = (op[1] if op[0].startswith("@") else op[0]).split(".")[0]
+        h[o] += int(r[iex])
+    tot = float(sum(h.values()))
+    res = {"source": os.path.basename(rep), "kernel": rows[0][1] if len(rows[0]) > 1 else None, "warp_instructions": tot,
+           "share": {k: v / tot for k, v in h.most_common(40)}}
+    packed = h["FFMA2"] + h["FMUL2"] + h["FADD2"]
+    res["packed_share"] = packed / tot
+    res["flops_per_packed_thread_inst"] = (4.0 * h["FFMA2"] + 2.0 * (h["FMUL2"] + h["FADD2"])) / max(packed, 1)
+    with open(out, "w") as fh:
+        json.dump(res, fh, indent=1)
+    print(json.dumps({k: v for k, v in res.items() if k != "share"}))
+
+
+def parse(path, out, mixfile=None):
     rows = list(csv.reader(open(path)))
     start = next(i for i, r in enumerate(rows) if r and r[0] == "ID")
     hdr = rows[start]
@@ -91,19 +124,30 @@ def parse(path, out):
            "dram_bytes_read": b("dram__bytes_read.sum"), "dram_bytes_write": b("dram__bytes_write.sum"),
            "traffic_bytes": b("dram__bytes_read.sum") + b("dram__bytes_write.sum"),
            "thread_inst_ffma": ffma, "thread_inst_fmul": fmul, "thread_inst_fadd": fadd,
-           # ncu's roofline convention; whether a packed FFMA2 counts once or twice per thread is read off by
-           # comparing with the algorithmic flops of the same launch (printed by `run`)
-           "executed_fp32_flops_ncu_convention": 2.0 * ffma + fmul + fadd,
-           "executed_fp32_flops_if_packed_counted_once": 2.0 * (2.0 * ffma + fmul + fadd),
+           "scalar_fp32_flops": 2.0 * ffma + fmul + fadd,         # ncu's roofline convention: scalar instructions only
            "metrics": d, "units": units}
     plain = os.path.join(os.path.dirname(path), "k2_plain.log")
     if os.path.exists(plain):
         for line in open(plain):
             if line.startswith("{"):
                 res["plain_run"] = json.loads(line)
+    if mixfile and os.path.exists(mixfile):
+        # executed FP32 arithmetic: warp instructions of the launch x 32 lanes x the executed-instruction mix (source
+        # page of the --set full capture of the same kernel) x flops per instruction (FFMA2 4, FMUL2 / FADD2 2,
+        # FFMA 2, FMUL / FADD 1).  MUFU, compares, min / max and conversions are not arithmetic flops here.
+        mx = json.load(open(mixfile))
+        sh = mx["share"]
+        w = {"FFMA2": 4.0, "FMUL2": 2.0, "FADD2": 2.0, "FFMA": 2.0, "FMUL": 1.0, "FADD": 1.0}
+        per_inst = sum(w[k] * sh.get(k, 0.0) for k in w)
+        res["mix"] = {"source": mx["source"], "share": {k: sh.get(k, 0.0) for k in list(w) + ["MUFU", "LDS", "STS", "SHFL", "BRA", "IMAD"]},
+                      "fp32_flops_per_warp_lane_instruction": per_inst}
+        res["executed_fp32_flops"] = 32.0 * (d.get("smsp__inst_executed.sum") or 0.0) * per_inst
+        # consistency of the mix with the counters: scalar FFMA thread instructions either way
+        res["scalar_ffma_from_mix"] = 32.0 * (d.get("smsp__inst_executed.sum") or 0.0) * sh.get("FFMA", 0.0)
     if res.get("plain_run"):
         res["algorithmic_flops"] = res["plain_run"]["algorithmic_flops"]
-        res["executed_over_algorithmic"] = res["executed_fp32_flops_ncu_convention"] / res["algorithmic_flops"]
+        if "executed_fp32_flops" in res:
+            res["executed_over_algorithmic"] = res["executed_fp32_flops"] / res["algorithmic_flops"]
     with open(out, "w") as fh:
         json.dump(res, fh, indent=1)
     print(json.dumps({k: v for k, v in res.items() if k not in ("metrics", "units")}, indent=1))
@@ -114,6 +158,8 @@ if __name__ == "__main__":
     if mode == "metrics":
         print(",".join(METRICS))
     elif mode == "parse":
-        parse(sys.argv[2], sys.argv[3])
+        parse(sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else None)
+    elif mode == "mix":
+        mix(sys.argv[2], sys.argv[3])
     else:
         run(int(sys.argv[2]) if len(sys.argv) > 2 else 3000, sys.argv[3] if len(sys.argv) > 3 else "f32")
