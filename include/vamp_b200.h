@@ -30,7 +30,8 @@
 extern "C" {
 #endif
 
-#define VAMP_ABI_VERSION 4   /* 2: vamp_detect_*, VAMP_MIXED for vamp_map_dev; 3: vamp_regions_set_multiplet */
+#define VAMP_ABI_VERSION 4   /* 2: vamp_detect_*, VAMP_MIXED for vamp_map_dev; 3: vamp_regions_set_multiplet;
+                                4: vamp_mcmc_args.step_kind / am_* (adaptive Metropolis) and pair_tail */
 
 enum { VAMP_F32 = 0, VAMP_F64 = 1,            /* arithmetic of the pixel math */
        VAMP_MIXED = 2 };                       /* vamp_map_dev only: fp32 objective during the simplex search,

@@ -43,13 +43,9 @@ def main(path):
         print("  warp stall reasons (avg warps stalled per issue-active cycle):")
         for v, h in sorted(stalls, reverse=True)[:8]:
             print("    %-60s %.3f" % (h.split("issue_stalled_")[1].replace("_per_issue_active.ratio", ""), v))
-        ff = sum(float(d.get("smsp__sass_thread_inst_executed_op_%s_pred_on.sum" % o, 0) or 0) * w
-                 for o, w in (("ffma", 2), ("fmul", 1), ("fadd", 1)))
-        t = float(d.get("gpu__time_duration.sum", 0) or 0)
-        unit = u.get("gpu__time_duration.sum", "")
-        scale = {"ns": 1e-9, "us": 1e-6, "usecond": 1e-6, "ms": 1e-3, "msecond": 1e-3, "s": 1.0, "second": 1.0, "nsecond": 1e-9}.get(unit, 1e-9)
-        if t:
-            print("  executed FP32 flops (ffma*2 + fmul + fadd): %.4g -> %.2f TFLOP/s under ncu clocks" % (ff, ff / (t * scale) / 1e12))
+        sc = [float(d.get("smsp__sass_thread_inst_executed_op_%s_pred_on.sum" % o, 0) or 0) for o in ("ffma", "fmul", "fadd")]
+        print("  scalar FP32 thread instructions (ffma, fmul, fadd): %.4g %.4g %.4g - the packed FFMA2 / FMUL2 / FADD2 are NOT in these "
+              "counters; executed flops: tools/capture_k2.py (instruction mix x warp instructions)" % tuple(sc))
 
 
 if __name__ == "__main__":
