@@ -30,8 +30,13 @@
 extern "C" {
 #endif
 
-#define VAMP_ABI_VERSION 4   /* 2: vamp_detect_*, VAMP_MIXED for vamp_map_dev; 3: vamp_regions_set_multiplet;
-                                4: vamp_mcmc_args.step_kind / am_* (adaptive Metropolis) and pair_tail */
+#define VAMP_ABI_VERSION 5   /* 2: vamp_detect_*, VAMP_MIXED for vamp_map_dev; 3: vamp_regions_set_multiplet;
+                                4: vamp_mcmc_args.step_kind / am_* (adaptive Metropolis) and pair_tail;
+                                5: regions of up to VAMP_MAX_FIT_PIXELS pixels in vamp_mcmc_* / vamp_map_dev,
+                                   vamp_mcmc_args.max_npix */
+#define VAMP_MAX_FIT_PIXELS 2048   /* longest region the sampler takes (the reference fits arrays of any length, e.g.
+                                      2000 pixels in vamp_1.0/vpfits_intro.ipynb); vamp_map_dev (CTA schedule) and
+                                      vamp_loglike_* take any length */
 
 enum { VAMP_F32 = 0, VAMP_F64 = 1,            /* arithmetic of the pixel math */
        VAMP_MIXED = 2 };                       /* vamp_map_dev only: fp32 objective during the simplex search,
@@ -145,6 +150,12 @@ typedef struct vamp_mcmc_args {
                                    instead of whole 128-pixel quads.  Chains with an even count compute the same
                                    either way; a caller must set it whenever such a chain is present (always, for
                                    results that do not depend on batching).  Ignored for multiplet / adaptive runs. */
+    int max_npix;               /* ABI 5: longest region among THIS launch's chains, 0 = the region set's longest.  Chains of
+                                   regions above 256 pixels run the long-region kernels (one chain per CTA, all
+                                   coordinate tiles of the region in shared memory: (max_ncomp + 4) x pixels x 8 bytes
+                                   (float64: 16) must fit 227 KB, error -3 otherwise; single lines and the scalar step
+                                   method only); a caller that launches its short regions separately keeps them on
+                                   the one-tile kernels. */
     double* am_state;           /* [n, cmax, VAMP_AM_STRIDE] adaptive state (NULL unless step_kind = VAMP_STEP_ADAPTIVE):
                                    chain mean [4] | covariance, packed lower triangle [10] | its Cholesky factor [10] |
                                    sum x [4] | sum x x^T [10] | samples in the covariance | samples since the update */

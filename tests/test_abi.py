@@ -24,7 +24,7 @@ def test_header_symbols_exported(built_lib):
         assert hasattr(lib, n), "symbol %s declared in include/vamp_b200.h but not exported" % n
         assert n in _lib.SIGNATURES, "no ctypes signature for %s" % n
     assert sorted(_lib.SIGNATURES) == names
-    assert lib.vamp_abi_version() == 4
+    assert lib.vamp_abi_version() == 5
 
 
 def test_struct_layouts_match_header():

@@ -25,10 +25,23 @@ def test_regions_reject_bad_noise_and_flux_before_upload():
             engine.Regions(_fake_ctx(), [good, tuple(arrs)])
 
 
-def test_sampler_refuses_regions_longer_than_a_tile_with_guidance():
-    regs = types.SimpleNamespace(ctx=_fake_ctx(), npix=np.array([200, 300], dtype=np.int32))
+def test_sampler_refuses_regions_it_cannot_hold_with_guidance():
+    """Regions above 2048 pixels (above 256 for multiplet region sets and the adaptive step method) are refused before
+    any device state is allocated, with the way out."""
+    regs = types.SimpleNamespace(ctx=_fake_ctx(), npix=np.array([200, 2100], dtype=np.int32), multiplet=None)
+    with pytest.raises(_lib.VampError, match="2100 pixels.*split_long_regions"):
+        engine.Sampler(regs, np.array([0, 1], np.int32), np.array([1, 1], np.int32), np.arange(2, dtype=np.uint64))
+    regs = types.SimpleNamespace(ctx=_fake_ctx(), npix=np.array([200, 300], dtype=np.int32), multiplet=[(1.0, 0.5, 1.0)] * 2)
     with pytest.raises(_lib.VampError, match="300 pixels.*split_long_regions"):
         engine.Sampler(regs, np.array([0, 1], np.int32), np.array([1, 1], np.int32), np.arange(2, dtype=np.uint64))
+    regs = types.SimpleNamespace(ctx=_fake_ctx(), npix=np.array([200, 300], dtype=np.int32), multiplet=None)
+    with pytest.raises(_lib.VampError, match="300 pixels.*split_long_regions"):
+        engine.Sampler(regs, np.array([0, 1], np.int32), np.array([1, 1], np.int32), np.arange(2, dtype=np.uint64),
+                       step_method="adaptive")
+
+
+def test_long_class_of_regions():
+    np.testing.assert_array_equal(engine.long_class([1, 256, 257, 512, 513, 1024, 1025, 2048]), [0, 0, 1, 1, 2, 2, 3, 3])
 
 
 def test_split_long_regions_flags_cuts_through_absorption():

@@ -33,7 +33,7 @@ class McmcArgs(C.Structure):
         ("comom", C.c_void_p), ("ntally", C.c_void_p), ("sum_lnL", C.c_void_p), ("sum_lnL2", C.c_void_p),
         ("trace", C.c_void_p), ("trace_cap", C.c_int), ("work", C.c_void_p),
         ("step_kind", C.c_int), ("am_delay", C.c_int), ("am_interval", C.c_int), ("pair_tail", C.c_int),
-        ("am_state", C.c_void_p),
+        ("max_npix", C.c_int), ("am_state", C.c_void_p),
     ]
 
 
@@ -101,7 +101,7 @@ def load():
         fn = getattr(lib, name)      # AttributeError if the symbol is missing
         fn.restype = res
         fn.argtypes = args
-    if lib.vamp_abi_version() != 4:
+    if lib.vamp_abi_version() != 5:
         raise VampError("libvamp_b200.so ABI version mismatch")
     _lib = lib
     return lib

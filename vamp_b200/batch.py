@@ -86,11 +86,13 @@ def fit_models(regions, models, voigt=False, sd_free=True, iterations=3000, burn
     item_region = np.repeat(np.array([r for r, _ in models], dtype=np.int32), per)
     item_ncomp = np.repeat(np.array([n for _, n in models], dtype=np.int32), per)
     uid = model_chain_uids(region_uids, models, G, Cn)
-    # sampler rows sorted by (component count, pixel class, model): CTAs are homogeneous, a kernel launches its
-    # rows from the end (most expensive chains first), and the chains of one component count are contiguous,
-    # so every count can run as its own launch on its own stream (below)
+    # sampler rows sorted by (long class, component count, pixel class, model): CTAs are homogeneous, a kernel launches
+    # its rows from the end (most expensive chains first), and the chains of one component count are contiguous,
+    # so every count can run as its own launch on its own stream (below).  Long class: regions above one coordinate
+    # tile (256 pixels) run the long-region kernels, one launch per buffer length - all 0 for the BASELINE configs.
     ppl = (regions.npix[item_region] + 31) // 32
-    order = np.lexsort((np.arange(M * per), ppl, item_ncomp))
+    lcls = engine.long_class(regions.npix[item_region])
+    order = np.lexsort((np.arange(M * per), ppl, item_ncomp, lcls))
     inv = np.empty_like(order)
     inv[order] = np.arange(order.size)
     cap = max(0, (int(iterations) - int(burn) + int(thin) - 1) // max(int(thin), 1) + 1) if trace else 0
@@ -189,7 +191,7 @@ def fit_models(regions, models, voigt=False, sd_free=True, iterations=3000, burn
     counts = sorted({n for _, n in models}, reverse=True)
     sorted_nc = item_ncomp[order]
     main = torch.cuda.current_stream(dev)
-    if overlap and len(counts) > 1:
+    if overlap and len(counts) > 1 and int(lcls.max()) == 0:
         side = []
         for rank, n in enumerate(counts):
             a, b = int(np.searchsorted(sorted_nc, n, "left")), int(np.searchsorted(sorted_nc, n, "right"))
@@ -215,13 +217,17 @@ def fit_models(regions, models, voigt=False, sd_free=True, iterations=3000, burn
         # 1 KB): a batch holding a few 17-component chains would run everybody at 2 CTAs per SM instead of 5.  The
         # rows are sorted by component count, so they go out in groups (<= 8, 9..10, 11..15, more), largest first on side
         # streams; a batch whose counts fit one group (BASELINE C2: n <= 6) is the single launch it always was.
-        bounds, a0 = [], 0
-        for hi in K2_GROUP_EDGES + (int(sorted_nc[-1]),):
-            b0 = int(np.searchsorted(sorted_nc, hi, "right"))
-            if b0 > a0:
-                bounds.append((a0, b0, int(sorted_nc[b0 - 1])))
-            a0 = max(a0, b0)
-        if len(bounds) == 1 or not K2_GROUPS:
+        bounds = []
+        sorted_lc = lcls[order]
+        for lc in np.unique(sorted_lc):                  # one pass per long class (a single pass of class 0 as a rule)
+            lo, hi_ = int(np.searchsorted(sorted_lc, lc, "left")), int(np.searchsorted(sorted_lc, lc, "right"))
+            nc, a0 = sorted_nc[lo:hi_], 0
+            for hi in K2_GROUP_EDGES + (int(nc[-1]),):
+                b0 = int(np.searchsorted(nc, hi, "right"))
+                if b0 > a0:
+                    bounds.append((lo + a0, lo + b0, int(nc[b0 - 1])))
+                a0 = max(a0, b0)
+        if len(bounds) == 1 or (not K2_GROUPS and sorted_lc[0] == sorted_lc[-1]):
             s.run(iterations)
         else:
             side = _polish_streams(dev, len(bounds))

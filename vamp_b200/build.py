@@ -51,6 +51,8 @@ def _jobs():
                     jobs.append((src, obj[:-2] + "_am.o", defs + ["-DVAMP_INST_AM=1"], hdr))
                     # ... and its pair-tail instantiations (regions with an odd number of 64-pixel row pairs)
                     jobs.append((src, obj[:-2] + "_tail.o", defs + ["-DVAMP_INST_TAIL=1"], hdr))
+                    # ... and its long-region instantiations (257 .. 2048 pixels, one chain per CTA)
+                    jobs.append((src, obj[:-2] + "_long.o", defs + ["-DVAMP_INST_LONG=1"], hdr))
     jobs.append((os.path.join(CSRC, "vamp_k4.cu"), os.path.join(OBJ, "vamp_k4.o"), [], hdr))
     jobs.append((os.path.join(CSRC, "vamp_cabi.cu"), os.path.join(OBJ, "vamp_cabi.o"), [], hdr))
     return jobs

@@ -186,13 +186,21 @@ McmcDev to_dev(const vamp_regions* rg, const vamp_mcmc_args* a) {
     return p;
 }
 
+// longest region among a launch's chains: the caller's figure (vamp_mcmc_args.max_npix) or the region set's
+int launch_npix(const vamp_regions* rg, const vamp_mcmc_args* a) {
+    return (a->max_npix > 0 && a->max_npix < rg->max_npix) ? a->max_npix : rg->max_npix;
+}
+
 int check_mcmc(const vamp_regions* rg, const vamp_mcmc_args* a) {
     if (!rg || !a) return fail(-1, "null argument");
     if (a->n_chains < 0 || a->cmax < 1 || a->max_ncomp < 1 || a->max_ncomp > a->cmax)
         return fail(-2, "bad sizes: n_chains=%d cmax=%d max_ncomp=%d", a->n_chains, a->cmax, a->max_ncomp);
-    if (rg->max_npix > VAMP_TILE_PIX)
-        return fail(-3, "MCMC/MAP kernels support regions of <= %d pixels (got %d); split the region", VAMP_TILE_PIX,
-                    rg->max_npix);
+    const int npix = launch_npix(rg, a);
+    if (npix > VAMP_K2_LONG_PIX)
+        return fail(-3, "the sampler takes regions of <= %d pixels (got %d); split the region", VAMP_K2_LONG_PIX, npix);
+    if (npix > VAMP_TILE_PIX && (rg->dev.mult || a->step_kind == VAMP_STEP_ADAPTIVE))
+        return fail(-3, "regions of more than %d pixels (got %d) are sampled by the single-line scalar Metropolis kernels only "
+                    "(no multiplet table, no adaptive step method)", VAMP_TILE_PIX, npix);
     if (!a->item_region || !a->item_ncomp || !a->chain_uid || !a->theta || !a->asf || !a->psd || !a->acc || !a->rej ||
         !a->acc_total || !a->logp || !a->lnL || !a->best_theta || !a->best_logp || !a->mean || !a->m2 || !a->comom ||
         !a->ntally || !a->sum_lnL || !a->sum_lnL2)
@@ -603,19 +611,24 @@ int vamp_mcmc_run_dev(vamp_ctx* ctx, const vamp_regions* rg, int dtype, int kind
     if (a->it1 < a->it0 || a->it0 < 0) return fail(-2, "bad iteration range [%d, %d)", a->it0, a->it1);
     VAMP_CUDA(cudaSetDevice(ctx->device));
     const McmcDev p = to_dev(rg, a);
-    if (a->step_kind == VAMP_STEP_ADAPTIVE) VAMP_CUDA(VAMP_DISPATCH4(vamp_launch_k2a, dtype, kind, p, rg->max_npix, a->max_ncomp, ctx->stream));
-    else if (a->pair_tail && !rg->dev.mult) VAMP_CUDA(VAMP_DISPATCH4(vamp_launch_k2t, dtype, kind, p, rg->max_npix, a->max_ncomp, ctx->stream));
-    else if (rg->dev.mult) VAMP_CUDA(VAMP_DISPATCH4(vamp_launch_k2m, dtype, kind, p, rg->max_npix, a->max_ncomp, ctx->stream));
-    else VAMP_CUDA(VAMP_DISPATCH4(vamp_launch_k2, dtype, kind, p, rg->max_npix, a->max_ncomp, ctx->stream));
+    const int npix = launch_npix(rg, a);
+    if (npix > VAMP_TILE_PIX) {
+        const cudaError_t e = VAMP_DISPATCH4(vamp_launch_k2l, dtype, kind, p, npix, a->max_ncomp, ctx->stream);
+        if (e == cudaErrorInvalidConfiguration)
+            return fail(-3, "a %d-pixel region with up to %d components does not fit the sampler's shared memory "
+                        "((components + 4) x pixels x %d bytes <= 227 KB): split the region or lower the component count",
+                        npix, a->max_ncomp, dtype == VAMP_F64 ? 16 : 8);
+        VAMP_CUDA(e);
+    } else if (a->step_kind == VAMP_STEP_ADAPTIVE) VAMP_CUDA(VAMP_DISPATCH4(vamp_launch_k2a, dtype, kind, p, npix, a->max_ncomp, ctx->stream));
+    else if (a->pair_tail && !rg->dev.mult) VAMP_CUDA(VAMP_DISPATCH4(vamp_launch_k2t, dtype, kind, p, npix, a->max_ncomp, ctx->stream));
+    else if (rg->dev.mult) VAMP_CUDA(VAMP_DISPATCH4(vamp_launch_k2m, dtype, kind, p, npix, a->max_ncomp, ctx->stream));
+    else VAMP_CUDA(VAMP_DISPATCH4(vamp_launch_k2, dtype, kind, p, npix, a->max_ncomp, ctx->stream));
     return 0;
 }
 
 int vamp_map_dev(vamp_ctx* ctx, const vamp_regions* rg, int dtype, int kind, const vamp_map_args* a) {
     if (!ctx || !rg || !a) return fail(-1, "null argument");
     if (a->n_starts < 0 || a->cmax < 1 || a->max_ncomp < 1 || a->max_ncomp > a->cmax) return fail(-2, "bad sizes");
-    if (rg->max_npix > VAMP_TILE_PIX)
-        return fail(-3, "MCMC/MAP kernels support regions of <= %d pixels (got %d); split the region", VAMP_TILE_PIX,
-                    rg->max_npix);
     if (!a->item_region || !a->item_ncomp || !a->theta || !a->out_logp || !a->out_lnL || !a->out_chi2 || !a->out_bic ||
         !a->out_iters || !a->out_nfev)
         return fail(-1, "null pointer in vamp_map_args");
@@ -639,12 +652,14 @@ int vamp_map_dev(vamp_ctx* ctx, const vamp_regions* rg, int dtype, int kind, con
     p.out_bic = a->out_bic;
     p.out_iters = a->out_iters;
     p.out_nfev = a->out_nfev;
-    if (dtype == VAMP_MIXED && rg->dev.lsf_taps <= 1) {
+    // (the warp-per-start schedule keeps a region in registers: one coordinate tile; longer regions and LSF region
+    //  sets take the CTA schedule, which streams the pixels tile by tile)
+    if (dtype == VAMP_MIXED && rg->dev.lsf_taps <= 1 && rg->max_npix <= VAMP_TILE_PIX) {
         VAMP_CUDA(kind == VAMP_VOIGT ? vamp_launch_k3w_mixed_voigt(p, rg->max_npix, a->max_ncomp, ctx->stream)
                                      : vamp_launch_k3w_mixed_gauss(p, rg->max_npix, a->max_ncomp, ctx->stream));
         return 0;
     }
-    // (VAMP_MIXED on an LSF region set: the CTA schedule in float64)
+    // (VAMP_MIXED on an LSF or long-region set: the CTA schedule in float64)
     VAMP_CUDA(VAMP_DISPATCH4(vamp_launch_k3, dtype == VAMP_MIXED ? VAMP_F64 : dtype, kind, p, rg->max_npix, a->max_ncomp, ctx->stream));
     return 0;
 }

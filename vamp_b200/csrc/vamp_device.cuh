@@ -20,6 +20,7 @@
 
 #define VAMP_FULL_MASK 0xffffffffu
 #define VAMP_TILE_PIX 256      // pixels per coordinate tile (= 32 lanes x 8 pixels)
+#define VAMP_K2_LONG_PIX 2048  // longest region of the sampler / MAP kernels (long-region objects: 8 tiles in shared memory)
 #define VAMP_MAX_PPL 8
 #define VAMP_MAX_LSF_TAPS 65
 

@@ -157,14 +157,14 @@ struct alignas(16) SdRec {
     int acc;
 };
 
-template <typename T, bool WT>
+template <typename T, bool WT, int NT = 1>        // NT: coordinate tiles (256 pixels) a pixel buffer holds - 1 except in the long-region objects
 struct K2Lay {
-    static constexpr int NE = VAMP_TILE_PIX / 2;
+    static constexpr int NE = NT * VAMP_TILE_PIX / 2;
     static constexpr int SLOT = NE * (int)sizeof(P2<T>);
     static constexpr int DU = 0, F = SLOT, W = 2 * SLOT, REGION = (WT ? 3 : 2) * SLOT;
     static constexpr int BASE = 0, H = SLOT;
     static __host__ __device__ size_t lsf_bytes(bool lsf) {
-        return lsf ? align16(sizeof(T) * (VAMP_TILE_PIX + VAMP_MAX_LSF_TAPS)) : 0;
+        return lsf ? align16(sizeof(T) * (NT * VAMP_TILE_PIX + VAMP_MAX_LSF_TAPS)) : 0;
     }
     static constexpr int SUMSCR = VAMP_K2_SMEMSUM ? 128 : 0;       // 32 floats of reduction scratch, first in the chain slice tail
     static constexpr int RNGSCR = VAMP_K2_SMEMRNG ? 64 * (int)sizeof(P2<T>) : 0;      // the 64 (z, lu) pairs of a Philox block
@@ -176,7 +176,7 @@ struct K2Lay {
 
 template <typename T>
 struct LsfCtx {
-    T* buf;            // warp-private [VAMP_TILE_PIX + taps]
+    T* buf;            // warp-private [NT * VAMP_TILE_PIX + taps]
     const T* taps_s;   // block-shared taps
     int taps, P;
     unsigned sum_scratch;   // shared address of the warp's 32-value reduction scratch (VAMP_K2_SMEMSUM)
@@ -213,9 +213,9 @@ __device__ __forceinline__ double warp_sum_smem(double v, unsigned, int) { retur
 
 // Residual sum of squares from a model row-pair buffer in natural order (LSF path only):
 // buf[h + p] holds m_p - 1; out = 1 + sum_t lsf[t] (m - 1)[p + h - t], zero outside [0, P).
-template <typename T, bool WT>
+template <typename T, bool WT, int NT = 1>
 __device__ __forceinline__ T lsf_residuals(const LsfCtx<T>& lc, const unsigned char* rb, int npairs, int lane) {
-    typedef K2Lay<T, WT> Lay;
+    typedef K2Lay<T, WT, NT> Lay;
     const int h = lc.taps >> 1;
     for (int i = lane; i < 2 * h; i += 32) lc.buf[(i < h) ? i : (64 * npairs + i)] = T(0);
     __syncwarp();
@@ -322,11 +322,11 @@ struct FuseArgs { T Ap, Ac; unsigned ahp; };
 // stop paying for 64 pixels of padding (BASELINE config C4: P ~ U{32..256}, 14 % of the sampler's lanes).  A chain whose
 // pair count is odd ALWAYS takes this path (engine.Sampler sets vamp_mcmc_args.pair_tail when its launch holds one),
 // a chain with an even count computes exactly what the quad kernel computes, so results do not depend on the launch.
-template <typename T, int KIND, bool WT, bool LSF, bool FRESH, bool MULT = false, bool FUSE = false, bool TAIL = false>
+template <typename T, int KIND, bool WT, bool LSF, bool FRESH, bool MULT = false, bool FUSE = false, bool TAIL = false, int NT = 1>
 __device__ __forceinline__ T chain_pass(const CompC<T>& cc, T An, unsigned ahc, unsigned ahs, unsigned ar, unsigned aw,
                                         const unsigned char* rb, int npairs, int lane, const LsfCtx<T>& lc, unsigned& nfar,
                                         unsigned& last_far, const Mult2<T>* ml = nullptr, const FuseArgs<T>* fz = nullptr) {
-    typedef K2Lay<T, WT> Lay;
+    typedef K2Lay<T, WT, NT> Lay;
     constexpr int SZ = (int)sizeof(P2<T>);
     constexpr int ROW = 32 * SZ;                       // bytes between the two pairs of a quad
     const P2<T> A2 = p2_bc<T>(An);
@@ -469,7 +469,7 @@ __device__ __forceinline__ T chain_pass(const CompC<T>& cc, T An, unsigned ahc, 
     S2 = p2_add(S2, S2b);
     last_far = (far ? 1u : 0u) + ((MULT && farb) ? 1u : 0u);
     T S = p2_lo(S2) + p2_hi(S2);
-    if (LSF) S = lsf_residuals<T, WT>(lc, rb, npairs, lane);
+    if (LSF) S = lsf_residuals<T, WT, NT>(lc, rb, npairs, lane);
 #if VAMP_K2_SMEMSUM
     return warp_sum_smem(S, lc.sum_scratch, lane);
 #else
@@ -488,10 +488,10 @@ __device__ __forceinline__ T chain_pass(const CompC<T>& cc, T An, unsigned ahc, 
 // vector load at the start, one read-modify-write at the end of the component), rejections are
 // derived (every parameter is proposed exactly once per iteration) and the post-burn acceptance
 // total is settled at tune / burn / exit events.
-template <typename T, int KIND, bool WT, bool LSF, bool MULT, bool TAIL = false>
+template <typename T, int KIND, bool WT, bool LSF, bool MULT, bool TAIL = false, int NT = 1>
 __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, const unsigned char* rb, unsigned char* wb, int ncomp_max,
                            const T* lsf_s) {
-    typedef K2Lay<T, WT> Lay;
+    typedef K2Lay<T, WT, NT> Lay;
     constexpr int NP = (KIND == VAMP_KIND_VOIGT) ? 4 : 3;
     const RegionSetDev& rs = p.rs;
     const int r = p.item_region[chain];
@@ -606,7 +606,7 @@ __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, const unsigned
     cz.A = cz.cb = cz.g = cz.y = cz.y2 = cz.L2 = T(0);
     unsigned dummy = 0u;
     unsigned dummy_far;
-    T Scur = chain_pass<T, KIND, WT, LSF, false, false, false, TAIL>(cz, T(0), slot_addr(n), 0u, ar0, aw0, rb, npairs, lane, lc, dummy, dummy_far);
+    T Scur = chain_pass<T, KIND, WT, LSF, false, false, false, TAIL, NT>(cz, T(0), slot_addr(n), 0u, ar0, aw0, rb, npairs, lane, lc, dummy, dummy_far);
     T sd = WT ? T(1) : sdrec->th;
     T logsd = WT ? T(0) : StepMath<T>::log_(sd);
     T hiv = WT ? T(0.5) : T(0.5) / (sd * sd);                 // 1 / (2 sd^2)
@@ -803,11 +803,11 @@ __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, const unsigned
                         fz.Ap = Ap_;
                         fz.Ac = -NK * pA;
                         fz.ahp = ap_;
-                        Snew = chain_pass<T, KIND, WT, LSF, false, false, true, TAIL>(cz, NK * prop, slot_addr(hc), 0u, ar0, aw0, rb, npairs,
+                        Snew = chain_pass<T, KIND, WT, LSF, false, false, true, TAIL, NT>(cz, NK * prop, slot_addr(hc), 0u, ar0, aw0, rb, npairs,
                                                                                 lane, lc, dummy, dummy_far, nullptr, &fz);
                     } else
 #endif
-                        Snew = chain_pass<T, KIND, WT, LSF, false, false, false, TAIL>(cz, NK * prop, slot_addr(hc), 0u, ar0, aw0, rb, npairs, lane,
+                        Snew = chain_pass<T, KIND, WT, LSF, false, false, false, TAIL, NT>(cz, NK * prop, slot_addr(hc), 0u, ar0, aw0, rb, npairs, lane,
                                                                    lc, dummy, dummy_far);
                     const T dprior = StepMath<T>::log_(prop * Real<T>::rcp(pA)) - (prop - pA);
 #if !VAMP_K2_NOCOUNT
@@ -857,7 +857,7 @@ __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, const unsigned
                         cc = make_comp_fast<T, KIND>(pA, cbase(qc), q1, q2);
                     unsigned nf = 0u;
                     unsigned last_far;
-                    const T Snew = chain_pass<T, KIND, WT, LSF, true, MULT, false, TAIL>(cc, NK * pA, 0u, slot_addr(hs), ar0, aw0, rb, npairs,
+                    const T Snew = chain_pass<T, KIND, WT, LSF, true, MULT, false, TAIL, NT>(cc, NK * pA, 0u, slot_addr(hs), ar0, aw0, rb, npairs,
                                                                             lane, lc, nf, last_far, &ml);
 #if !VAMP_K2_NOCOUNT
                     n_far += nf;
@@ -1439,14 +1439,18 @@ __device__ void mcmc_chain_am(const McmcDev& p, int chain, int lane, const unsig
 #ifdef VAMP_K2_MAXNREG              // experiments with other CTA sizes: a plain register cap instead of launch bounds
 #define VAMP_K2_BOUNDS __maxnreg__(VAMP_K2_MAXNREG)
 #else
-#define VAMP_K2_BOUNDS __launch_bounds__(K2_WARPS * 32, (sizeof(T) == 4) ? VAMP_K2_MINBLOCKS : 2)
+#define VAMP_K2_BOUNDS __launch_bounds__(KW * 32, (NT > 1) ? 1 : (sizeof(T) == 4) ? VAMP_K2_MINBLOCKS : 2)
 #endif
-template <typename T, int KIND, bool WT, bool LSF, bool MULT, bool AM = false, bool TAIL = false>
+// NT > 1 (long-region objects, -DVAMP_INST_LONG=1): regions of up to NT coordinate tiles.  Every pixel buffer is NT
+// tiles long, KW = 1 chain per CTA, and the region slice is staged with ALL its tiles relative to the base of the
+// first one (the sum is formed in float64 and rounded once: in float32 a coordinate 2048 pixels from the base keeps
+// 1.2e-4 pixel, far below any proposal scale), so the chain itself is the single-tile code.
+template <typename T, int KIND, bool WT, bool LSF, bool MULT, bool AM = false, bool TAIL = false, int NT = 1, int KW = K2_WARPS>
 __global__ void VAMP_K2_BOUNDS
 k2_mcmc_kernel(McmcDev p, int ncomp_max) {
-    typedef K2Lay<T, WT> Lay;
+    typedef K2Lay<T, WT, NT> Lay;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ int s_region[K2_WARPS];
+    __shared__ int s_region[KW];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     T* lsf_s = reinterpret_cast<T*>(smem_raw);
     const size_t head = LSF ? align16(sizeof(T) * VAMP_MAX_LSF_TAPS) : 0;
@@ -1455,18 +1459,19 @@ k2_mcmc_kernel(McmcDev p, int ncomp_max) {
     }
     // launch order: the host sorts chains by ascending cost; the longest chains go first so the
     // tail of the grid is made of short ones
-    const int chain = p.B - 1 - (blockIdx.x * K2_WARPS + warp);
+    const int chain = p.B - 1 - (blockIdx.x * KW + warp);
     const int my_region = (chain >= 0) ? p.item_region[chain] : -1;
     if (lane == 0) s_region[warp] = my_region;
     __syncthreads();
     unsigned char* rb = smem_raw + head;
     unsigned char* wb = rb + Lay::REGION + (size_t)warp * (Lay::bytes(ncomp_max, LSF) + (AM ? align16((size_t)ncomp_max * 10 * sizeof(T)) : 0));
-    for (int round = 0; round < K2_WARPS; ++round) {
+    for (int round = 0; round < KW; ++round) {
         const int rr = s_region[round];
         bool skip = rr < 0;
         for (int j = 0; j < round; ++j) skip = skip || (s_region[j] == rr);
         if (skip) continue;                              // CTA-uniform
         if (round > 0) __syncthreads();                  // the previous region's chains are done
+        if (p.rs.npix[rr] > NT * VAMP_TILE_PIX) __trap();  // a caller's vamp_mcmc_args.max_npix below its longest region: fail loudly
         {
             const RegionSetDev& rs = p.rs;
             const int off = rs.pix_off[rr] >> 1, ne = 32 * ((rs.npix[rr] + 63) >> 6);
@@ -1477,6 +1482,11 @@ k2_mcmc_kernel(McmcDev p, int ncomp_max) {
             for (int e = threadIdx.x; e < nq; e += blockDim.x) {
                 const bool in = e < ne;
                 sd_[e] = in ? p2_from(__ldg(RS<T>::pdu(rs) + off + e)) : p2_bc<T>(T(1.0e12));
+                if (NT > 1 && in) {
+                    // element e = 32 jj + lane holds pixels 64 jj + lane (+ 32): tile jj >> 2; its coordinates move to tile 0's base
+                    const double sh = rs.ubase[rs.tile_off[rr] + (e >> 7)] - rs.ubase[rs.tile_off[rr]];
+                    sd_[e] = p2_make(T((double)p2_lo(sd_[e]) + sh), T((double)p2_hi(sd_[e]) + sh));
+                }
                 sf_[e] = in ? p2_from(__ldg(RS<T>::pf(rs) + off + e)) : p2_bc<T>(T(1));
                 if (WT) sw_[e] = in ? p2_from(__ldg(RS<T>::pw(rs) + off + e)) : p2_bc<T>(T(0));
             }
@@ -1484,7 +1494,7 @@ k2_mcmc_kernel(McmcDev p, int ncomp_max) {
         __syncthreads();
         if (my_region == rr) {
             if (AM) mcmc_chain_am<T, KIND, WT, LSF>(p, chain, lane, rb, wb, ncomp_max, lsf_s);
-            else mcmc_chain<T, KIND, WT, LSF, MULT, TAIL>(p, chain, lane, rb, wb, ncomp_max, lsf_s);
+            else mcmc_chain<T, KIND, WT, LSF, MULT, TAIL, NT>(p, chain, lane, rb, wb, ncomp_max, lsf_s);
         }
     }
 }
@@ -1562,24 +1572,27 @@ __global__ void init_state_kernel(McmcDev p) {
 #ifndef VAMP_INST_TAIL
 #define VAMP_INST_TAIL 0          // 1: this object holds the pair-tail instantiations (vamp_launch_k2t_*)
 #endif
+#ifndef VAMP_INST_LONG
+#define VAMP_INST_LONG 0          // 1: this object holds the long-region instantiations (vamp_launch_k2l_*): 257 .. 2048 pixels
+#endif
 
-template <typename T, int KIND, bool WT, bool LSF>
+template <typename T, int KIND, bool WT, bool LSF, int NT = 1, int KW = K2_WARPS>
 cudaError_t launch_k2_t(const McmcDev& p, int max_ncomp, cudaStream_t st) {
     constexpr bool AM = VAMP_INST_AM != 0;
-    const size_t smem = (LSF ? align16(sizeof(T) * VAMP_MAX_LSF_TAPS) : 0) + K2Lay<T, WT>::REGION +
-                        K2_WARPS * (K2Lay<T, WT>::bytes(max_ncomp, LSF) + (AM ? align16((size_t)max_ncomp * 10 * sizeof(T)) : 0));
-    auto kern = k2_mcmc_kernel<T, KIND, WT, LSF, VAMP_INST_MULT != 0, AM, VAMP_INST_TAIL != 0>;
+    const size_t smem = (LSF ? align16(sizeof(T) * VAMP_MAX_LSF_TAPS) : 0) + K2Lay<T, WT, NT>::REGION +
+                        KW * (K2Lay<T, WT, NT>::bytes(max_ncomp, LSF) + (AM ? align16((size_t)max_ncomp * 10 * sizeof(T)) : 0));
+    auto kern = k2_mcmc_kernel<T, KIND, WT, LSF, VAMP_INST_MULT != 0, AM, VAMP_INST_TAIL != 0, NT, KW>;
     if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    const int grid = (p.B + K2_WARPS - 1) / K2_WARPS;
-    kern<<<grid, K2_WARPS * 32, smem, st>>>(p, max_ncomp);
+    const int grid = (p.B + KW - 1) / KW;
+    kern<<<grid, KW * 32, smem, st>>>(p, max_ncomp);
     return cudaGetLastError();
 }
 
 }  // namespace
 
-#if VAMP_INST_F64 == 0 && VAMP_INST_MULT == 0 && VAMP_INST_AM == 0 && VAMP_INST_TAIL == 0
+#if VAMP_INST_F64 == 0 && VAMP_INST_MULT == 0 && VAMP_INST_AM == 0 && VAMP_INST_TAIL == 0 && VAMP_INST_LONG == 0
 // precision-independent helpers live in the f32 objects only
 cudaError_t VAMP_CAT3(vamp_launch_init_prior, any, VAMP_KN)(const McmcDev& p, cudaStream_t st) {
     if (p.B <= 0) return cudaSuccess;
@@ -1597,6 +1610,28 @@ cudaError_t vamp_launch_init_state(const McmcDev& p, cudaStream_t st) {
 
 // -DVAMP_INST_MULT=1 objects hold the multiplet instantiations (vamp_launch_k2m_*), chosen by the C ABI when the
 // region set carries a multiplet table
+#if VAMP_INST_LONG
+// Regions of 257 .. 2048 pixels (the reference fits whole arrays of any length, e.g. 2000 pixels in vpfits_intro.ipynb):
+// single lines, scalar Metropolis.  Two buffer lengths, <= 512 and <= 2048 pixels; shared memory is
+// (max_ncomp + 4) x NT KB per chain (float32), so the launch fails with cudaErrorInvalidConfiguration beyond
+// max_ncomp = 52 (1024 pixels, float32) / 24 (2048 pixels) - vamp_mcmc_run reports it.
+template <int NT>
+static cudaError_t launch_k2_long(const McmcDev& p, int max_ncomp, cudaStream_t st) {
+    const bool lsf = p.rs.lsf_taps > 1;
+    if (p.sd_free)
+        return lsf ? launch_k2_t<InstT, InstKind, false, true, NT, 1>(p, max_ncomp, st)
+                   : launch_k2_t<InstT, InstKind, false, false, NT, 1>(p, max_ncomp, st);
+    return lsf ? launch_k2_t<InstT, InstKind, true, true, NT, 1>(p, max_ncomp, st)
+               : launch_k2_t<InstT, InstKind, true, false, NT, 1>(p, max_ncomp, st);
+}
+cudaError_t VAMP_INST_NAME(vamp_launch_k2l)(const McmcDev& p, int max_npix, int max_ncomp, cudaStream_t st) {
+    if (p.B <= 0 || p.it1 <= p.it0) return cudaSuccess;
+    if (max_npix > VAMP_K2_LONG_PIX || p.rs.mult) return cudaErrorInvalidValue;
+    if (max_npix <= 2 * VAMP_TILE_PIX) return launch_k2_long<2>(p, max_ncomp, st);
+    if (max_npix <= 4 * VAMP_TILE_PIX) return launch_k2_long<4>(p, max_ncomp, st);
+    return launch_k2_long<VAMP_K2_LONG_PIX / VAMP_TILE_PIX>(p, max_ncomp, st);
+}
+#else
 #if VAMP_INST_AM
 cudaError_t VAMP_INST_NAME(vamp_launch_k2a)(const McmcDev& p, int max_npix, int max_ncomp, cudaStream_t st) {
     if (!p.am) return cudaErrorInvalidValue;
@@ -1616,3 +1651,4 @@ cudaError_t VAMP_INST_NAME(vamp_launch_k2)(const McmcDev& p, int max_npix, int m
     return lsf ? launch_k2_t<InstT, InstKind, true, true>(p, max_ncomp, st)
                : launch_k2_t<InstT, InstKind, true, false>(p, max_ncomp, st);
 }
+#endif   // VAMP_INST_LONG

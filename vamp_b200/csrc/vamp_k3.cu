@@ -24,11 +24,11 @@ constexpr double FWHM_PER_SIGMA = 2.35482004503094938202;
 __host__ __device__ inline size_t k3_align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
 template <typename T>
-__host__ __device__ inline size_t k3_smem_bytes(int kmax, int ts, bool lsf, int ncmax) {
+__host__ __device__ inline size_t k3_smem_bytes(int kmax, int ts, bool lsf, int ncmax, int max_npix = VAMP_TILE_PIX) {
     size_t b = 0;
     b += k3_align16(sizeof(double) * ((size_t)(kmax + 1) * ts + (kmax + 1) + 4 * ts + 4 * K3_WARPS));
     b += k3_align16(sizeof(CompC<T>) * K3_WARPS * (size_t)ncmax);
-    if (lsf) b += k3_align16(sizeof(T) * (VAMP_TILE_PIX + 2 * VAMP_MAX_LSF_TAPS));
+    if (lsf) b += k3_align16(sizeof(T) * (((size_t)max_npix + 63) / 64 * 64 + 2 * VAMP_MAX_LSF_TAPS));
     return b;
 }
 
@@ -40,6 +40,7 @@ struct Objective {
     int nl;                // lines per evaluation: n, or 2 n in a multiplet region
     const double* mrow;    // the region's row of the multiplet table, or nullptr
     double ubase, lognorm, c_hi, w_hi;
+    const double* tub;     // bases of the region's coordinate tiles (tub[0] = ubase): rows of tile t are moved to tile 0's base
     const T* gdu;
     const T* gf;
     const T* gw;
@@ -89,7 +90,8 @@ struct Objective {
         unsigned dummy = 0u;
         for (int row = warp; row < nrows; row += K3_WARPS) {
             const int px = row * 32 + lane;
-            const T du = __ldg(gdu + px);                 // rows are padded with neutral pixels
+            T du = __ldg(gdu + px);                       // rows are padded with neutral pixels
+            if (nrows > VAMP_TILE_PIX / 32) du = T((double)du + (tub[row / (VAMP_TILE_PIX / 32)] - ubase));   // regions of several tiles
             T tau = T(0);
             // two components at a time as the halves of a two-wide value (two independent dependency chains: this
             // kernel is bound by the latency of one evaluation); one path per component pair and row
@@ -167,6 +169,7 @@ __device__ void nm_run(const MapDev& p, int s, double* sm, CompC<T>* ccw, int nc
     f.warp = tid >> 5;
     f.nrows = 2 * ((f.P + 63) >> 6);
     f.ubase = rs.ubase[rs.tile_off[r]];
+    f.tub = rs.ubase + rs.tile_off[r];
     f.lognorm = rs.lognorm[r];
     f.c_hi = (double)(f.P - 1);
     f.w_hi = 0.5 * (double)(f.P - 1) * (KIND == VAMP_KIND_VOIGT ? FWHM_PER_SIGMA : 1.0);
@@ -638,12 +641,12 @@ k3w_map_kernel(MapDev p, int kmax, int ncomp_max) {
 cudaError_t VAMP_INST_NAME(vamp_launch_k3)(const MapDev& p, int max_npix, int max_ncomp, cudaStream_t st) {
     typedef InstT T;
     if (p.S <= 0) return cudaSuccess;
-    if (max_npix > VAMP_TILE_PIX) return cudaErrorInvalidValue;
+    // (this schedule reads the pixels from global memory row by row: regions of any length, tile by tile)
     const bool LSF = p.rs.lsf_taps > 1;
     const int NP = (InstKind == VAMP_KIND_VOIGT) ? 4 : 3;
     const int kmax = NP * max_ncomp + 1;
     const int nl_max = max_ncomp * (p.rs.mult ? 2 : 1);                 // multiplet regions: two lines per component
-    const size_t smem = k3_align16(sizeof(T) * VAMP_MAX_LSF_TAPS) + k3_smem_bytes<T>(kmax, p.tstride, LSF, nl_max);
+    const size_t smem = k3_align16(sizeof(T) * VAMP_MAX_LSF_TAPS) + k3_smem_bytes<T>(kmax, p.tstride, LSF, nl_max, max_npix);
     if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
     auto kern = k3_map_kernel<T, InstKind>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

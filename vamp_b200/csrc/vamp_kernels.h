@@ -69,6 +69,8 @@ VAMP_DECL4(cudaError_t, vamp_launch_k2t, const McmcDev& p, int max_npix, int max
 VAMP_DECL4(cudaError_t, vamp_launch_k2a, const McmcDev& p, int max_npix, int max_ncomp, cudaStream_t st)
 // multiplet instantiations (region sets with a multiplet table: two tied lines per component)
 VAMP_DECL4(cudaError_t, vamp_launch_k2m, const McmcDev& p, int max_npix, int max_ncomp, cudaStream_t st)
+// long-region instantiations (257 .. VAMP_K2_LONG_PIX pixels: one chain per CTA, all tiles of the region in shared memory)
+VAMP_DECL4(cudaError_t, vamp_launch_k2l, const McmcDev& p, int max_npix, int max_ncomp, cudaStream_t st)
 
 // ---- K3 (vamp_k3.cu)
 struct MapDev {

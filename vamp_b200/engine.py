@@ -16,7 +16,15 @@ from . import _lib
 from ._lib import VAMP_F32, VAMP_F64, VAMP_MIXED, VAMP_GAUSS, VAMP_VOIGT, McmcArgs, MapArgs, check
 
 FWHM_PER_SIGMA = 2.0 * np.sqrt(2.0 * np.log(2.0))
-MAX_SAMPLER_PIXELS = 256      # VAMP_TILE_PIX of the sampler / MAP kernels (include/vamp_b200.h)
+TILE_PIXELS = 256             # one coordinate tile: the regions the one-tile sampler / warp-per-start MAP kernels take
+MAX_SAMPLER_PIXELS = 2048     # VAMP_MAX_FIT_PIXELS (include/vamp_b200.h): longest region of the long-region sampler kernels
+LONG_CLASS_EDGES = (256, 512, 1024)     # pixel classes of the sampler launches: <= 256 (one tile), <= 512, <= 1024, <= 2048
+
+
+def long_class(npix):
+    """Pixel class of regions of ``npix`` pixels (0: one coordinate tile; 1..3: the long-region kernels' buffer
+    lengths).  Chains of different classes go out as separate launches (``batch.fit_models``)."""
+    return np.searchsorted(np.asarray(LONG_CLASS_EDGES), np.asarray(npix), side="left")
 _DTYPES = {"f32": VAMP_F32, "f64": VAMP_F64, "float32": VAMP_F32, "float64": VAMP_F64, VAMP_F32: VAMP_F32,
            VAMP_F64: VAMP_F64}
 
@@ -300,13 +308,14 @@ class Sampler:
         self.item_ncomp_h = np.asarray(item_ncomp, dtype=np.int32)
         self.max_ncomp = int(self.item_ncomp_h.max())
         longest = int(regions.npix[self.item_region_h].max()) if self.B else 0
-        if longest > MAX_SAMPLER_PIXELS:
+        if longest > MAX_SAMPLER_PIXELS or (longest > TILE_PIXELS and (regions.multiplet is not None or step_method == "adaptive")):
             # the C ABI answers -3 at launch; say it here, before any state is allocated, with the way out
             raise _lib.VampError(
-                "the MCMC / MAP kernels hold one region per %d-pixel coordinate tile; a region of %d pixels was given. "
-                "Fit it as several regions (VPspectrum.split_long_regions cuts where the flux is closest to the "
-                "continuum and flags cuts through absorption), or evaluate likelihoods of long arrays with "
-                "engine.loglike (K1 takes any length)" % (MAX_SAMPLER_PIXELS, longest))
+                "the sampler holds a whole region in shared memory: up to %d pixels (%d for multiplet regions and the "
+                "adaptive step method); a region of %d pixels was given.  Fit it as several regions "
+                "(VPspectrum.split_long_regions cuts where the flux is closest to the continuum and flags cuts "
+                "through absorption), or evaluate likelihoods of long arrays with engine.loglike (K1 takes any length)"
+                % (MAX_SAMPLER_PIXELS, TILE_PIXELS, longest))
         self.cmax = int(cmax or self.max_ncomp)
         self.ts = 4 * self.cmax + 1
         self.np_per = 4 if self.voigt else 3
@@ -372,6 +381,8 @@ class Sampler:
         # a chain whose region has an odd number of 64-pixel row pairs always runs the pair-tail kernel
         pairs = (self.regions.npix[self.item_region_h[a0:b0]] + 63) // 64
         a.pair_tail = int(self.regions.multiplet is None and bool(np.any(pairs & 1)))
+        # the launch's longest region decides between the one-tile kernels and the long-region ones
+        a.max_npix = int(self.regions.npix[self.item_region_h[a0:b0]].max()) if b0 > a0 else 0
         am = self.t["am_state"]
         a.am_state = (am.data_ptr() + a0 * am.stride(0) * am.element_size()) if am is not None else None
         return a

@@ -95,14 +95,19 @@ class VPspectrum():
 
     def __init__(self, line, spectrum_file=None, out_folder=None, voigt=False, chi_limit=1.5, mcmc_cov=False,
                  get_mcmc_err=True, convergence_attempts=10, chi_sq_maximum=10., max_single_region_components=15,
-                 ideal_single_region_components=5, min_region_percentage=2., doublet=None, **fit_kwargs):
+                 ideal_single_region_components=5, min_region_percentage=2., doublet=None, max_region_pixels=256,
+                 **fit_kwargs):
         """vpspectrum.py:23-55.  ``fit_kwargs`` (new): GPU controls forwarded to ``fit_regions``
         (iterations, burn, thin, restarts, chains_per_restart, window, nmax, dtype, seed, lsf ...).
         ``doublet`` (new; BASELINE config C3): a name in ``physics.DOUBLETS`` ("CIV", "MgII") or a pair of
         ``(wavelength, f, Gamma)`` lines, ``line`` being the first: the detection regions of the two lines are
         paired (``pair_doublet_regions``) and every absorber is fitted as a doublet with tied velocity, Doppler
-        width and column density; the reported parameters are those of the first line."""
+        width and column density; the reported parameters are those of the first line.
+        ``max_region_pixels`` (new): detection regions longer than this are split before the fit
+        (``split_long_regions``).  256 (default) keeps every region on the one-tile sampler kernels; up to 2048
+        (single lines) the region is fitted whole, as the reference does, by the long-region kernels."""
         self.line = line
+        self.max_region_pixels = int(max_region_pixels)
         self.doublet = doublet
         self.multiplet = None
         if doublet is not None:
@@ -192,7 +197,8 @@ class VPspectrum():
         self.region_waves = [[self.wavelength_array[s], self.wavelength_array[e]] for s, e in self.region_pixels]
 
     def split_long_regions(self, max_pixels=256, n_sigma=4.0):
-        """New (GPU constraint): the sampler kernels hold one region per 256-pixel coordinate tile.  A longer
+        """New (GPU constraint): the sampler kernels hold a whole region in shared memory - one 256-pixel coordinate
+        tile in the fast kernels, up to 2048 pixels in the long-region ones (``max_region_pixels``).  A longer
         detection region is cut where the flux comes closest to the continuum (the same choice
         ``split_difficult_region`` makes, vpspectrum.py:200-232): recursively at the highest-flux pixel of the
         middle half, so both parts keep at least a quarter of the pixels.  Absorbers separated by continuum are
@@ -279,7 +285,7 @@ class VPspectrum():
             self.compute_detection_regions(min_region_width=2)
             self.split_difficult_region()
         self.pair_doublet_regions()
-        self.split_long_regions()
+        self.split_long_regions(self.max_region_pixels if self.multiplet is None else min(self.max_region_pixels, 256))
         R = len(self.region_pixels)
         self.params = {'b': np.array([]), 'b_std': np.array([]), 'N': np.array([]), 'N_std': np.array([]),
                        'EW': np.array([]), 'centers': np.array([]), 'region_numbers': np.array([])}
