@@ -594,10 +594,10 @@ def run_gpu(args):
         ladder = {"unavailable": str(exc)}
 
     if world == 1:
-        cpu_v, cpu_e, cpu_w = reference_sample(1, 1500, seed=7, n_fixed=3)
+        cpu_v, cpu_e, cpu_w = reference_sample(1, 6000, seed=7, n_fixed=3)
         cpu_baseline = {"value": cpu_v, "unit": UNIT, "cores": 1, "kind": "port",
                         "sample": "restated PyMC2 scalar Metropolis over the reference density (numpy + scipy wofz), C2 region, "
-                                  "one chain of the n=3 candidate, 1500 iterations on one core (%.1f s); the restated sampler "
+                                  "one chain of the n=3 candidate, 6000 iterations on one core (%.1f s); the restated sampler "
                                   "recomputes all n components per scalar step and is credited with them" % cpu_w}
     else:
         cpu_baseline = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "timed at N = 1 only"}
