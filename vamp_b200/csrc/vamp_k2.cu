@@ -774,7 +774,7 @@ __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, const unsigned
                     --rebuild;
                 }
                 bool fused = false;
-#if VAMP_K2_FUSEBASE
+#if VAMP_K2_FUSEBASE && !defined(VAMP_K2_EXPERIMENT_NOAMP_MOVE)
                 fused = (mode == 2) && (prop > T(0));
 #endif
                 if (mode == 1) {
@@ -795,7 +795,11 @@ __device__ void mcmc_chain(const McmcDev& p, int chain, int lane, const unsigned
                                                                p2_fma(Ap, SM<T>::template ld<0>(ap), SM<T>::template ld<Lay::BASE>(a))));
                 }
                 // ---- amplitude: cached shape
+#ifdef VAMP_K2_EXPERIMENT_NOAMP       // (timing experiment only: what the amplitude step's pass costs)
+                if (false) {
+#else
                 if (prop > T(0)) {
+#endif
                     T Snew;
 #if VAMP_K2_FUSEBASE
                     if (fused) {
