@@ -157,3 +157,46 @@ def test_limits_fail_loudly(ctx):
     with pytest.raises(_lib.VampError, match="adaptive"):
         engine.Sampler(regs, np.zeros(2, np.int32), np.ones(2, np.int32), np.arange(2, dtype=np.uint64), voigt=True,
                        step_method="adaptive")
+
+
+def test_vpspectrum_fits_a_blended_complex_whole(ctx):
+    """A 360-pixel blended complex (no continuum inside).  The default (``max_region_pixels=256``) has to cut it through
+    absorption and says so; ``max_region_pixels=2048`` fits the detection region whole on the long-region kernels, as
+    the reference does, and recovers every line."""
+    import warnings
+    from vamp_b200 import physics, vpspectrum as VS
+    P, snr = 900, 60.0
+    rng = np.random.default_rng(3)
+    wave = 1215.0 + 0.0203 * np.arange(P)
+    nu = physics.Wave2freq(wave)
+    tau, truth = np.zeros(P), []
+    for c in 300 + 45 * np.arange(7):
+        amp, sig_px = rng.uniform(1.0, 2.0), rng.uniform(10.0, 13.0)
+        sig = abs(nu[c] - nu[c + 1]) * sig_px
+        tau += amp * np.exp(-0.5 * ((nu - nu[c]) / sig) ** 2)
+        truth.append((amp, nu[c], sig))
+    truth = np.array(truth)
+    noise = np.full(P, 1.0 / snr)
+    flux = np.exp(-tau) + rng.normal(0, 1.0 / snr, P)
+    kw = dict(voigt=False, chi_limit=1.5, convergence_attempts=2, iterations=3000, burn=300, thin=15, restarts=3,
+              chains_per_restart=16, window=2, nmax=4, seed=6)
+    sp = VS.VPspectrum(1215.0, **kw).set_spectrum(wave, flux, noise)
+    sp.compute_detection_regions(min_region_width=2)
+    assert len(sp.region_pixels) == 1 and sp.region_pixels[0][1] - sp.region_pixels[0][0] > 256
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        sp.split_long_regions()
+    assert len(sp.region_pixels) >= 2 and len(sp.cuts_through_absorption) >= 1 and len(w) >= 1
+
+    sp = VS.VPspectrum(1215.0, max_region_pixels=2048, **kw).set_spectrum(wave, flux, noise)
+    params = sp.fit_spectrum()
+    assert len(sp.region_pixels) == 1 and "cuts_through_absorption" not in sp.flux_model
+    assert sp.flux_model["chi_squared"][0] < 1.5
+    assert np.max(np.abs(sp.flux_model["total"] - np.exp(-tau))) < 0.08
+    cen_true = physics.Freq2wave(truth[:, 1])
+    N_true = physics.ColumnDensity(truth[:, 0], truth[:, 2])
+    assert len(params["centers"]) >= 7
+    for Nt, ct in zip(N_true, cen_true):
+        k = int(np.argmin(np.abs(params["centers"] - ct)))
+        assert abs(params["centers"][k] - ct) < 1.0 * 0.0203
+        assert params["N"][k] == pytest.approx(Nt, rel=0.2)
