@@ -203,9 +203,9 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def k1_point(ctx, engine, flops, synth, peak_tf, P=256, C=8, B=262144, dtype="f32"):
+def k1_point(ctx, engine, flops, synth, peak_tf, P=256, C=8, B=262144, dtype="f32", prior=False):
     """One likelihood-only launch (K1): B parameter vectors x 8 Voigt components x 256 pixels, posterior-like
-    parameters.  Algorithmic flops from vamp_b200/flops.py with the path mix of the kernel's own pair policy (all 64
+    parameters (``prior``: prior draws instead - SURVEY 8d asks for both, the w(z) branch mix differs).  Algorithmic flops from vamp_b200/flops.py with the path mix of the kernel's own pair policy (all 64
     pixels of a row pair at |z|^2 >= R2 -> continued fraction) evaluated on the host.  ``dtype`` "f64": the float64
     Faddeeva (Weideman N = 32), against the FP64 peak."""
     import torch
@@ -216,7 +216,10 @@ def k1_point(ctx, engine, flops, synth, peak_tf, P=256, C=8, B=262144, dtype="f3
     regs = engine.Regions(ctx, [(reg["nu"], reg["flux"], reg["noise"])])
     rng = np.random.default_rng(5)
     nb = 4096
-    th = np.stack([synth.prior_draw_theta(reg["nu"], C, True, rng, posterior_like=reg["truth"]) for _ in range(nb)])
+    th = np.stack([synth.prior_draw_theta(reg["nu"], C, True, rng, posterior_like=None if prior else reg["truth"])
+                   for _ in range(nb)])
+    if prior:
+        th[:, :, 2:] = np.maximum(th[:, :, 2:], 1e-3 * (reg["nu"][1] - reg["nu"][0]))      # widths > 0 (the prior's open bound)
     ths = regs.to_scaled(th, np.zeros(nb, np.int32))
     u = (reg["nu"] - regs.nu0[0]) / regs.scale[0]
     du = (u - u[(P - 1) // 2]).reshape(P // 64, 64)                       # row pairs
@@ -252,10 +255,28 @@ def k1_point(ctx, engine, flops, synth, peak_tf, P=256, C=8, B=262144, dtype="f3
     f = flops.F64 if f64 else flops.F32
     fl = evals * (far_frac * f["far"] + (1 - far_frac) * f["core"] + f["shape_common"] + 2) + float(P) * B * (f["like"] + 1)
     regs.close()
-    return {"workload": "K1 %s: %d parameter vectors x %d Voigt components x %d px, posterior-like" % (dtype, B, C, P),
+    return {"workload": "K1 %s: %d parameter vectors x %d Voigt components x %d px, %s" % (
+                dtype, B, C, P, "prior draws" if prior else "posterior-like"),
             "evals_per_sec": evals / t, "kernel_ms": t * 1e3, "far_path_fraction": far_frac,
             "achieved_tflops": fl / t / 1e12, ("frac_of_fp64_peak" if f64 else "frac_of_fp32_peak"): fl / t / 1e12 / peak_tf,
             "hbm_gbs": B * (P * (24 if f64 else 12) / 8 + 32 * C + 16) / t / 1e9}
+
+
+def cpu_likelihood_sample(synth, P=256, C=8, seconds=2.5):
+    """SURVEY 8d, CPU baseline (1): likelihood only - the oracle's reference-line path (numpy + scipy.special.wofz, what
+    vpfits.py:58-76, 334-341 compute through astropy / PyMC) on ONE host core, K1's workload shape, for ~``seconds``."""
+    from oracle import density as D
+    reg = synth.make_region(P, 8, 50.0, 7000 + P + C, voigt=True)
+    rng = np.random.default_rng(5)
+    ths = [synth.prior_draw_theta(reg["nu"], C, True, rng, posterior_like=reg["truth"]) for _ in range(64)]
+    n, t0, acc = 0, time.perf_counter(), 0.0
+    while time.perf_counter() - t0 < seconds:
+        th = ths[n % len(ths)]
+        acc += D.normal_loglike(reg["flux"], D.model_flux(reg["nu"], th, True), sd=0.02)
+        n += 1
+    dt = time.perf_counter() - t0
+    return {"evals_per_sec": n * P * C / dt, "cores": 1, "kind": "port", "vectors": n, "seconds": dt,
+            "what": "oracle density: exp(-sum of wofz Voigt profiles) + Normal lnL, %d components x %d px per vector" % (C, P)}
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
@@ -515,6 +536,10 @@ def run_gpu(args):
     # -------- BASELINE config C5 is "fp32 vs fp64": the same K2 launch (same chain set, 3000 iterations) and a K1
     #          launch in float64 (Weideman N = 32 Faddeeva), against the FP64 peak SMs x 64 x 2 x clock
     k1 = k1_point(ctx, engine, flops, synth, peak_tf)
+    k1p = k1_point(ctx, engine, flops, synth, peak_tf, prior=True)
+    k1["prior_draws"] = {k: k1p[k] for k in ("evals_per_sec", "kernel_ms", "far_path_fraction", "achieved_tflops", "frac_of_fp32_peak")}
+    if world == 1:
+        k1["cpu_port"] = cpu_likelihood_sample(synth)
     k1_64 = k1_point(ctx, engine, flops, synth, peak_tf64, B=65536, dtype="f64")
     precisions = {
         "k2_f64": {"workload": "the roofline's K2 launch in float64: %d chains x %d iterations" % (chains, ITERS),
