@@ -62,3 +62,16 @@ def test_split_long_regions_flags_cuts_through_absorption():
     assert len(sp.cuts_through_absorption) == len(w) >= 1     # region A had to be cut through absorption
     assert all(flux[c] < 1.0 - 4.0 * 0.01 for c in sp.cuts_through_absorption)
     assert 620 not in sp.cuts_through_absorption
+
+
+def test_vpfit_std_deviation_is_the_normal_precision():
+    """vpfits.py:39: ``std_deviation`` holds 1 / sd^2 (sd free) or 1 / noise^2; vpfits_intro.ipynb cell 37 passes it to
+    ``VPfit.Chisquared`` as a number."""
+    from vamp_b200.vpfits import VPfit
+    f = VPfit(noise=np.full(5, 0.1))
+    np.testing.assert_allclose(f.std_deviation.value, 100.0)
+    f = VPfit()
+    assert np.isnan(f.std_deviation.value)            # no fit yet
+    f._sd = 0.05
+    assert f.std_deviation.value == pytest.approx(400.0)
+    assert VPfit.Chisquared(np.ones(3), np.zeros(3), f.std_deviation) == pytest.approx(3.0 / 400.0 ** 2)

@@ -41,6 +41,11 @@ class _Node:
     def value(self):
         return self._getter()
 
+    def __array__(self, dtype=None, copy=None):
+        # numpy arithmetic on a node uses its current value (PyMC 2 variables overload the operators; the intro
+        # notebook passes ``vpfit.std_deviation`` straight into ``VPfit.Chisquared``)
+        return np.asarray(self.value, dtype=dtype)
+
 
 class _MAP:
     """``mc.MAP`` read-backs used by the reference and notebooks: BIC, AIC, lnL, logp."""
@@ -119,6 +124,11 @@ class VPfit():
         self.polish_top = int(polish_top)
         self._ctx = ctx
         self._seed = int(np.random.SeedSequence().entropy & 0xFFFFFFFFFFFFFFFF) if seed is None else int(seed)
+        self._sd = None
+        # vpfits.py:39: the Normal's PRECISION, 1 / sd^2 with sd ~ U(0, 1) free, or 1 / noise^2 (the reference keeps the
+        # name ``std_deviation`` for it); ``.value`` follows the fit's current sd
+        self.std_deviation = _Node("std_deviation", lambda: (1.0 / self.noise ** 2) if self.noise is not None else
+                                   (1.0 / self._sd ** 2 if self._sd else np.nan))
 
     # ------------------------------------------------------------------ static helpers (API surface)
     @staticmethod
