@@ -75,3 +75,20 @@ def test_vpfit_std_deviation_is_the_normal_precision():
     f._sd = 0.05
     assert f.std_deviation.value == pytest.approx(400.0)
     assert VPfit.Chisquared(np.ones(3), np.zeros(3), f.std_deviation) == pytest.approx(3.0 / 400.0 ** 2)
+
+
+def test_ladder_examined_matches_the_replay():
+    """``batch.ladder_examined`` = the last candidate ``ladder_replay`` looks at, whatever lies beyond it in the table."""
+    from vamp_b200 import batch
+    rng = np.random.default_rng(0)
+    for trial in range(300):
+        n0, k = int(rng.integers(1, 5)), int(rng.integers(1, 7))
+        tables = {n0 + j: (rng.normal(-50 - 3 * j * rng.integers(-1, 3), 4.0, 3), rng.uniform(0.8, 3.0, 3)) for j in range(k)}
+        kept, exit_n, decided = batch.ladder_replay(n0, tables, 1.5)
+        last = batch.ladder_examined(n0, tables, 1.5)
+        assert n0 <= last <= n0 + k - 1
+        # cutting the table behind `last` changes nothing; cutting `last` itself leaves the rule undecided (or at n0)
+        cut = {n: v for n, v in tables.items() if n <= last}
+        assert batch.ladder_replay(n0, cut, 1.5) == (kept, exit_n, decided)
+        if decided and last > n0:
+            assert batch.ladder_replay(n0, {n: v for n, v in tables.items() if n < last}, 1.5)[2] is False

@@ -158,4 +158,7 @@ def test_records_do_not_depend_on_world_size_or_batching(ctx):
         np.testing.assert_array_equal(allr, one.records)
     many = fit_regions(host, uids=uids, seed=3, distributed=False, max_batch_regions=5, **kw)
     assert many.checksum() == one.checksum()
+    # candidates fitted ahead of the rule in thin late rounds (never / always): left out of the records
+    for spec in (0, 10 ** 9):
+        assert fit_regions(host, uids=uids, seed=3, distributed=False, spec_below=spec, **kw).checksum() == one.checksum()
     assert fit_regions(host, uids=uids, seed=4, distributed=False, **kw).checksum() != one.checksum()

@@ -289,6 +289,25 @@ def fit_models(regions, models, voigt=False, sd_free=True, iterations=3000, burn
     return mb
 
 
+def ladder_examined(n0, tables, chi_limit=1.5):
+    """The largest candidate count ``ladder_replay`` LOOKS AT on these tables, i.e. what the reference's sequential
+    ladder would have fitted: candidates fitted ahead of the rule (``fit_local``'s speculative window) lie beyond it
+    and are left out of a region's record, so records do not depend on how the candidates were scheduled."""
+    n = int(n0)
+    if n not in tables:
+        return n
+    bic_old = tables[n][0][-1]
+    n += 1
+    while n in tables:
+        bic_array, red = tables[n]
+        cur = float(np.average(bic_array))
+        if not bic_old > cur or np.average(red) < chi_limit:
+            return n
+        bic_old = cur
+        n += 1
+    return n - 1
+
+
 def ladder_replay(n0, tables, chi_limit=1.5, verbose=False, log=print):
     """Replay of ``VPregion.region_fit``'s acceptance rule (vamp_1.0/vpregion.py:54-91) on
     precomputed tables ``tables[n] = (bic_array, red_chi_array)``.

@@ -191,17 +191,26 @@ def unpack_record(rec, nmax, G, cmax):
                         lnL=lnL, theta=arrs[0], mean=arrs[1], std=arrs[2], sd=sd, sd_mean=sd_mean, sd_std=sd_std)
 
 
+# ladder rounds with fewer models than this fit one candidate AHEAD of the rule (see fit_local); 256 models x 24 chains
+# are two waves of sampler CTAs on a B200
+SPEC_BELOW_MODELS = int(__import__("os").environ.get("VAMP_SPEC_BELOW", "256"))
+
+
 def fit_local(regions_host, uids, voigt=False, sd_free=True, iterations=3000, burn=300, thin=15, restarts=3,
               chains_per_restart=32, window=3, max_rounds=None, chi_limit=1.5, dtype="f32", seed=0, lsf=None,
               n0=None, nmax=12, ctx=None, polish_top=None, tune_interval=50, stats=None, cmax_rec=None, polish_dtype="f64",
-              multiplet=None, polish_from="best", step_method="metropolis"):
+              multiplet=None, polish_from="best", step_method="metropolis", spec_below=None):
     """Fit the given regions on this process's GPU.  Returns ``[R, record_len]`` float64.
     ``multiplet``: per-region ``(freq_ratio, amp_ratio[, lorentz_ratio])`` or None (``engine.Regions``);
     ``polish_from``: see ``batch.fit_models``.
     ``window``: candidate counts fitted per ladder round for every region still undecided - an int, or
     ``(first, later)`` (e.g. ``(2, 1)``: the two candidates the first comparison needs, then one more per round: no
     speculative fits at all, as the reference's sequential ladder, at the price of more rounds).  The ladder's
-    decisions do not depend on it (chains are keyed by (region, n)); ``max_rounds`` defaults to what ``nmax`` needs."""
+    decisions do not depend on it (chains are keyed by (region, n)); ``max_rounds`` defaults to what ``nmax`` needs.
+    ``spec_below``: a late round whose models would not fill the GPU anyway (fewer than this many; default
+    ``SPEC_BELOW_MODELS``, 0 = never) fits one candidate more per region than the rule needs next - such a round lasts
+    as long as its longest chain whatever it holds, so the look-ahead is free and halves the number of these rounds.
+    Candidates the rule never looks at are left out of the record (``batch.ladder_examined``)."""
     R = len(regions_host)
     G = int(restarts)
     if R == 0:                                   # nothing to fit (an empty shard): no device work, no context
@@ -236,6 +245,8 @@ def fit_local(regions_host, uids, voigt=False, sd_free=True, iterations=3000, bu
             break
         models, owner = [], []
         wnd = w_first if rnd == 0 else w_later
+        if rnd > 0 and len(active) * wnd < (SPEC_BELOW_MODELS if spec_below is None else int(spec_below)):
+            wnd += 1
         for i in active:
             for n in range(nxt[i], min(nxt[i] + wnd, n0[i] + nmax)):
                 if n <= cap[i] or n == nxt[i]:
@@ -246,6 +257,11 @@ def fit_local(regions_host, uids, voigt=False, sd_free=True, iterations=3000, bu
                               seed=seed, region_uids=uids, tune_interval=tune_interval, polish_dtype=polish_dtype,
                               polish_from=polish_from, step_method=step_method,
                               timing=None if stats is None else stats.setdefault("timing", {}))
+        if stats is not None and stats.get("trace_rounds"):
+            tmr = stats["timing"]
+            stats.setdefault("rounds", []).append((rnd, len(active), len(models), max(n for _, n in models),
+                                                   round(tmr.get("k2_ms", 0.0)), round(tmr.get("polish_ms", 0.0)),
+                                                   round(_time.perf_counter() - stats.setdefault("t0", _time.perf_counter()), 3)))
         if stats is not None:
             stats["voigt_evals"] = stats.get("voigt_evals", 0) + mb.voigt_evals
             stats["voigt_evals_actual"] = stats.get("voigt_evals_actual", 0) + mb.work["shape_pix"]
@@ -274,6 +290,9 @@ def fit_local(regions_host, uids, voigt=False, sd_free=True, iterations=3000, bu
     out = np.empty((R, _record_len(nmax, G, cmax_rec)))
     for i in range(R):
         kept, exit_n, status = outcome[i]
+        if status == 0:                    # decided: drop the candidates fitted ahead of the rule
+            last = batch.ladder_examined(n0[i], tables[i], chi_limit)
+            tables[i] = {n: v for n, v in tables[i].items() if n <= last}
         mb, m = fits[i][kept]
         g = int(np.nanargmin(mb.bic[m])) if np.any(np.isfinite(mb.bic[m])) else 0
         # covariance of (amplitude, Gaussian width) from the co-moments of the winning chain: Gauss (A, sigma) =
