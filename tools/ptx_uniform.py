@@ -9,8 +9,8 @@ no lane-strided loop) becomes ``bra.uni``.  Static SASS 4096 -> 3488 instruction
 
     python tools/ptx_uniform.py            # -> tools/variants/b_uni.so   (time it with tools/k2_variants.py run)
 
-The whitelist holds LINE NUMBERS of the source as it was when the experiment ran (commit 35cd3ce); re-derive it before
-reusing the tool (list the branch locations with ``--list``).
+The whitelist holds LINE NUMBERS; the tool checks the SHA-256 of the two sources it was derived for and refuses any
+other version (``--list`` prints every conditional branch location of the kernels to re-derive it).
 """
 import os
 import re
@@ -20,8 +20,11 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 WHITELIST = {"vamp_k2.cu": {357, 430, 540, 585, 597, 614, 658, 692, 693, 697, 699, 701, 733, 763, 764, 767, 782, 783, 786, 789,
-                            793, 798, 816, 844, 867, 904, 907, 929, 931, 1464, 1467, 1468, 1469, 1485},
+                            793, 801, 820, 848, 871, 908, 911, 933, 935, 1472, 1475, 1476, 1477, 1499},
              "vamp_device.cuh": {684}}
+# the sources the line numbers above belong to: the tool refuses any other (a stale line could mark a divergent branch)
+SOURCE_SHA256 = {"vamp_k2.cu": "de4f80f2ea70295fe18e624d3a05e1c794320af446c7dcd69aaaf289db6cbeac",
+                 "vamp_device.cuh": "b338939e4b04261f69fab737dbc34d1058aa65031379af0a9aac81b743b921c8"}
 
 
 def patch(ptx_in, ptx_out, list_only=False):
@@ -53,7 +56,12 @@ def patch(ptx_in, ptx_out, list_only=False):
 
 
 def main():
+    import hashlib
     from vamp_b200 import build as B
+    for name, want in SOURCE_SHA256.items():
+        got = hashlib.sha256(open(os.path.join(B.CSRC, name), "rb").read()).hexdigest()
+        if got != want and "--list" not in sys.argv:
+            raise SystemExit("%s changed since the whitelist was derived: re-derive WHITELIST (--list) and SOURCE_SHA256" % name)
     B.build()
     nvcc = B._nvcc()
     keep = os.path.join(ROOT, "tools", "variants", "_uni")
