@@ -40,6 +40,9 @@ constexpr int K2_TRIPUNROLL = VAMP_K2_TRIPUNROLL;
 #ifndef VAMP_K2_MINBLOCKS
 #define VAMP_K2_MINBLOCKS 5
 #endif
+#ifndef VAMP_K2_MINBLOCKS64
+#define VAMP_K2_MINBLOCKS64 2     // float64 objects: CTAs per SM the register allocation aims at (190 registers).  3 (158 registers, no
+#endif                            //    spills): 11 % faster on a 600-iteration launch, 2 % SLOWER on the bench's 3000-iteration one (measured)
 #ifndef VAMP_K2_STEPUNROLL
 #define VAMP_K2_STEPUNROLL 1      // 1: the centroid / width steps of a component are unrolled (no selects)
 #endif
@@ -1443,7 +1446,7 @@ __device__ void mcmc_chain_am(const McmcDev& p, int chain, int lane, const unsig
 #ifdef VAMP_K2_MAXNREG              // experiments with other CTA sizes: a plain register cap instead of launch bounds
 #define VAMP_K2_BOUNDS __maxnreg__(VAMP_K2_MAXNREG)
 #else
-#define VAMP_K2_BOUNDS __launch_bounds__(KW * 32, (NT > 1) ? 1 : (sizeof(T) == 4) ? VAMP_K2_MINBLOCKS : 2)
+#define VAMP_K2_BOUNDS __launch_bounds__(KW * 32, (NT > 1) ? 1 : (sizeof(T) == 4) ? VAMP_K2_MINBLOCKS : VAMP_K2_MINBLOCKS64)
 #endif
 // NT > 1 (long-region objects, -DVAMP_INST_LONG=1): regions of up to NT coordinate tiles.  Every pixel buffer is NT
 // tiles long, KW = 1 chain per CTA, and the region slice is staged with ALL its tiles relative to the base of the
