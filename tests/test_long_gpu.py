@@ -200,3 +200,35 @@ def test_vpspectrum_fits_a_blended_complex_whole(ctx):
         k = int(np.argmin(np.abs(params["centers"] - ct)))
         assert abs(params["centers"][k] - ct) < 1.0 * 0.0203
         assert params["N"][k] == pytest.approx(Nt, rel=0.2)
+
+
+def test_long_map_with_lsf_reports_the_oracle_values(ctx):
+    """K3 on a 900-pixel LSF-convolved region: the reported log-posterior, lnL and chi^2 at the returned optimum are the
+    oracle's (LSF staging buffer sized by the region, tiles streamed from global memory), and the polish improves on
+    its start."""
+    lsf = synth.gaussian_lsf(2.0, 7)
+    reg = synth.make_region(900, 2, 50.0, 4321, voigt=True, lsf=lsf)
+    regs = engine.Regions(ctx, [(reg["nu"], reg["flux"], reg["noise"])], lsf=lsf)
+    u = _scaled_grid(regs)
+    n, cmax, S = 2, 2, 3
+    rng = np.random.default_rng(8)
+    truth_s = regs.to_scaled(reg["truth"][None], [0])[0]
+    starts = np.zeros((S, 4 * cmax + 1))
+    for i in range(S):
+        starts[i, : 4 * n] = (truth_s * (1 + rng.uniform(-0.15, 0.15, truth_s.shape))).reshape(-1)
+        starts[i, 4 * cmax] = 0.05
+    s = engine.Sampler(regs, np.zeros(S, np.int32), np.full(S, n, np.int32), np.arange(S, dtype=np.uint64), voigt=True,
+                       sd_free=True, dtype="f64", cmax=cmax)
+    res = s.map_polish(starts, np.zeros(S, np.int32), np.full(S, n, np.int32), maxiter=3000, xtol=1e-4, ftol=1e-3, dtype="f64")
+    th = res["theta"].cpu().numpy()
+    c_lo, c_hi, w_max = D.prior_bounds(u, True)
+    const = n * np.log(c_hi - c_lo) + n * 2 * np.log(w_max)
+    for i in range(S):
+        comps = th[i][: 4 * n].reshape(n, 4)
+        lp = D.log_posterior(comps, u, reg["flux"], True, sd=th[i][4 * cmax], lsf=lsf) + const
+        assert float(res["logp"][i]) == pytest.approx(lp, rel=1e-9, abs=1e-7)
+        model = D.model_flux(u, comps, True, lsf=lsf)
+        assert float(res["lnL"][i]) == pytest.approx(D.normal_loglike(reg["flux"], model, sd=th[i][4 * cmax]), rel=1e-9)
+        assert float(res["chi2"][i]) == pytest.approx(D.chisquared(reg["flux"], model, reg["noise"]), rel=1e-8)
+        lp0 = D.log_posterior(starts[i][: 4 * n].reshape(n, 4), u, reg["flux"], True, sd=0.05, lsf=lsf) + const
+        assert lp > lp0
