@@ -460,6 +460,9 @@ def run_gpu(args):
                 "n_equals_truth": float(np.mean(nfit == truth)), "n_within_1": float(np.mean(np.abs(nfit - truth) <= 1)),
                 "ladder_decided": float(np.mean(res4.status == 0)), "records_sha256": res4.checksum(),
                 "rank0_device_ms": {"k2": round(tm.get("k2_ms", 0.0), 1), "polish": round(tm.get("polish_ms", 0.0), 1)},
+                # the sampler's rate on this workload (rank 0's shard): shape pixels it evaluated / its K2 device time
+                "rank0_k2_evals_per_sec": (st4.get("voigt_evals_actual", 0.0) / (tm["k2_ms"] * 1e-3)) if tm.get("k2_ms") else None,
+                "rank0_chains": int(st4.get("chains", 0)),
                 "rank0_host_s": {k: round(tm.get(k, 0.0), 3) for k in ("upload_s", "host_setup_s", "host_launch_s",
                                                                        "host_wait_s", "host_post_s", "ladder_s", "records_s")}}
 
