@@ -24,8 +24,9 @@ def chain_uids(region_uid, n, restarts, chains_per_restart):
 # component-count edges of the polish launch groups (<= 4, 5..8, 9..12, more): see ``fit_models.polish``
 POLISH_GROUP_EDGES = (4, 8, 12)
 POLISH_STREAMS = __import__("os").environ.get("VAMP_POLISH_STREAMS", "1") != "0"
-# component-count edges of the sampler launch groups, by CTAs per SM (<= 8: 5, 9..10: 4, 11..15: 3, more: 2); VAMP_K2_GROUPS=0: one launch
-K2_GROUP_EDGES = (8, 10, 15)
+# component-count edges of the sampler launch groups, by CTAs per SM (<= 6: 5, 7..8: 4 - shared memory is 38.5 / 46.7 KB per CTA -
+# 9..10: 4, 11..15: 3, more: 2); VAMP_K2_GROUPS=0: one launch.  (6 | 8) instead of (8): 12 500 C4 regions K2 13.64 -> 13.16 s
+K2_GROUP_EDGES = tuple(int(v) for v in __import__("os").environ.get("VAMP_K2_EDGES", "6,8,10,15").split(","))
 K2_GROUPS = __import__("os").environ.get("VAMP_K2_GROUPS", "1") != "0"
 
 
