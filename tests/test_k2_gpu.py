@@ -289,7 +289,7 @@ def test_full_size_c2_independent_of_batching(ctx):
 
 
 def test_launch_groups_do_not_change_results(ctx, monkeypatch):
-    """Sampler rows and polish starts go out in component-count groups on side streams (batch.K2_GROUP_EDGES,
+    """Sampler rows and polish starts go out in component-count groups on side streams (batch.k2_group_edges,
     POLISH_GROUP_EDGES; the warp schedule keeps launch-sized simplex vertices in shared memory): every chain and
     every simplex is independent of how it was launched - bit-identical tables with one group and with many."""
     from vamp_b200 import batch

@@ -21,12 +21,34 @@ def chain_uids(region_uid, n, restarts, chains_per_restart):
     return (np.uint64(int(region_uid) & 0xFFFFFFFFFF) << np.uint64(24)) | (np.uint64(int(n) & 0xFF) << np.uint64(16)) | c
 
 
-# component-count edges of the polish launch groups (<= 4, 5..8, 9..12, more): see ``fit_models.polish``
-POLISH_GROUP_EDGES = (4, 8, 12)
+# component-count edges of the polish launch groups: see ``fit_models.polish``
+# (None: <= 2, 3..4, then one group per component count - 12 500 C4 regions, polish 3.31 s with the edges (4, 8, 12) -> 3.06 s)
+POLISH_GROUP_EDGES = (tuple(int(v) for v in __import__("os").environ["VAMP_POLISH_EDGES"].split(","))
+                      if __import__("os").environ.get("VAMP_POLISH_EDGES") else None)
+
+
+def polish_group_edges(n_largest):
+    """Upper component counts of the polish launch groups of a batch whose largest count is ``n_largest``."""
+    if POLISH_GROUP_EDGES is not None:
+        return tuple(POLISH_GROUP_EDGES) + (int(n_largest),)
+    return (2, 4) + tuple(range(5, max(5, int(n_largest)) + 1))
 POLISH_STREAMS = __import__("os").environ.get("VAMP_POLISH_STREAMS", "1") != "0"
-# component-count edges of the sampler launch groups, by CTAs per SM (<= 6: 5, 7..8: 4 - shared memory is 38.5 / 46.7 KB per CTA -
-# 9..10: 4, 11..15: 3, more: 2); VAMP_K2_GROUPS=0: one launch.  (6 | 8) instead of (8): 12 500 C4 regions K2 13.64 -> 13.16 s
-K2_GROUP_EDGES = tuple(int(v) for v in __import__("os").environ.get("VAMP_K2_EDGES", "6,8,10,15").split(","))
+# Sampler launch groups by component count: K2's shared memory per chain is (n_max + 2) KB with n_max the LAUNCH's largest
+# count, and that footprint decides how many CTAs share an SM (<= 6 components: 5, 7: 5, 8..10: 4, 11..14: 3, more: 2).
+# Chains of <= 6 components go out together, every larger count as its own launch (VAMP_K2_EDGES: explicit edges;
+# VAMP_K2_GROUPS=0: one launch).  12 500 C4 regions, K2: 13.64 s (groups <= 8 / 9-10 / 11-15 / more) -> 13.16 (<= 6 split
+# off) -> 12.52 s (one group per count), same records.
+K2_GROUP_FIRST = 6
+_k2_edges_env = __import__("os").environ.get("VAMP_K2_EDGES")
+
+
+def k2_group_edges(n_largest):
+    """Upper component counts of the sampler launch groups of a batch whose largest count is ``n_largest``."""
+    if _k2_edges_env:
+        return tuple(int(v) for v in _k2_edges_env.split(",")) + (int(n_largest),)
+    return tuple(range(K2_GROUP_FIRST, max(K2_GROUP_FIRST, int(n_largest)) + 1))
+
+
 K2_GROUPS = __import__("os").environ.get("VAMP_K2_GROUPS", "1") != "0"
 
 
@@ -141,7 +163,7 @@ def fit_models(regions, models, voigt=False, sd_free=True, iterations=3000, burn
         ncount = np.bincount(np.array([models[m][1] for m in model_ids]), minlength=2) * (G * K)
         groups, a = [], 0
         if polish_dtype == "mixed":
-            for hi in POLISH_GROUP_EDGES + (len(ncount) - 1,):
+            for hi in polish_group_edges(len(ncount) - 1):
                 b = int(ncount[: hi + 1].sum())
                 if b > a:
                     groups.append((a, b, int(np.nonzero(ncount[: hi + 1])[0].max())))
@@ -223,13 +245,25 @@ def fit_models(regions, models, voigt=False, sd_free=True, iterations=3000, burn
         for lc in np.unique(sorted_lc):                  # one pass per long class (a single pass of class 0 as a rule)
             lo, hi_ = int(np.searchsorted(sorted_lc, lc, "left")), int(np.searchsorted(sorted_lc, lc, "right"))
             nc, a0 = sorted_nc[lo:hi_], 0
-            for hi in K2_GROUP_EDGES + (int(nc[-1]),):
+            for hi in k2_group_edges(nc[-1]):
                 b0 = int(np.searchsorted(nc, hi, "right"))
                 if b0 > a0:
                     bounds.append((lo + a0, lo + b0, int(nc[b0 - 1])))
                 a0 = max(a0, b0)
         if len(bounds) == 1 or (not K2_GROUPS and sorted_lc[0] == sorted_lc[-1]):
             s.run(iterations)
+        elif __import__("os").environ.get("VAMP_K2_GROUP_TIMES"):
+            # (diagnostic: the groups one after the other, each timed - how the sampler's time splits over component counts)
+            for a0, b0, nmax_g in reversed(bounds):
+                g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                g0.record()
+                s.run(iterations, rows=(a0, b0), max_ncomp=nmax_g, advance=False)
+                g1.record()
+                torch.cuda.synchronize()
+                px = regions.npix[item_region[order][a0:b0]]
+                print("   K2 group n <= %2d: %7d chains (%.0f%% of <= 128 px) %8.1f ms" % (
+                    nmax_g, b0 - a0, 100.0 * float(np.mean(px <= 128)), g0.elapsed_time(g1)), flush=True)
+            s.iteration += int(iterations)
         else:
             side = _polish_streams(dev, len(bounds))
             for st, (a0, b0, nmax_g) in zip(side, reversed(bounds)):
